@@ -1,0 +1,502 @@
+"""CPU oracle for the MAL photometric hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a restatement, in plain torch-on-CPU fp32, of the arithmetic the
+reference (YuejiangDong/MAL) performs on the path SURVEY.md section 8 scopes:
+backproject -> project -> bilinear warp -> SSIM+L1 -> min-reprojection/automask
+-> MAL temporal/distillation selection, the plane-sweep matching cost volume,
+the smoothness term and the host-side loss balancers.
+
+Rules (see DESIGN.md "Oracle"):
+  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+    --impl reference legs may import this file.  The product package
+    `mal_b200` never imports it and has no CPU fallback.
+  * Every function cites the reference file:line it restates (paths relative
+    to /root/reference).
+  * Parity is PINNED: oracle/pin_against_reference.py imports the reference's
+    own modules in the build container and asserts bitwise equality with this
+    restatement on seeded inputs; tests/golden/*.npz are outputs of the
+    reference itself (made by tests/golden/make_golden.py) and
+    tests/test_oracle_golden.py re-checks this file against them anywhere.
+  * The arithmetic below is the reference's, op for op (same torch calls in
+    the same order) because the selection indices must match bit for bit.
+
+Third-party arithmetic the reference leans on and that is restated here through
+the same torch 2.11 ATen CPU kernels: grid_sampler_2d, avg_pool2d,
+reflection_pad2d, upsample_bilinear2d, argmin/min.  torch_sparse.coalesce
+(dynamicdepth/rigid_warp.py:577, version unpinned, absent from the tree) is
+restated from its published semantics (duplicate-index max reduction).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MANYDEPTH = 0   # Project3D normalisation x/(W-1), grid_sample align_corners=True
+DUALREFINE = 1  # Project3D 2(x+0.5)/W-1, grid_sample align_corners=False
+
+
+# --------------------------------------------------------------------------
+# geometry
+# --------------------------------------------------------------------------
+def disp_to_depth(disp, min_depth, max_depth):
+    """manydepth/layers.py:14-23."""
+    lo = 1 / max_depth
+    hi = 1 / min_depth
+    scaled = lo + (hi - lo) * disp
+    return scaled, 1 / scaled
+
+
+def rot_from_axisangle(vec):
+    """manydepth/layers.py:61-100 (Rodrigues, 4x4)."""
+    angle = torch.norm(vec, 2, 2, True)
+    axis = vec / (angle + 1e-7)
+    ca, sa = torch.cos(angle), torch.sin(angle)
+    C = 1 - ca
+    x, y, z = (axis[..., i].unsqueeze(1) for i in range(3))
+    xs, ys, zs = x * sa, y * sa, z * sa
+    xC, yC, zC = x * C, y * C, z * C
+    xyC, yzC, zxC = x * yC, y * zC, z * xC
+    rot = torch.zeros((vec.shape[0], 4, 4), device=vec.device)
+    entries = {(0, 0): x * xC + ca, (0, 1): xyC - zs, (0, 2): zxC + ys,
+               (1, 0): xyC + zs, (1, 1): y * yC + ca, (1, 2): yzC - xs,
+               (2, 0): zxC - ys, (2, 1): yzC + xs, (2, 2): z * zC + ca}
+    for (r, c), v in entries.items():
+        rot[:, r, c] = torch.squeeze(v)
+    rot[:, 3, 3] = 1
+    return rot
+
+
+def get_translation_matrix(t):
+    """manydepth/layers.py:45-58."""
+    T = torch.zeros(t.shape[0], 4, 4, device=t.device)
+    for i in range(4):
+        T[:, i, i] = 1
+    T[:, :3, 3, None] = t.contiguous().view(-1, 3, 1)
+    return T
+
+
+def transformation_from_parameters(axisangle, translation, invert=False):
+    """manydepth/layers.py:26-42."""
+    R = rot_from_axisangle(axisangle)
+    t = translation.clone()
+    if invert:
+        R = R.transpose(1, 2)
+        t *= -1
+    T = get_translation_matrix(t)
+    return torch.matmul(R, T) if invert else torch.matmul(T, R)
+
+
+def pixel_grid(batch, height, width):
+    """Homogeneous pixel coordinates (B,3,HW), x = column; layers.py:149-161."""
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float32),
+                            torch.arange(width, dtype=torch.float32), indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(height * width)], 0)
+    return pix.unsqueeze(0).repeat(batch, 1, 1)
+
+
+def backproject(depth, inv_K):
+    """BackprojectDepth.forward, manydepth/layers.py:163-168 -> (B,4,HW)."""
+    B, _, H, W = depth.shape
+    rays = torch.matmul(inv_K[:, :3, :3], pixel_grid(B, H, W))
+    cam = depth.view(B, 1, -1) * rays
+    return torch.cat([cam, torch.ones(B, 1, H * W)], 1)
+
+
+def project3d(points, K, T, height, width, convention=MANYDEPTH, eps=1e-7, return_z=False):
+    """Project3D.forward: manydepth/layers.py:184-199, dualrefine/layers.py:216-226."""
+    B = points.shape[0]
+    P = torch.matmul(K, T)[:, :3, :]
+    cam = torch.matmul(P, points)
+    pix = cam[:, :2, :] / (cam[:, 2, :].unsqueeze(1) + eps)
+    pix = pix.view(B, 2, height, width).permute(0, 2, 3, 1)
+    if convention == MANYDEPTH:
+        pix[..., 0] /= width - 1
+        pix[..., 1] /= height - 1
+        pix = (pix - 0.5) * 2
+    else:
+        pix[..., 0] = 2 * (pix[..., 0] + 0.5) / width - 1
+        pix[..., 1] = 2 * (pix[..., 1] + 0.5) / height - 1
+    if return_z:
+        return pix, cam[:, 2, :].unsqueeze(1).view(B, 1, height, width)
+    return pix
+
+
+def warp(img, grid, convention=MANYDEPTH, padding_mode="border"):
+    """F.grid_sample call sites: manydepth/trainer.py:1122-1125 (align_corners=True),
+    dualrefine/trainer.py:444-447 (align_corners=False)."""
+    return F.grid_sample(img, grid, padding_mode=padding_mode,
+                         align_corners=(convention == MANYDEPTH))
+
+
+def upsample_disp(disp, height, width):
+    """manydepth/trainer.py:1093-1094."""
+    return F.interpolate(disp, [height, width], mode="bilinear", align_corners=False)
+
+
+# --------------------------------------------------------------------------
+# photometric terms
+# --------------------------------------------------------------------------
+_C1 = 0.01 ** 2
+_C2 = 0.03 ** 2
+
+
+def ssim(x, y):
+    """SSIM.forward, manydepth/layers.py:243-257 (3x3 box, reflection pad 1)."""
+    x = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    y = F.pad(y, (1, 1, 1, 1), mode="reflect")
+    box = lambda t: F.avg_pool2d(t, 3, 1)
+    mu_x, mu_y = box(x), box(y)
+    sigma_x = box(x ** 2) - mu_x ** 2
+    sigma_y = box(y ** 2) - mu_y ** 2
+    sigma_xy = box(x * y) - mu_x * mu_y
+    num = (2 * mu_x * mu_y + _C1) * (2 * sigma_xy + _C2)
+    den = (mu_x ** 2 + mu_y ** 2 + _C1) * (sigma_x + sigma_y + _C2)
+    return torch.clamp((1 - num / den) / 2, 0, 1)
+
+
+def reprojection_loss(pred, target, no_ssim=False):
+    """manydepth/loss_utils.py:46-55, manydepth/trainer.py:1211-1223."""
+    l1 = torch.abs(target - pred).mean(1, True)
+    if no_ssim:
+        return l1
+    return 0.85 * ssim(pred, target).mean(1, True) + 0.15 * l1
+
+
+def loss_masks(reproj, identity):
+    """manydepth/loss_utils.py:27-44."""
+    if identity is None:
+        return torch.ones_like(reproj)
+    idx = torch.argmin(torch.cat([reproj, identity], dim=1), dim=1, keepdim=True)
+    return (idx == 0).float()
+
+
+def smooth_loss(disp, img):
+    """get_smooth_loss, manydepth/layers.py:210-223."""
+    gdx = torch.abs(disp[:, :, :, :-1] - disp[:, :, :, 1:])
+    gdy = torch.abs(disp[:, :, :-1, :] - disp[:, :, 1:, :])
+    gix = torch.mean(torch.abs(img[:, :, :, :-1] - img[:, :, :, 1:]), 1, keepdim=True)
+    giy = torch.mean(torch.abs(img[:, :, :-1, :] - img[:, :, 1:, :]), 1, keepdim=True)
+    gdx = gdx * torch.exp(-gix)
+    gdy = gdy * torch.exp(-giy)
+    return gdx.mean() + gdy.mean()
+
+
+def normalised_smooth_loss(disp, img):
+    """manydepth/loss_utils.py:119-121 (mean-normalised disparity)."""
+    mean_disp = disp.mean(2, True).mean(3, True)
+    return smooth_loss(disp / (mean_disp + 1e-7), img)
+
+
+# --------------------------------------------------------------------------
+# trainer-resident glue (restated; manydepth.trainer cannot be imported)
+# --------------------------------------------------------------------------
+def images_pred(inputs, outputs, frame_ids=(0, -1, 1), num_scales=1, height=192, width=640,
+                min_depth=0.1, max_depth=100.0, is_multi=False, convention=MANYDEPTH,
+                automask=True):
+    """Trainer.generate_images_pred, manydepth/trainer.py:1078-1158 (v1_multiscale off)."""
+    for scale in range(num_scales):
+        disp = upsample_disp(outputs[("disp", scale)], height, width)
+        _, depth = disp_to_depth(disp, min_depth, max_depth)
+        outputs[("depth", 0, scale)] = depth
+        for fid in frame_ids[1:]:
+            T = outputs[("cam_T_cam", 0, fid)]
+            if is_multi:
+                T = T.detach()
+            cam = backproject(depth, inputs[("inv_K", 0)])
+            grid = project3d(cam, inputs[("K", 0)], T, height, width, convention)
+            outputs[("sample", fid, scale)] = grid
+            outputs[("color", fid, scale)] = warp(inputs[("color", fid, 0)], grid, convention)
+            if automask:
+                outputs[("color_identity", fid, scale)] = inputs[("color", fid, 0)]
+    return outputs
+
+
+def images_pred_ensemble(inputs, T_prev, T_next, disp, frame_ids=(0, -1, 1), height=192,
+                         width=640, min_depth=0.1, max_depth=100.0, no_ssim=False):
+    """Trainer.generate_images_pred_ensemble, manydepth/trainer.py:1172-1207."""
+    disp = upsample_disp(disp, height, width)
+    _, depth = disp_to_depth(disp, min_depth, max_depth)
+    target = inputs[("color", 0, 0)]
+    cands = []
+    for T, fid in zip((T_prev, T_next), frame_ids[1:]):
+        cam = backproject(depth, inputs[("inv_K", 0)])
+        grid = project3d(cam, inputs[("K", 0)], T, height, width)
+        cands.append(reprojection_loss(warp(inputs[("color", fid, 0)], grid), target, no_ssim))
+    return torch.min(torch.cat(cands, 1), dim=1, keepdim=True)[0]
+
+
+def matching_mask(outputs):
+    """Trainer.compute_matching_mask, manydepth/trainer.py:1066-1076."""
+    mono = outputs[("mono_depth", 0, 0)]
+    matching = 1 / outputs["lowest_cost"].unsqueeze(1)
+    mask = ((matching - mono) / mono) < 1.0
+    mask *= ((mono - matching) / matching) < 1.0
+    return mask[:, 0]
+
+
+def mono_losses(inputs, outputs, temporal, has_ins, noise=None, no_ssim=False):
+    """compute_mono_losses, manydepth/loss_utils.py:57-129.
+
+    `noise` replaces the reference's in-line torch.randn(shape) draw (:105) so both
+    sides of a parity test see the same tie-break bits; None draws it like the
+    reference does."""
+    target = inputs[("color", 0, 0)]
+    cands = [reprojection_loss(outputs[("color", f, 0)], target, no_ssim) for f in (-1, 1)]
+    if temporal and has_ins:
+        cands += [reprojection_loss(outputs[("syn", f, 0)], target, no_ssim) for f in (-1, 1)]
+    cands = torch.cat(cands, 1)
+    ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, no_ssim)
+                       for f in (-1, 1)], 1)
+    ident, _ = torch.min(ident, dim=1, keepdim=True)
+    reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
+    if noise is None:
+        noise = torch.randn(ident.shape)
+    ident = ident + noise * 0.00001
+    mask = loss_masks(reproj, ident)
+    reproj_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+    losses = {"reproj_loss/0": reproj_loss}
+    loss = reproj_loss + 1e-3 * normalised_smooth_loss(outputs[("disp", 0)],
+                                                       inputs[("color", 0, 0)]) / (2 ** 0)
+    losses["loss/0"] = loss
+    losses["loss"] = 0 + loss
+    aux = {"frame_idx": frame_idx, "automask": mask}
+    return losses, torch.min(cands, dim=1, keepdim=True)[0], aux
+
+
+def main_losses(inputs, outputs, mono_reproj, ensemble_reproj, *, batch_size,
+                multi_has_ins=False, dual_distil=False, loss_blc=False, w_list=None,
+                noise=None, no_ssim=False):
+    """compute_main_losses, manydepth/loss_utils.py:131-281 (pareto / learn_ens off).
+
+    The automask computed at :181 is discarded at :192, as in the reference; only
+    the RNG draw matters to callers that share a generator."""
+    target = inputs[("color", 0, 0)]
+    cands = [reprojection_loss(outputs[("color", f, 0)], target, no_ssim) for f in (-1, 1)]
+    if multi_has_ins:
+        cands += [reprojection_loss(outputs[("syn", f, 0)], target, no_ssim) for f in (-1, 1)]
+    cands = torch.cat(cands, 1)
+    reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
+    multi_reproj = reproj.clone()
+    if noise is None:
+        noise = torch.randn(reproj.shape)  # drawn then unused, loss_utils.py:178-192
+
+    mask = torch.ones_like(reproj)
+    mask = mask * outputs["consistency_mask"].unsqueeze(1)
+    mask = mask * (1 - outputs["augmentation_mask"][:batch_size])
+    cons_mask = (1 - mask).float()
+
+    reproj_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+    multi_depth = outputs[("depth", 0, 0)]
+    mono_depth = outputs[("mono_depth", 0, 0)].detach()
+    cons_loss = (torch.abs(multi_depth - mono_depth) * cons_mask).mean()
+    cons_target = 1 / (mono_depth.detach() * cons_mask + multi_depth.detach() * (1 - cons_mask))
+
+    losses = {"consistency_loss/0": cons_loss, "reproj_loss/0": reproj_loss}
+    loss = reproj_loss + cons_loss
+    loss = loss + 1e-3 * normalised_smooth_loss(outputs[("disp", 0)], inputs[("color", 0, 0)])
+
+    if ensemble_reproj is None:
+        _, sel = torch.min(torch.cat([mono_reproj, multi_reproj], 1), dim=1, keepdim=True)
+        teacher = outputs[("mono_depth", 0, 0)] if dual_distil else mono_depth
+        distil_depth = torch.where(sel == 0, teacher, multi_depth)
+    else:
+        _, sel = torch.min(torch.cat([mono_reproj, ensemble_reproj, multi_reproj], 1),
+                           dim=1, keepdim=True)
+        ens_depth = (mono_depth + multi_depth) / 2.0
+        distil_depth = torch.where(sel == 0, mono_depth, ens_depth)
+        distil_depth = torch.where(sel == 2, multi_depth, distil_depth)
+    distil_loss = (torch.abs(distil_depth - multi_depth) * (1 - cons_mask)).mean()
+
+    losses["distil_loss"] = distil_loss
+    if loss_blc:
+        loss_list = [loss.clone(), distil_loss]
+        new_w = w_list
+    else:
+        loss = loss + distil_loss
+        loss_list, new_w = None, None
+    losses["loss/0"] = loss
+    losses["loss"] = loss
+    aux = {"frame_idx": frame_idx, "distil_idx": sel, "multi_reproj": multi_reproj,
+           "consistency_target": cons_target}
+    return losses, new_w, loss_list, aux
+
+
+def trainer_compute_losses(inputs, outputs, *, num_scales=1, is_multi=False, temporal=False,
+                           has_ins=False, automask=True, motion_masking=True,
+                           matching_augmentation=True, batch_size=None, no_ssim=False,
+                           smoothness=1e-3, noises=None):
+    """Trainer.compute_losses, manydepth/trainer.py:1248-1475 (the non-distil path,
+    one pass per scale, total / num_scales).  dynamicdepth/trainer.py:1006-1128 uses
+    the same chain over opt.scales."""
+    losses, total = {}, 0
+    aux = {}
+    target = inputs[("color", 0, 0)]
+    for scale in range(num_scales):
+        cands = [reprojection_loss(outputs[("color", f, scale)], target, no_ssim) for f in (-1, 1)]
+        if (not is_multi) and temporal and has_ins:
+            cands += [reprojection_loss(outputs[("syn", f, scale)], target, no_ssim)
+                      for f in (-1, 1)]
+        cands = torch.cat(cands, 1)
+        ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, no_ssim)
+                           for f in (-1, 1)], 1)
+        ident, _ = torch.min(ident, dim=1, keepdim=True)
+        reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
+        if automask:
+            nz = noises[scale] if noises is not None else torch.randn(ident.shape)
+            ident = ident + nz * 0.00001
+            mask = loss_masks(reproj, ident)
+        else:
+            mask = loss_masks(reproj, None)
+        cons_loss = 0
+        if is_multi:
+            mask = torch.ones_like(mask)
+            if motion_masking:
+                mask = mask * outputs["consistency_mask"].unsqueeze(1)
+            if matching_augmentation:
+                mask = mask * (1 - outputs["augmentation_mask"][:batch_size])
+            cons_mask = (1 - mask).float()
+        reproj_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+        if is_multi:
+            multi_depth = outputs[("depth", 0, scale)]
+            mono_depth = outputs[("mono_depth", 0, scale)].detach()
+            cons_loss = (torch.abs(multi_depth - mono_depth) * cons_mask).mean()
+            losses[f"consistency_loss/{scale}"] = cons_loss
+        losses[f"reproj_loss/{scale}"] = reproj_loss
+        loss = reproj_loss + cons_loss
+        loss = loss + smoothness * normalised_smooth_loss(
+            outputs[("disp", scale)], inputs[("color", 0, scale)]) / (2 ** scale)
+        total = total + loss
+        losses[f"loss/{scale}"] = loss
+        aux[("frame_idx", scale)] = frame_idx
+        aux[("mask", scale)] = mask
+    losses["loss"] = total / num_scales
+    return losses, aux
+
+
+# --------------------------------------------------------------------------
+# plane-sweep matching cost volume
+# --------------------------------------------------------------------------
+def depth_bins(min_depth_bin, max_depth_bin, num_bins=96, binning="linear"):
+    """ResnetEncoderMatching.compute_depth_bins, networks/resnet_encoder.py:121-141."""
+    lo, hi = float(min_depth_bin), float(max_depth_bin)
+    if binning == "linear":
+        return torch.linspace(lo, hi, num_bins)
+    if binning == "inverse":
+        b = 1 / np.linspace(1 / hi, 1 / lo, num_bins)[::-1]
+        return torch.from_numpy(np.ascontiguousarray(b)).float()
+    if binning == "log":
+        base, it = torch.log(torch.tensor(lo)), torch.log(torch.tensor(hi / lo))
+        return torch.exp(torch.Tensor([base + it * i / num_bins for i in range(num_bins)]))
+    raise NotImplementedError(binning)
+
+
+def match_features(current_feats, lookup_feats, relative_poses, K, invK, bins,
+                   convention=MANYDEPTH, set_missing_to_max=True):
+    """ResnetEncoderMatching.match_features, networks/resnet_encoder.py:151-233
+    (dualrefine/networks/resnet_encoder.py:163-245 differs in align_corners only)."""
+    B, C, h, w = current_feats.shape
+    nb = len(bins)
+    planes = bins.view(nb, 1, 1, 1).float().expand(nb, 1, h, w).contiguous()
+    volumes, masks = [], []
+    for b in range(B):
+        cost = torch.zeros(nb, h, w)
+        counts = torch.zeros(nb, h, w)
+        world = backproject(planes, invK[b:b + 1])
+        for li in range(lookup_feats.shape[1]):
+            pose = relative_poses[b:b + 1, li]
+            if pose.sum() == 0:
+                continue
+            feat = lookup_feats[b:b + 1, li].repeat([nb, 1, 1, 1])
+            locs = project3d(world, K[b:b + 1], pose, h, w)
+            warped = F.grid_sample(feat, locs, padding_mode="zeros", mode="bilinear",
+                                   align_corners=(convention == MANYDEPTH))
+            xv = (locs[..., 0] / 2 + 0.5) * (w - 1)
+            yv = (locs[..., 1] / 2 + 0.5) * (h - 1)
+            edge = ((xv >= 2.0) * (xv <= w - 2) * (yv >= 2.0) * (yv <= h - 2)).float()
+            inner = torch.zeros_like(edge)
+            inner[:, 2:-2, 2:-2] = 1.0
+            edge = edge * inner
+            diffs = torch.abs(warped - current_feats[b:b + 1]).mean(1) * edge
+            cost = cost + diffs
+            counts = counts + (diffs > 0).float()
+        cost = cost / (counts + 1e-7)
+        missing = (cost == 0).float()
+        if set_missing_to_max:
+            cost = cost * (1 - missing) + cost.max(0)[0].unsqueeze(0) * missing
+        volumes.append(cost)
+        masks.append(missing)
+    return torch.stack(volumes, 0), torch.stack(masks, 0)
+
+
+def confidence_mask(cost_volume, num_bins_threshold=None):
+    """compute_confidence_mask, networks/resnet_encoder.py:255-262."""
+    if num_bins_threshold is None:
+        num_bins_threshold = cost_volume.shape[1]
+    return ((cost_volume > 0).sum(1) == num_bins_threshold).float()
+
+
+def lowest_cost(cost_volume, bins):
+    """networks/resnet_encoder.py:309-313 + indices_to_disparity :247-253."""
+    viz = cost_volume.clone()
+    viz[viz == 0] = 100
+    _, idx = torch.min(viz, 1)
+    return 1 / bins[idx.reshape(-1)].reshape(idx.shape), idx
+
+
+def cost_volume_head(current_feats, lookup_feats, relative_poses, K, invK, bins,
+                     convention=MANYDEPTH):
+    """ResnetEncoderMatching.forward :303-317: volume, confidence, argmin, masked volume."""
+    cv, missing = match_features(current_feats, lookup_feats, relative_poses, K, invK, bins,
+                                 convention)
+    conf = confidence_mask(cv * (1 - missing))
+    low, idx = lowest_cost(cv, bins)
+    return cv * conf.unsqueeze(1), low, conf, idx, missing
+
+
+# --------------------------------------------------------------------------
+# host-side loss balancers (fp64 numpy state, as the reference)
+# --------------------------------------------------------------------------
+class LossBalancing:
+    """manydepth/loss_utils.py:283-345."""
+
+    def __init__(self, num_loss, num_train_data, bs):
+        self.num_loss, self.num_data, self.bs = num_loss, num_train_data, bs
+        self.w_list = np.array([1. / num_loss, 1. / num_loss])
+        self.scale0 = np.array([1. / num_loss, 1. / num_loss])
+        self.train_scores = np.zeros((num_train_data, num_loss))
+        self.initialised = False
+        self.last_rebalancing_iter = 0
+        self.previous_total_loss = 0
+        self.previous_loss = 0
+
+    def compute_loss(self, loss_list, index_iter):
+        loss = 0
+        for ib in range(self.bs):
+            rec = self.bs * index_iter + ib
+            if rec < self.num_data:
+                for k in range(self.num_loss):
+                    loss = loss + self.w_list[k] * loss_list[k]
+                for k in range(self.num_loss):
+                    self.train_scores[rec, k] = float(loss_list[k])
+        return loss
+
+    def update_weight(self, i, lam):
+        mean = self.train_scores[self.last_rebalancing_iter * self.bs:(i + 1) * self.bs].mean(axis=0)
+        total = np.sum(mean * self.w_list)
+        if not self.initialised:
+            for k in range(self.num_loss):
+                self.w_list[k] = (total * self.scale0[k]) / mean[k]
+            self.initialised = True
+        else:
+            prev_w = np.array(self.w_list)
+            if self.previous_total_loss > 0:
+                for k in range(self.num_loss):
+                    adj = 1 + lam * ((total / self.previous_total_loss) *
+                                     (self.previous_loss[k] / mean[k]) - 1)
+                    self.w_list[k] = prev_w[k] * min(max(adj, 0.5), 2.0)
+        self.previous_total_loss = np.sum(mean * self.w_list)
+        self.previous_loss = mean
+        return self.w_list[0], self.w_list[1]

@@ -1,0 +1,293 @@
+"""Pin oracle/mal_oracle.py against the reference's own Python.  TEST INFRASTRUCTURE.
+
+Runs ONLY in the build container, where /root/reference exists (the GPU box does not
+have it).  It imports the reference's modules unmodified - with import stubs for
+packages that are absent from this image (matplotlib, accelerate, detectron2, wandb,
+skimage, torchmetrics, manydepth.pareto, manydepth.vis ...) and that the hot path never
+executes - runs them on seeded synthetic inputs and asserts that the restatement in
+mal_oracle.py is BITWISE identical.  tests/golden/make_golden.py reuses `load_reference`
+to write the committed fixtures from the reference's outputs.
+
+Usage:  python -m oracle.pin_against_reference
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+from types import SimpleNamespace
+from unittest import mock
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("MAL_REFERENCE_ROOT", "/root/reference")
+
+_STUB_PREFIXES = ("matplotlib", "accelerate", "detectron2", "wandb", "skimage", "torchmetrics",
+                  "tensorboardX", "termcolor", "torch_sparse", "manydepth.pareto",
+                  "manydepth.vis", "mask2former", "cv2", "IPython", "timm", "fvcore")
+
+
+# stubbed even though a directory of that name exists: the vendored segmenter needs detectron2
+_ALWAYS_STUB = ("manydepth.pareto", "manydepth.vis", "mask2former")
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Serve MagicMock-backed modules for imports the image lacks."""
+
+    def find_spec(self, name, path=None, target=None):
+        if any(name == p or name.startswith(p + ".") for p in _STUB_PREFIXES):
+            try:
+                for f in sys.meta_path:
+                    if f is self:
+                        continue
+                    spec = f.find_spec(name, path, target) if hasattr(f, "find_spec") else None
+                    if spec is not None and not name.startswith(_ALWAYS_STUB):
+                        return None  # really installed
+            except Exception:
+                pass
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = mock.MagicMock(name=spec.name)
+        m.__name__, m.__path__, m.__spec__ = spec.name, [], spec
+        m.__loader__ = self
+        # torchmetrics.Metric is subclassed by the trainer: give it a real base class.
+        if spec.name == "torchmetrics":
+            m.Metric = type("Metric", (torch.nn.Module,), {})
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+_loaded = None
+
+
+def load_reference():
+    """Import the reference packages (once) and return them in a namespace."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not os.path.isdir(REFERENCE_ROOT):
+        raise FileNotFoundError(f"{REFERENCE_ROOT} not present: pinning runs in the build container only")
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REFERENCE_ROOT)
+    ns = SimpleNamespace()
+    ns.layers = importlib.import_module("manydepth.layers")
+    ns.loss_utils = importlib.import_module("manydepth.loss_utils")
+    ns.resnet_encoder = importlib.import_module("manydepth.networks.resnet_encoder")
+    ns.multilossmanager = importlib.import_module("manydepth.multilossmanager")
+    ns.dualrefine_layers = importlib.import_module("dualrefine.layers")
+    ns.dynamicdepth_layers = importlib.import_module("dynamicdepth.layers")
+    try:
+        ns.trainer = importlib.import_module("manydepth.trainer")
+    except Exception as e:  # pragma: no cover - informational
+        ns.trainer = None
+        ns.trainer_error = repr(e)
+    _loaded = ns
+    return ns
+
+
+# --------------------------------------------------------------------------
+def reference_matcher(ref, height, width, bins):
+    """A ResnetEncoderMatching shell with only the state match_features reads."""
+    enc = ref.resnet_encoder.ResnetEncoderMatching.__new__(ref.resnet_encoder.ResnetEncoderMatching)
+    torch.nn.Module.__init__(enc)
+    h, w = height // 4, width // 4
+    enc.num_depth_bins = len(bins)
+    enc.matching_height, enc.matching_width = h, w
+    enc.set_missing_to_max = True
+    enc.depth_binning = "linear"
+    enc.device = torch.device("cpu")
+    enc.depth_bins = bins
+    enc.warp_depths = torch.stack([torch.ones((1, h, w)) * d for d in bins], 0).float()
+    enc.backprojector = ref.layers.BackprojectDepth(len(bins), h, w)
+    enc.projector = ref.layers.Project3D(len(bins), h, w)
+    return enc
+
+
+def reference_trainer_shell(ref, batch, height, width, **opt):
+    """A fake `self` good enough for Trainer's pure methods (manydepth/trainer.py)."""
+    o = dict(sclm=0, v1_multiscale=False, height=height, width=width, min_depth=0.1,
+             max_depth=100.0, frame_ids=[0, -1, 1], disable_automasking=False, temporal=False,
+             main_temporal=False, no_ssim=False, disable_motion_masking=False,
+             no_matching_augmentation=False, batch_size=batch, loss_pct=False, ensemble=False,
+             disparity_smoothness=1e-3, debug=False)
+    o.update(opt)
+    shell = SimpleNamespace(opt=SimpleNamespace(**o), device=torch.device("cpu"),
+                            ssim=ref.layers.SSIM(), has_ins=False, multi_has_ins=False, step=1,
+                            is_main=False)
+    shell.backproject_depth = {0: ref.layers.BackprojectDepth(batch, height, width)}
+    shell.project_3d = {0: ref.layers.Project3D(batch, height, width)}
+    T = ref.trainer.Trainer
+    for name in ("generate_images_pred", "generate_images_pred_ensemble", "compute_reprojection_loss",
+                 "compute_losses", "compute_matching_mask"):
+        setattr(shell, name, types.MethodType(getattr(T, name), shell))
+    shell.compute_loss_masks = T.compute_loss_masks
+    return shell
+
+
+def _eq(name, a, b):
+    ok = torch.equal(a, b)
+    print(f"  {'OK ' if ok else 'FAIL'} {name}: shape {tuple(a.shape)}"
+          + ("" if ok else f"  max|d|={float((a - b).abs().max()):.3e}"))
+    return ok
+
+
+def run_pin(batch=2, height=96, width=160, seed=7):
+    """Bitwise comparison of the restatement with the reference on one seeded batch."""
+    from mal_b200.utils.synthetic import make_photometric_inputs, make_cost_volume_inputs
+    from oracle import mal_oracle as O
+    ref = load_reference()
+    ok = True
+    inputs, t = make_photometric_inputs(batch, height, width, num_scales=2, seed=seed)
+
+    # --- geometry + warp + SSIM ------------------------------------------------
+    disp = O.upsample_disp(t[("mono_disp", 1)], height, width)
+    _, depth = ref.layers.disp_to_depth(disp, 0.1, 100.0)
+    ok &= _eq("disp_to_depth", O.disp_to_depth(disp, 0.1, 100.0)[1], depth)
+    bp, pj = ref.layers.BackprojectDepth(batch, height, width), ref.layers.Project3D(batch, height, width)
+    cam = bp(depth, inputs[("inv_K", 0)])
+    ok &= _eq("backproject", O.backproject(depth, inputs[("inv_K", 0)]), cam)
+    T = t[("cam_T_cam", 0, 1)]
+    grid = pj(cam, inputs[("K", 0)], T)
+    ok &= _eq("project3d", O.project3d(cam, inputs[("K", 0)], T, height, width), grid)
+    pj2 = ref.dualrefine_layers.Project3D(batch, height, width)
+    ok &= _eq("project3d(dualrefine)", O.project3d(cam, inputs[("K", 0)], T, height, width, O.DUALREFINE),
+              pj2(cam, inputs[("K", 0)], T))
+    ssim = ref.layers.SSIM()
+    x, y = inputs[("color", 1, 0)], inputs[("color", 0, 0)]
+    ok &= _eq("ssim", O.ssim(x, y), ssim(x, y))
+    ok &= _eq("reprojection_loss", O.reprojection_loss(x, y), ref.loss_utils.compute_reprojection_loss(ssim, x, y))
+    ok &= _eq("smooth_loss", O.smooth_loss(disp, y), ref.layers.get_smooth_loss(disp, y))
+    for inv in (False, True):
+        ok &= _eq(f"transformation_from_parameters(invert={inv})",
+                  O.transformation_from_parameters(t[("axisangle", 1)], t[("translation", 1)], inv),
+                  ref.layers.transformation_from_parameters(t[("axisangle", 1)], t[("translation", 1)], inv))
+
+    # --- trainer glue + MAL losses --------------------------------------------
+    if ref.trainer is None:
+        print("  SKIP trainer glue:", ref.trainer_error)
+        ok = False
+    else:
+        shell = reference_trainer_shell(ref, batch, height, width)
+        mono_ref = {("disp", 0): t[("mono_disp", 0)].clone().requires_grad_(True)}
+        mono_ora = {("disp", 0): t[("mono_disp", 0)].clone().requires_grad_(True)}
+        for f in (-1, 1):
+            mono_ref[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+            mono_ora[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+            mono_ref[("syn", f, 0)] = t[("syn", f, 0)]
+            mono_ora[("syn", f, 0)] = t[("syn", f, 0)]
+        shell.generate_images_pred(inputs, mono_ref)
+        O.images_pred(inputs, mono_ora, height=height, width=width)
+        for f in (-1, 1):
+            ok &= _eq(f"generate_images_pred color {f}", mono_ora[("color", f, 0)], mono_ref[("color", f, 0)])
+        for temporal in (False, True):
+            torch.manual_seed(11)
+            l_ref, mr_ref = ref.loss_utils.compute_mono_losses(ssim, inputs, mono_ref, temporal, True)
+            torch.manual_seed(11)
+            l_ora, mr_ora, _ = O.mono_losses(inputs, mono_ora, temporal, True)
+            ok &= _eq(f"compute_mono_losses(temporal={temporal}) loss", l_ora["loss"], l_ref["loss"])
+            ok &= _eq(f"compute_mono_losses(temporal={temporal}) mono_reproj", mr_ora, mr_ref)
+        g_ref, = torch.autograd.grad(l_ref["loss"], mono_ref[("disp", 0)])
+        g_ora, = torch.autograd.grad(l_ora["loss"], mono_ora[("disp", 0)])
+        ok &= _eq("d mono loss / d disp", g_ora, g_ref)
+
+        # student / multi path
+        def multi_outputs():
+            o = {("disp", 0): t[("multi_disp", 0)].clone().requires_grad_(True),
+                 "consistency_mask": t["consistency_mask"], "augmentation_mask": t["augmentation_mask"],
+                 ("mono_depth", 0, 0): mono_ref[("depth", 0, 0)].detach(),
+                 ("mono_disp", 0): t[("mono_disp", 0)]}
+            for f in (-1, 1):
+                o[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+                o[("syn", f, 0)] = t[("syn", f, 0)]
+            return o
+        out_ref, out_ora = multi_outputs(), multi_outputs()
+        disp_ens = (t[("mono_disp", 0)] + t[("multi_disp", 0)]) / 2.0
+        ens_ref = shell.generate_images_pred_ensemble(inputs, t[("cam_T_cam", 0, -1)], t[("cam_T_cam", 0, 1)], disp_ens)
+        ens_ora = O.images_pred_ensemble(inputs, t[("cam_T_cam", 0, -1)], t[("cam_T_cam", 0, 1)], disp_ens,
+                                         height=height, width=width)
+        ok &= _eq("generate_images_pred_ensemble", ens_ora, ens_ref)
+        shell.generate_images_pred(inputs, out_ref, is_multi=True)
+        O.images_pred(inputs, out_ora, height=height, width=width, is_multi=True)
+        low = 1 / (mono_ref[("depth", 0, 0)].detach()[:, 0] * (0.5 + t["consistency_mask"] * 2.0))
+        for o in (out_ref, out_ora):
+            o["lowest_cost"] = low
+        ok &= _eq("compute_matching_mask", O.matching_mask(out_ora), shell.compute_matching_mask(out_ref))
+        for ens, has_ins, blc in ((ens_ref, False, True), (None, True, False)):
+            opt = SimpleNamespace(batch_size=batch, dual_distil=False, learn_ens=False, pareto=False,
+                                  loss_blc=blc, min_depth=0.1, max_depth=100.0)
+            torch.manual_seed(5)
+            l_ref, _, ll_ref = ref.loss_utils.compute_main_losses(ssim, inputs, out_ref, mr_ref.detach(), ens, opt,
+                                                                  None, None, has_ins)
+            torch.manual_seed(5)
+            l_ora, _, ll_ora, _ = O.main_losses(inputs, out_ora, mr_ora.detach(), ens, batch_size=batch,
+                                                multi_has_ins=has_ins, loss_blc=blc)
+            tag = f"compute_main_losses(ens={'y' if ens is not None else 'n'},ins={has_ins},blc={blc})"
+            for k in ("loss", "distil_loss", "reproj_loss/0", "consistency_loss/0"):
+                ok &= _eq(f"{tag} {k}", l_ora[k], l_ref[k])
+            tot_ref = l_ref["loss"] + (0.5 * ll_ref[1] if blc else 0)
+            tot_ora = l_ora["loss"] + (0.5 * ll_ora[1] if blc else 0)
+            g_ref, = torch.autograd.grad(tot_ref, out_ref[("disp", 0)], retain_graph=True)
+            g_ora, = torch.autograd.grad(tot_ora, out_ora[("disp", 0)], retain_graph=True)
+            ok &= _eq(f"{tag} d/d disp", g_ora, g_ref)
+
+        # Trainer.compute_losses (non-distil path), 2 scales
+        shell2 = reference_trainer_shell(ref, batch, height, width, sclm=1)
+        def pyr(name):
+            o = {("disp", s): t[(name + "_disp", s)] for s in range(2)}
+            for f in (-1, 1):
+                o[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+            return o
+        p_ref, p_ora = pyr("mono"), pyr("mono")
+        shell2.generate_images_pred(inputs, p_ref)
+        O.images_pred(inputs, p_ora, num_scales=2, height=height, width=width)
+        torch.manual_seed(3)
+        l_ref, _ = shell2.compute_losses(inputs, p_ref, is_multi=False)
+        torch.manual_seed(3)
+        l_ora, _ = O.trainer_compute_losses(inputs, p_ora, num_scales=2, batch_size=batch)
+        ok &= _eq("Trainer.compute_losses(2 scales) loss", l_ora["loss"], l_ref["loss"])
+
+    # --- cost volume -----------------------------------------------------------
+    cv = make_cost_volume_inputs(batch, height, width, channels=16, num_bins=24, seed=seed,
+                                 zero_pose_sample=batch - 1)
+    enc = reference_matcher(ref, height, width, cv["bins"])
+    cv_ref, miss_ref = enc.match_features(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"],
+                                          cv["K"], cv["inv_K"])
+    cv_ora, miss_ora = O.match_features(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"],
+                                        cv["K"], cv["inv_K"], cv["bins"])
+    ok &= _eq("match_features volume", cv_ora, cv_ref)
+    ok &= _eq("match_features missing", miss_ora, miss_ref)
+    ok &= _eq("compute_confidence_mask", O.confidence_mask(cv_ora * (1 - miss_ora)),
+              enc.compute_confidence_mask(cv_ref * (1 - miss_ref)))
+    viz = cv_ref.clone(); viz[viz == 0] = 100
+    _, am = torch.min(viz, 1)
+    ok &= _eq("lowest_cost", O.lowest_cost(cv_ora, cv["bins"])[0], enc.indices_to_disparity(am))
+
+    # --- LossBalancing ---------------------------------------------------------
+    lb_ref = ref.loss_utils.LossBalancing(2, 64, 4)
+    lb_ora = O.LossBalancing(2, 64, 4)
+    good = True
+    gen = torch.Generator().manual_seed(1)
+    for it in range(6):
+        ll = [torch.rand((), generator=gen) + 0.1, torch.rand((), generator=gen) * 0.01 + 1e-3]
+        with mock.patch.object(torch.Tensor, "cuda", lambda self, *a, **k: self):
+            a = lb_ref.compute_loss(ll, it)
+        b = lb_ora.compute_loss(ll, it)
+        good &= bool(torch.equal(torch.as_tensor(a), torch.as_tensor(b)))
+        good &= lb_ref.update_weight(it, 0.3) == lb_ora.update_weight(it, 0.3)
+    print(f"  {'OK ' if good else 'FAIL'} LossBalancing (6 iterations, weights + loss)")
+    ok &= good
+    return bool(ok)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    good = run_pin()
+    print("PINNED" if good else "PIN FAILED")
+    sys.exit(0 if good else 1)
