@@ -1,0 +1,75 @@
+"""ctypes binding of the C ABI declared in include/mal_b200.h.
+
+`lib()` loads `libmal_b200.so` (built in-tree by mal_b200/build.py for sm_100a) and fails
+loudly when it is missing: there is no CPU fallback.  `bind(handle)` attaches the prototypes
+to any handle exporting the same ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmal_b200.so")
+
+c_float_p = C.c_void_p  # raw device addresses are passed as integers
+
+
+class PhotoArgs(C.Structure):
+    """struct mal_photo_args (include/mal_b200.h)."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("mode", C.c_int32), ("convention", C.c_int32), ("depth_is_disp", C.c_int32),
+        ("no_ssim", C.c_int32), ("with_grad", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double), ("eps", C.c_float),
+        ("target", C.c_void_p), ("src", C.c_void_p * 2), ("syn", C.c_void_p * 2),
+        ("depth", C.c_void_p), ("K", C.c_void_p), ("inv_K", C.c_void_p), ("T", C.c_void_p * 2),
+        ("identity_min", C.c_void_p), ("noise", C.c_void_p), ("pixel_mask", C.c_void_p),
+        ("sample_mask", C.c_void_p),
+        ("min_reproj", C.c_void_p), ("selection", C.c_void_p), ("weight", C.c_void_p),
+        ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
+        ("sums", C.c_void_p), ("grad_P", C.c_void_p),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "mal_abi_version": (C.c_int, []),
+    "mal_last_error": (C.c_char_p, []),
+    "mal_check_device": (C.c_int, [C.c_int]),
+    "mal_photo_partials_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
+}
+
+ABI_VERSION = 1
+
+
+def bind(handle):
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    v = handle.mal_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"libmal_b200 ABI version {v}, binding expects {ABI_VERSION}")
+    return handle
+
+
+_lib = None
+
+
+def lib():
+    """The CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m mal_b200.build` "
+                "(mal_b200 has no CPU fallback)")
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        h = handle or lib()
+        raise RuntimeError(f"libmal_b200 error {rc}: {h.mal_last_error().decode()}")

@@ -1,0 +1,109 @@
+// mal_common.cuh - shared plumbing for the mal_b200 CUDA sources (sm_100a).
+//
+// * error reporting for the C-ABI (no C++ exception crosses the boundary)
+// * kernel launch helper (also the hook the host-side test emulator uses)
+// * exact, never-contracted fp32 arithmetic (x*) for everything that feeds a
+//   selection comparison, see DESIGN.md "Arithmetic contract"
+// * block reductions
+#pragma once
+
+#ifdef MAL_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mal_b200.h"
+
+namespace mal {
+
+// ------------------------------------------------------------------ errors
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MAL_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  return MAL_OK;
+}
+#define MAL_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) return ::mal::fail(MAL_ERR_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+// ------------------------------------------------------------------ launch
+// One entry point for every kernel launch so the host emulator can intercept it.
+template <class... KArgs, class... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                   Args... args) {
+#ifdef MAL_EMU
+  (void)stream;
+  emu::launch(grid, block, smem, [=]() { kernel(args...); });
+#else
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<grid, block, smem, stream>>>(args...);
+#endif
+}
+
+// dynamic shared memory base, 16-byte aligned
+__device__ __forceinline__ unsigned char* dyn_smem() {
+#ifdef MAL_EMU
+  unsigned char* p = emu::current()->smem.data();
+  return p + ((16 - ((uintptr_t)p & 15)) & 15);
+#else
+  extern __shared__ __align__(16) unsigned char mal_dyn_smem_[];
+  return mal_dyn_smem_;
+#endif
+}
+
+// ------------------------------------------------------------------ exact fp32
+// Round-to-nearest single operations that the compiler may not fuse or reorder.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// Correctly rounded x / C for a compile-time constant C (Markstein: q = RN(x*r), rem = fma(-C,q,x),
+// RN(q + rem*r)); identical to IEEE division for every finite x except the sign of -0 (checked
+// exhaustively over all 2^32 inputs, tests/test_exact_arithmetic.py).  3 instructions instead of ~10.
+template <int C>
+__device__ __forceinline__ float xdivc(float x) {
+  const float r = 1.0f / (float)C;
+  float q = __fmul_rn(x, r);
+  float rem = __fmaf_rn(-(float)C, q, x);
+  return __fmaf_rn(rem, r, q);
+}
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // ReflectionPad2d(1) index map, also safe for |overshoot| <= n-1
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+}  // namespace mal

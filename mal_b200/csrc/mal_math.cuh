@@ -1,0 +1,162 @@
+// mal_math.cuh - per-pixel device math of the MAL photometric path.
+//
+// Arithmetic contract: every value that can decide a comparison in the
+// reference (min over candidates, automask, distillation argmin) is computed with the SAME
+// sequence of IEEE-754 single operations the reference's torch CPU kernels execute, using
+// the never-contracted x* helpers:
+//   * (K@T)[:3,:]            sequential, unfused      (ATen small-bmm path; layers.py:185)
+//   * invK[:3,:3]@[x,y,1]    k-sequential FMA chain   (BLAS sgemm;          layers.py:164)
+//   * P@[cam;1]              k-sequential FMA chain   (BLAS sgemm;          layers.py:187)
+//   * grid_sample bilinear   nw*a, then 3 FMAs        (GridSamplerKernel.cpp, contracted)
+//   * avg_pool2d 3x3         row-major running sum, then /9   (AvgPoolKernel.cpp)
+//   * SSIM formula, mean over channels ((c0+c1)+c2)/3, 0.85*s+0.15*l: one rounding per op
+// tests/test_bitexact_model.py replays this contract on the host against torch.
+#pragma once
+#include "mal_common.cuh"
+
+namespace mal {
+
+struct Geom {        // per-sample camera constants, staged in shared memory
+  float P[2][12];    // (K@T_f)[:3,:] row-major, frames -1,+1
+  float iK[9];       // inv_K[:3,:3] row-major
+};
+
+// (K@T)[:3,:] entry (i,j): ((K_i0*T_0j + K_i1*T_1j) + K_i2*T_2j) + K_i3*T_3j
+__device__ __forceinline__ float kt_entry(const float* K, const float* T, int i, int j) {
+  float acc = xmul(K[i * 4 + 0], T[0 * 4 + j]);
+  acc = xadd(acc, xmul(K[i * 4 + 1], T[1 * 4 + j]));
+  acc = xadd(acc, xmul(K[i * 4 + 2], T[2 * 4 + j]));
+  acc = xadd(acc, xmul(K[i * 4 + 3], T[3 * 4 + j]));
+  return acc;
+}
+
+struct Ray { float x, y, z; };
+
+// inv_K[:3,:3] @ [px,py,1]
+__device__ __forceinline__ Ray pixel_ray(const float* iK, float px, float py) {
+  Ray r;
+  r.x = xfma(iK[2], 1.0f, xfma(iK[1], py, xmul(iK[0], px)));
+  r.y = xfma(iK[5], 1.0f, xfma(iK[4], py, xmul(iK[3], px)));
+  r.z = xfma(iK[8], 1.0f, xfma(iK[7], py, xmul(iK[6], px)));
+  return r;
+}
+
+struct Sample {
+  float ix, iy;    // clipped source pixel coordinates
+  float gmx, gmy;  // d(clipped)/d(unclipped): 0 where clamped (ATen clip_coordinates_set_grad)
+  float X, Y, Zp;  // P@[cam;1] numerators and (z + eps)
+};
+
+// depth * ray -> P -> /(z+eps) -> Project3D normalisation -> grid_sample unnormalise -> border clip
+template <int CONV>
+__device__ __forceinline__ Sample project_pixel(const float* P, Ray ray, float depth, float eps,
+                                                int H, int W) {
+  float cx = xmul(depth, ray.x), cy = xmul(depth, ray.y), cz = xmul(depth, ray.z);
+  Sample s;
+  s.X = xfma(P[3], 1.0f, xfma(P[2], cz, xfma(P[1], cy, xmul(P[0], cx))));
+  s.Y = xfma(P[7], 1.0f, xfma(P[6], cz, xfma(P[5], cy, xmul(P[4], cx))));
+  float Z = xfma(P[11], 1.0f, xfma(P[10], cz, xfma(P[9], cy, xmul(P[8], cx))));
+  s.Zp = xadd(Z, eps);
+  float px = xdiv(s.X, s.Zp), py = xdiv(s.Y, s.Zp);
+  float ux, uy;
+  if (CONV == MAL_CONV_MANYDEPTH) {
+    float gx = xmul(xsub(xdiv(px, (float)(W - 1)), 0.5f), 2.0f);
+    float gy = xmul(xsub(xdiv(py, (float)(H - 1)), 0.5f), 2.0f);
+    ux = xmul(xadd(gx, 1.0f), (float)(W - 1) / 2.0f);
+    uy = xmul(xadd(gy, 1.0f), (float)(H - 1) / 2.0f);
+  } else {
+    float gx = xsub(xdiv(xmul(2.0f, xadd(px, 0.5f)), (float)W), 1.0f);
+    float gy = xsub(xdiv(xmul(2.0f, xadd(py, 0.5f)), (float)H), 1.0f);
+    ux = xsub(xmul(xadd(gx, 1.0f), (float)W / 2.0f), 0.5f);
+    uy = xsub(xmul(xadd(gy, 1.0f), (float)H / 2.0f), 0.5f);
+  }
+  // padding_mode="border": clamp, and the coordinate gradient vanishes where clamped
+  s.gmx = (ux <= 0.0f || ux >= (float)(W - 1)) ? 0.0f : 1.0f;
+  s.gmy = (uy <= 0.0f || uy >= (float)(H - 1)) ? 0.0f : 1.0f;
+  s.ix = fminf((float)(W - 1), fmaxf(ux, 0.0f));
+  s.iy = fminf((float)(H - 1), fmaxf(uy, 0.0f));
+  return s;
+}
+
+struct Taps {
+  int o00, o01, o10, o11;      // plane offsets (valid where the flag is set)
+  bool v00, v01, v10, v11;     // in-bounds flags (out-of-bounds taps read as 0)
+  float nw, ne, sw, se;        // bilinear weights
+  float tx, ty;                // fractional parts
+};
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
+  Taps t;
+  float x0 = floorf(ix), y0 = floorf(iy);
+  t.tx = xsub(ix, x0);
+  t.ty = xsub(iy, y0);
+  float e = xsub(1.0f, t.tx), s = xsub(1.0f, t.ty);
+  t.nw = xmul(s, e); t.ne = xmul(s, t.tx); t.sw = xmul(t.ty, e); t.se = xmul(t.ty, t.tx);
+  int xi = (int)x0, yi = (int)y0;
+  bool xl = xi >= 0 && xi < W, xr = xi + 1 >= 0 && xi + 1 < W;
+  bool yt = yi >= 0 && yi < H, yb = yi + 1 >= 0 && yi + 1 < H;
+  t.v00 = xl && yt; t.v01 = xr && yt; t.v10 = xl && yb; t.v11 = xr && yb;
+  t.o00 = yi * W + xi; t.o01 = t.o00 + 1; t.o10 = t.o00 + W; t.o11 = t.o10 + 1;
+  return t;
+}
+
+__device__ __forceinline__ float bilinear(const float* __restrict__ plane, const Taps& t,
+                                          float* a = nullptr, float* b = nullptr, float* c = nullptr,
+                                          float* d = nullptr) {
+  float v00 = t.v00 ? __ldg(plane + t.o00) : 0.0f;
+  float v01 = t.v01 ? __ldg(plane + t.o01) : 0.0f;
+  float v10 = t.v10 ? __ldg(plane + t.o10) : 0.0f;
+  float v11 = t.v11 ? __ldg(plane + t.o11) : 0.0f;
+  if (a) { *a = v00; *b = v01; *c = v10; *d = v11; }
+  return xfma(v11, t.se, xfma(v10, t.sw, xfma(v01, t.ne, xmul(v00, t.nw))));
+}
+
+// ---- SSIM ------------------------------------------------------------------------------
+// running row-major sum of a 3x3 window, as avg_pool2d accumulates it
+__device__ __forceinline__ float sum9(const float* w) {
+  float s = w[0];
+#pragma unroll
+  for (int i = 1; i < 9; i++) s = xadd(s, w[i]);
+  return s;
+}
+__device__ __forceinline__ float sum9_prod(const float* a, const float* b) {
+  float s = xmul(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 9; i++) s = xadd(s, xmul(a[i], b[i]));
+  return s;
+}
+
+struct SsimTerms { float mu_x, mu_y, A, Bq, Cq, D, n, d, v; };
+
+#define MAL_C1 0.0001f   /* 0.01**2 */
+#define MAL_C2 0.0009f   /* 0.03**2 */
+
+// SSIM loss value for one channel from the 5 pooled moments (layers.py:247-257)
+__device__ __forceinline__ SsimTerms ssim_terms(float mu_x, float mu_y, float exx, float eyy, float exy) {
+  SsimTerms t;
+  t.mu_x = mu_x; t.mu_y = mu_y;
+  float sig_x = xsub(exx, xmul(mu_x, mu_x));
+  float sig_y = xsub(eyy, xmul(mu_y, mu_y));
+  float sig_xy = xsub(exy, xmul(mu_x, mu_y));
+  t.A = xadd(xmul(xmul(2.0f, mu_x), mu_y), MAL_C1);
+  t.Bq = xadd(xmul(2.0f, sig_xy), MAL_C2);
+  t.Cq = xadd(xadd(xmul(mu_x, mu_x), xmul(mu_y, mu_y)), MAL_C1);
+  t.D = xadd(xadd(sig_x, sig_y), MAL_C2);
+  t.n = xmul(t.A, t.Bq);
+  t.d = xmul(t.Cq, t.D);
+  t.v = xmul(xsub(1.0f, xdiv(t.n, t.d)), 0.5f);   // (1 - n/d) / 2, /2 is exact as *0.5
+  return t;
+}
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// d clamp(v)/d{mu_x, E[xx], E[xy]} (the y-side moments carry no gradient: the target is data)
+__device__ __forceinline__ void ssim_coefs(const SsimTerms& t, float& alpha, float& beta, float& gamma) {
+  if (!(t.v >= 0.0f && t.v <= 1.0f)) { alpha = beta = gamma = 0.0f; return; }
+  float inv_d = 1.0f / t.d;
+  float r = t.n * inv_d;
+  alpha = -(t.mu_y * (t.Bq - t.A) - r * t.mu_x * (t.D - t.Cq)) * inv_d;
+  beta = 0.5f * r * t.Cq * inv_d;
+  gamma = -t.A * inv_d;
+}
+
+}  // namespace mal

@@ -1,0 +1,429 @@
+// photo.cu - fused photometric loss (forward + un-normalised backward) for sm_100a.
+//
+// One CTA owns a TW x TH tile of one sample.  Phases (separated by __syncthreads):
+//   A  stage the target tile (+halo) and every candidate tile in shared memory; in WARP mode
+//      the two warped candidates are produced in place:  disp->depth->backproject->project->
+//      bilinear gather (border)  (manydepth/layers.py:14-23,163-199, trainer.py:1122-1125)
+//   B  per pixel of the loss region: 3x3 SSIM + L1 per candidate (layers.py:243-257,
+//      loss_utils.py:46-55), min/argmin over candidates (:103), tie-break noise + automask
+//      (:105-109, :27-44), multi-frame mask (:192-194); masked partial sums (:112-113).
+//      With gradients, the SSIM derivative coefficients of the selected candidate are left in
+//      shared memory for the ring of pixels around the tile.
+//   C  (grad) per tile pixel: gather the 3x3 neighbourhood's coefficients (atomics-free SSIM
+//      backward), add the L1 term, then chain through the bilinear sampler, the projection and
+//      backprojection to d/d depth and d/d(K@T); per-CTA partials go to a workspace.
+// A second tiny kernel reduces the per-CTA partials in a fixed order (deterministic).
+//
+// HBM traffic per pixel (WARP mode, 2+2 candidates, grad): reads 9 (target+2 src... gathers hit
+// L2/L1) x 4 B x 3 ch + depth/noise/identity/mask 16 B, writes min_reproj 4 + sel 1 + grad 4 B.
+#include "mal_math.cuh"
+
+namespace mal {
+
+constexpr int PH_TW = 32;
+constexpr int PH_TH = 16;
+constexpr int PH_NT = 256;
+constexpr int PH_NPART = 26;  // 2 x 12 dL/dP + sum(w*reproj) + sum(w)
+
+struct PhotoTile {
+  int HV, HL;          // value halo, loss halo
+  int VW, VH, VN;      // value tile dims
+  int LW, LH, LN;      // loss tile dims
+};
+__host__ __device__ inline PhotoTile photo_tile(bool grad) {
+  PhotoTile t;
+  t.HV = grad ? 2 : 1;
+  t.HL = grad ? 1 : 0;
+  t.VW = PH_TW + 2 * t.HV; t.VH = PH_TH + 2 * t.HV; t.VN = t.VW * t.VH;
+  t.LW = PH_TW + 2 * t.HL; t.LH = PH_TH + 2 * t.HL; t.LN = t.LW * t.LH;
+  return t;
+}
+inline size_t photo_smem_bytes(bool grad, int ncand) {
+  PhotoTile t = photo_tile(grad);
+  size_t fl = sizeof(Geom) / 4 + 8 * PH_NPART + 8;
+  fl += (size_t)3 * t.VN * (1 + ncand);
+  if (grad) fl += (size_t)11 * t.LN;
+  return fl * 4 + 16;
+}
+
+template <bool WARP, bool GRAD, int CONV>
+__global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, const int ncand,
+                                                     const float min_disp, const float disp_range) {
+  const PhotoTile tl = photo_tile(GRAD);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * PH_TW, y0 = blockIdx.y * PH_TH;
+  const int H = a.height, W = a.width;
+  const size_t HW = (size_t)H * W;
+
+  float* smem = reinterpret_cast<float*>(dyn_smem());
+  Geom* geom = reinterpret_cast<Geom*>(smem);
+  float* red = smem + sizeof(Geom) / 4;                 // [8][PH_NPART]
+  float* sy = red + 8 * PH_NPART + 8;                   // [3][VN]
+  float* sx = sy + 3 * tl.VN;                           // [ncand][3][VN]
+  float* coef = sx + (size_t)ncand * 3 * tl.VN;         // [9][LN]      (GRAD)
+  float* lw = coef + 9 * tl.LN;                         // [LN] weights (GRAD)
+  int* lsel = reinterpret_cast<int*>(lw + tl.LN);       // [LN] selected warped candidate or -1
+
+  // ---- phase 0: camera constants --------------------------------------------------------
+  if (WARP) {
+    if (tid < 24) {
+      int f = tid / 12, e = tid % 12;
+      geom->P[f][e] = kt_entry(a.K + b * 16, a.T[f] + b * 16, e / 4, e % 4);
+    } else if (tid < 33) {
+      int e = tid - 24;
+      geom->iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
+    }
+    __syncthreads();
+  }
+
+  // ---- phase A: stage value tiles ---------------------------------------------------------
+  const float* tgt = a.target + (size_t)b * 3 * HW;
+  for (int i = tid; i < tl.VN; i += PH_NT) {
+    int ty = i / tl.VW, tx = i - ty * tl.VW;
+    int ry = reflect_index(y0 - tl.HV + ty, H), rx = reflect_index(x0 - tl.HV + tx, W);
+    ry = min(max(ry, 0), H - 1);
+    rx = min(max(rx, 0), W - 1);
+    size_t o = (size_t)ry * W + rx;
+#pragma unroll
+    for (int c = 0; c < 3; c++) sy[c * tl.VN + i] = __ldg(tgt + c * HW + o);
+    if (ncand > 2) {
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          sx[((2 + k) * 3 + c) * tl.VN + i] = __ldg(a.syn[k] + ((size_t)b * 3 + c) * HW + o);
+    }
+    if (WARP) {
+      float dv = __ldg(a.depth + (size_t)b * HW + o);
+      if (a.depth_is_disp) dv = xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv)));
+      Ray ray = pixel_ray(geom->iK, (float)rx, (float)ry);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        Sample s = project_pixel<CONV>(geom->P[f], ray, dv, a.eps, H, W);
+        Taps t = make_taps(s.ix, s.iy, H, W);
+        const float* src = a.src[f] + (size_t)b * 3 * HW;
+#pragma unroll
+        for (int c = 0; c < 3; c++) sx[(f * 3 + c) * tl.VN + i] = bilinear(src + c * HW, t);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 2; f++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          sx[(f * 3 + c) * tl.VN + i] = __ldg(a.src[f] + ((size_t)b * 3 + c) * HW + o);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: losses, selection, weights -----------------------------------------------
+  const bool automask = a.identity_min != nullptr;
+  float acc_loss = 0.0f, acc_w = 0.0f;
+  for (int i = tid; i < tl.LN; i += PH_NT) {
+    int ly = i / tl.LW, lx = i - ly * tl.LW;
+    int gy = y0 - tl.HL + ly, gx = x0 - tl.HL + lx;
+    bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    if (!in_img) {
+      if (GRAD) { lsel[i] = -1; lw[i] = 0.0f; }
+      continue;
+    }
+    const int vc = (ly + tl.HV - tl.HL) * tl.VW + (lx + tl.HV - tl.HL);  // window centre in value tile
+    float ssum[4], lsum[4];
+    float cf0[9], cf1[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float yw[9];
+#pragma unroll
+      for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++) yw[dy * 3 + dx] = sy[c * tl.VN + vc + (dy - 1) * tl.VW + dx - 1];
+      float mu_y = 0.f, eyy = 0.f;
+      if (!a.no_ssim) {
+        mu_y = xdivc<9>(sum9(yw));
+        eyy = xdivc<9>(sum9_prod(yw, yw));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < ncand) {
+          const float* X = sx + (k * 3 + c) * tl.VN + vc;
+          float xw[9];
+#pragma unroll
+          for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) xw[dy * 3 + dx] = X[(dy - 1) * tl.VW + dx - 1];
+          float l1 = fabsf(xsub(yw[4], xw[4]));
+          lsum[k] = (c == 0) ? l1 : xadd(lsum[k], l1);
+          if (!a.no_ssim) {
+            float mu_x = xdivc<9>(sum9(xw));
+            float exx = xdivc<9>(sum9_prod(xw, xw));
+            float exy = xdivc<9>(sum9_prod(xw, yw));
+            SsimTerms t = ssim_terms(mu_x, mu_y, exx, eyy, exy);
+            float sv = clamp01(t.v);
+            ssum[k] = (c == 0) ? sv : xadd(ssum[k], sv);
+            if (GRAD && k < 2) {
+              float al, be, ga;
+              ssim_coefs(t, al, be, ga);
+              if (k == 0) { cf0[c * 3] = al; cf0[c * 3 + 1] = be; cf0[c * 3 + 2] = ga; }
+              else        { cf1[c * 3] = al; cf1[c * 3 + 1] = be; cf1[c * 3 + 2] = ga; }
+            }
+          }
+        }
+      }
+    }
+    float rmin = 0.f;
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < ncand) {
+        float l1m = xdivc<3>(lsum[k]);
+        float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
+        if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
+      }
+    }
+    const size_t po = (size_t)b * HW + (size_t)gy * W + gx;
+    int mbit = 1;
+    if (automask) {
+      float ident = xadd(__ldg(a.identity_min + po), xmul(__ldg(a.noise + po), 0.00001f));
+      mbit = (ident < rmin) ? 0 : 1;  // argmin([reproj, identity]) == 0, first index wins ties
+    }
+    float w = (float)mbit;
+    if (a.pixel_mask) w = xmul(w, __ldg(a.pixel_mask + po));
+    if (a.sample_mask) w = xmul(w, xsub(1.0f, __ldg(a.sample_mask + b)));
+    const bool interior = ly >= tl.HL && ly < tl.HL + PH_TH && lx >= tl.HL && lx < tl.HL + PH_TW;
+    if (interior) {
+      if (a.min_reproj) a.min_reproj[po] = rmin;
+      if (a.selection) a.selection[po] = (uint8_t)(idx | (mbit << 7));
+      if (a.weight) a.weight[po] = w;
+      acc_loss += xmul(rmin, w);
+      acc_w += w;
+    }
+    if (GRAD) {
+      const bool live = idx < 2 && w != 0.0f;
+      lsel[i] = live ? idx : -1;
+      lw[i] = w;
+      if (live && !a.no_ssim) {
+        const float sc = w * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
+#pragma unroll
+        for (int j = 0; j < 9; j++) coef[j * tl.LN + i] = (idx == 0 ? cf0[j] : cf1[j]) * sc;
+      }
+    }
+  }
+
+  // ---- phase C: gradients -------------------------------------------------------------------
+  float gP[24];
+#pragma unroll
+  for (int j = 0; j < 24; j++) gP[j] = 0.0f;
+  if (GRAD) {
+    __syncthreads();
+    for (int i = tid; i < PH_TW * PH_TH; i += PH_NT) {
+      int qy = i / PH_TW, qx = i - qy * PH_TW;
+      int gy = y0 + qy, gx = x0 + qx;
+      if (gy >= H || gx >= W) continue;
+      const int lc = (qy + tl.HL) * tl.LW + qx + tl.HL;
+      const int vc = (qy + tl.HV) * tl.VW + qx + tl.HV;
+      float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+      float xq0[3], xq1[3], yq[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        xq0[c] = sx[(0 * 3 + c) * tl.VN + vc];
+        xq1[c] = sx[(1 * 3 + c) * tl.VN + vc];
+        yq[c] = sy[c * tl.VN + vc];
+      }
+      if (!a.no_ssim) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+          int py = gy + dy;
+          if (py < 0 || py >= H) continue;
+          // ReflectionPad2d(1): a border row sees its inner neighbour twice
+          float my = ((py == 0 && dy == -1) || (py == H - 1 && dy == 1)) ? 2.0f : 1.0f;
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            int px = gx + dx;
+            if (px < 0 || px >= W) continue;
+            float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
+            int li = lc + dy * tl.LW + dx;
+            int s = lsel[li];
+            if (s < 0) continue;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float al = coef[(c * 3) * tl.LN + li], be = coef[(c * 3 + 1) * tl.LN + li],
+                    ga = coef[(c * 3 + 2) * tl.LN + li];
+              float xq = s == 0 ? xq0[c] : xq1[c];
+              float v = m * (al + 2.0f * xq * be + yq[c] * ga);
+              if (s == 0) g0[c] += v; else g1[c] += v;
+            }
+          }
+        }
+      }
+      {
+        int s = lsel[lc];
+        if (s >= 0) {
+          float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            float d = yq[c] - (s == 0 ? xq0[c] : xq1[c]);      // target - pred
+            float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);   // d|t-p|/dp = -sign(t-p)
+            if (s == 0) g0[c] += sg; else g1[c] += sg;
+          }
+        }
+      }
+      const size_t po = (size_t)gy * W + gx;
+      if (!WARP) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          a.grad_pred[0][((size_t)b * 3 + c) * HW + po] = g0[c];
+          a.grad_pred[1][((size_t)b * 3 + c) * HW + po] = g1[c];
+        }
+      } else {
+        float dv_in = __ldg(a.depth + (size_t)b * HW + po);
+        float dv = a.depth_is_disp ? xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv_in))) : dv_in;
+        Ray ray = pixel_ray(geom->iK, (float)gx, (float)gy);
+        float cam[3] = {dv * ray.x, dv * ray.y, dv * ray.z};
+        float gdepth = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          const float* g = f == 0 ? g0 : g1;
+          if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+          const float* P = geom->P[f];
+          Sample s = project_pixel<CONV>(P, ray, dv, a.eps, H, W);
+          Taps t = make_taps(s.ix, s.iy, H, W);
+          const float* src = a.src[f] + (size_t)b * 3 * HW;
+          float gix = 0.f, giy = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            float v00, v01, v10, v11;
+            bilinear(src + c * HW, t, &v00, &v01, &v10, &v11);
+            gix += g[c] * ((v01 - v00) * (1.0f - t.ty) + (v11 - v10) * t.ty);
+            giy += g[c] * ((v10 - v00) * (1.0f - t.tx) + (v11 - v01) * t.tx);
+          }
+          gix *= s.gmx;  // d(ix)/d(px) == 1 for both conventions (normalise o unnormalise)
+          giy *= s.gmy;
+          float iz = 1.0f / s.Zp;
+          float gX = gix * iz, gY = giy * iz;
+          float gZ = -(gX * s.X + gY * s.Y) * iz;
+          gdepth += gX * (P[0] * ray.x + P[1] * ray.y + P[2] * ray.z) +
+                    gY * (P[4] * ray.x + P[5] * ray.y + P[6] * ray.z) +
+                    gZ * (P[8] * ray.x + P[9] * ray.y + P[10] * ray.z);
+          float* gp = gP + f * 12;
+          gp[0] += gX * cam[0]; gp[1] += gX * cam[1]; gp[2] += gX * cam[2]; gp[3] += gX;
+          gp[4] += gY * cam[0]; gp[5] += gY * cam[1]; gp[6] += gY * cam[2]; gp[7] += gY;
+          gp[8] += gZ * cam[0]; gp[9] += gZ * cam[1]; gp[10] += gZ * cam[2]; gp[11] += gZ;
+        }
+        if (a.depth_is_disp) gdepth *= -disp_range * dv * dv;  // d depth / d disp
+        a.grad_depth[(size_t)b * HW + po] = gdepth;
+      }
+    }
+  }
+
+  // ---- per-CTA partials ---------------------------------------------------------------------
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int j = 0; j < 24; j++) {
+    float v = (GRAD && WARP) ? warp_sum(gP[j]) : 0.0f;
+    if (lane == 0) red[warp * PH_NPART + j] = v;
+  }
+  {
+    float v = warp_sum(acc_loss);
+    if (lane == 0) red[warp * PH_NPART + 24] = v;
+    v = warp_sum(acc_w);
+    if (lane == 0) red[warp * PH_NPART + 25] = v;
+  }
+  __syncthreads();
+  if (tid < PH_NPART) {
+    float s = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < PH_NT / 32; wv++) s += red[wv * PH_NPART + tid];
+    size_t blk = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    a.partials[blk * PH_NPART + tid] = s;
+  }
+}
+
+// Deterministic reduction of the per-CTA partials: grad_P (B,2,12) and the masked mean.
+__global__ void __launch_bounds__(1024) photo_finalize_kernel(const float* __restrict__ partials, int batch,
+                                                             int tiles, float* __restrict__ sums,
+                                                             float* __restrict__ grad_P) {
+  double* per_sample = reinterpret_cast<double*>(dyn_smem());  // [batch][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int pair = warp; pair < batch * PH_NPART; pair += nwarp) {
+    int b = pair / PH_NPART, v = pair - b * PH_NPART;
+    double s = 0.0;
+    for (int t = lane; t < tiles; t += 32) s += (double)partials[((size_t)b * tiles + t) * PH_NPART + v];
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (v < 24) { if (grad_P) grad_P[b * 24 + v] = (float)s; }
+      else per_sample[b * 2 + (v - 24)] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ls = 0.0, ws = 0.0;
+    for (int b = 0; b < batch; b++) { ls += per_sample[b * 2]; ws += per_sample[b * 2 + 1]; }
+    float lf = (float)ls, wf = (float)ws;
+    sums[0] = lf;
+    sums[1] = wf;
+    sums[2] = lf / (wf + 1e-7f);   // loss_utils.py:113
+    sums[3] = 0.0f;
+  }
+}
+
+template <bool WARP, bool GRAD>
+static void photo_dispatch(const mal_photo_args& a, int ncand, float min_disp, float range, dim3 grid,
+                           size_t smem, cudaStream_t st) {
+  if (a.convention == MAL_CONV_MANYDEPTH)
+    launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+  else
+    launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+}
+
+}  // namespace mal
+
+using namespace mal;
+
+extern "C" size_t mal_photo_partials_floats(int batch, int height, int width) {
+  size_t tiles = (size_t)((width + PH_TW - 1) / PH_TW) * ((height + PH_TH - 1) / PH_TH);
+  return (size_t)batch * tiles * PH_NPART;
+}
+
+extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream) {
+  MAL_REQUIRE(args != nullptr, "mal_photo_forward: args is NULL");
+  const mal_photo_args& a = *args;
+  MAL_REQUIRE(a.batch > 0 && a.height >= 3 && a.width >= 3, "mal_photo_forward: bad shape %dx%dx%d", a.batch,
+              a.height, a.width);
+  MAL_REQUIRE(a.batch <= 65535, "mal_photo_forward: batch %d exceeds gridDim.z", a.batch);
+  MAL_REQUIRE(a.mode == MAL_PHOTO_WARP || a.mode == MAL_PHOTO_PRED, "mal_photo_forward: bad mode %d", a.mode);
+  MAL_REQUIRE(a.convention == MAL_CONV_MANYDEPTH || a.convention == MAL_CONV_DUALREFINE,
+              "mal_photo_forward: bad convention %d", a.convention);
+  MAL_REQUIRE(a.target && a.src[0] && a.src[1], "mal_photo_forward: target/src pointers are required");
+  MAL_REQUIRE((a.syn[0] == nullptr) == (a.syn[1] == nullptr), "mal_photo_forward: give both syn candidates or none");
+  MAL_REQUIRE((a.identity_min == nullptr) == (a.noise == nullptr),
+              "mal_photo_forward: automask needs identity_min and noise together");
+  MAL_REQUIRE(a.partials && a.sums, "mal_photo_forward: partials/sums workspaces are required");
+  if (a.mode == MAL_PHOTO_WARP) {
+    MAL_REQUIRE(a.depth && a.K && a.inv_K && a.T[0] && a.T[1], "mal_photo_forward: WARP mode needs depth,K,inv_K,T");
+    if (a.with_grad) MAL_REQUIRE(a.grad_depth && a.grad_P, "mal_photo_forward: WARP+grad needs grad_depth, grad_P");
+    if (a.depth_is_disp) MAL_REQUIRE(a.min_depth > 0 && a.max_depth > a.min_depth, "mal_photo_forward: bad depth range");
+  } else if (a.with_grad) {
+    MAL_REQUIRE(a.grad_pred[0] && a.grad_pred[1], "mal_photo_forward: PRED+grad needs grad_pred");
+  }
+  const int ncand = a.syn[0] ? 4 : 2;
+  const bool grad = a.with_grad != 0;
+  // disp_to_depth scalars exactly as python computes them (double), then rounded once to fp32
+  const double lo = 1.0 / a.max_depth, hi = 1.0 / a.min_depth;
+  const float min_disp = (float)lo, range = (float)(hi - lo);
+  dim3 grid((a.width + PH_TW - 1) / PH_TW, (a.height + PH_TH - 1) / PH_TH, a.batch);
+  MAL_REQUIRE(grid.y <= 65535, "mal_photo_forward: image too tall");
+  size_t smem = photo_smem_bytes(grad, ncand);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a.mode == MAL_PHOTO_WARP) {
+    if (grad) photo_dispatch<true, true>(a, ncand, min_disp, range, grid, smem, st);
+    else photo_dispatch<true, false>(a, ncand, min_disp, range, grid, smem, st);
+  } else {
+    if (grad) photo_dispatch<false, true>(a, ncand, min_disp, range, grid, smem, st);
+    else photo_dispatch<false, false>(a, ncand, min_disp, range, grid, smem, st);
+  }
+  int rc = check_launch("photo_kernel");
+  if (rc) return rc;
+  launch(photo_finalize_kernel, dim3(1), dim3(1024), (size_t)a.batch * 16 + 16, st, (const float*)a.partials,
+         a.batch, (int)(grid.x * grid.y), a.sums, (grad && a.mode == MAL_PHOTO_WARP) ? a.grad_P : (float*)nullptr);
+  return check_launch("photo_finalize_kernel");
+}

@@ -1,0 +1,140 @@
+"""Fused photometric kernel (mal_photo_forward) against the reference's golden outputs and
+against the oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): selection indices and automask bit-exact; per-pixel
+min-reprojection bit-exact (it feeds the distillation argmin); loss within 1e-5 relative;
+gradients within 1e-4 relative (of the gradient's max magnitude).
+"""
+import numpy as np
+import pytest
+import torch
+
+from mal_b200 import raw
+from mal_b200.utils.synthetic import make_photometric_inputs
+from oracle import mal_oracle as O
+from tests.backends import BACKENDS, handle_and_device
+from tests.helpers import photometric_golden
+
+LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4
+
+
+def _grad_err(a, b):
+    scale = float(b.abs().max())
+    if scale == 0.0:
+        return float(a.abs().max())
+    return float((a - b).abs().max()) / scale
+
+
+def _run_mono(h, dev, inputs, t, temporal, with_grad=True):
+    d = lambda x: x.to(dev)
+    tgt = d(inputs[("color", 0, 0)])
+    src = [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])]
+    ident = raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+    out = raw.photo(h, target=tgt, src=src,
+                    syn=[d(t[("syn", -1, 0)]), d(t[("syn", 1, 0)])] if temporal else None,
+                    depth=d(t[("mono_disp", 0)]), K=d(inputs[("K", 0)]), inv_K=d(inputs[("inv_K", 0)]),
+                    T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])],
+                    identity_min=ident, noise=d(t["noise"][0]), with_grad=with_grad, want_weight=True)
+    return ident, out
+
+
+def _oracle_mono(inputs, t, temporal):
+    H, W = inputs[("color", 0, 0)].shape[-2:]
+    Ts = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
+    o = {("disp", 0): t[("mono_disp", 0)].clone().requires_grad_(True)}
+    for f in (-1, 1):
+        o[("cam_T_cam", 0, f)] = Ts[f]
+        o[("syn", f, 0)] = t[("syn", f, 0)]
+    O.images_pred(inputs, o, height=H, width=W)
+    losses, mono_reproj, aux = O.mono_losses(inputs, o, temporal, True, noise=t["noise"][0])
+    g = torch.autograd.grad(losses["reproj_loss/0"], [o[("disp", 0)], Ts[-1], Ts[1]])
+    return losses, mono_reproj, aux, g
+
+
+def _check_grads(out, inputs, g):
+    scale = 1.0 / (out["sums"][1].cpu() + 1e-7)
+    assert _grad_err(out["grad_depth"].cpu() * scale, g[0]) < GRAD_RTOL
+    Kt = inputs[("K", 0)][:, :3, :].transpose(1, 2)
+    gP = out["grad_P"].cpu() * scale
+    for i in range(2):
+        assert _grad_err(Kt @ gP[:, i].view(-1, 3, 4), g[1 + i]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name", ["photometric_smooth.npz", "photometric_noise.npz"])
+@pytest.mark.parametrize("temporal,tag", [(False, "plain"), (True, "temporal")])
+def test_mono_pass_against_reference_golden(backend, name, temporal, tag):
+    h, dev = handle_and_device(backend)
+    inputs, t, ref = photometric_golden(name)
+    ident, out = _run_mono(h, dev, inputs, t, temporal)
+    assert np.array_equal(ident.cpu().numpy(), ref["identity_min"])
+    sel = out["selection"].cpu().numpy()
+    assert np.array_equal(sel & 0x7F, ref[f"mono_{tag}_frame_idx"])          # bit-exact argmin
+    assert np.array_equal(sel >> 7, ref[f"mono_{tag}_automask"])              # bit-exact automask
+    assert np.array_equal(out["min_reproj"].cpu().numpy(), ref[f"mono_{tag}_min_reproj"])
+    assert np.array_equal(out["weight"].cpu().numpy(), ref[f"mono_{tag}_automask"].astype(np.float32))
+    got, want = float(out["sums"][2]), float(ref[f"mono_{tag}_reproj_loss"])
+    assert abs(got - want) <= LOSS_RTOL * abs(want)
+    _, _, _, g = _oracle_mono(inputs, t, temporal)
+    _check_grads(out, inputs, g)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("shape,seed,white", [((1, 40, 72), 5, False), ((2, 35, 50), 6, True), ((1, 16, 32), 7, False)])
+def test_mono_pass_against_oracle_ragged(backend, shape, seed, white):
+    """Sizes that are not tile multiples (tile 32x16) and a one-tile image."""
+    h, dev = handle_and_device(backend)
+    B, H, W = shape
+    inputs, t = make_photometric_inputs(B, H, W, seed=seed, white_noise=white)
+    for temporal in (False, True):
+        ident, out = _run_mono(h, dev, inputs, t, temporal)
+        losses, mono_reproj, aux, g = _oracle_mono(inputs, t, temporal)
+        sel = out["selection"].cpu().numpy()
+        assert np.array_equal(sel & 0x7F, aux["frame_idx"].numpy().astype(np.uint8))
+        assert np.array_equal(sel >> 7, aux["automask"].numpy().astype(np.uint8))
+        assert torch.equal(out["min_reproj"].cpu(), mono_reproj)
+        want = float(losses["reproj_loss/0"])
+        assert abs(float(out["sums"][2]) - want) <= LOSS_RTOL * abs(want)
+        _check_grads(out, inputs, g)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_no_grad_variant_matches_grad_variant(backend):
+    h, dev = handle_and_device(backend)
+    inputs, t = make_photometric_inputs(1, 48, 64, seed=9)
+    _, a = _run_mono(h, dev, inputs, t, True, with_grad=True)
+    _, b = _run_mono(h, dev, inputs, t, True, with_grad=False)
+    assert torch.equal(a["min_reproj"], b["min_reproj"]) and torch.equal(a["selection"], b["selection"])
+    assert torch.equal(a["sums"], b["sums"])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_pred_mode_gradients(backend):
+    """PRED mode: loss from already-warped images, d/d pred against autograd on the oracle."""
+    h, dev = handle_and_device(backend)
+    inputs, t = make_photometric_inputs(2, 33, 47, seed=10)
+    tgt = inputs[("color", 0, 0)]
+    preds = [t[("syn", f, 0)].clone().requires_grad_(True) for f in (-1, 1)]
+    cands = torch.cat([O.reprojection_loss(p, tgt) for p in preds], 1)
+    reproj, idx = torch.min(cands, 1, keepdim=True)
+    mask = t["consistency_mask"].unsqueeze(1)[:, :, :33, :47] * (1 - t["augmentation_mask"])
+    loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+    g = torch.autograd.grad(loss, preds)
+    out = raw.photo(h, target=tgt.to(dev), src=[p.detach().to(dev) for p in preds], mode=raw.PHOTO_PRED,
+                    pixel_mask=mask[:, 0].contiguous().to(dev), with_grad=True)
+    assert np.array_equal(out["selection"].cpu().numpy() & 0x7F, idx.numpy().astype(np.uint8))
+    assert abs(float(out["sums"][2]) - float(loss)) <= LOSS_RTOL * abs(float(loss))
+    scale = 1.0 / (out["sums"][1].cpu() + 1e-7)
+    for i in range(2):
+        assert _grad_err(out["grad_pred"][i].cpu() * scale, g[i]) < GRAD_RTOL
+
+
+def test_argument_errors_are_reported():
+    from tests.emu.emu_lib import emu
+    h = emu()
+    inputs, t = make_photometric_inputs(1, 16, 32, seed=1)
+    with pytest.raises(RuntimeError, match="WARP mode needs"):
+        raw.photo(h, target=inputs[("color", 0, 0)], src=[inputs[("color", -1, 0)], inputs[("color", 1, 0)]])
+    with pytest.raises(ValueError):
+        raw.photo(h, target=inputs[("color", 0, 0)], src=[inputs[("color", -1, 0)][:, :, :8], inputs[("color", 1, 0)]],
+                  mode=raw.PHOTO_PRED)
