@@ -47,29 +47,43 @@ struct Sample {
   float X, Y, Zp;  // P@[cam;1] numerators and (z + eps)
 };
 
-// depth * ray -> P -> /(z+eps) -> Project3D normalisation -> grid_sample unnormalise -> border clip
+struct GridPoint { float gx, gy, X, Y, Zp; };
+
+// depth * ray -> P@[cam;1] -> /(z+eps) -> Project3D normalisation to [-1,1]
+template <int CONV>
+__device__ __forceinline__ GridPoint project_grid(const float* P, Ray ray, float depth, float eps, int H, int W) {
+  float cx = xmul(depth, ray.x), cy = xmul(depth, ray.y), cz = xmul(depth, ray.z);
+  GridPoint g;
+  g.X = xfma(P[3], 1.0f, xfma(P[2], cz, xfma(P[1], cy, xmul(P[0], cx))));
+  g.Y = xfma(P[7], 1.0f, xfma(P[6], cz, xfma(P[5], cy, xmul(P[4], cx))));
+  float Z = xfma(P[11], 1.0f, xfma(P[10], cz, xfma(P[9], cy, xmul(P[8], cx))));
+  g.Zp = xadd(Z, eps);
+  float px = xdiv(g.X, g.Zp), py = xdiv(g.Y, g.Zp);
+  if (CONV == MAL_CONV_MANYDEPTH) {
+    g.gx = xmul(xsub(xdiv(px, (float)(W - 1)), 0.5f), 2.0f);
+    g.gy = xmul(xsub(xdiv(py, (float)(H - 1)), 0.5f), 2.0f);
+  } else {
+    g.gx = xsub(xdiv(xmul(2.0f, xadd(px, 0.5f)), (float)W), 1.0f);
+    g.gy = xsub(xdiv(xmul(2.0f, xadd(py, 0.5f)), (float)H), 1.0f);
+  }
+  return g;
+}
+
+// grid_sample's unnormalisation of a [-1,1] coordinate (align_corners = CONV==MANYDEPTH)
+template <int CONV>
+__device__ __forceinline__ float unnormalize(float g, int size) {
+  if (CONV == MAL_CONV_MANYDEPTH) return xmul(xadd(g, 1.0f), (float)(size - 1) / 2.0f);
+  return xsub(xmul(xadd(g, 1.0f), (float)size / 2.0f), 0.5f);
+}
+
+// ... -> grid_sample unnormalise -> border clip
 template <int CONV>
 __device__ __forceinline__ Sample project_pixel(const float* P, Ray ray, float depth, float eps,
                                                 int H, int W) {
-  float cx = xmul(depth, ray.x), cy = xmul(depth, ray.y), cz = xmul(depth, ray.z);
+  GridPoint g = project_grid<CONV>(P, ray, depth, eps, H, W);
   Sample s;
-  s.X = xfma(P[3], 1.0f, xfma(P[2], cz, xfma(P[1], cy, xmul(P[0], cx))));
-  s.Y = xfma(P[7], 1.0f, xfma(P[6], cz, xfma(P[5], cy, xmul(P[4], cx))));
-  float Z = xfma(P[11], 1.0f, xfma(P[10], cz, xfma(P[9], cy, xmul(P[8], cx))));
-  s.Zp = xadd(Z, eps);
-  float px = xdiv(s.X, s.Zp), py = xdiv(s.Y, s.Zp);
-  float ux, uy;
-  if (CONV == MAL_CONV_MANYDEPTH) {
-    float gx = xmul(xsub(xdiv(px, (float)(W - 1)), 0.5f), 2.0f);
-    float gy = xmul(xsub(xdiv(py, (float)(H - 1)), 0.5f), 2.0f);
-    ux = xmul(xadd(gx, 1.0f), (float)(W - 1) / 2.0f);
-    uy = xmul(xadd(gy, 1.0f), (float)(H - 1) / 2.0f);
-  } else {
-    float gx = xsub(xdiv(xmul(2.0f, xadd(px, 0.5f)), (float)W), 1.0f);
-    float gy = xsub(xdiv(xmul(2.0f, xadd(py, 0.5f)), (float)H), 1.0f);
-    ux = xsub(xmul(xadd(gx, 1.0f), (float)W / 2.0f), 0.5f);
-    uy = xsub(xmul(xadd(gy, 1.0f), (float)H / 2.0f), 0.5f);
-  }
+  s.X = g.X; s.Y = g.Y; s.Zp = g.Zp;
+  float ux = unnormalize<CONV>(g.gx, W), uy = unnormalize<CONV>(g.gy, H);
   // padding_mode="border": clamp, and the coordinate gradient vanishes where clamped
   s.gmx = (ux <= 0.0f || ux >= (float)(W - 1)) ? 0.0f : 1.0f;
   s.gmy = (uy <= 0.0f || uy >= (float)(H - 1)) ? 0.0f : 1.0f;
