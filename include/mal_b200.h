@@ -98,6 +98,115 @@ typedef struct mal_photo_args {
 size_t mal_photo_partials_floats(int batch, int height, int width);
 int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 5. Plane-sweep matching cost volume, forward only (the reference builds it under
+ *    torch.no_grad(): manydepth/networks/resnet_encoder.py:292-307).
+ *
+ * Replaces ResnetEncoderMatching.match_features (manydepth/networks/resnet_encoder.py:151-233;
+ * dualrefine/networks/resnet_encoder.py:163-245 with MAL_CONV_DUALREFINE) and, when the optional
+ * outputs are given, the head of forward(): compute_confidence_mask (:255-262), the "viz"
+ * arg-min and indices_to_disparity (:247-253, :309-313) and cost_volume *= confidence (:317).
+ * A lookup frame whose 4x4 pose sums to 0 is skipped on the device (:183-185, no host sync).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_cost_volume_args {
+  int32_t batch, channels, height, width; /* matching resolution (H/4, W/4)                  */
+  int32_t num_lookup, num_bins;
+  int32_t convention;          /* MAL_CONV_*                                                 */
+  int32_t set_missing_to_max;  /* self.set_missing_to_max (:223)                              */
+  int32_t apply_confidence;    /* 1: cost_volume is multiplied by the confidence mask (:317)  */
+  int32_t num_bins_threshold;  /* compute_confidence_mask threshold; <=0: num_bins            */
+  float eps;                   /* Project3D eps                                               */
+
+  const float* current;        /* (B,C,h,w)   current_feats                                   */
+  const float* lookup;         /* (B,F,C,h,w) lookup_feats                                    */
+  const float* poses;          /* (B,F,4,4)   relative_poses                                  */
+  const float* K;              /* (B,4,4)     K at the matching scale                         */
+  const float* inv_K;          /* (B,4,4)                                                     */
+  const float* bins;           /* (num_bins)  depth_bins (compute_depth_bins :121-141)        */
+
+  float* cost_volume;          /* (B,num_bins,h,w)                                            */
+  float* missing_mask;         /* (B,num_bins,h,w) optional                                   */
+  float* confidence;           /* (B,h,w) optional                                            */
+  int32_t* argmin;             /* (B,h,w) optional: arg-min bin of the 0->100 "viz" volume    */
+  float* lowest_cost;          /* (B,h,w) optional: 1 / bins[argmin]                          */
+  float* packed;               /* workspace, mal_cost_volume_workspace_floats() floats, 16-B aligned */
+} mal_cost_volume_args;
+
+size_t mal_cost_volume_workspace_floats(int batch, int channels, int height, int width, int num_lookup);
+int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Edge-aware smoothness, forward + backward in one call.
+ *
+ * Replaces get_smooth_loss (manydepth/layers.py:210-223) and, with `normalise`, the
+ * mean-normalisation in front of it (manydepth/loss_utils.py:119-121, trainer.py:1440-1442).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_smooth_args {
+  int32_t batch, height, width;
+  int32_t normalise;          /* 1: disp / (disp.mean(2,True).mean(3,True) + 1e-7) first      */
+  int32_t with_grad;
+  const float* disp;          /* (B,1,h,w)                                                    */
+  const float* img;           /* (B,3,h,w)                                                    */
+  float* grad_disp;           /* (B,1,h,w) with_grad: d loss / d disp                         */
+  float* workspace;           /* mal_smooth_workspace_floats() floats                         */
+  float* loss;                /* (1)                                                          */
+} mal_smooth_args;
+
+size_t mal_smooth_workspace_floats(int batch, int height, int width);
+int mal_smooth_forward(const mal_smooth_args* args, mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. MAL student ("main") terms at scale 0: consistency L1 and the distillation selection.
+ *
+ * Replaces the per-pixel part of compute_main_losses (manydepth/loss_utils.py:192-254):
+ * mask / consistency mask (:192-196), consistency loss + target (:205-213), the arg-min over
+ * [mono_reproj, (ensemble_reproj), multi_reproj] (:228-229 / :237-238), torch.where depth
+ * selection (:231-245) and the distillation loss (:253-254), with their backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_main_terms_args {
+  int32_t batch, height, width;
+  int32_t inputs_are_disp;    /* 1: multi/mono hold sigmoid disparity (disp_to_depth applied)  */
+  int32_t dual_distil;        /* opt.dual_distil: the mono teacher also receives a gradient    */
+  int32_t with_grad;
+  double min_depth, max_depth;
+  const float* multi;         /* (B,1,H,W) outputs[("depth",0,0)] or ("disp",0)                */
+  const float* mono;          /* (B,1,H,W) outputs[("mono_depth",0,0)] or ("mono_disp",0)      */
+  const float* pixel_mask;    /* (B,H,W)   outputs["consistency_mask"]                         */
+  const float* sample_mask;   /* (B)       outputs["augmentation_mask"], optional              */
+  const float* mono_reproj;   /* (B,1,H,W) teacher min reprojection                            */
+  const float* ens_reproj;    /* (B,1,H,W) optional ensemble min reprojection                  */
+  const float* multi_reproj;  /* (B,1,H,W) student min reprojection                            */
+  uint8_t* distil_index;      /* (B,1,H,W) optional: arg-min                                   */
+  float* consistency_target;  /* (B,1,H,W) optional: outputs["consistency_target/0"] (:211-213)*/
+  float* grad_cons;           /* (B,1,H,W) with_grad: d consistency_loss / d multi             */
+  float* grad_distil;         /* (B,1,H,W) with_grad: d distil_loss / d multi                  */
+  float* grad_distil_mono;    /* (B,1,H,W) with_grad && dual_distil: d distil_loss / d mono    */
+  float* partials;            /* workspace, mal_main_terms_partials_floats() floats            */
+  float* sums;                /* (2): [consistency_loss, distil_loss]                          */
+} mal_main_terms_args;
+
+size_t mal_main_terms_partials_floats(int batch, int height, int width);
+int mal_main_terms_forward(const mal_main_terms_args* args, mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trainer.compute_matching_mask (manydepth/trainer.py:1066-1076) fused with the nearest
+ * up-sampling of lowest_cost / confidence (manydepth/networks/repdepth.py:331-336) and the
+ * product at trainer.py:592-593:
+ *   out = nearest(confidence) * [ (m-t)/t < 1  and  (t-m)/m < 1 ],  m = 1/nearest(lowest_cost).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_matching_mask_args {
+  int32_t batch, height, width;      /* full resolution                                       */
+  int32_t low_height, low_width;     /* resolution of lowest_cost / confidence (may equal H,W)*/
+  int32_t mono_is_disp;
+  double min_depth, max_depth;
+  const float* lowest_cost;          /* (B,h,w)                                               */
+  const float* confidence;           /* (B,h,w) optional                                      */
+  const float* mono;                 /* (B,1,H,W) mono depth (or disparity)                   */
+  float* out_mask;                   /* (B,H,W) float {0,1} (x confidence)                    */
+} mal_matching_mask_args;
+
+int mal_matching_mask(const mal_matching_mask_args* args, mal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,56 @@ class PhotoArgs(C.Structure):
     ]
 
 
+class CostVolumeArgs(C.Structure):
+    """struct mal_cost_volume_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("num_lookup", C.c_int32), ("num_bins", C.c_int32), ("convention", C.c_int32),
+        ("set_missing_to_max", C.c_int32), ("apply_confidence", C.c_int32),
+        ("num_bins_threshold", C.c_int32), ("eps", C.c_float),
+        ("current", C.c_void_p), ("lookup", C.c_void_p), ("poses", C.c_void_p), ("K", C.c_void_p),
+        ("inv_K", C.c_void_p), ("bins", C.c_void_p),
+        ("cost_volume", C.c_void_p), ("missing_mask", C.c_void_p), ("confidence", C.c_void_p),
+        ("argmin", C.c_void_p), ("lowest_cost", C.c_void_p), ("packed", C.c_void_p),
+    ]
+
+
+class SmoothArgs(C.Structure):
+    """struct mal_smooth_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("normalise", C.c_int32), ("with_grad", C.c_int32),
+        ("disp", C.c_void_p), ("img", C.c_void_p), ("grad_disp", C.c_void_p),
+        ("workspace", C.c_void_p), ("loss", C.c_void_p),
+    ]
+
+
+class MainTermsArgs(C.Structure):
+    """struct mal_main_terms_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("inputs_are_disp", C.c_int32), ("dual_distil", C.c_int32), ("with_grad", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double),
+        ("multi", C.c_void_p), ("mono", C.c_void_p), ("pixel_mask", C.c_void_p),
+        ("sample_mask", C.c_void_p), ("mono_reproj", C.c_void_p), ("ens_reproj", C.c_void_p),
+        ("multi_reproj", C.c_void_p),
+        ("distil_index", C.c_void_p), ("consistency_target", C.c_void_p), ("grad_cons", C.c_void_p),
+        ("grad_distil", C.c_void_p), ("grad_distil_mono", C.c_void_p), ("partials", C.c_void_p),
+        ("sums", C.c_void_p),
+    ]
+
+
+class MatchingMaskArgs(C.Structure):
+    """struct mal_matching_mask_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("low_height", C.c_int32), ("low_width", C.c_int32), ("mono_is_disp", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double),
+        ("lowest_cost", C.c_void_p), ("confidence", C.c_void_p), ("mono", C.c_void_p),
+        ("out_mask", C.c_void_p),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mal_abi_version": (C.c_int, []),
@@ -39,6 +89,13 @@ EXPORTS = {
     "mal_check_device": (C.c_int, [C.c_int]),
     "mal_photo_partials_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
+    "mal_cost_volume_workspace_floats": (C.c_size_t, [C.c_int] * 5),
+    "mal_cost_volume_forward": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),
+    "mal_smooth_workspace_floats": (C.c_size_t, [C.c_int] * 3),
+    "mal_smooth_forward": (C.c_int, [C.POINTER(SmoothArgs), C.c_void_p]),
+    "mal_main_terms_partials_floats": (C.c_size_t, [C.c_int] * 3),
+    "mal_main_terms_forward": (C.c_int, [C.POINTER(MainTermsArgs), C.c_void_p]),
+    "mal_matching_mask": (C.c_int, [C.POINTER(MatchingMaskArgs), C.c_void_p]),
 }
 
 ABI_VERSION = 1

@@ -1,0 +1,357 @@
+// cost_volume.cu - plane-sweep matching cost volume (forward only) for sm_100a.
+//
+// Replaces ResnetEncoderMatching.match_features (manydepth/networks/resnet_encoder.py:151-233,
+// dualrefine/networks/resnet_encoder.py:163-245) together with the head that consumes it in
+// forward(): compute_confidence_mask (:255-262), the "viz" arg-min -> lowest_cost (:309-313,
+// indices_to_disparity :247-253) and cost_volume *= confidence (:317).  The reference builds the
+// volume under torch.no_grad(), so there is no backward.
+//
+// The reference materialises a (bins, C, h, w) warped tensor per sample (189 MB at 96x64x48x160,
+// three times over); here nothing larger than the inputs and the (B, bins, h, w) result touches HBM.
+//
+// Work decomposition
+//   kernel 1  cv_pack_kernel: current/lookup features NCHW -> channel-quad interleaved float4
+//             planes [C/4][h][w] (zero padded to a multiple of 16 channels) so that one 128-bit load
+//             fetches 4 channels of one bilinear tap.
+//   kernel 2  cv_sweep_kernel: one CTA = 32 consecutive pixels of one sample x all bins.
+//             warp  <-> a 16-channel chunk (the cascade-sum granule of the reference, see below)
+//             lane  <-> pixel
+//             Bins are processed in groups of CV_BG.  Per group:
+//               P  all threads: one projection per (pixel, bin) -> {tap offset | masked, tx, ty} in smem
+//               C  each warp sweeps the group's bins for its chunk.  The 2x2x16 texel block lives in
+//                  registers and is only re-fetched when the integer tap origin moves: consecutive
+//                  depth planes land in the same texel cell for most of the sweep, which removes
+//                  ~4/5 of the gather traffic.  Chunk sums go to smem.
+//               F  all threads: combine the chunk sums in the reference's order, mean, edge mask,
+//                  accumulate over lookup frames.
+//             Epilogue: / (counts + 1e-7), per-pixel max over bins, missing fill, confidence,
+//             first-index arg-min, coalesced plane-by-plane stores.
+//
+// Arithmetic contract (bit-exact against torch CPU, pinned by tests/golden/cost_volume.npz):
+//   projection / grid_sample arithmetic as in mal_math.cuh;  mean over channels = ATen cascade_sum
+//   (SumKernel.cpp multi_row_sum): 16 channels summed sequentially from 0, chunk sums added
+//   sequentially, then / C.
+#include "mal_math.cuh"
+
+namespace mal {
+
+constexpr int CV_PX = 32;      // pixels per CTA (one per lane)
+constexpr int CV_WARPS = 4;    // channel chunks in flight
+constexpr int CV_NT = CV_PX * CV_WARPS;
+constexpr int CV_BG = 32;      // bins per group
+constexpr int CV_CHUNK = 16;   // channels per chunk (cascade_sum level step)
+
+struct CvGeom {
+  float P[12];
+  float iK[9];
+  int live;   // lookup pose .sum() != 0
+};
+
+__host__ __device__ inline int cv_padded_channels(int C) { return (C + CV_CHUNK - 1) / CV_CHUNK * CV_CHUNK; }
+
+inline size_t cv_smem_bytes(int nchunks, int num_bins) {
+  size_t fl = sizeof(CvGeom) / 4 + 4;
+  fl += (size_t)3 * CV_BG * CV_PX;                 // descriptors: off, tx, ty
+  fl += (size_t)nchunks * CV_BG * CV_PX;           // chunk sums
+  fl += (size_t)2 * num_bins * CV_PX;              // cost, counts
+  fl += (size_t)4 * CV_WARPS * CV_PX;              // epilogue scratch
+  return fl * 4 + 16;
+}
+
+// NCHW -> [C/4][h][w] float4, zero padded to Cp channels.  One thread per (quad, pixel).
+__global__ void __launch_bounds__(256) cv_pack_kernel(const float* __restrict__ src, float4* __restrict__ dst,
+                                                      int C, int Cp, int hw, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int p = (int)(i % hw);
+  long long r = i / hw;
+  int q = (int)(r % (Cp / 4));
+  long long img = r / (Cp / 4);
+  const float* s = src + (img * C + (long long)q * 4) * hw + p;
+  float4 v;
+  v.x = (q * 4 + 0 < C) ? __ldg(s) : 0.0f;
+  v.y = (q * 4 + 1 < C) ? __ldg(s + hw) : 0.0f;
+  v.z = (q * 4 + 2 < C) ? __ldg(s + 2 * (size_t)hw) : 0.0f;
+  v.w = (q * 4 + 3 < C) ? __ldg(s + 3 * (size_t)hw) : 0.0f;
+  dst[i] = v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) {
+#ifdef MAL_EMU
+  return *p;
+#else
+  return __ldg(p);
+#endif
+}
+
+// sum_{c in quad} |bilinear(c) - cur(c)|, continuing the sequential chain in `acc`
+__device__ __forceinline__ float quad_l1(float acc, const float4& a, const float4& b, const float4& c,
+                                         const float4& d, const float4& cur, float nw, float ne, float sw,
+                                         float se) {
+  float w0 = xfma(d.x, se, xfma(c.x, sw, xfma(b.x, ne, xmul(a.x, nw))));
+  float w1 = xfma(d.y, se, xfma(c.y, sw, xfma(b.y, ne, xmul(a.y, nw))));
+  float w2 = xfma(d.z, se, xfma(c.z, sw, xfma(b.z, ne, xmul(a.z, nw))));
+  float w3 = xfma(d.w, se, xfma(c.w, sw, xfma(b.w, ne, xmul(a.w, nw))));
+  acc = xadd(acc, fabsf(xsub(w0, cur.x)));
+  acc = xadd(acc, fabsf(xsub(w1, cur.y)));
+  acc = xadd(acc, fabsf(xsub(w2, cur.z)));
+  acc = xadd(acc, fabsf(xsub(w3, cur.w)));
+  return acc;
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(CV_NT) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = a.height, w = a.width, hw = h * w;
+  const int nb = a.num_bins, nchunks = Cp / CV_CHUNK, nquads = Cp / 4;
+  const int tiles = (hw + CV_PX - 1) / CV_PX;
+  const int b = blockIdx.x / tiles;
+  const int p = (blockIdx.x - b * tiles) * CV_PX + lane;   // this lane's pixel (flat index)
+  const bool pix_ok = p < hw;
+  const int py = pix_ok ? p / w : 0, px = pix_ok ? p - py * w : 0;
+
+  float* smem = reinterpret_cast<float*>(dyn_smem());
+  CvGeom* geom = reinterpret_cast<CvGeom*>(smem);
+  int* d_off = reinterpret_cast<int*>(smem + sizeof(CvGeom) / 4 + 4);   // [BG][PX]
+  float* d_tx = reinterpret_cast<float*>(d_off + CV_BG * CV_PX);
+  float* d_ty = d_tx + CV_BG * CV_PX;
+  float* part = d_ty + CV_BG * CV_PX;                    // [nchunks][BG][PX]
+  float* cost = part + (size_t)nchunks * CV_BG * CV_PX;  // [nb][PX]
+  float* cnt = cost + (size_t)nb * CV_PX;                // [nb][PX]
+  float* scr = cnt + (size_t)nb * CV_PX;                 // [4][WARPS][PX]
+
+  for (int i = tid; i < nb * CV_PX; i += CV_NT) { cost[i] = 0.0f; cnt[i] = 0.0f; }
+
+  const float4* curq = reinterpret_cast<const float4*>(a.packed) + (size_t)b * nquads * hw;
+  const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
+  // the pixel's own border mask (current_mask[:, 2:-2, 2:-2], resnet_encoder.py:203-205)
+  const bool inner = pix_ok && py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
+
+  for (int f = 0; f < a.num_lookup; f++) {
+    __syncthreads();   // previous frame's geometry and descriptors are no longer read
+    if (tid < 12) {
+      geom->P[tid] = kt_entry(a.K + b * 16, a.poses + ((size_t)b * a.num_lookup + f) * 16, tid / 4, tid % 4);
+    } else if (tid < 21) {
+      int e = tid - 12;
+      geom->iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
+    } else if (tid == 21) {
+      const float* T = a.poses + ((size_t)b * a.num_lookup + f) * 16;
+      float s = 0.0f;
+      for (int e = 0; e < 16; e++) s += T[e];
+      geom->live = (s != 0.0f) ? 1 : 0;   // "ignore missing images", resnet_encoder.py:183-185
+    }
+    __syncthreads();
+    if (!geom->live) continue;   // uniform across the CTA
+
+    const Ray ray = pixel_ray(geom->iK, (float)px, (float)py);
+    const float4* lq = lookq + ((size_t)b * a.num_lookup + f) * nquads * hw;
+
+    for (int g0 = 0; g0 < nb; g0 += CV_BG) {
+      const int gn = min(CV_BG, nb - g0);
+      // ---- P: projection descriptors ---------------------------------------------------------
+      for (int k = warp; k < gn; k += CV_WARPS) {
+        int off = -1;
+        float tx = 0.0f, ty = 0.0f;
+        if (inner) {
+          float depth = __ldg(a.bins + g0 + k);
+          GridPoint gp = project_grid<CONV>(geom->P, ray, depth, a.eps, h, w);
+          // edge mask on the sampling location (resnet_encoder.py:196-201)
+          float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
+          float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
+          bool edge = xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2);
+          if (edge) {
+            float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+            float x0 = floorf(ux), y0 = floorf(uy);
+            int xi = (int)x0, yi = (int)y0;
+            // zeros padding: taps outside the image read 0.  With the edge mask on, (xi,yi) is
+            // inside for the align_corners=True convention; the half-pixel convention can differ
+            // by one cell, so clamp the origin and zero the weights of out-of-range taps below.
+            if (xi >= 0 && xi + 1 < w && yi >= 0 && yi + 1 < h) {
+              off = yi * w + xi;
+              tx = xsub(ux, x0);
+              ty = xsub(uy, y0);
+            } else {
+              off = -2;   // rare: unmasked but touching the border -> slow exact path
+              tx = ux; ty = uy;
+            }
+          }
+        }
+        d_off[k * CV_PX + lane] = off;
+        d_tx[k * CV_PX + lane] = tx;
+        d_ty[k * CV_PX + lane] = ty;
+      }
+      __syncthreads();
+
+      // ---- C: channel sweep, one 16-channel chunk per warp pass ------------------------------
+      for (int ch = warp; ch < nchunks; ch += CV_WARPS) {
+        float4 cq[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          cq[j] = pix_ok ? ldg4(curq + (size_t)(ch * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t00[4], t01[4], t10[4], t11[4];
+        int coff = -1;
+        for (int k = 0; k < gn; k++) {
+          const int off = d_off[k * CV_PX + lane];
+          if (__all_sync(0xffffffffu, off == -1)) continue;
+          float acc = 0.0f;
+          if (off >= 0) {
+            if (off != coff) {
+              coff = off;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const float4* base = lq + (size_t)(ch * 4 + j) * hw + off;
+                t00[j] = ldg4(base); t01[j] = ldg4(base + 1);
+                t10[j] = ldg4(base + w); t11[j] = ldg4(base + w + 1);
+              }
+            }
+            const float tx = d_tx[k * CV_PX + lane], ty = d_ty[k * CV_PX + lane];
+            const float e = xsub(1.0f, tx), s = xsub(1.0f, ty);
+            const float nw = xmul(s, e), ne = xmul(s, tx), sw = xmul(ty, e), se = xmul(ty, tx);
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc = quad_l1(acc, t00[j], t01[j], t10[j], t11[j], cq[j], nw, ne, sw, se);
+          } else if (off == -2) {
+            // exact zeros-padding path (taps outside the image contribute 0)
+            Taps t = make_taps(d_tx[k * CV_PX + lane], d_ty[k * CV_PX + lane], h, w);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float4* base = lq + (size_t)(ch * 4 + j) * hw;
+              float4 v00 = t.v00 ? ldg4(base + t.o00) : z, v01 = t.v01 ? ldg4(base + t.o01) : z;
+              float4 v10 = t.v10 ? ldg4(base + t.o10) : z, v11 = t.v11 ? ldg4(base + t.o11) : z;
+              acc = quad_l1(acc, v00, v01, v10, v11, cq[j], t.nw, t.ne, t.sw, t.se);
+            }
+          }
+          part[((size_t)ch * CV_BG + k) * CV_PX + lane] = acc;
+        }
+      }
+      __syncthreads();
+
+      // ---- F: combine chunks, mean, accumulate over lookup frames ----------------------------
+      for (int k = warp; k < gn; k += CV_WARPS) {
+        if (d_off[k * CV_PX + lane] != -1) {
+          float s = part[(size_t)k * CV_PX + lane];                       // 0 + c0
+          for (int ch = 1; ch < nchunks; ch++) s = xadd(s, part[((size_t)ch * CV_BG + k) * CV_PX + lane]);
+          float diff = xdiv(s, (float)a.channels);                         // .mean(1), edge mask == 1
+          int o = (g0 + k) * CV_PX + lane;
+          cost[o] = xadd(cost[o], diff);
+          if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+        }
+      }
+      // the next group's P phase rewrites the descriptors only after the barrier below
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // ---- epilogue -------------------------------------------------------------------------------
+  // warp q owns a contiguous range of bins for every pixel of the tile
+  const int per = (nb + CV_WARPS - 1) / CV_WARPS;
+  const int k0 = min(nb, warp * per), k1 = min(nb, k0 + per);
+  float vmax = -INFINITY;
+  for (int k = k0; k < k1; k++) {
+    int o = k * CV_PX + lane;
+    float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));   // cost_volume / (counts + 1e-7)
+    cost[o] = v;
+    vmax = fmaxf(vmax, v);
+  }
+  scr[warp * CV_PX + lane] = vmax;
+  __syncthreads();
+  vmax = scr[lane];
+#pragma unroll
+  for (int q = 1; q < CV_WARPS; q++) vmax = fmaxf(vmax, scr[q * CV_PX + lane]);
+  __syncthreads();
+
+  float npos = 0.0f, best = INFINITY;
+  int besti = 0x7fffffff;
+  for (int k = k0; k < k1; k++) {
+    int o = k * CV_PX + lane;
+    float v = cost[o];
+    float miss = (v == 0.0f) ? 1.0f : 0.0f;
+    float out = v;
+    if (a.set_missing_to_max) out = xadd(xmul(v, xsub(1.0f, miss)), xmul(vmax, miss));
+    cost[o] = out;
+    cnt[o] = miss;
+    // compute_confidence_mask(cost_volume * (1 - missing_mask))
+    if (xmul(out, xsub(1.0f, miss)) > 0.0f) npos += 1.0f;
+    float viz = (out == 0.0f) ? 100.0f : out;       // viz_cost_vol[viz_cost_vol == 0] = 100
+    if (viz < best || (viz != viz && best == best)) { best = viz; besti = k; }   // first min; NaN wins like torch
+  }
+  scr[(0 * CV_WARPS + warp) * CV_PX + lane] = npos;
+  scr[(1 * CV_WARPS + warp) * CV_PX + lane] = best;
+  reinterpret_cast<int*>(scr)[(2 * CV_WARPS + warp) * CV_PX + lane] = besti;
+  __syncthreads();
+  float conf_n = 0.0f;
+  best = INFINITY; besti = 0x7fffffff;
+  bool have = false;
+#pragma unroll
+  for (int q = 0; q < CV_WARPS; q++) {
+    conf_n += scr[(0 * CV_WARPS + q) * CV_PX + lane];
+    float v = scr[(1 * CV_WARPS + q) * CV_PX + lane];
+    int vi = reinterpret_cast<int*>(scr)[(2 * CV_WARPS + q) * CV_PX + lane];
+    if (vi == 0x7fffffff) continue;
+    if (!have || v < best || (v != v && best == best)) { best = v; besti = vi; have = true; }
+  }
+  const int thr = a.num_bins_threshold > 0 ? a.num_bins_threshold : nb;
+  const float conf = (conf_n == (float)thr) ? 1.0f : 0.0f;
+  if (pix_ok) {
+    const size_t vol = (size_t)b * nb * hw;
+    for (int k = k0; k < k1; k++) {
+      int o = k * CV_PX + lane;
+      float out = cost[o];
+      if (a.apply_confidence) out = xmul(out, conf);
+      a.cost_volume[vol + (size_t)k * hw + p] = out;
+      if (a.missing_mask) a.missing_mask[vol + (size_t)k * hw + p] = cnt[o];
+    }
+    if (warp == 0) {
+      const size_t po = (size_t)b * hw + p;
+      if (a.confidence) a.confidence[po] = conf;
+      if (a.argmin) a.argmin[po] = besti;
+      if (a.lowest_cost) a.lowest_cost[po] = xdiv(1.0f, __ldg(a.bins + besti));
+    }
+  }
+}
+
+}  // namespace mal
+
+using namespace mal;
+
+extern "C" size_t mal_cost_volume_workspace_floats(int batch, int channels, int height, int width, int num_lookup) {
+  return (size_t)batch * (1 + num_lookup) * cv_padded_channels(channels) * height * width;
+}
+
+extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream) {
+  MAL_REQUIRE(args != nullptr, "mal_cost_volume_forward: args is NULL");
+  const mal_cost_volume_args& a = *args;
+  MAL_REQUIRE(a.batch > 0 && a.channels > 0 && a.height >= 5 && a.width >= 5 && a.num_lookup > 0 && a.num_bins > 0,
+              "mal_cost_volume_forward: bad shape B=%d C=%d h=%d w=%d F=%d bins=%d", a.batch, a.channels, a.height,
+              a.width, a.num_lookup, a.num_bins);
+  MAL_REQUIRE(a.channels <= 256, "mal_cost_volume_forward: %d channels (> 256) changes the reference's summation tree",
+              a.channels);
+  MAL_REQUIRE(a.convention == MAL_CONV_MANYDEPTH || a.convention == MAL_CONV_DUALREFINE,
+              "mal_cost_volume_forward: bad convention %d", a.convention);
+  MAL_REQUIRE(a.current && a.lookup && a.poses && a.K && a.inv_K && a.bins && a.cost_volume && a.packed,
+              "mal_cost_volume_forward: current/lookup/poses/K/inv_K/bins/cost_volume/packed are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = cv_padded_channels(a.channels);
+  const int hw = a.height * a.width;
+  {
+    long long total = (long long)a.batch * (Cp / 4) * hw;
+    launch(cv_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a.current,
+           reinterpret_cast<float4*>(a.packed), a.channels, Cp, hw, total);
+    long long total_l = total * a.num_lookup;
+    launch(cv_pack_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
+           reinterpret_cast<float4*>(a.packed) + total, a.channels, Cp, hw, total_l);
+    int rc = check_launch("cv_pack_kernel");
+    if (rc) return rc;
+  }
+  const int tiles = (hw + CV_PX - 1) / CV_PX;
+  const size_t smem = cv_smem_bytes(Cp / CV_CHUNK, a.num_bins);
+  MAL_REQUIRE(smem <= 227 * 1024, "mal_cost_volume_forward: %d bins x %d channels need %zu B of shared memory",
+              a.num_bins, a.channels, smem);
+  dim3 grid((unsigned)((size_t)a.batch * tiles));
+  if (a.convention == MAL_CONV_MANYDEPTH)
+    launch(cv_sweep_kernel<MAL_CONV_MANYDEPTH>, grid, dim3(CV_NT), smem, st, a, Cp);
+  else
+    launch(cv_sweep_kernel<MAL_CONV_DUALREFINE>, grid, dim3(CV_NT), smem, st, a, Cp);
+  return check_launch("cv_sweep_kernel");
+}

@@ -105,3 +105,106 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
     out["_keepalive"] = (partials,)
     return out
+
+
+def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CONV_MANYDEPTH,
+                set_missing_to_max=True, apply_confidence=False, num_bins_threshold=0, eps=1e-7,
+                want_missing=True, want_head=True):
+    """mal_cost_volume_forward.  `want_head` adds confidence / argmin / lowest_cost."""
+    B, Cn, h, w = current.shape
+    F_ = lookup.shape[1]
+    nb = bins.shape[0]
+    current = _f32(current, "current", (B, Cn, h, w))
+    lookup = _f32(lookup, "lookup", (B, F_, Cn, h, w))
+    poses = _f32(poses, "poses", (B, F_, 4, 4))
+    K, inv_K = _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
+    bins = _f32(bins, "bins", (nb,))
+    dev = _same_device([current, lookup, poses, K, inv_K, bins])
+    new = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
+    out = {"cost_volume": new((B, nb, h, w))}
+    out["missing_mask"] = new((B, nb, h, w)) if want_missing else None
+    out["confidence"] = new((B, h, w)) if want_head else None
+    out["argmin"] = new((B, h, w), torch.int32) if want_head else None
+    out["lowest_cost"] = new((B, h, w)) if want_head else None
+    packed = new((handle.mal_cost_volume_workspace_floats(B, Cn, h, w, F_),))
+    a = _capi.CostVolumeArgs()
+    a.batch, a.channels, a.height, a.width, a.num_lookup, a.num_bins = B, Cn, h, w, F_, nb
+    a.convention, a.set_missing_to_max = convention, int(set_missing_to_max)
+    a.apply_confidence, a.num_bins_threshold, a.eps = int(apply_confidence), int(num_bins_threshold), float(eps)
+    a.current, a.lookup, a.poses = _ptr(current), _ptr(lookup), _ptr(poses)
+    a.K, a.inv_K, a.bins = _ptr(K), _ptr(inv_K), _ptr(bins)
+    a.cost_volume, a.missing_mask = _ptr(out["cost_volume"]), _ptr(out["missing_mask"])
+    a.confidence, a.argmin, a.lowest_cost = _ptr(out["confidence"]), _ptr(out["argmin"]), _ptr(out["lowest_cost"])
+    a.packed = _ptr(packed)
+    _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
+    out["_keepalive"] = (packed,)
+    return out
+
+
+def smooth(handle, *, disp, img, normalise=True, with_grad=False):
+    """mal_smooth_forward -> {"loss": (1,), "grad_disp": (B,1,h,w)}."""
+    B, _, h, w = disp.shape
+    disp, img = _f32(disp, "disp", (B, 1, h, w)), _f32(img, "img", (B, 3, h, w))
+    dev = _same_device([disp, img])
+    new = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {"loss": new((1,)), "grad_disp": new((B, 1, h, w)) if with_grad else None}
+    ws = new((handle.mal_smooth_workspace_floats(B, h, w),))
+    a = _capi.SmoothArgs()
+    a.batch, a.height, a.width, a.normalise, a.with_grad = B, h, w, int(normalise), int(with_grad)
+    a.disp, a.img, a.grad_disp, a.workspace, a.loss = _ptr(disp), _ptr(img), _ptr(out["grad_disp"]), _ptr(ws), _ptr(out["loss"])
+    _capi.check(handle.mal_smooth_forward(C.byref(a), _stream(disp)), handle)
+    out["_keepalive"] = (ws,)
+    return out
+
+
+def main_terms(handle, *, multi, mono, pixel_mask, sample_mask=None, mono_reproj, multi_reproj,
+               ens_reproj=None, inputs_are_disp=False, dual_distil=False, with_grad=False,
+               min_depth=0.1, max_depth=100.0, want_index=True, want_target=True):
+    """mal_main_terms_forward."""
+    B, _, H, W = multi.shape
+    plane = (B, 1, H, W)
+    multi, mono = _f32(multi, "multi", plane), _f32(mono, "mono", plane)
+    pixel_mask = _f32(pixel_mask, "pixel_mask", (B, H, W))
+    if sample_mask is not None:
+        sample_mask = _f32(sample_mask.reshape(-1), "sample_mask", (B,))
+    mono_reproj, multi_reproj = _f32(mono_reproj, "mono_reproj", plane), _f32(multi_reproj, "multi_reproj", plane)
+    ens_reproj = _f32(ens_reproj, "ens_reproj", plane)
+    dev = _same_device([multi, mono, pixel_mask, sample_mask, mono_reproj, multi_reproj, ens_reproj])
+    new = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
+    out = {"sums": new((2,))}
+    out["distil_index"] = new(plane, torch.uint8) if want_index else None
+    out["consistency_target"] = new(plane) if want_target else None
+    out["grad_cons"] = new(plane) if with_grad else None
+    out["grad_distil"] = new(plane) if with_grad else None
+    out["grad_distil_mono"] = new(plane) if (with_grad and dual_distil) else None
+    partials = new((handle.mal_main_terms_partials_floats(B, H, W),))
+    a = _capi.MainTermsArgs()
+    a.batch, a.height, a.width = B, H, W
+    a.inputs_are_disp, a.dual_distil, a.with_grad = int(inputs_are_disp), int(dual_distil), int(with_grad)
+    a.min_depth, a.max_depth = float(min_depth), float(max_depth)
+    a.multi, a.mono, a.pixel_mask, a.sample_mask = _ptr(multi), _ptr(mono), _ptr(pixel_mask), _ptr(sample_mask)
+    a.mono_reproj, a.ens_reproj, a.multi_reproj = _ptr(mono_reproj), _ptr(ens_reproj), _ptr(multi_reproj)
+    a.distil_index, a.consistency_target = _ptr(out["distil_index"]), _ptr(out["consistency_target"])
+    a.grad_cons, a.grad_distil, a.grad_distil_mono = _ptr(out["grad_cons"]), _ptr(out["grad_distil"]), _ptr(out["grad_distil_mono"])
+    a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
+    _capi.check(handle.mal_main_terms_forward(C.byref(a), _stream(multi)), handle)
+    out["_keepalive"] = (partials,)
+    return out
+
+
+def matching_mask(handle, *, lowest_cost, mono, confidence=None, height=None, width=None,
+                  mono_is_disp=False, min_depth=0.1, max_depth=100.0):
+    """mal_matching_mask -> (B,H,W) float mask (x nearest-upsampled confidence when given)."""
+    B, h, w = lowest_cost.shape
+    H, W = mono.shape[-2:]
+    lowest_cost = _f32(lowest_cost, "lowest_cost", (B, h, w))
+    confidence = _f32(confidence, "confidence", (B, h, w))
+    mono = _f32(mono, "mono", (B, 1, H, W))
+    dev = _same_device([lowest_cost, confidence, mono])
+    out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    a = _capi.MatchingMaskArgs()
+    a.batch, a.height, a.width, a.low_height, a.low_width = B, H, W, h, w
+    a.mono_is_disp, a.min_depth, a.max_depth = int(mono_is_disp), float(min_depth), float(max_depth)
+    a.lowest_cost, a.confidence, a.mono, a.out_mask = _ptr(lowest_cost), _ptr(confidence), _ptr(mono), _ptr(out)
+    _capi.check(handle.mal_matching_mask(C.byref(a), _stream(mono)), handle)
+    return out

@@ -410,7 +410,7 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, bins,
             if pose.sum() == 0:
                 continue
             feat = lookup_feats[b:b + 1, li].repeat([nb, 1, 1, 1])
-            locs = project3d(world, K[b:b + 1], pose, h, w)
+            locs = project3d(world, K[b:b + 1], pose, h, w, convention)
             warped = F.grid_sample(feat, locs, padding_mode="zeros", mode="bilinear",
                                    align_corners=(convention == MANYDEPTH))
             xv = (locs[..., 0] / 2 + 0.5) * (w - 1)
