@@ -74,7 +74,8 @@ typedef struct mal_photo_args {
   float eps;           /* Project3D eps (1e-7)                                              */
 
   const float* target;      /* (B,3,H,W) inputs[("color",0,0)]                              */
-  const float* src[2];      /* (B,3,H,W) frames -1,+1: WARP: sampled; PRED: pre-warped preds */
+  const float* src[2];      /* (B,3,H,W) frames -1,+1: WARP: sampled; PRED: pre-warped preds;
+                               PRED with src[1]==NULL: one candidate (compute_reprojection_loss) */
   const float* syn[2];      /* (B,3,H,W) optional MAL temporal-hint candidates, both or none */
   const float* depth;       /* (B,1,H,W) depth or disparity (WARP mode)                     */
   const float* K;           /* (B,4,4)                                                      */
@@ -206,6 +207,35 @@ typedef struct mal_matching_mask_args {
 } mal_matching_mask_args;
 
 int mal_matching_mask(const mal_matching_mask_args* args, mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 7. The reference's layer classes on their own (forward + backward).
+ *
+ *   mal_backproject        BackprojectDepth.forward  manydepth/layers.py:163-168
+ *                          depth (B,1,H,W), inv_K (B,4,4) -> cam points (B,4,H*W)
+ *   mal_project3d          Project3D.forward         manydepth/layers.py:184-199 (MAL_CONV_MANYDEPTH),
+ *                          dualrefine/layers.py:216-226 (MAL_CONV_DUALREFINE)
+ *                          points (B,4,H*W), K, T (B,4,4) -> pix (B,H,W,2) [+ z (B,1,H,W) when `z`
+ *                          is given: the `dc=True` second return value]
+ *   mal_ssim               SSIM.forward              manydepth/layers.py:243-257
+ *                          x, y (planes = B*C, H, W) -> clamp((1 - SSIM) / 2, 0, 1), same shape
+ * Backward entry points take the upstream gradient and return the input gradients; grad_P is
+ * d/d (K@T)[:3,:] as (B,12) (the caller chains it to T and K with two 4x4 products).
+ * ------------------------------------------------------------------------------------------ */
+int mal_backproject(const float* depth, const float* inv_K, int batch, int height, int width, float* out,
+                    mal_stream_t stream);
+int mal_backproject_backward(const float* grad_out, const float* inv_K, int batch, int height, int width,
+                             float* grad_depth, mal_stream_t stream);
+size_t mal_project3d_partials_floats(int batch, int height, int width);
+int mal_project3d(const float* points, const float* K, const float* T, int batch, int height, int width,
+                  int convention, float eps, float* pix, float* z, mal_stream_t stream);
+int mal_project3d_backward(const float* points, const float* K, const float* T, const float* grad_pix,
+                           const float* grad_z, int batch, int height, int width, int convention, float eps,
+                           float* grad_points, float* grad_P, float* partials, mal_stream_t stream);
+int mal_ssim(const float* x, const float* y, int planes, int height, int width, float* out, mal_stream_t stream);
+/* workspace: 4 * planes * height * width floats; grad_y may be NULL */
+int mal_ssim_backward(const float* x, const float* y, const float* grad_out, int planes, int height, int width,
+                      float* grad_x, float* grad_y, float* workspace, mal_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,13 @@ EXPORTS = {
     "mal_main_terms_partials_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_main_terms_forward": (C.c_int, [C.POINTER(MainTermsArgs), C.c_void_p]),
     "mal_matching_mask": (C.c_int, [C.POINTER(MatchingMaskArgs), C.c_void_p]),
+    "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),
+    "mal_project3d": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mal_project3d_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 4),
+    "mal_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }
 
 ABI_VERSION = 1

@@ -109,9 +109,11 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
     } else {
 #pragma unroll
       for (int f = 0; f < 2; f++)
+        if (f < ncand) {
 #pragma unroll
-        for (int c = 0; c < 3; c++)
-          sx[(f * 3 + c) * tl.VN + i] = __ldg(a.src[f] + ((size_t)b * 3 + c) * HW + o);
+          for (int c = 0; c < 3; c++)
+            sx[(f * 3 + c) * tl.VN + i] = __ldg(a.src[f] + ((size_t)b * 3 + c) * HW + o);
+        }
     }
   }
   __syncthreads();
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         xq0[c] = sx[(0 * 3 + c) * tl.VN + vc];
-        xq1[c] = sx[(1 * 3 + c) * tl.VN + vc];
+        xq1[c] = ncand > 1 ? sx[(1 * 3 + c) * tl.VN + vc] : 0.0f;
         yq[c] = sy[c * tl.VN + vc];
       }
       if (!a.no_ssim) {
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           a.grad_pred[0][((size_t)b * 3 + c) * HW + po] = g0[c];
-          a.grad_pred[1][((size_t)b * 3 + c) * HW + po] = g1[c];
+          if (ncand > 1) a.grad_pred[1][((size_t)b * 3 + c) * HW + po] = g1[c];
         }
       } else {
         float dv_in = __ldg(a.depth + (size_t)b * HW + po);
@@ -393,7 +395,10 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   MAL_REQUIRE(a.mode == MAL_PHOTO_WARP || a.mode == MAL_PHOTO_PRED, "mal_photo_forward: bad mode %d", a.mode);
   MAL_REQUIRE(a.convention == MAL_CONV_MANYDEPTH || a.convention == MAL_CONV_DUALREFINE,
               "mal_photo_forward: bad convention %d", a.convention);
-  MAL_REQUIRE(a.target && a.src[0] && a.src[1], "mal_photo_forward: target/src pointers are required");
+  MAL_REQUIRE(a.target && a.src[0], "mal_photo_forward: target/src[0] pointers are required");
+  const bool single = a.src[1] == nullptr;   // compute_reprojection_loss on one prediction
+  if (single)
+    MAL_REQUIRE(a.mode == MAL_PHOTO_PRED && !a.syn[0], "mal_photo_forward: a single candidate needs PRED mode, no syn");
   MAL_REQUIRE((a.syn[0] == nullptr) == (a.syn[1] == nullptr), "mal_photo_forward: give both syn candidates or none");
   MAL_REQUIRE((a.identity_min == nullptr) == (a.noise == nullptr),
               "mal_photo_forward: automask needs identity_min and noise together");
@@ -403,9 +408,9 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     if (a.with_grad) MAL_REQUIRE(a.grad_depth && a.grad_P, "mal_photo_forward: WARP+grad needs grad_depth, grad_P");
     if (a.depth_is_disp) MAL_REQUIRE(a.min_depth > 0 && a.max_depth > a.min_depth, "mal_photo_forward: bad depth range");
   } else if (a.with_grad) {
-    MAL_REQUIRE(a.grad_pred[0] && a.grad_pred[1], "mal_photo_forward: PRED+grad needs grad_pred");
+    MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }
-  const int ncand = a.syn[0] ? 4 : 2;
+  const int ncand = single ? 1 : (a.syn[0] ? 4 : 2);
   const bool grad = a.with_grad != 0;
   // disp_to_depth scalars exactly as python computes them (double), then rounded once to fp32
   const double lo = 1.0 / a.max_depth, hi = 1.0 / a.min_depth;

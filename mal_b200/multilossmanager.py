@@ -1,0 +1,63 @@
+"""MultiLossManager (manydepth/multilossmanager.py:6-88): multi-loss re-balancing after
+"Multi-loss Rebalancing Algorithm for Monocular Depth Estimation" (ECCV 2020).
+
+The reference never imports this class but BASELINE.json names it, so the API is
+kept: get_total_loss(losses, current_batch_size, update, weights_list) and
+rebalancing(current_lambda, epoch, logfile).  It is a handful of scalar updates per epoch and
+stays on the host side of the boundary, in torch, on whatever device it is given.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class MultiLossManager:
+    def __init__(self, batch_size, num_losses, num_for_rebalance, device, update_once=False):
+        self.weight_initialized = False
+        self.num_losses = num_losses
+        self.update_once = update_once
+        self.loss_weights = torch.zeros(num_losses, device=device)
+        self.train_losses = torch.zeros((num_for_rebalance + batch_size, num_losses), device=device)
+        self.initialize_weights()
+        self.cur_ptr = 0
+        self.previous_total_loss = 0
+        self.previous_loss = None
+
+    def initialize_weights(self):
+        self.loss_weights[:] = 1 / self.num_losses
+
+    def get_total_loss(self, losses, current_batch_size, update=True, weights_list=None):
+        """Weighted sum of `losses` (num_losses,) -> (loss, cur_ptr); records the weighted terms."""
+        if weights_list:
+            self.loss_weights = weights_list
+        loss_item = self.loss_weights * losses
+        loss = loss_item.sum(dim=0)
+        if update:
+            for idx in range(self.num_losses):
+                self.train_losses[self.cur_ptr:self.cur_ptr + current_batch_size, idx] = loss_item[idx].detach()
+            self.cur_ptr += current_batch_size
+        return loss, self.cur_ptr
+
+    def rebalancing(self, current_lambda, epoch, logfile=None):
+        mean = self.train_losses[:self.cur_ptr, :].mean(axis=0)
+        total_loss = torch.sum(mean * self.loss_weights)
+        if not self.weight_initialized:
+            for k in range(self.num_losses):
+                self.loss_weights[k] = (total_loss * self.loss_weights[k]) / mean[k]
+            self.weight_initialized = True
+            self.previous_total_loss = torch.sum(mean * self.loss_weights)
+            self.previous_loss = mean
+        elif not self.update_once:
+            previous = self.loss_weights.clone()
+            if self.previous_total_loss > 0:
+                for k in range(self.num_losses):
+                    adjust = 1 + current_lambda * ((total_loss / self.previous_total_loss) *
+                                                   (self.previous_loss[k] / mean[k]) - 1)
+                    adjust = min(max(float(adjust), 1.0 / 2.0), 2.0 / 1.0)
+                    self.loss_weights[k] = previous[k] * adjust
+            self.previous_total_loss = torch.sum(mean * self.loss_weights)
+            self.previous_loss = mean
+        self.cur_ptr = 0
+        if logfile:
+            with open(logfile, "a") as f:
+                f.write(f"{epoch}\t{self.loss_weights[0]}\t{self.loss_weights[1]}\t{total_loss}\n")

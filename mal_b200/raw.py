@@ -64,6 +64,8 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
     img = (B, 3, H, W)
     target = _f32(target, "target", img)
     src = [_f32(s, f"src[{i}]", img) for i, s in enumerate(src)]
+    if len(src) == 1:
+        src = [src[0], None]
     syn = [_f32(s, f"syn[{i}]", img) for i, s in enumerate(syn)] if syn is not None else [None, None]
     plane = (B, 1, H, W)
     depth = _f32(depth, "depth", plane)
@@ -84,7 +86,7 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
     if with_grad and mode == PHOTO_WARP:
         out["grad_depth"], out["grad_P"] = new(plane), new((B, 2, 12))
     if with_grad and mode == PHOTO_PRED:
-        out["grad_pred"] = [new(img), new(img)]
+        out["grad_pred"] = [new(img), new(img) if src[1] is not None else None]
     partials = new((handle.mal_photo_partials_floats(B, H, W),))
 
     a = _capi.PhotoArgs()
@@ -208,3 +210,76 @@ def matching_mask(handle, *, lowest_cost, mono, confidence=None, height=None, wi
     a.lowest_cost, a.confidence, a.mono, a.out_mask = _ptr(lowest_cost), _ptr(confidence), _ptr(mono), _ptr(out)
     _capi.check(handle.mal_matching_mask(C.byref(a), _stream(mono)), handle)
     return out
+
+
+def _vp(t):
+    return None if t is None else t.data_ptr()
+
+
+def backproject(handle, depth, inv_K):
+    B, _, H, W = depth.shape
+    depth, inv_K = _f32(depth, "depth", (B, 1, H, W)), _f32(inv_K, "inv_K", (B, 4, 4))
+    _same_device([depth, inv_K])
+    out = torch.empty((B, 4, H * W), dtype=torch.float32, device=depth.device)
+    _capi.check(handle.mal_backproject(_vp(depth), _vp(inv_K), B, H, W, _vp(out), _stream(depth)), handle)
+    return out
+
+
+def backproject_backward(handle, grad_out, inv_K, height, width):
+    B = grad_out.shape[0]
+    grad_out, inv_K = _f32(grad_out, "grad_out", (B, 4, height * width)), _f32(inv_K, "inv_K", (B, 4, 4))
+    g = torch.empty((B, 1, height, width), dtype=torch.float32, device=grad_out.device)
+    _capi.check(handle.mal_backproject_backward(_vp(grad_out), _vp(inv_K), B, height, width, _vp(g),
+                                                _stream(grad_out)), handle)
+    return g
+
+
+def project3d(handle, points, K, T, height, width, convention=CONV_MANYDEPTH, eps=1e-7, want_z=False):
+    B = points.shape[0]
+    points = _f32(points, "points", (B, 4, height * width))
+    K, T = _f32(K, "K", (B, 4, 4)), _f32(T, "T", (B, 4, 4))
+    _same_device([points, K, T])
+    pix = torch.empty((B, height, width, 2), dtype=torch.float32, device=points.device)
+    z = torch.empty((B, 1, height, width), dtype=torch.float32, device=points.device) if want_z else None
+    _capi.check(handle.mal_project3d(_vp(points), _vp(K), _vp(T), B, height, width, convention, float(eps),
+                                     _vp(pix), _vp(z), _stream(points)), handle)
+    return pix, z
+
+
+def project3d_backward(handle, points, K, T, grad_pix, grad_z, height, width, convention=CONV_MANYDEPTH,
+                       eps=1e-7):
+    B = points.shape[0]
+    points = _f32(points, "points", (B, 4, height * width))
+    K, T = _f32(K, "K", (B, 4, 4)), _f32(T, "T", (B, 4, 4))
+    grad_pix = _f32(grad_pix, "grad_pix", (B, height, width, 2))
+    grad_z = _f32(grad_z, "grad_z", (B, 1, height, width))
+    g_points = torch.empty_like(points)
+    g_P = torch.empty((B, 12), dtype=torch.float32, device=points.device)
+    partials = torch.empty((handle.mal_project3d_partials_floats(B, height, width),), dtype=torch.float32,
+                           device=points.device)
+    _capi.check(handle.mal_project3d_backward(_vp(points), _vp(K), _vp(T), _vp(grad_pix), _vp(grad_z), B, height,
+                                              width, convention, float(eps), _vp(g_points), _vp(g_P),
+                                              _vp(partials), _stream(points)), handle)
+    return g_points, g_P
+
+
+def ssim(handle, x, y):
+    if x.shape != y.shape or x.dim() != 4:
+        raise ValueError("ssim: x and y must be (B,C,H,W) of the same shape")
+    B, Cn, H, W = x.shape
+    x, y = _f32(x, "x"), _f32(y, "y")
+    _same_device([x, y])
+    out = torch.empty_like(x)
+    _capi.check(handle.mal_ssim(_vp(x), _vp(y), B * Cn, H, W, _vp(out), _stream(x)), handle)
+    return out
+
+
+def ssim_backward(handle, x, y, grad_out, want_grad_y=True):
+    B, Cn, H, W = x.shape
+    x, y, grad_out = _f32(x, "x"), _f32(y, "y"), _f32(grad_out, "grad_out", x.shape)
+    gx = torch.empty_like(x)
+    gy = torch.empty_like(x) if want_grad_y else None
+    ws = torch.empty((4 * x.numel(),), dtype=torch.float32, device=x.device)
+    _capi.check(handle.mal_ssim_backward(_vp(x), _vp(y), _vp(grad_out), B * Cn, H, W, _vp(gx), _vp(gy), _vp(ws),
+                                         _stream(x)), handle)
+    return gx, gy

@@ -1,0 +1,193 @@
+"""The pure (state-free) hot-path methods of the reference Trainers, as functions over `opt`.
+
+    generate_images_pred            manydepth/trainer.py:1078-1165   (dualrefine/trainer.py:395-455,
+                                                                      dynamicdepth/trainer.py:906-955)
+    generate_images_pred_ensemble   manydepth/trainer.py:1172-1207
+    compute_matching_mask           manydepth/trainer.py:1066-1076
+    compute_losses                  manydepth/trainer.py:1248-1475   (non-distil path, opt.sclm+1 scales)
+    process_batch_losses            manydepth/trainer.py:574-644     (the loss half of process_batch)
+
+`opt` is any object with the reference's option names (height, width, min_depth, max_depth,
+frame_ids, sclm, batch_size, temporal, main_temporal, distil, no_ens, loss_blc, dual_distil,
+disable_automasking, disable_motion_masking, no_matching_augmentation, disparity_smoothness,
+no_ssim, v1_multiscale, ensemble).  Missing names take the reference's defaults
+(manydepth/options.py).
+
+generate_images_pred does not materialise warped images by default: it leaves a WarpSpec in
+outputs[("warp_spec", scale)] and the loss functions run the fused kernel.  Pass
+materialize=True to also get outputs[("sample", f, s)] / ("color", f, s) like the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops, raw
+from .layers import disp_to_depth
+from .loss_utils import (WarpSpec, _draw_noise, _no_ssim, compute_main_losses, compute_mono_losses,
+                         identity_reprojection)
+
+_DEFAULTS = dict(height=192, width=640, min_depth=0.1, max_depth=100.0, frame_ids=[0, -1, 1], sclm=0,
+                 temporal=False, main_temporal=False, distil=False, no_ens=False, loss_blc=False,
+                 dual_distil=False, learn_ens=False, pareto=False, disable_automasking=False,
+                 disable_motion_masking=False, no_matching_augmentation=False,
+                 disparity_smoothness=1e-3, no_ssim=False, v1_multiscale=False, ensemble=False,
+                 convention=raw.CONV_MANYDEPTH)
+
+
+def _o(opt, name):
+    return getattr(opt, name, _DEFAULTS[name])
+
+
+class _Ssim:
+    """Carrier for opt.no_ssim where a function wants the reference's `ssim` module argument."""
+
+    def __init__(self, no_ssim):
+        self.no_ssim = bool(no_ssim)
+
+
+def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False):
+    """Per scale: up-sample disp, disp -> depth, and describe the two source-frame warps."""
+    H, W = _o(opt, "height"), _o(opt, "width")
+    if _o(opt, "v1_multiscale"):
+        raise NotImplementedError("v1_multiscale (per-scale source images) is not on the MAL path")
+    for scale in range(_o(opt, "sclm") + 1):
+        disp = outputs[("disp", scale)]
+        if disp.shape[-2:] != (H, W):
+            disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+        _, depth = disp_to_depth(disp, _o(opt, "min_depth"), _o(opt, "max_depth"))
+        outputs[("depth", 0, scale)] = depth
+        Ts = []
+        for frame_id in _o(opt, "frame_ids")[1:]:
+            T = outputs[("cam_T_cam", 0, frame_id)]
+            Ts.append(T.detach() if is_multi else T)   # "don't update posenet based on multi frame prediction"
+            if not _o(opt, "disable_automasking"):
+                outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
+        outputs[("warp_spec", scale)] = WarpSpec(disp, inputs[("K", 0)], inputs[("inv_K", 0)], Ts,
+                                                 _o(opt, "convention"), _o(opt, "min_depth"), _o(opt, "max_depth"))
+        if materialize:
+            from .layers import BackprojectDepth, Project3D
+            B = disp.shape[0]
+            back, proj = BackprojectDepth(B, H, W), Project3D(B, H, W, convention=_o(opt, "convention"))
+            for T, frame_id in zip(Ts, _o(opt, "frame_ids")[1:]):
+                cam = back(depth, inputs[("inv_K", 0)])
+                pix = proj(cam, inputs[("K", 0)], T)
+                outputs[("sample", frame_id, scale)] = pix
+                outputs[("color", frame_id, scale)] = F.grid_sample(
+                    inputs[("color", frame_id, 0)], pix, padding_mode="border",
+                    align_corners=_o(opt, "convention") == raw.CONV_MANYDEPTH)
+    return outputs
+
+
+def generate_images_pred_ensemble(inputs, T_l, T_n, disp, opt):
+    """min over the two source frames of the reprojection loss under `disp` (no gradient)."""
+    H, W = _o(opt, "height"), _o(opt, "width")
+    if disp.shape[-2:] != (H, W):
+        disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+    with torch.no_grad():
+        _, min_reproj, _ = ops.photo(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in (-1, 1)],
+                                     depth=disp.detach(), K=inputs[("K", 0)], inv_K=inputs[("inv_K", 0)],
+                                     T=[T_l.detach(), T_n.detach()], mode=raw.PHOTO_WARP,
+                                     convention=_o(opt, "convention"), depth_is_disp=True,
+                                     no_ssim=_o(opt, "no_ssim"), min_depth=_o(opt, "min_depth"),
+                                     max_depth=_o(opt, "max_depth"))
+    return min_reproj
+
+
+def compute_matching_mask(outputs):
+    """Where the cost-volume depth and the teacher depth agree within a factor of two -> bool (B,H,W)."""
+    return ops.matching_mask(outputs["lowest_cost"], outputs[("mono_depth", 0, 0)]) > 0
+
+
+def compute_losses(inputs, outputs, opt, is_multi=False, has_ins=False, noises=None):
+    """Trainer.compute_losses: the non-distil loss over opt.sclm+1 scales.  Returns (losses, [])."""
+    losses, total_loss = {}, 0
+    target = inputs[("color", 0, 0)]
+    ssim = _Ssim(_o(opt, "no_ssim"))
+    num_scales = _o(opt, "sclm") + 1
+    ident = None
+    for scale in range(num_scales):
+        spec = outputs[("warp_spec", scale)]
+        with_syn = (not is_multi) and _o(opt, "temporal") and has_ins
+        kw = dict(src=[inputs[("color", f, 0)] for f in (-1, 1)],
+                  syn=[outputs[("syn", f, scale)] for f in (-1, 1)] if with_syn else None, depth=spec.disp,
+                  K=spec.K, inv_K=spec.inv_K, T=spec.T, convention=spec.convention, depth_is_disp=True,
+                  min_depth=spec.min_depth, max_depth=spec.max_depth, no_ssim=ssim.no_ssim)
+        consistency_loss = 0
+        if not is_multi:
+            if not _o(opt, "disable_automasking"):
+                ident = identity_reprojection(ssim, inputs) if ident is None else ident
+                noise = _draw_noise(ident.shape, target.device, None if noises is None else noises[scale])
+                kw.update(identity_min=ident, noise=noise)
+            sums, _, sel = ops.photo(target, **kw)
+        else:
+            if not _o(opt, "disable_automasking") and noises is None:
+                torch.randn(target.shape[0], 1, *target.shape[-2:])   # keep the reference's RNG stream
+            pm = outputs["consistency_mask"] if not _o(opt, "disable_motion_masking") else torch.ones_like(target[:, 0])
+            sm = None if _o(opt, "no_matching_augmentation") else outputs["augmentation_mask"][:opt.batch_size]
+            sums, multi_reproj, sel = ops.photo(target, pixel_mask=pm, sample_mask=sm, **kw)
+            consistency_loss, _, _, tgt = ops.main_terms(
+                outputs[("depth", 0, scale)], outputs[("mono_depth", 0, scale)].detach(), pm, sm,
+                multi_reproj, None, multi_reproj)
+            outputs["consistency_target/{}".format(scale)] = tgt
+            losses["consistency_loss/{}".format(scale)] = consistency_loss
+            if _o(opt, "ensemble"):
+                multi_depth, mono_depth = outputs[("depth", 0, scale)], outputs[("mono_depth", 0, scale)].detach()
+                mask = pm.unsqueeze(1) * (1 - sm if sm is not None else 1)
+                ensemble_loss = (torch.abs((mono_depth + multi_depth) / 2.0 - multi_depth) * mask).mean()
+                losses["ensemble_loss/{}".format(scale)] = ensemble_loss
+                consistency_loss = consistency_loss + ensemble_loss
+        outputs[("mal_selection", scale)] = sel
+        losses["reproj_loss/{}".format(scale)] = sums[2]
+        loss = sums[2] + consistency_loss
+        smooth_loss = ops.smooth(outputs[("disp", scale)], inputs[("color", 0, scale)], normalise=True)
+        loss = loss + _o(opt, "disparity_smoothness") * smooth_loss / (2 ** scale)
+        total_loss = total_loss + loss
+        losses["loss/{}".format(scale)] = loss
+    losses["loss"] = total_loss / num_scales
+    return losses, []
+
+
+def process_batch_losses(inputs, mono_outputs, outputs, opt, *, has_ins=False, multi_has_ins=False,
+                         loss_blc=None, index_iter=0, current_lambda_for_adjust=0.0, w_list=None,
+                         noises=None, freeze_tp=False):
+    """Everything Trainer.process_batch does after the networks have run (trainer.py:574-644):
+    teacher warps + losses, teacher -> student hand-over, matching mask, ensemble reprojection,
+    student warps + MAL losses, loss balancing.  Returns (outputs, losses)."""
+    ssim = _Ssim(_o(opt, "no_ssim"))
+    temporal = _o(opt, "temporal")
+    generate_images_pred(inputs, mono_outputs, opt)
+    has_ins = has_ins and temporal
+    if _o(opt, "distil"):
+        mono_losses, mono_reproj = compute_mono_losses(ssim, inputs, mono_outputs, temporal, has_ins,
+                                                       noise=None if noises is None else noises[0])
+    else:
+        mono_losses, _ = compute_losses(inputs, mono_outputs, opt, is_multi=False, has_ins=has_ins, noises=noises)
+    for key in list(mono_outputs.keys()):
+        if isinstance(key, tuple) and key[0] in ("depth", "disp"):
+            outputs[("mono_" + key[0],) + tuple(key[1:])] = mono_outputs[key]
+    # outputs["consistency_mask"] * compute_matching_mask(outputs), trainer.py:592-593
+    outputs["consistency_mask"] = outputs["consistency_mask"] * ops.matching_mask(
+        outputs["lowest_cost"], outputs[("mono_depth", 0, 0)])
+    ensemble_reproj = None
+    if _o(opt, "distil") and not _o(opt, "no_ens"):
+        disp_ensemble = (mono_outputs[("disp", 0)].detach() + outputs[("disp", 0)].detach()) / 2.0
+        ensemble_reproj = generate_images_pred_ensemble(
+            inputs, outputs[("cam_T_cam", 0, -1)].detach(), outputs[("cam_T_cam", 0, 1)].detach(), disp_ensemble, opt)
+    generate_images_pred(inputs, outputs, opt, is_multi=True)
+    loss_list = None
+    if _o(opt, "distil"):
+        losses, w_list, loss_list = compute_main_losses(
+            ssim, inputs, outputs, mono_reproj, ensemble_reproj, opt, None, w_list,
+            multi_has_ins and _o(opt, "main_temporal"), noise=None if noises is None else noises[1])
+    else:
+        losses, _ = compute_losses(inputs, outputs, opt, is_multi=True, noises=noises)
+    if not freeze_tp:
+        for key, val in mono_losses.items():
+            losses[key] = losses[key] + val if key in losses else val
+        if _o(opt, "loss_blc") and loss_list is not None:
+            loss_list[0] = loss_list[0] + mono_losses["loss"]
+    if _o(opt, "loss_blc") and loss_blc is not None and loss_list is not None:
+        losses["loss"] = loss_blc.compute_loss(loss_list, index_iter)
+        losses["w_ori"], losses["w_distil"] = loss_blc.update_weight(index_iter, current_lambda_for_adjust)
+    return outputs, losses

@@ -20,3 +20,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=[pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def op_device(request, monkeypatch):
+    """Device on which the mal_b200 operators run.  `emu` points the operator layer at the
+    host-emulated twin of the kernels (tests/emu) so the autograd / dict plumbing is covered on
+    CPU; this hook exists only here - the package itself refuses CPU tensors."""
+    import torch
+    if request.param == "emu":
+        from mal_b200 import ops
+        from tests.emu.emu_lib import emu
+        handle = emu()
+        monkeypatch.setattr(ops, "_lib", lambda t: handle)
+        return torch.device("cpu")
+    return torch.device("cuda:0")

@@ -1,0 +1,267 @@
+"""The reference-shaped Python surface (mal_b200.layers / loss_utils / trainer_ops / matching)
+against the oracle: same dict keys in, same losses / indices / gradients out."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mal_b200 import layers, loss_utils, matching, ops, trainer_ops
+from mal_b200.utils.synthetic import make_cost_volume_inputs, make_photometric_inputs, to_device
+from oracle import mal_oracle as O
+
+LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4
+
+
+def _gerr(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    s = float(b.abs().max())
+    return float((a - b).abs().max()) / (s if s > 0 else 1.0)
+
+
+def _close(a, b, rtol=LOSS_RTOL):
+    a, b = float(a), float(b)
+    return abs(a - b) <= rtol * abs(b)
+
+
+def _opt(B, H, W, **kw):
+    base = dict(height=H, width=W, batch_size=B, min_depth=0.1, max_depth=100.0, frame_ids=[0, -1, 1], sclm=0,
+                temporal=True, main_temporal=False, distil=True, no_ens=False, loss_blc=True, dual_distil=False)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def _leaves(t, dev):
+    leaves = {"mono_disp": t[("mono_disp", 0)].clone().to(dev).requires_grad_(True),
+              "multi_disp": t[("multi_disp", 0)].clone().to(dev).requires_grad_(True)}
+    for f in (-1, 1):
+        leaves[f"T{f}"] = t[("cam_T_cam", 0, f)].clone().to(dev).requires_grad_(True)
+    return leaves
+
+
+def _step_dicts(inputs, t, leaves, dev, lowest_cost):
+    inputs_d = to_device(inputs, dev)
+    mono = {("disp", 0): leaves["mono_disp"]}
+    multi = {("disp", 0): leaves["multi_disp"], "consistency_mask": t["consistency_mask"].to(dev),
+             "augmentation_mask": t["augmentation_mask"].to(dev), "lowest_cost": lowest_cost.to(dev)}
+    for f in (-1, 1):
+        mono[("cam_T_cam", 0, f)] = multi[("cam_T_cam", 0, f)] = leaves[f"T{f}"]
+        mono[("syn", f, 0)] = multi[("syn", f, 0)] = t[("syn", f, 0)].to(dev)
+    return inputs_d, mono, multi
+
+
+def _oracle_step(inputs, t, lowest_cost, opt, has_ins, multi_has_ins):
+    """process_batch's loss half through the oracle (manydepth/trainer.py:574-644)."""
+    H, W, B = opt.height, opt.width, opt.batch_size
+    L = _leaves(t, "cpu")
+    _, mono, multi = _step_dicts(inputs, t, L, "cpu", lowest_cost)
+    O.images_pred(inputs, mono, height=H, width=W)
+    mono_losses, mono_reproj, _ = O.mono_losses(inputs, mono, opt.temporal, has_ins, noise=t["noise"][0])
+    multi[("mono_depth", 0, 0)] = mono[("depth", 0, 0)]
+    multi["consistency_mask"] = multi["consistency_mask"] * O.matching_mask(multi)
+    ens = None
+    if not opt.no_ens:
+        ens = O.images_pred_ensemble(inputs, L["T-1"].detach(), L["T1"].detach(),
+                                     (L["mono_disp"].detach() + L["multi_disp"].detach()) / 2.0, height=H, width=W)
+    O.images_pred(inputs, multi, height=H, width=W, is_multi=True)
+    losses, _, loss_list, aux = O.main_losses(inputs, multi, mono_reproj, ens, batch_size=B,
+                                              multi_has_ins=multi_has_ins, dual_distil=opt.dual_distil,
+                                              loss_blc=opt.loss_blc, noise=t["noise"][1])
+    for k, v in mono_losses.items():
+        losses[k] = losses[k] + v
+    if opt.loss_blc:
+        loss_list[0] = loss_list[0] + mono_losses["loss"]
+        total = 0.5 * loss_list[0] + 0.5 * loss_list[1]
+    else:
+        total = losses["loss"]
+    grads = torch.autograd.grad(total, [L["mono_disp"], L["multi_disp"], L["T-1"], L["T1"]])
+    return losses, total, grads, aux, multi
+
+
+@pytest.mark.parametrize("no_ens,has_ins,multi_has_ins,loss_blc,dual", [
+    (False, True, False, True, False),     # --temporal --distil --loss_blc (the README command)
+    (True, False, True, False, True),      # no ensemble, main_temporal, dual distillation
+])
+def test_mal_step_matches_oracle(op_device, no_ens, has_ins, multi_has_ins, loss_blc, dual):
+    dev = op_device
+    B, H, W = 2, 32, 64
+    inputs, t = make_photometric_inputs(B, H, W, seed=77)
+    opt = _opt(B, H, W, no_ens=no_ens, loss_blc=loss_blc, dual_distil=dual, main_temporal=multi_has_ins)
+    mono_depth = O.disp_to_depth(t[("mono_disp", 0)], 0.1, 100.0)[1]
+    lowest = 1 / (mono_depth[:, 0] * (1.0 + 0.8 * torch.tanh(t["noise"][0][:, 0])))   # ratio in (0.2, 1.8): mixed mask
+    want, want_total, want_g, aux, o_multi = _oracle_step(inputs, t, lowest, opt, has_ins, multi_has_ins)
+
+    L = _leaves(t, dev)
+    inputs_d, mono, multi = _step_dicts(inputs, t, L, dev, lowest)
+    blc = loss_utils.LossBalancing(2, 100, B) if loss_blc else None
+    outputs, losses = trainer_ops.process_batch_losses(
+        inputs_d, mono, multi, opt, has_ins=has_ins, multi_has_ins=multi_has_ins, loss_blc=blc,
+        noises=[n.to(dev) for n in t["noise"]])
+    for k in ("reproj_loss/0", "consistency_loss/0", "distil_loss", "loss/0"):
+        assert _close(losses[k], want[k]), k
+    assert torch.equal(outputs["consistency_mask"].cpu(), o_multi["consistency_mask"])
+    assert np.array_equal(outputs["mal_distil_index"].cpu().numpy(), aux["distil_idx"].numpy().astype(np.uint8))
+    assert np.array_equal(outputs[("mal_selection", 0)].cpu().numpy() & 0x7F, aux["frame_idx"].numpy().astype(np.uint8))
+    assert torch.equal(outputs["consistency_target/0"].cpu(), aux["consistency_target"])
+    if loss_blc:
+        # LossBalancing.compute_loss returns batch_size x the weighted sum (loss_utils.py:305-318)
+        assert _close(losses["loss"], B * float(want_total))
+        total = losses["loss"] / B
+    else:
+        total = losses["loss"]
+        assert _close(total, want_total)
+    g = torch.autograd.grad(total, [L["mono_disp"], L["multi_disp"], L["T-1"], L["T1"]])
+    for a, b, name in zip(g, want_g, ("mono_disp", "multi_disp", "T-1", "T1")):
+        assert _gerr(a, b) < GRAD_RTOL, name
+
+
+def test_compute_losses_multiscale_matches_oracle(op_device):
+    """Trainer.compute_losses (non-distil) over 3 scales, teacher and student passes."""
+    dev = op_device
+    B, H, W, S = 1, 32, 64, 3
+    inputs, t = make_photometric_inputs(B, H, W, num_scales=S, seed=88)
+    opt = _opt(B, H, W, sclm=S - 1, distil=False, temporal=True)
+    for is_multi in (False, True):
+        name = "multi" if is_multi else "mono"
+        disps_c = [t[(name + "_disp", s)].clone().requires_grad_(True) for s in range(S)]
+        Tc = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
+        o = {("disp", s): disps_c[s] for s in range(S)}
+        o.update({("cam_T_cam", 0, f): Tc[f] for f in (-1, 1)})
+        o.update({"consistency_mask": t["consistency_mask"], "augmentation_mask": t["augmentation_mask"]})
+        for s in range(S):
+            for f in (-1, 1):
+                o[("syn", f, s)] = t[("syn", f, 0)]
+        O.images_pred(inputs, o, num_scales=S, height=H, width=W, is_multi=is_multi)
+        if is_multi:
+            for s in range(S):
+                o[("mono_depth", 0, s)] = O.disp_to_depth(F.interpolate(t[("mono_disp", s)], [H, W], mode="bilinear",
+                                                                         align_corners=False), 0.1, 100.0)[1]
+        want, aux = O.trainer_compute_losses(inputs, o, num_scales=S, is_multi=is_multi, temporal=True, has_ins=True,
+                                             batch_size=B, noises=t["noise"][:S] + t["noise"][:1])
+        leaves = disps_c + ([] if is_multi else [Tc[-1], Tc[1]])
+        want_g = torch.autograd.grad(want["loss"], leaves)
+
+        inputs_d = to_device(inputs, dev)
+        disps = [t[(name + "_disp", s)].clone().to(dev).requires_grad_(True) for s in range(S)]
+        Td = {f: t[("cam_T_cam", 0, f)].clone().to(dev).requires_grad_(True) for f in (-1, 1)}
+        od = {("disp", s): disps[s] for s in range(S)}
+        od.update({("cam_T_cam", 0, f): Td[f] for f in (-1, 1)})
+        od.update({"consistency_mask": t["consistency_mask"].to(dev), "augmentation_mask": t["augmentation_mask"].to(dev)})
+        for s in range(S):
+            for f in (-1, 1):
+                od[("syn", f, s)] = t[("syn", f, 0)].to(dev)
+            if is_multi:
+                od[("mono_depth", 0, s)] = o[("mono_depth", 0, s)].to(dev)
+        trainer_ops.generate_images_pred(inputs_d, od, opt, is_multi=is_multi)
+        noises = [n.to(dev) for n in (t["noise"][:S] + t["noise"][:1])]
+        got, _ = trainer_ops.compute_losses(inputs_d, od, opt, is_multi=is_multi, has_ins=True, noises=noises)
+        for k in want:
+            assert _close(got[k], want[k]), (name, k)
+        for s in range(S):
+            assert np.array_equal(od[("mal_selection", s)].cpu().numpy() & 0x7F,
+                                  aux[("frame_idx", s)].numpy().astype(np.uint8))
+        g = torch.autograd.grad(got["loss"], disps + ([] if is_multi else [Td[-1], Td[1]]))
+        for a, b in zip(g, want_g):
+            assert _gerr(a, b) < GRAD_RTOL, name
+
+
+@pytest.mark.parametrize("convention", [layers.CONV_MANYDEPTH, layers.CONV_DUALREFINE])
+def test_layer_classes_forward_backward(op_device, convention):
+    """BackprojectDepth -> Project3D -> grid_sample -> SSIM / compute_reprojection_loss, used one by
+    one like the reference trainers do, against the oracle and its autograd."""
+    dev = op_device
+    B, H, W = 2, 24, 40
+    inputs, t = make_photometric_inputs(B, H, W, seed=99)
+    K, iK = inputs[("K", 0)], inputs[("inv_K", 0)]
+    src, tgt = inputs[("color", -1, 0)], inputs[("color", 0, 0)]
+
+    def chain(mod, dev_, depth, T, Kt):
+        if mod is O:
+            cam = O.backproject(depth, iK)
+            grid, z = O.project3d(cam, Kt, T, H, W, convention, return_z=True)
+            warped = O.warp(src, grid, convention)
+            return cam, grid, z, O.ssim(warped, tgt), O.reprojection_loss(warped, tgt)
+        back = layers.BackprojectDepth(B, H, W)
+        proj = layers.Project3D(B, H, W, dc=True, convention=convention)
+        cam = back(depth, iK.to(dev_))
+        grid, z = proj(cam, Kt, T)
+        warped = F.grid_sample(src.to(dev_), grid, padding_mode="border", align_corners=convention == layers.CONV_MANYDEPTH)
+        return cam, grid, z, layers.SSIM()(warped, tgt.to(dev_)), loss_utils.compute_reprojection_loss(
+            layers.SSIM(), warped, tgt.to(dev_))
+
+    depth0 = O.disp_to_depth(t[("mono_disp", 0)], 0.1, 100.0)[1]
+    outs, grads = [], []
+    for mod, dv in ((O, "cpu"), (layers, dev)):
+        depth = depth0.clone().to(dv).requires_grad_(True)
+        T = t[("cam_T_cam", 0, -1)].clone().to(dv).requires_grad_(True)
+        Kt = K.clone().to(dv).requires_grad_(True)
+        cam, grid, z, s, r = chain(mod, dv, depth, T, Kt)
+        total = (s * torch.linspace(0.5, 1.5, W, device=dv)).sum() + (r ** 2).sum() * 3 + z.mean()
+        outs.append((cam, grid, z, s, r))
+        grads.append(torch.autograd.grad(total, [depth, T, Kt]))
+    for a, b, name in zip(outs[1], outs[0], ("cam", "grid", "z", "ssim", "reproj")):
+        assert torch.equal(a.detach().cpu(), b.detach()), name      # forward is bit-exact
+    for a, b, name in zip(grads[1], grads[0], ("depth", "T", "K")):
+        assert _gerr(a, b) < GRAD_RTOL, name
+
+
+def test_ssim_gradient_both_sides(op_device):
+    dev = op_device
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 17, 23, generator=gen)
+    y = (x + 0.2 * torch.rand(2, 3, 17, 23, generator=gen)).clamp(0, 1)
+    w = torch.rand(2, 3, 17, 23, generator=gen)
+    res = []
+    for fn, dv in ((O.ssim, "cpu"), (layers.SSIM(), dev)):
+        a, b = x.clone().to(dv).requires_grad_(True), y.clone().to(dv).requires_grad_(True)
+        out = fn(a, b)
+        res.append((out, torch.autograd.grad((out * w.to(dv)).sum(), [a, b])))
+    assert torch.equal(res[1][0].detach().cpu(), res[0][0].detach())
+    for a, b in zip(res[1][1], res[0][1]):
+        assert _gerr(a, b) < GRAD_RTOL
+
+
+def test_smooth_and_masks(op_device):
+    dev = op_device
+    inputs, t = make_photometric_inputs(2, 16, 40, seed=3)
+    disp = t[("mono_disp", 0)].clone().to(dev).requires_grad_(True)
+    got = layers.get_smooth_loss(disp, inputs[("color", 0, 0)].to(dev))
+    want_d = t[("mono_disp", 0)].clone().requires_grad_(True)
+    want = O.smooth_loss(want_d, inputs[("color", 0, 0)])
+    assert _close(got, want)
+    assert _gerr(torch.autograd.grad(got, disp)[0], torch.autograd.grad(want, want_d)[0]) < GRAD_RTOL
+    a, b = torch.rand(2, 1, 8, 8), torch.rand(2, 1, 8, 8)
+    b[0, 0, 0] = a[0, 0, 0]   # ties -> index 0 -> mask 1
+    assert torch.equal(loss_utils.compute_loss_masks(a, b), O.loss_masks(a, b))
+    assert torch.equal(loss_utils.compute_loss_masks(a, None), torch.ones_like(a))
+
+
+def test_matcher_methods(op_device):
+    dev = op_device
+    cv = make_cost_volume_inputs(2, 48, 64, channels=16, num_lookup=1, num_bins=24, seed=17, max_bin=10.0)
+    m = matching.CostVolumeMatcher(num_depth_bins=24, min_depth_bin=0.1, max_depth_bin=10.0)
+    assert torch.equal(m.depth_bins, cv["bins"])
+    d = to_device(cv, dev)
+    vol, miss = m.match_features(d["current_feats"], d["lookup_feats"], d["relative_poses"], d["K"], d["inv_K"])
+    want_vol, want_miss = O.match_features(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
+                                           cv["inv_K"], cv["bins"])
+    assert torch.equal(vol.cpu(), want_vol) and torch.equal(miss.cpu(), want_miss)
+    conf = m.compute_confidence_mask(vol * (1 - miss))
+    assert torch.equal(conf.cpu(), O.confidence_mask(want_vol * (1 - want_miss)))
+    cvm, low, conf2 = m.matching_head(d["current_feats"], d["lookup_feats"], d["relative_poses"], d["K"], d["inv_K"])
+    want_cvm, want_low, want_conf, want_idx, _ = O.cost_volume_head(
+        cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"], cv["inv_K"], cv["bins"])
+    assert torch.equal(cvm.cpu(), want_cvm) and torch.equal(low.cpu(), want_low) and torch.equal(conf2.cpu(), want_conf)
+    assert torch.equal(m.indices_to_disparity(want_idx.to(dev)).cpu(), want_low)
+    for binning in ("inverse", "log"):
+        mm = matching.CostVolumeMatcher(num_depth_bins=24, depth_binning=binning)
+        assert torch.equal(mm.compute_depth_bins(0.3, 7.0),
+                           O.depth_bins(0.3, 7.0, 24, binning))
+
+
+def test_operators_refuse_cpu_tensors():
+    """No CPU fallback: without the test hook, a CPU tensor is an error, not a slow path."""
+    inputs, t = make_photometric_inputs(1, 16, 32, seed=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA tensors only"):
+        ops.smooth(t[("mono_disp", 0)], inputs[("color", 0, 0)])
