@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py - MAL loss + cost-volume hot path, frames/s at 192x640 on 1..8 B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                             one rank per GPU (weak scaling)
+
+A "step" is one pass of the hot path over one synthetic KITTI-shaped batch (configs[1]: batch 12
+per GPU, frames [0,-1,1], 96 depth bins, --temporal --distil --loss_blc): cost-volume head,
+teacher + ensemble + student photometric passes with the MAL selection terms, loss balancing and
+the backward to the network outputs (mal_b200/step.py).  A "frame" is one batch element.
+
+Printed keys (one JSON line on rank 0): value = frames/s with inputs resident in HBM (CUDA events,
+max over ranks); e2e = the same through host pinned buffers with the H2D copies and the D2H loss
+read inside the timed region; roofline = the dominant kernel against the measured HBM peak;
+cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MAL loss+cost-volume fwd/bwd frames/s @192x640"
+UNIT = "frames/s"
+HEIGHT, WIDTH = 192, 640
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=12, help="frames per GPU per step")
+    p.add_argument("--sets", type=int, default=3, help="distinct input sets rotated through (L2 hygiene)")
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--cpu-frames", type=int, default=2, help="frames per CPU-baseline step")
+    p.add_argument("--skip-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_config(args, batch):
+    return {"workload": "ManyDepth+MAL KITTI training-step hot path (configs[1]): --temporal --distil --loss_blc, "
+                        "frames [0,-1,1], 1 scale, 96 depth bins x 64 ch at 48x160",
+            "height": HEIGHT, "width": WIDTH, "batch_per_gpu": batch, "global_batch": batch * args.gpus,
+            "parallelism": "dp%d (batch-sharded replicas, no data-path collective)" % args.gpus,
+            "l2": "inputs rotate over %d sets of ~150 MB (> 126 MB L2)" % args.sets,
+            "cuda_graph": not args.no_graph}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if not any(a <= ts <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle port; the only legs of this file that touch oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(frames):
+    from mal_b200 import step as S
+    from oracle.step_oracle import oracle_step   # the oracle's composition of the reference functions
+    opt = S.default_opt(frames, HEIGHT, WIDTH)
+    batch = S.synthetic_batch(opt, seed=4242)
+    return lambda: oracle_step(batch, opt)
+
+
+def time_cpu(frames, steps, warmup, budget_s=None):
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(cores)
+    fn = cpu_step_fn(frames)
+    for _ in range(warmup):
+        fn()
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_all > budget_s:
+            break
+    total = sum(times)
+    return {"value": frames * len(times) / total, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
+            "cores": cores, "frames": frames}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu(args.cpu_frames, args.steps, min(args.warmup, 1))
+    sample = "%d frames/step x %d steps of the same workload (oracle/mal_oracle.py, torch CPU fp32)" % (
+        r["frames"], r["steps"])
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.cpu_frames),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def kernel_rooflines(st, opt, peak_gbs, iters=20):
+    """CUDA-event timing of the three heaviest C-ABI calls on the launching stream, each in a loop
+    long enough that the GPU, not Python, sets the pace.  Bytes are the algorithmic bytes of
+    DESIGN.md ("Kernels")."""
+    from mal_b200 import _capi, raw
+    h = _capi.lib()
+    bufs = [s["buf"] for s in st.slots]
+    B, H, W = opt.batch_size, opt.height, opt.width
+    px = B * H * W
+    lowpx = B * (H // 4) * (W // 4)
+    C, nb = opt.matching_channels, opt.num_depth_bins
+    with torch.no_grad():
+        ident = [raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], mode=raw.PHOTO_PRED,
+                           want_selection=False)["min_reproj"] for b in bufs]
+
+    def photo4(i):
+        b = bufs[i % len(bufs)]
+        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], syn=[b["syn_-1"], b["syn_1"]],
+                  depth=b["mono_disp"].detach(), K=b["K"], inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()],
+                  identity_min=ident[i % len(bufs)], noise=b["noise_mono"], with_grad=True)
+
+    def photo2(i):
+        b = bufs[i % len(bufs)]
+        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], depth=b["multi_disp"].detach(), K=b["K"],
+                  inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()], pixel_mask=b["noise_main"][:, 0],
+                  sample_mask=b["augmentation_mask"].reshape(-1), with_grad=True)
+
+    def cv(i):
+        b = bufs[i % len(bufs)]
+        raw.cost_volume(h, current=b["current_feats"], lookup=b["lookup_feats"], poses=b["relative_poses"], K=b["K2"],
+                        inv_K=b["inv_K2"], bins=b["bins"], apply_confidence=True, want_missing=False)
+
+    # algorithmic bytes per launch (fp32, every tensor once):
+    cases = [
+        # target 12 + src 24 + syn 24 + disp 4 + identity 4 + noise 4 read; min_reproj 4 + sel 1 + grad 4 written
+        ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass)", photo4, 81 * px),
+        # target 12 + src 24 + disp 4 + mask 4 read; min_reproj 4 + sel 1 + grad 4 written
+        ("photo_kernel<WARP,GRAD> 2 candidates + masks (student pass)", photo2, 53 * px),
+        # pack: 2*C*4 read + 2*C*4 written; sweep: 2*C*4 read, bins*4 + 12 written
+        ("cv_pack + cv_sweep_kernel (cost-volume head)", cv, (3 * 2 * C * 4 + nb * 4 + 12) * lowpx),
+    ]
+    out = []
+    for name, fn, nbytes in cases:
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out.append({"kernel": name, "us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_gbs": gbs,
+                    "frac": gbs / peak_gbs})
+    return out
+
+
+def ours(args):
+    import torch.distributed as dist
+    from mal_b200 import _capi, step as S
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mal_b200 has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.check(_capi.lib().mal_check_device(local))
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak_gbs, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+    opt = S.default_opt(args.batch, HEIGHT, WIDTH)
+    host = []
+    for i in range(args.sets):
+        b = S.synthetic_batch(opt, seed=1234 + 17 * i + 1000 * rank)
+        host.append({k: v.pin_memory() for k, v in b.items()})
+    st = S.MalStep(opt, device=dev, use_graph=not args.no_graph, slots=args.sets)
+    h2d = 0
+    for i in range(args.sets):
+        h2d = st.load(host[i], slot=i)
+    torch.cuda.synchronize()
+    for i in range(args.sets):          # capture / first run of every slot
+        st(i)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    windows = []
+
+    def timed(step_fn):
+        for i in range(args.warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(args.steps):
+            step_fn(args.warmup + i)
+        e1.record()
+        barrier()
+        windows.append((t0, time.time()))
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / args.steps
+
+    # (1) inputs resident in HBM
+    ms_dev = timed(lambda i: st(i % args.sets))
+
+    # (2) end to end: pinned host inputs -> H2D -> step -> D2H of the loss scalars, every step
+    def e2e_step(i):
+        st.load(host[i % args.sets], slot=i % args.sets)
+        st(i % args.sets)                # reads the loss scalars back (pinned) and syncs for LossBalancing
+
+    ms_e2e = timed(e2e_step)
+    launches = st.launches_per_step * args.steps + 0
+
+    line = None
+    if rank == 0:
+        roof = kernel_rooflines(st, opt, peak_gbs)
+        sampler.stop()
+        clocks = sampler.summary(windows)
+        dom = max(roof, key=lambda r: r["us_per_launch"])
+        frames = args.batch * world
+        value = frames / (ms_dev * 1e-3)
+        e2e = frames / (ms_e2e * 1e-3)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom["kernel"].split("<")[0].split(" ")[0])
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.batch),
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 16},
+                "gpu_launches": launches, "launches_per_step": st.launches_per_step, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs,
+                             "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                             "us_per_launch": dom["us_per_launch"], "algorithmic_bytes": dom["algorithmic_bytes"],
+                             "limiter": "fp32 issue (exact-arithmetic SSIM / bilinear), see DESIGN.md"},
+                "kernels": roof,
+                # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
+                "step_hbm": {"survey_bytes_per_frame": 20636160,
+                             "frac_of_peak": value / world * 20636160 / (peak_gbs * 1e9)}}
+        if not args.skip_cpu_baseline and world == 1:
+            r = time_cpu(args.cpu_frames, steps=8, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": "%d frames/step x %d steps of the same workload through "
+                                              "oracle/mal_oracle.py (torch CPU fp32)" % (r["frames"], r["steps"])}
+        else:
+            line["cpu_baseline"] = None
+    else:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

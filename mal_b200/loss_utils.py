@@ -187,6 +187,14 @@ class LossBalancing:
                 self.train_scores[index_record, :] = scores
         return loss
 
+    def record_scores(self, index_iter, scores):
+        """The bookkeeping half of compute_loss for callers that formed the weighted sum on the
+        device (mal_b200.step.MalStep under a CUDA graph): same train_scores rows, no tensors."""
+        for index_batch in range(self.bs):
+            index_record = self.bs * index_iter + index_batch
+            if index_record < self.num_data:
+                self.train_scores[index_record, :] = scores
+
     def update_weight(self, i, current_lambda_for_adjust):
         mean = self.train_scores[self.last_rebalancing_iter * self.bs:(i + 1) * self.bs, :].mean(axis=0)
         total_loss = np.sum(mean * self.w_list)

@@ -15,6 +15,8 @@ import torch
 from . import _capi
 
 CONV_MANYDEPTH, CONV_DUALREFINE = 0, 1
+# kernels launched through this module since the caller last reset it (bench.py's gpu_launches)
+LAUNCHES = [0]
 PHOTO_WARP, PHOTO_PRED = 0, 1
 
 
@@ -105,6 +107,7 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
     a.grad_depth, a.grad_P = _ptr(out.get("grad_depth")), _ptr(out.get("grad_P"))
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
+    LAUNCHES[0] += 2   # photo_kernel + photo_finalize_kernel
     out["_keepalive"] = (partials,)
     return out
 
@@ -139,6 +142,7 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     a.confidence, a.argmin, a.lowest_cost = _ptr(out["confidence"]), _ptr(out["argmin"]), _ptr(out["lowest_cost"])
     a.packed = _ptr(packed)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
+    LAUNCHES[0] += 3   # cv_pack_kernel x2 + cv_sweep_kernel
     out["_keepalive"] = (packed,)
     return out
 
@@ -155,6 +159,7 @@ def smooth(handle, *, disp, img, normalise=True, with_grad=False):
     a.batch, a.height, a.width, a.normalise, a.with_grad = B, h, w, int(normalise), int(with_grad)
     a.disp, a.img, a.grad_disp, a.workspace, a.loss = _ptr(disp), _ptr(img), _ptr(out["grad_disp"]), _ptr(ws), _ptr(out["loss"])
     _capi.check(handle.mal_smooth_forward(C.byref(a), _stream(disp)), handle)
+    LAUNCHES[0] += 2 + int(normalise) + int(normalise and with_grad)   # [mean] main finalize [fix]
     out["_keepalive"] = (ws,)
     return out
 
@@ -190,6 +195,7 @@ def main_terms(handle, *, multi, mono, pixel_mask, sample_mask=None, mono_reproj
     a.grad_cons, a.grad_distil, a.grad_distil_mono = _ptr(out["grad_cons"]), _ptr(out["grad_distil"]), _ptr(out["grad_distil_mono"])
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     _capi.check(handle.mal_main_terms_forward(C.byref(a), _stream(multi)), handle)
+    LAUNCHES[0] += 2   # main_terms_kernel + main_terms_finalize_kernel
     out["_keepalive"] = (partials,)
     return out
 
@@ -209,6 +215,7 @@ def matching_mask(handle, *, lowest_cost, mono, confidence=None, height=None, wi
     a.mono_is_disp, a.min_depth, a.max_depth = int(mono_is_disp), float(min_depth), float(max_depth)
     a.lowest_cost, a.confidence, a.mono, a.out_mask = _ptr(lowest_cost), _ptr(confidence), _ptr(mono), _ptr(out)
     _capi.check(handle.mal_matching_mask(C.byref(a), _stream(mono)), handle)
+    LAUNCHES[0] += 1
     return out
 
 

@@ -1,0 +1,172 @@
+"""One MAL hot-path step: everything ManyDepth+MAL's Trainer.process_batch does between the
+conv networks and `loss.backward()` reaching them (manydepth/trainer.py:555-644 with
+`--temporal --distil --loss_blc`, README.md:19-25), for one batch:
+
+    cost-volume head (ResnetEncoderMatching.forward :292-317)
+ -> teacher warps + compute_mono_losses            (loss_utils.py:57-129)
+ -> teacher->student hand-over, matching mask       (trainer.py:584-593)
+ -> ensemble reprojection                           (trainer.py:1172-1207)
+ -> student warps + compute_main_losses             (loss_utils.py:131-281)
+ -> LossBalancing weighting                         (loss_utils.py:303-345)
+ -> backward to the disparities and poses the networks produced.
+
+`MalStep` owns static device buffers for the batch and (by default) captures the whole step -
+forward and backward, 20-odd launches - into one CUDA graph, so a training loop pays one launch
+per step instead of Python dispatch per kernel.  The LossBalancing state stays on the host in
+fp64 exactly like the reference: the two loss scalars come back after each replay and the new
+weights go up before the next one.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import loss_utils, ops, raw, trainer_ops
+from .utils.synthetic import make_cost_volume_inputs, make_photometric_inputs
+
+INPUT_KEYS = ("color_0", "color_-1", "color_1", "syn_-1", "syn_1", "mono_disp", "multi_disp", "T_-1", "T_1",
+              "K", "inv_K", "K2", "inv_K2", "current_feats", "lookup_feats", "relative_poses",
+              "augmentation_mask", "noise_mono", "noise_main", "bins")
+LEAVES = ("mono_disp", "multi_disp", "T_-1", "T_1")
+
+
+def default_opt(batch, height=192, width=640, **kw):
+    """The README's ManyDepth+MAL flags: --temporal --distil --loss_blc."""
+    o = dict(height=height, width=width, batch_size=batch, min_depth=0.1, max_depth=100.0, frame_ids=[0, -1, 1],
+             sclm=0, temporal=True, main_temporal=False, distil=True, no_ens=False, loss_blc=True,
+             dual_distil=False, num_depth_bins=96, min_depth_bin=0.1, max_depth_bin=20.0, matching_channels=64)
+    o.update(kw)
+    return SimpleNamespace(**o)
+
+
+def synthetic_batch(opt, seed=1234, normalised_K=None):
+    """Seeded synthetic KITTI-shaped host tensors for one step, keyed by INPUT_KEYS."""
+    kw = {} if normalised_K is None else {"normalised_K": normalised_K}
+    inputs, t = make_photometric_inputs(opt.batch_size, opt.height, opt.width, seed=seed, **kw)
+    cv = make_cost_volume_inputs(opt.batch_size, opt.height, opt.width, channels=opt.matching_channels,
+                                 num_lookup=1, num_bins=opt.num_depth_bins, seed=seed + 1,
+                                 min_bin=opt.min_depth_bin, max_bin=opt.max_depth_bin, **kw)
+    b = {"color_0": inputs[("color", 0, 0)], "color_-1": inputs[("color", -1, 0)], "color_1": inputs[("color", 1, 0)],
+         "syn_-1": t[("syn", -1, 0)], "syn_1": t[("syn", 1, 0)], "mono_disp": t[("mono_disp", 0)],
+         "multi_disp": t[("multi_disp", 0)], "T_-1": t[("cam_T_cam", 0, -1)], "T_1": t[("cam_T_cam", 0, 1)],
+         "K": inputs[("K", 0)], "inv_K": inputs[("inv_K", 0)], "K2": cv["K"], "inv_K2": cv["inv_K"],
+         "current_feats": cv["current_feats"], "lookup_feats": cv["lookup_feats"],
+         "relative_poses": cv["relative_poses"], "augmentation_mask": t["augmentation_mask"],
+         "noise_mono": t["noise"][0], "noise_main": t["noise"][1], "bins": cv["bins"]}
+    return {k: v.contiguous() for k, v in b.items()}
+
+
+def step_losses(b, opt, leaves, weights=None, has_ins=True, multi_has_ins=False):
+    """The step on a dict of device tensors `b` (INPUT_KEYS) with `leaves` standing in for the
+    network outputs.  Returns (total, loss_list, losses, outputs)."""
+    inputs = {("color", 0, 0): b["color_0"], ("color", -1, 0): b["color_-1"], ("color", 1, 0): b["color_1"],
+              ("K", 0): b["K"], ("inv_K", 0): b["inv_K"]}
+    cv, lowest_cost, confidence, *_ = _head(b, opt)
+    mono = {("disp", 0): leaves["mono_disp"]}
+    outputs = {("disp", 0): leaves["multi_disp"], "lowest_cost": lowest_cost, "consistency_mask": confidence,
+               "augmentation_mask": b["augmentation_mask"], "cost_volume": cv}
+    for f in (-1, 1):
+        mono[("cam_T_cam", 0, f)] = outputs[("cam_T_cam", 0, f)] = leaves["T_%d" % f]
+        mono[("syn", f, 0)] = outputs[("syn", f, 0)] = b["syn_%d" % f]
+    outputs, losses = trainer_ops.process_batch_losses(
+        inputs, mono, outputs, opt, has_ins=has_ins, multi_has_ins=multi_has_ins, loss_blc=None,
+        noises=[b["noise_mono"], b["noise_main"]])
+    if opt.loss_blc:
+        # LossBalancing.compute_loss: sum_k w_k * L_k, added once per batch element (loss_utils.py:305-318)
+        loss_list = [losses["loss"], losses["distil_loss"]]
+        w = weights if weights is not None else torch.full((2,), 0.5, device=b["color_0"].device)
+        total = opt.batch_size * (w[0] * loss_list[0] + w[1] * loss_list[1])
+    else:
+        loss_list = [losses["loss"]]
+        total = losses["loss"]
+    return total, loss_list, losses, outputs
+
+
+def _head(b, opt):
+    return _head_op(b["current_feats"], b["lookup_feats"], b["relative_poses"], b["K2"], b["inv_K2"], b["bins"])
+
+
+def _head_op(cur, look, poses, K, inv_K, bins):
+    cv, _, conf, _, low = ops.cost_volume(cur, look, poses, K, inv_K, bins, apply_confidence=True)
+    return cv, low, conf
+
+
+class MalStep:
+    """Static-buffer, graph-captured MAL step for one GPU.
+
+    `slots` independent sets of static input buffers (each with its own captured graph) let a
+    loader fill slot i+1 while slot i is being replayed, and let a benchmark rotate over more
+    input bytes than the L2 holds."""
+
+    def __init__(self, opt, device="cuda:0", use_graph=True, slots=1, num_train_data=1 << 20,
+                 lambda_for_adjust=0.0):
+        self.opt, self.device, self.use_graph = opt, torch.device(device), use_graph
+        self.slots = [dict(buf=None, graph=None, static=None) for _ in range(slots)]
+        self.weights = torch.full((2,), 0.5, device=self.device)
+        self.blc = loss_utils.LossBalancing(2, num_train_data, opt.batch_size) if opt.loss_blc else None
+        self.lambda_for_adjust = lambda_for_adjust
+        self.index_iter = 0
+        self._w_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        self._scalars_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        self.launches_per_step = None
+
+    # -- buffers -------------------------------------------------------------------------------
+    def load(self, batch, slot=0, non_blocking=True):
+        """Copy one batch (host or device tensors keyed by INPUT_KEYS) into a slot's static buffers.
+        Returns the bytes copied."""
+        sl = self.slots[slot]
+        if sl["buf"] is None:
+            sl["buf"] = {k: torch.empty_like(batch[k], device=self.device) for k in INPUT_KEYS}
+            for k in LEAVES:
+                sl["buf"][k].requires_grad_(True)
+        with torch.no_grad():
+            for k in INPUT_KEYS:
+                sl["buf"][k].copy_(batch[k], non_blocking=non_blocking)
+        return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
+
+    # -- one step ------------------------------------------------------------------------------
+    def _run(self, buf):
+        leaves = {k: buf[k] for k in LEAVES}
+        total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights)
+        grads = torch.autograd.grad(total, [leaves[k] for k in LEAVES])
+        scalars = torch.stack([total.detach(), loss_list[0].detach(), loss_list[-1].detach(),
+                               losses["reproj_loss/0"].detach()])
+        return scalars, grads, outputs
+
+    def _capture(self, sl):
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run(sl["buf"])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        raw.LAUNCHES[0] = 0
+        sl["graph"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(sl["graph"]):
+            sl["static"] = self._run(sl["buf"])
+        self.launches_per_step = raw.LAUNCHES[0]
+
+    def __call__(self, slot=0, sync_weights=True):
+        """Run the step on the batch loaded in `slot`.  Returns (scalars, grads, outputs): scalars is
+        a device tensor [total, loss, distil_loss, reproj_loss/0]; grads follow LEAVES."""
+        sl = self.slots[slot]
+        if self.use_graph:
+            if sl["graph"] is None:
+                self._capture(sl)
+            sl["graph"].replay()
+            res = sl["static"]
+        else:
+            raw.LAUNCHES[0] = 0
+            res = self._run(sl["buf"])
+            self.launches_per_step = raw.LAUNCHES[0]
+        if self.blc is not None and sync_weights:
+            self._scalars_host.copy_(res[0], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self.blc.record_scores(self.index_iter, [float(self._scalars_host[1]), float(self._scalars_host[2])])
+            w0, w1 = self.blc.update_weight(self.index_iter, self.lambda_for_adjust)
+            self._w_host[0], self._w_host[1] = float(w0), float(w1)
+            self.weights.copy_(self._w_host, non_blocking=True)
+        self.index_iter += 1
+        return res

@@ -167,8 +167,14 @@ def process_batch_losses(inputs, mono_outputs, outputs, opt, *, has_ins=False, m
         if isinstance(key, tuple) and key[0] in ("depth", "disp"):
             outputs[("mono_" + key[0],) + tuple(key[1:])] = mono_outputs[key]
     # outputs["consistency_mask"] * compute_matching_mask(outputs), trainer.py:592-593
-    outputs["consistency_mask"] = outputs["consistency_mask"] * ops.matching_mask(
-        outputs["lowest_cost"], outputs[("mono_depth", 0, 0)])
+    if outputs["lowest_cost"].shape[-2:] != outputs[("mono_depth", 0, 0)].shape[-2:]:
+        # matching-resolution lowest_cost / confidence straight from the cost-volume head: the
+        # nearest up-sampling of repdepth.py:331-336 happens inside the kernel
+        outputs["consistency_mask"] = ops.matching_mask(outputs["lowest_cost"], outputs[("mono_depth", 0, 0)],
+                                                        confidence=outputs["consistency_mask"])
+    else:
+        outputs["consistency_mask"] = outputs["consistency_mask"] * ops.matching_mask(
+            outputs["lowest_cost"], outputs[("mono_depth", 0, 0)])
     ensemble_reproj = None
     if _o(opt, "distil") and not _o(opt, "no_ens"):
         disp_ensemble = (mono_outputs[("disp", 0)].detach() + outputs[("disp", 0)].detach()) / 2.0

@@ -1,0 +1,78 @@
+"""mal_b200.step: the whole MAL hot-path step (cost-volume head -> teacher -> matching mask ->
+ensemble -> student -> balancing -> backward) against the oracle's composition of the same
+reference functions, and the CUDA-graph replay against the eager run."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mal_b200 import step as S
+from mal_b200.utils.synthetic import to_device
+from oracle import mal_oracle as O
+from oracle.step_oracle import oracle_step
+
+LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4
+
+
+def _gerr(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    s = float(b.abs().max())
+    return float((a - b).abs().max()) / (s if s > 0 else 1.0)
+
+
+def _check(got_total, got_list, got_grads, outputs, want):
+    total, loss_list, grads, aux = want
+    assert abs(float(got_total) - float(total)) <= LOSS_RTOL * abs(float(total))
+    for a, b in zip(got_list, loss_list):
+        assert abs(float(a) - float(b)) <= LOSS_RTOL * abs(float(b))
+    assert torch.equal(outputs["cost_volume"].cpu(), aux["cv"])
+    assert torch.equal(outputs["consistency_mask"].cpu(), aux["mask"])
+    assert np.array_equal(outputs["mal_distil_index"].cpu().numpy(), aux["distil_idx"].numpy().astype(np.uint8))
+    for a, b, k in zip(got_grads, grads, S.LEAVES):
+        assert _gerr(a, b) < GRAD_RTOL, k
+
+
+def test_step_losses_match_oracle(op_device):
+    opt = S.default_opt(2, 32, 64, num_depth_bins=16, matching_channels=16, max_depth_bin=10.0)
+    b = S.synthetic_batch(opt, seed=5)
+    want = oracle_step(b, opt)
+    d = to_device(b, op_device)
+    leaves = {k: d[k].clone().requires_grad_(True) for k in S.LEAVES}
+    total, loss_list, losses, outputs = S.step_losses(d, opt, leaves)
+    grads = torch.autograd.grad(total, [leaves[k] for k in S.LEAVES])
+    _check(total, loss_list, grads, outputs, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_malstep_graph_and_eager(use_graph):
+    opt = S.default_opt(2, 64, 96, num_depth_bins=32, matching_channels=32, max_depth_bin=10.0)
+    b = S.synthetic_batch(opt, seed=6)
+    want = oracle_step(b, opt)
+    st = S.MalStep(opt, use_graph=use_graph)
+    st.load(b)
+    for it in range(3):   # replays must reproduce the first run (weights start at 0.5, lambda 0 keeps them)
+        scalars, grads, outputs = st(0, sync_weights=False)
+        torch.cuda.synchronize()
+        _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
+    assert st.launches_per_step and st.launches_per_step >= 15
+
+
+@pytest.mark.gpu
+def test_malstep_loss_balancing_follows_reference():
+    """Host-side LossBalancing driven from the graph replays == the oracle's LossBalancing driven
+    by the oracle's losses (weights change every step, loss_utils.py:320-345)."""
+    opt = S.default_opt(2, 32, 64, num_depth_bins=16, matching_channels=16, max_depth_bin=10.0)
+    b = S.synthetic_batch(opt, seed=7)
+    st = S.MalStep(opt, use_graph=True, num_train_data=64, lambda_for_adjust=3.0)
+    ref = O.LossBalancing(2, 64, opt.batch_size)
+    w = (0.5, 0.5)
+    for it in range(3):
+        b["noise_mono"] = torch.randn(b["noise_mono"].shape, generator=torch.Generator().manual_seed(100 + it))
+        st.load(b)
+        scalars, _, _ = st()
+        total, loss_list, _, _ = oracle_step(b, opt, w)
+        assert abs(float(scalars[0]) - float(total)) <= 2e-5 * abs(float(total))
+        ref.compute_loss(loss_list, it)
+        w = ref.update_weight(it, 3.0)
+        assert np.allclose(st.blc.w_list, ref.w_list, rtol=1e-4)
