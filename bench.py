@@ -39,8 +39,8 @@ HEIGHT, WIDTH = 192, 640
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=30)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=12, help="frames per GPU per step")
     p.add_argument("--sets", type=int, default=3, help="distinct input sets rotated through (L2 hygiene)")
@@ -150,7 +150,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_cpu(args.cpu_frames, args.steps, min(args.warmup, 1))
+    r = time_cpu(args.cpu_frames, args.steps, min(args.warmup, 1), budget_s=150.0)
     sample = "%d frames/step x %d steps of the same workload (oracle/mal_oracle.py, torch CPU fp32)" % (
         r["frames"], r["steps"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,

@@ -23,7 +23,7 @@ from types import SimpleNamespace
 import torch
 
 from . import loss_utils, ops, raw, trainer_ops
-from .utils.synthetic import make_cost_volume_inputs, make_photometric_inputs
+from .utils.synthetic import make_cost_volume_inputs, make_photometric_inputs, warp_by_depth
 
 INPUT_KEYS = ("color_0", "color_-1", "color_1", "syn_-1", "syn_1", "mono_disp", "multi_disp", "T_-1", "T_1",
               "K", "inv_K", "K2", "inv_K2", "current_feats", "lookup_feats", "relative_poses",
@@ -40,13 +40,33 @@ def default_opt(batch, height=192, width=640, **kw):
     return SimpleNamespace(**o)
 
 
-def synthetic_batch(opt, seed=1234, normalised_K=None):
-    """Seeded synthetic KITTI-shaped host tensors for one step, keyed by INPUT_KEYS."""
+def synthetic_batch(opt, seed=1234, normalised_K=None, translation_scale=0.2, adaptive_bins=True):
+    """Seeded synthetic KITTI-shaped host tensors for one step, keyed by INPUT_KEYS.
+
+    The camera baseline is a fifth of the nearest depth and (adaptive_bins) the depth hypotheses
+    span the teacher's depth range the way the reference's DepthBins tracker sets them
+    (manydepth/trainer.py:75-103, 634), so that the confidence and matching masks cover a
+    realistic share of the image instead of being empty."""
     kw = {} if normalised_K is None else {"normalised_K": normalised_K}
-    inputs, t = make_photometric_inputs(opt.batch_size, opt.height, opt.width, seed=seed, **kw)
+    inputs, t = make_photometric_inputs(opt.batch_size, opt.height, opt.width, seed=seed,
+                                        translation_scale=translation_scale, **kw)
+    lo, hi = opt.min_depth_bin, opt.max_depth_bin
+    if adaptive_bins:
+        scaled = 1.0 / opt.max_depth + (1.0 / opt.min_depth - 1.0 / opt.max_depth) * t[("mono_disp", 0)]
+        depth = 1.0 / scaled
+        lo, hi = 0.9 * float(depth.min()), 1.1 * float(depth.max())
     cv = make_cost_volume_inputs(opt.batch_size, opt.height, opt.width, channels=opt.matching_channels,
-                                 num_lookup=1, num_bins=opt.num_depth_bins, seed=seed + 1,
-                                 min_bin=opt.min_depth_bin, max_bin=opt.max_depth_bin, **kw)
+                                 num_lookup=1, num_bins=opt.num_depth_bins, seed=seed + 1, min_bin=lo, max_bin=hi,
+                                 translation_scale=translation_scale, **kw)
+    cv["relative_poses"][:, 0] = t[("cam_T_cam", 0, -1)]   # the lookup frame is frame -1
+    if adaptive_bins:
+        # photo-consistent features: the current frame's features are the lookup frame's, seen
+        # through the teacher depth (plus noise), so the sweep's arg-min lands near that depth
+        low_depth = torch.nn.functional.avg_pool2d(depth, 4)
+        gen = torch.Generator().manual_seed(seed + 2)
+        look = cv["lookup_feats"][:, 0]
+        cur = warp_by_depth(look, low_depth, cv["K"], cv["inv_K"], cv["relative_poses"][:, 0])
+        cv["current_feats"] = (cur + 0.05 * torch.rand(cur.shape, generator=gen)).contiguous()
     b = {"color_0": inputs[("color", 0, 0)], "color_-1": inputs[("color", -1, 0)], "color_1": inputs[("color", 1, 0)],
          "syn_-1": t[("syn", -1, 0)], "syn_1": t[("syn", 1, 0)], "mono_disp": t[("mono_disp", 0)],
          "multi_disp": t[("multi_disp", 0)], "T_-1": t[("cam_T_cam", 0, -1)], "T_1": t[("cam_T_cam", 0, 1)],

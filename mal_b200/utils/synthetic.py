@@ -45,7 +45,7 @@ def intrinsics(batch, height, width, scale=0, normalised=KITTI_K):
 
 def make_photometric_inputs(batch=2, height=192, width=640, num_scales=1, seed=1234,
                             white_noise=False, with_syn=True, normalised_K=KITTI_K,
-                            contrast=4.0):
+                            contrast=4.0, translation_scale=1.0):
     """One batch of hot-path inputs.
 
     Returns (inputs, tensors): `inputs` uses the reference's dict keys
@@ -78,6 +78,7 @@ def make_photometric_inputs(batch=2, height=192, width=640, num_scales=1, seed=1
         aa = torch.randn(batch, 1, 3, generator=gen) * 0.01
         tr = torch.randn(batch, 1, 3, generator=gen) * 0.05
         tr[..., 2] += 0.1
+        tr = tr * translation_scale
         t[("axisangle", f)], t[("translation", f)] = aa, tr
         t[("cam_T_cam", 0, f)] = _rodrigues(aa, tr, invert=(f < 0))
         if with_syn:
@@ -95,7 +96,7 @@ def make_photometric_inputs(batch=2, height=192, width=640, num_scales=1, seed=1
 
 def make_cost_volume_inputs(batch=2, height=192, width=640, channels=64, num_lookup=1,
                             num_bins=96, seed=4321, zero_pose_sample=None,
-                            normalised_K=KITTI_K, min_bin=0.1, max_bin=20.0):
+                            normalised_K=KITTI_K, min_bin=0.1, max_bin=20.0, translation_scale=1.0):
     """Matching-branch inputs at 1/4 resolution (networks/resnet_encoder.py:264-305)."""
     gen = torch.Generator().manual_seed(seed)
     h, w = height // 4, width // 4
@@ -107,7 +108,7 @@ def make_cost_volume_inputs(batch=2, height=192, width=640, channels=64, num_loo
         aa = torch.randn(batch, 1, 3, generator=gen) * 0.01
         tr = torch.randn(batch, 1, 3, generator=gen) * 0.05
         tr[..., 2] += 0.1
-        poses.append(_rodrigues(aa, tr, invert=True))
+        poses.append(_rodrigues(aa, tr * translation_scale, invert=True))
     poses = torch.stack(poses, 1)
     if zero_pose_sample is not None:
         poses[zero_pose_sample] = 0
@@ -115,6 +116,24 @@ def make_cost_volume_inputs(batch=2, height=192, width=640, channels=64, num_loo
     bins = torch.linspace(min_bin, max_bin, num_bins)
     return {"current_feats": cur, "lookup_feats": look, "relative_poses": poses, "K": K,
             "inv_K": inv_K, "bins": bins}
+
+
+def warp_by_depth(feat, depth, K, inv_K, T):
+    """Sample `feat` (B,C,h,w) where the pixels of a view with `depth` (B,1,h,w) land after the
+    rigid motion T: plain-torch pinhole geometry, used only to make synthetic feature pairs
+    that are photo-consistent under a known depth."""
+    B, _, h, w = depth.shape
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
+                            indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)], 0).unsqueeze(0)
+    cam = depth.view(B, 1, -1) * (inv_K[:, :3, :3] @ pix)
+    cam = torch.cat([cam, torch.ones(B, 1, h * w)], 1)
+    p = (K @ T)[:, :3, :] @ cam
+    xy = p[:, :2] / (p[:, 2:3] + 1e-7)
+    gx = (xy[:, 0] / (w - 1) - 0.5) * 2
+    gy = (xy[:, 1] / (h - 1) - 0.5) * 2
+    grid = torch.stack([gx, gy], -1).view(B, h, w, 2)
+    return F.grid_sample(feat, grid, padding_mode="border", align_corners=True)
 
 
 def to_device(obj, device):
