@@ -19,9 +19,13 @@
 //             Bins are processed in groups of CV_BG.  Per group:
 //               P  all threads: one projection per (pixel, bin) -> {tap offset | masked, tx, ty} in smem
 //               C  each warp sweeps the group's bins for its chunk.  The 2x2x16 texel block lives in
-//                  registers and is only re-fetched when the integer tap origin moves: consecutive
-//                  depth planes land in the same texel cell for most of the sweep, which removes
-//                  ~4/5 of the gather traffic.  Chunk sums go to smem.
+//                  registers and is only re-fetched when the integer tap origin moves.  Operand
+//                  delivery is the real limit of this op: a sweep that loaded its 4 taps + 1 feature
+//                  for each of the 566 M (pixel, bin, channel) evaluations would need 88 M L1
+//                  wavefronts (~300 us at 128 B/clk/SM) - measured with a lane-per-bin variant that
+//                  hit 82% L1 throughput at 449 us, profiles/r1_notes.md - so the taps have to be
+//                  reused from registers across consecutive depth planes.
+//                  Chunk sums go to smem.
 //               F  all threads: combine the chunk sums in the reference's order, mean, edge mask,
 //                  accumulate over lookup frames.
 //             Epilogue: / (counts + 1e-7), per-pixel max over bins, missing fill, confidence,
@@ -31,6 +35,8 @@
 //   projection / grid_sample arithmetic as in mal_math.cuh;  mean over channels = ATen cascade_sum
 //   (SumKernel.cpp multi_row_sum): 16 channels summed sequentially from 0, chunk sums added
 //   sequentially, then / C.
+#include <cstdlib>
+
 #include "mal_math.cuh"
 
 namespace mal {
@@ -38,8 +44,10 @@ namespace mal {
 constexpr int CV_PX = 32;      // pixels per CTA (one per lane)
 constexpr int CV_WARPS = 4;    // channel chunks in flight
 constexpr int CV_NT = CV_PX * CV_WARPS;
-constexpr int CV_BG = 32;      // bins per group
+constexpr int CV_BG = 16;      // bins per group
 constexpr int CV_CHUNK = 16;   // channels per chunk (cascade_sum level step)
+constexpr int CV_MAXF = 8;     // lookup frames
+constexpr int CV_DEFAULT_MINB = 4;
 
 struct CvGeom {
   float P[12];
@@ -99,8 +107,8 @@ __device__ __forceinline__ float quad_l1(float acc, const float4& a, const float
   return acc;
 }
 
-template <int CONV>
-__global__ void __launch_bounds__(CV_NT) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp) {
+template <int CONV, int MINB>
+__global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = a.height, w = a.width, hw = h * w;
   const int nb = a.num_bins, nchunks = Cp / CV_CHUNK, nquads = Cp / 4;
@@ -163,17 +171,13 @@ __global__ void __launch_bounds__(CV_NT) cv_sweep_kernel(const mal_cost_volume_a
             float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
             float x0 = floorf(ux), y0 = floorf(uy);
             int xi = (int)x0, yi = (int)y0;
-            // zeros padding: taps outside the image read 0.  With the edge mask on, (xi,yi) is
-            // inside for the align_corners=True convention; the half-pixel convention can differ
-            // by one cell, so clamp the origin and zero the weights of out-of-range taps below.
-            if (xi >= 0 && xi + 1 < w && yi >= 0 && yi + 1 < h) {
-              off = yi * w + xi;
-              tx = xsub(ux, x0);
-              ty = xsub(uy, y0);
-            } else {
-              off = -2;   // rare: unmasked but touching the border -> slow exact path
-              tx = ux; ty = uy;
-            }
+            // with the edge mask on, all four taps are inside the image for both conventions
+            // (zeros padding never triggers); the clamp only guards pathological inputs
+            xi = min(max(xi, 0), w - 2);
+            yi = min(max(yi, 0), h - 2);
+            off = yi * w + xi;
+            tx = xsub(ux, x0);
+            ty = xsub(uy, y0);
           }
         }
         d_off[k * CV_PX + lane] = off;
@@ -184,51 +188,46 @@ __global__ void __launch_bounds__(CV_NT) cv_sweep_kernel(const mal_cost_volume_a
 
       // ---- C: channel sweep, one 16-channel chunk per warp pass ------------------------------
       for (int ch = warp; ch < nchunks; ch += CV_WARPS) {
+        const float4* lqc = lq + (size_t)ch * 4 * hw;
         float4 cq[4];
 #pragma unroll
         for (int j = 0; j < 4; j++)
           cq[j] = pix_ok ? ldg4(curq + (size_t)(ch * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 t00[4], t01[4], t10[4], t11[4];
         int coff = -1;
+        const int* po = d_off + lane;
+        const float* ptx = d_tx + lane;
+        const float* pty = d_ty + lane;
+        float* pp = part + (size_t)ch * CV_BG * CV_PX + lane;
         for (int k = 0; k < gn; k++) {
-          const int off = d_off[k * CV_PX + lane];
-          if (__all_sync(0xffffffffu, off == -1)) continue;
+          const int off = po[k * CV_PX];
           float acc = 0.0f;
           if (off >= 0) {
             if (off != coff) {
               coff = off;
+              const float4* base = lqc + off;
 #pragma unroll
               for (int j = 0; j < 4; j++) {
-                const float4* base = lq + (size_t)(ch * 4 + j) * hw + off;
                 t00[j] = ldg4(base); t01[j] = ldg4(base + 1);
-                t10[j] = ldg4(base + w); t11[j] = ldg4(base + w + 1);
+                const float4* row1 = base + w;
+                t10[j] = ldg4(row1); t11[j] = ldg4(row1 + 1);
+                base += hw;
               }
             }
-            const float tx = d_tx[k * CV_PX + lane], ty = d_ty[k * CV_PX + lane];
+            const float tx = ptx[k * CV_PX], ty = pty[k * CV_PX];
             const float e = xsub(1.0f, tx), s = xsub(1.0f, ty);
             const float nw = xmul(s, e), ne = xmul(s, tx), sw = xmul(ty, e), se = xmul(ty, tx);
 #pragma unroll
             for (int j = 0; j < 4; j++) acc = quad_l1(acc, t00[j], t01[j], t10[j], t11[j], cq[j], nw, ne, sw, se);
-          } else if (off == -2) {
-            // exact zeros-padding path (taps outside the image contribute 0)
-            Taps t = make_taps(d_tx[k * CV_PX + lane], d_ty[k * CV_PX + lane], h, w);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const float4* base = lq + (size_t)(ch * 4 + j) * hw;
-              float4 v00 = t.v00 ? ldg4(base + t.o00) : z, v01 = t.v01 ? ldg4(base + t.o01) : z;
-              float4 v10 = t.v10 ? ldg4(base + t.o10) : z, v11 = t.v11 ? ldg4(base + t.o11) : z;
-              acc = quad_l1(acc, v00, v01, v10, v11, cq[j], t.nw, t.ne, t.sw, t.se);
-            }
           }
-          part[((size_t)ch * CV_BG + k) * CV_PX + lane] = acc;
+          pp[k * CV_PX] = acc;
         }
       }
       __syncthreads();
 
       // ---- F: combine chunks, mean, accumulate over lookup frames ----------------------------
       for (int k = warp; k < gn; k += CV_WARPS) {
-        if (d_off[k * CV_PX + lane] != -1) {
+        if (d_off[k * CV_PX + lane] >= 0) {
           float s = part[(size_t)k * CV_PX + lane];                       // 0 + c0
           for (int ch = 1; ch < nchunks; ch++) s = xadd(s, part[((size_t)ch * CV_BG + k) * CV_PX + lane]);
           float diff = xdiv(s, (float)a.channels);                         // .mean(1), edge mask == 1
@@ -349,9 +348,18 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   MAL_REQUIRE(smem <= 227 * 1024, "mal_cost_volume_forward: %d bins x %d channels need %zu B of shared memory",
               a.num_bins, a.channels, smem);
   dim3 grid((unsigned)((size_t)a.batch * tiles));
-  if (a.convention == MAL_CONV_MANYDEPTH)
-    launch(cv_sweep_kernel<MAL_CONV_MANYDEPTH>, grid, dim3(CV_NT), smem, st, a, Cp);
-  else
-    launch(cv_sweep_kernel<MAL_CONV_DUALREFINE>, grid, dim3(CV_NT), smem, st, a, Cp);
+  // resident CTAs per SM the register allocation is tuned for (profiles/r1_notes.md); the
+  // environment override exists for tuning runs only
+  int minb = CV_DEFAULT_MINB;
+  if (const char* e = getenv("MAL_CV_MINB")) minb = atoi(e);
+#define MAL_CV_LAUNCH(CONV_)                                                                  \
+  do {                                                                                        \
+    if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3>, grid, dim3(CV_NT), smem, st, a, Cp);      \
+    else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4>, grid, dim3(CV_NT), smem, st, a, Cp); \
+    else launch(cv_sweep_kernel<CONV_, 5>, grid, dim3(CV_NT), smem, st, a, Cp);                \
+  } while (0)
+  if (a.convention == MAL_CONV_MANYDEPTH) MAL_CV_LAUNCH(MAL_CONV_MANYDEPTH);
+  else MAL_CV_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_CV_LAUNCH
   return check_launch("cv_sweep_kernel");
 }

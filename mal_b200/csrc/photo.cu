@@ -341,19 +341,46 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
 }
 
 // Deterministic reduction of the per-CTA partials: grad_P (B,2,12) and the masked mean.
+// One warp per (sample, value) pair, four pairs and eight tiles per lane in flight at a time so the
+// whole reduction is a handful of memory round trips; every sum is formed in a fixed order.
+constexpr int PF_PAIRS = 4, PF_TILES = 8;
 __global__ void __launch_bounds__(1024) photo_finalize_kernel(const float* __restrict__ partials, int batch,
                                                              int tiles, float* __restrict__ sums,
                                                              float* __restrict__ grad_P) {
   double* per_sample = reinterpret_cast<double*>(dyn_smem());  // [batch][2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int pair = warp; pair < batch * PH_NPART; pair += nwarp) {
-    int b = pair / PH_NPART, v = pair - b * PH_NPART;
-    double s = 0.0;
-    for (int t = lane; t < tiles; t += 32) s += (double)partials[((size_t)b * tiles + t) * PH_NPART + v];
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (v < 24) { if (grad_P) grad_P[b * 24 + v] = (float)s; }
-      else per_sample[b * 2 + (v - 24)] = s;
+  const int v0 = grad_P ? 0 : 24;                 // without gradients only the two loss sums are live
+  const int nv = PH_NPART - v0, npairs = batch * nv;
+  for (int base = warp * PF_PAIRS; base < npairs; base += nwarp * PF_PAIRS) {
+    double s[PF_PAIRS];
+#pragma unroll
+    for (int u = 0; u < PF_PAIRS; u++) s[u] = 0.0;
+    for (int t0 = 0; t0 < tiles; t0 += 32 * PF_TILES) {
+      float x[PF_PAIRS][PF_TILES];
+#pragma unroll
+      for (int u = 0; u < PF_PAIRS; u++) {
+        const int pair = base + u;
+        const int b = pair / nv, v = v0 + pair - b * nv;
+#pragma unroll
+        for (int k = 0; k < PF_TILES; k++) {
+          const int t = t0 + k * 32 + lane;
+          x[u][k] = (pair < npairs && t < tiles) ? __ldg(partials + ((size_t)b * tiles + t) * PH_NPART + v) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF_PAIRS; u++)
+#pragma unroll
+        for (int k = 0; k < PF_TILES; k++) s[u] += (double)x[u][k];
+    }
+#pragma unroll
+    for (int u = 0; u < PF_PAIRS; u++) {
+      const int pair = base + u;
+      const double r = warp_sum(s[u]);
+      if (lane == 0 && pair < npairs) {
+        const int b = pair / nv, v = v0 + pair - b * nv;
+        if (v < 24) grad_P[b * 24 + v] = (float)r;
+        else per_sample[b * 2 + (v - 24)] = r;
+      }
     }
   }
   __syncthreads();
