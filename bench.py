@@ -291,8 +291,13 @@ def ours(args):
     ms_dev = timed(lambda i: st(i % args.sets))
 
     # (2) end to end: pinned host inputs -> H2D -> step -> D2H of the loss scalars, every step
+    # Every step's inputs start in pinned host memory and are copied inside the timed region; the
+    # copy for step i+1 runs on a second stream while step i computes (one copy per step, K in all).
+    st.load_async(host[0], slot=0)
+
     def e2e_step(i):
-        st.load(host[i % args.sets], slot=i % args.sets)
+        nxt = (i + 1) % args.sets
+        st.load_async(host[nxt], slot=nxt)
         st(i % args.sets)                # reads the loss scalars back (pinned) and syncs for LossBalancing
 
     ms_e2e = timed(e2e_step)

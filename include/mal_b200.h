@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 1
+#define MAL_ABI_VERSION 2
 
 enum {
   MAL_OK = 0,
@@ -94,6 +94,8 @@ typedef struct mal_photo_args {
   float* partials;          /* workspace, mal_photo_partials_floats() floats                */
   float* sums;              /* (4): [sum w*reproj, sum w, sum w*reproj/(sum w+1e-7), 0]      */
   float* grad_P;            /* (B,2,12) WARP+grad: d(sum w*reproj)/d (K@T)[:3,:] per frame   */
+  const float* depth_b;     /* (B,1,H,W) optional: the kernel uses (depth + depth_b) / 2, the
+                               ensemble disparity of manydepth/trainer.py:598; no gradient      */
 } mal_photo_args;
 
 size_t mal_photo_partials_floats(int batch, int height, int width);
@@ -236,6 +238,40 @@ int mal_ssim(const float* x, const float* y, int planes, int height, int width, 
 /* workspace: 4 * planes * height * width floats; grad_y may be NULL */
 int mal_ssim_backward(const float* x, const float* y, const float* grad_out, int planes, int height, int width,
                       float* grad_x, float* grad_y, float* workspace, mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The scalar tail of one `--distil` training step and the gradient hand-over, in one launch:
+ * compute_mono_losses' / compute_main_losses' final sums (manydepth/loss_utils.py:115-127,
+ * :215-281), the teacher->student accumulation (manydepth/trainer.py:624-629),
+ * LossBalancing.compute_loss (loss_utils.py:303-318) and the backward of all of it down to the
+ * disparity maps and poses the networks produced.  Inputs are the `sums` / loss scalars and the
+ * un-normalised gradient planes the other entry points left on the device.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_step_combine_args {
+  int32_t batch, height, width;
+  float smoothness;             /* opt.disparity_smoothness (1e-3)                            */
+  const float* weights;         /* (2) LossBalancing.w_list on the device; NULL: no loss_blc  */
+  const float* sums_teacher;    /* (4) mal_photo_forward sums of the teacher pass             */
+  const float* sums_student;    /* (4) ... of the student pass                                */
+  const float* smooth_teacher;  /* (1) mal_smooth_forward loss, teacher disparity             */
+  const float* smooth_student;  /* (1) ... student disparity                                  */
+  const float* main_sums;       /* (2) mal_main_terms_forward sums                            */
+  const float* K;               /* (B,4,4)                                                    */
+  const float* gd_teacher;      /* (B,1,H,W) grad_depth of the teacher pass                   */
+  const float* gs_teacher;      /* (B,1,H,W) smoothness grad_disp, teacher                    */
+  const float* gP_teacher;      /* (B,2,12)  grad_P of the teacher pass                       */
+  const float* gd_student;      /* (B,1,H,W) grad_depth of the student pass                   */
+  const float* gs_student;      /* (B,1,H,W) smoothness grad_disp, student                    */
+  const float* g_cons;          /* (B,1,H,W) mal_main_terms_forward grad_cons                 */
+  const float* g_distil;        /* (B,1,H,W) ... grad_distil                                  */
+  const float* g_distil_mono;   /* (B,1,H,W) ... grad_distil_mono (dual_distil) or NULL       */
+  float* scalars;               /* (8) [total, loss_list[0], loss_list[1], R_t, R_s, C, L_t, L_s] */
+  float* grad_disp_teacher;     /* (B,1,H,W) d total / d teacher disparity                    */
+  float* grad_disp_student;     /* (B,1,H,W) d total / d student disparity                    */
+  float* grad_T[2];             /* (B,4,4)   d total / d cam_T_cam for frames -1,+1           */
+} mal_step_combine_args;
+
+int mal_step_combine(const mal_step_combine_args* args, mal_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,20 @@ class PhotoArgs(C.Structure):
         ("sample_mask", C.c_void_p),
         ("min_reproj", C.c_void_p), ("selection", C.c_void_p), ("weight", C.c_void_p),
         ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
-        ("sums", C.c_void_p), ("grad_P", C.c_void_p),
+        ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
+    ]
+
+
+class StepCombineArgs(C.Structure):
+    """struct mal_step_combine_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("smoothness", C.c_float),
+        ("weights", C.c_void_p), ("sums_teacher", C.c_void_p), ("sums_student", C.c_void_p),
+        ("smooth_teacher", C.c_void_p), ("smooth_student", C.c_void_p), ("main_sums", C.c_void_p),
+        ("K", C.c_void_p), ("gd_teacher", C.c_void_p), ("gs_teacher", C.c_void_p), ("gP_teacher", C.c_void_p),
+        ("gd_student", C.c_void_p), ("gs_student", C.c_void_p), ("g_cons", C.c_void_p), ("g_distil", C.c_void_p),
+        ("g_distil_mono", C.c_void_p), ("scalars", C.c_void_p), ("grad_disp_teacher", C.c_void_p),
+        ("grad_disp_student", C.c_void_p), ("grad_T", C.c_void_p * 2),
     ]
 
 
@@ -96,6 +109,7 @@ EXPORTS = {
     "mal_main_terms_partials_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_main_terms_forward": (C.c_int, [C.POINTER(MainTermsArgs), C.c_void_p]),
     "mal_matching_mask": (C.c_int, [C.POINTER(MatchingMaskArgs), C.c_void_p]),
+    "mal_step_combine": (C.c_int, [C.POINTER(StepCombineArgs), C.c_void_p]),
     "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),
@@ -105,7 +119,7 @@ EXPORTS = {
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 def bind(handle):

@@ -69,11 +69,14 @@ __device__ __forceinline__ GridPoint project_grid(const float* P, Ray ray, float
   return g;
 }
 
-// grid_sample's unnormalisation of a [-1,1] coordinate (align_corners = CONV==MANYDEPTH)
+// grid_sample's unnormalisation of a [-1,1] coordinate (align_corners = CONV==MANYDEPTH).
+// ATen's vectorised CPU kernel computes (g + 1) * (size / 2) - 0.5 for align_corners=False and the
+// compiler contracts the multiply-subtract into one FMA (measured against F.grid_sample for both
+// padding modes); the align_corners=True form has nothing to contract.
 template <int CONV>
 __device__ __forceinline__ float unnormalize(float g, int size) {
   if (CONV == MAL_CONV_MANYDEPTH) return xmul(xadd(g, 1.0f), (float)(size - 1) / 2.0f);
-  return xsub(xmul(xadd(g, 1.0f), (float)size / 2.0f), 0.5f);
+  return xfma(xadd(g, 1.0f), (float)size / 2.0f, -0.5f);
 }
 
 // ... -> grid_sample unnormalise -> border clip

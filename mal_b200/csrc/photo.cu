@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
     }
     if (WARP) {
       float dv = __ldg(a.depth + (size_t)b * HW + o);
+      if (a.depth_b) dv = xmul(xadd(dv, __ldg(a.depth_b + (size_t)b * HW + o)), 0.5f);   // (a + b) / 2.0
       if (a.depth_is_disp) dv = xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv)));
       Ray ray = pixel_ray(geom->iK, (float)rx, (float)ry);
 #pragma unroll
@@ -433,6 +434,7 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   if (a.mode == MAL_PHOTO_WARP) {
     MAL_REQUIRE(a.depth && a.K && a.inv_K && a.T[0] && a.T[1], "mal_photo_forward: WARP mode needs depth,K,inv_K,T");
     if (a.with_grad) MAL_REQUIRE(a.grad_depth && a.grad_P, "mal_photo_forward: WARP+grad needs grad_depth, grad_P");
+    if (a.with_grad) MAL_REQUIRE(!a.depth_b, "mal_photo_forward: the averaged (ensemble) disparity carries no gradient");
     if (a.depth_is_disp) MAL_REQUIRE(a.min_depth > 0 && a.max_depth > a.min_depth, "mal_photo_forward: bad depth range");
   } else if (a.with_grad) {
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");

@@ -54,7 +54,7 @@ def _same_device(ts):
     return dev
 
 
-def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=None,
+def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, inv_K=None, T=None,
           identity_min=None, noise=None, pixel_mask=None, sample_mask=None,
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
@@ -70,7 +70,7 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
         src = [src[0], None]
     syn = [_f32(s, f"syn[{i}]", img) for i, s in enumerate(syn)] if syn is not None else [None, None]
     plane = (B, 1, H, W)
-    depth = _f32(depth, "depth", plane)
+    depth, depth_b = _f32(depth, "depth", plane), _f32(depth_b, "depth_b", plane)
     K, inv_K = _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
     T = [_f32(t, f"T[{i}]", (B, 4, 4)) for i, t in enumerate(T)] if T is not None else [None, None]
     identity_min, noise = _f32(identity_min, "identity_min", plane), _f32(noise, "noise", plane)
@@ -100,7 +100,7 @@ def photo(handle, *, target, src, syn=None, depth=None, K=None, inv_K=None, T=No
     for i in range(2):
         a.src[i], a.syn[i], a.T[i] = _ptr(src[i]), _ptr(syn[i]), _ptr(T[i])
         a.grad_pred[i] = _ptr(out["grad_pred"][i]) if "grad_pred" in out else None
-    a.depth, a.K, a.inv_K = _ptr(depth), _ptr(K), _ptr(inv_K)
+    a.depth, a.depth_b, a.K, a.inv_K = _ptr(depth), _ptr(depth_b), _ptr(K), _ptr(inv_K)
     a.identity_min, a.noise = _ptr(identity_min), _ptr(noise)
     a.pixel_mask, a.sample_mask = _ptr(pixel_mask), _ptr(sample_mask)
     a.min_reproj, a.selection, a.weight = _ptr(out["min_reproj"]), _ptr(out["selection"]), _ptr(out["weight"])
@@ -290,3 +290,31 @@ def ssim_backward(handle, x, y, grad_out, want_grad_y=True):
     _capi.check(handle.mal_ssim_backward(_vp(x), _vp(y), _vp(grad_out), B * Cn, H, W, _vp(gx), _vp(gy), _vp(ws),
                                          _stream(x)), handle)
     return gx, gy
+
+
+def step_combine(handle, *, batch, height, width, weights, sums_teacher, sums_student, smooth_teacher,
+                 smooth_student, main_sums, K, gd_teacher, gs_teacher, gP_teacher, gd_student, gs_student,
+                 g_cons, g_distil, g_distil_mono=None, smoothness=1e-3):
+    """mal_step_combine -> {"scalars": (8,), "grad_disp_teacher", "grad_disp_student", "grad_T": [2 x (B,4,4)]}."""
+    dev = gd_teacher.device
+    plane = (batch, 1, height, width)
+    new = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {"scalars": new((8,)), "grad_disp_teacher": new(plane), "grad_disp_student": new(plane),
+           "grad_T": [new((batch, 4, 4)), new((batch, 4, 4))]}
+    a = _capi.StepCombineArgs()
+    a.batch, a.height, a.width, a.smoothness = batch, height, width, float(smoothness)
+    a.weights = _ptr(_f32(weights, "weights", (2,)))
+    a.sums_teacher, a.sums_student = _ptr(_f32(sums_teacher, "sums", (4,))), _ptr(_f32(sums_student, "sums", (4,)))
+    a.smooth_teacher, a.smooth_student = _ptr(_f32(smooth_teacher, "smooth", (1,))), _ptr(_f32(smooth_student, "smooth", (1,)))
+    a.main_sums, a.K = _ptr(_f32(main_sums, "main_sums", (2,))), _ptr(_f32(K, "K", (batch, 4, 4)))
+    a.gd_teacher, a.gs_teacher = _ptr(_f32(gd_teacher, "gd_teacher", plane)), _ptr(_f32(gs_teacher, "gs_teacher", plane))
+    a.gP_teacher = _ptr(_f32(gP_teacher, "gP_teacher", (batch, 2, 12)))
+    a.gd_student, a.gs_student = _ptr(_f32(gd_student, "gd_student", plane)), _ptr(_f32(gs_student, "gs_student", plane))
+    a.g_cons, a.g_distil = _ptr(_f32(g_cons, "g_cons", plane)), _ptr(_f32(g_distil, "g_distil", plane))
+    a.g_distil_mono = _ptr(_f32(g_distil_mono, "g_distil_mono", plane))
+    a.scalars = _ptr(out["scalars"])
+    a.grad_disp_teacher, a.grad_disp_student = _ptr(out["grad_disp_teacher"]), _ptr(out["grad_disp_student"])
+    a.grad_T[0], a.grad_T[1] = _ptr(out["grad_T"][0]), _ptr(out["grad_T"][1])
+    _capi.check(handle.mal_step_combine(C.byref(a), _stream(gd_teacher)), handle)
+    LAUNCHES[0] += 1
+    return out

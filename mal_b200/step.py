@@ -112,6 +112,59 @@ def _head_op(cur, look, poses, K, inv_K, bins):
     return cv, low, conf
 
 
+def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False):
+    """The same step as `step_losses` + backward, as 24 launches of libmal_b200 and nothing else:
+    no autograd graph, no intermediate depth maps, no one-element torch kernels.  The scalar tail
+    and the gradient hand-over are `mal_step_combine` (csrc/step.cu).  Needs opt.distil.
+
+    Returns (scalars, grads, outputs): scalars = [total, loss_list[0], loss_list[1], reproj_loss/0
+    of the teacher, of the student, consistency, teacher loss, student loss]; grads follow LEAVES."""
+    if not opt.distil:
+        raise ValueError("fused_step implements the --distil step; use step_losses otherwise")
+    B, H, W = opt.batch_size, opt.height, opt.width
+    lo, hi = opt.min_depth, opt.max_depth
+    tgt, src = b["color_0"], [b["color_-1"], b["color_1"]]
+    syn = [b["syn_-1"], b["syn_1"]]
+    T = [b["T_-1"], b["T_1"]]
+    mono, multi = b["mono_disp"].detach(), b["multi_disp"].detach()
+    geom = dict(K=b["K"], inv_K=b["inv_K"], T=[t.detach() for t in T], min_depth=lo, max_depth=hi)
+    head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"], poses=b["relative_poses"],
+                           K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"], apply_confidence=True, want_missing=False)
+    ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+    teacher = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None, depth=mono,
+                        identity_min=ident, noise=b["noise_mono"], with_grad=True, **geom)
+    sm_t = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True)
+    mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
+                             mono_is_disp=True, min_depth=lo, max_depth=hi)
+    ens = None
+    if not opt.no_ens:
+        ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
+                        **geom)["min_reproj"]
+    sample_mask = b["augmentation_mask"].reshape(-1)[:B]
+    student = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
+                        depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, **geom)
+    dual = bool(opt.dual_distil) and ens is None
+    main = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
+                          mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
+                          inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
+    sm_s = raw.smooth(handle, disp=multi, img=tgt, normalise=True, with_grad=True)
+    comb = raw.step_combine(handle, batch=B, height=H, width=W, weights=weights if opt.loss_blc else None,
+                            sums_teacher=teacher["sums"], sums_student=student["sums"], smooth_teacher=sm_t["loss"],
+                            smooth_student=sm_s["loss"], main_sums=main["sums"], K=b["K"],
+                            gd_teacher=teacher["grad_depth"], gs_teacher=sm_t["grad_disp"],
+                            gP_teacher=teacher["grad_P"], gd_student=student["grad_depth"],
+                            gs_student=sm_s["grad_disp"], g_cons=main["grad_cons"], g_distil=main["grad_distil"],
+                            g_distil_mono=main["grad_distil_mono"])
+    outputs = {"cost_volume": head["cost_volume"], "lowest_cost": head["lowest_cost"],
+               "confidence_mask": head["confidence"], "consistency_mask": mask,
+               "mal_distil_index": main["distil_index"], "consistency_target/0": main["consistency_target"],
+               ("mal_selection", 0): student["selection"], "mono_reproj": teacher["min_reproj"],
+               "multi_reproj": student["min_reproj"], "ensemble_reproj": ens,
+               "_keepalive": (head, teacher, student, sm_t, sm_s, main, comb, ident)}
+    grads = (comb["grad_disp_teacher"], comb["grad_disp_student"], comb["grad_T"][0], comb["grad_T"][1])
+    return comb["scalars"], grads, outputs
+
+
 class MalStep:
     """Static-buffer, graph-captured MAL step for one GPU.
 
@@ -120,18 +173,39 @@ class MalStep:
     input bytes than the L2 holds."""
 
     def __init__(self, opt, device="cuda:0", use_graph=True, slots=1, num_train_data=1 << 20,
-                 lambda_for_adjust=0.0):
+                 lambda_for_adjust=0.0, fused=True):
         self.opt, self.device, self.use_graph = opt, torch.device(device), use_graph
+        self.fused = fused and opt.distil   # libmal_b200-only schedule; False: op-by-op through autograd
         self.slots = [dict(buf=None, graph=None, static=None) for _ in range(slots)]
         self.weights = torch.full((2,), 0.5, device=self.device)
         self.blc = loss_utils.LossBalancing(2, num_train_data, opt.batch_size) if opt.loss_blc else None
         self.lambda_for_adjust = lambda_for_adjust
         self.index_iter = 0
         self._w_host = torch.empty(2, dtype=torch.float32).pin_memory()
-        self._scalars_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        self._scalars_host = torch.empty(8, dtype=torch.float32).pin_memory()
         self.launches_per_step = None
+        self.copy_stream = torch.cuda.Stream(self.device)
 
     # -- buffers -------------------------------------------------------------------------------
+    def load_async(self, batch, slot=0):
+        """Enqueue the host->device copy of a (pinned) batch into `slot` on the copy stream, so it
+        overlaps the step running on another slot.  The copy waits for the last step that read the
+        slot; the next `__call__(slot)` waits for the copy."""
+        sl = self.slots[slot]
+        if sl["buf"] is None:
+            return self.load(batch, slot)
+        cur = torch.cuda.current_stream(self.device)
+        if sl.get("done") is not None:
+            self.copy_stream.wait_event(sl["done"])
+        else:
+            self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream), torch.no_grad():
+            for k in INPUT_KEYS:
+                sl["buf"][k].copy_(batch[k], non_blocking=True)
+            sl["ready"] = torch.cuda.Event()
+            sl["ready"].record(self.copy_stream)
+        return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
+
     def load(self, batch, slot=0, non_blocking=True):
         """Copy one batch (host or device tensors keyed by INPUT_KEYS) into a slot's static buffers.
         Returns the bytes copied."""
@@ -147,6 +221,10 @@ class MalStep:
 
     # -- one step ------------------------------------------------------------------------------
     def _run(self, buf):
+        if self.fused:
+            from . import _capi
+            with torch.no_grad():
+                return fused_step(_capi.lib(), buf, self.opt, self.weights)
         leaves = {k: buf[k] for k in LEAVES}
         total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights)
         grads = torch.autograd.grad(total, [leaves[k] for k in LEAVES])
@@ -172,6 +250,10 @@ class MalStep:
         """Run the step on the batch loaded in `slot`.  Returns (scalars, grads, outputs): scalars is
         a device tensor [total, loss, distil_loss, reproj_loss/0]; grads follow LEAVES."""
         sl = self.slots[slot]
+        cur = torch.cuda.current_stream(self.device)
+        if sl.get("ready") is not None:
+            cur.wait_event(sl["ready"])
+            sl["ready"] = None
         if self.use_graph:
             if sl["graph"] is None:
                 self._capture(sl)
@@ -181,8 +263,10 @@ class MalStep:
             raw.LAUNCHES[0] = 0
             res = self._run(sl["buf"])
             self.launches_per_step = raw.LAUNCHES[0]
+        sl["done"] = torch.cuda.Event()
+        sl["done"].record(cur)
         if self.blc is not None and sync_weights:
-            self._scalars_host.copy_(res[0], non_blocking=True)
+            self._scalars_host[:res[0].numel()].copy_(res[0], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             self.blc.record_scores(self.index_iter, [float(self._scalars_host[1]), float(self._scalars_host[2])])
             w0, w1 = self.blc.update_weight(self.index_iter, self.lambda_for_adjust)

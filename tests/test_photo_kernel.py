@@ -138,3 +138,54 @@ def test_argument_errors_are_reported():
     with pytest.raises(ValueError):
         raw.photo(h, target=inputs[("color", 0, 0)], src=[inputs[("color", -1, 0)][:, :, :8], inputs[("color", 1, 0)]],
                   mode=raw.PHOTO_PRED)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("shape,K_name", [((1, 48, 128), "CITYSCAPES_K"), ((2, 24, 80), "KITTI_K")])
+def test_dualrefine_convention_and_cityscapes_intrinsics(backend, shape, K_name):
+    """BASELINE configs 3 and 4: Cityscapes-shaped intrinsics (192x512 aspect) and DualRefine's
+    half-pixel Project3D + align_corners=False sampling (dualrefine/layers.py:224-225,
+    dualrefine/trainer.py:444-447), forward selections bit-exact and gradients vs autograd."""
+    from mal_b200.utils import synthetic
+    h, dev = handle_and_device(backend)
+    B, H, W = shape
+    inputs, t = make_photometric_inputs(B, H, W, seed=23, normalised_K=getattr(synthetic, K_name),
+                                        translation_scale=0.3)
+    d = lambda x: x.to(dev)
+    for conv, oconv in ((raw.CONV_DUALREFINE, O.DUALREFINE), (raw.CONV_MANYDEPTH, O.MANYDEPTH)):
+        Ts = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
+        o = {("disp", 0): t[("mono_disp", 0)].clone().requires_grad_(True)}
+        for f in (-1, 1):
+            o[("cam_T_cam", 0, f)] = Ts[f]
+        O.images_pred(inputs, o, height=H, width=W, convention=oconv)
+        losses, mono_reproj, aux = O.mono_losses(inputs, o, False, False, noise=t["noise"][0])
+        g = torch.autograd.grad(losses["reproj_loss/0"], [o[("disp", 0)], Ts[-1], Ts[1]])
+        tgt = d(inputs[("color", 0, 0)])
+        src = [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])]
+        ident = raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+        out = raw.photo(h, target=tgt, src=src, depth=d(t[("mono_disp", 0)]), K=d(inputs[("K", 0)]),
+                        inv_K=d(inputs[("inv_K", 0)]), T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])],
+                        identity_min=ident, noise=d(t["noise"][0]), with_grad=True, convention=conv)
+        sel = out["selection"].cpu().numpy()
+        assert np.array_equal(sel & 0x7F, aux["frame_idx"].numpy().astype(np.uint8))
+        assert np.array_equal(sel >> 7, aux["automask"].numpy().astype(np.uint8))
+        assert torch.equal(out["min_reproj"].cpu(), mono_reproj)
+        want = float(losses["reproj_loss/0"].detach())
+        assert abs(float(out["sums"][2]) - want) <= LOSS_RTOL * abs(want)
+        _check_grads(out, inputs, g)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_ensemble_disparity_average_in_kernel(backend):
+    """depth_b: the kernel averages two disparities like (a.detach() + b.detach()) / 2.0
+    (manydepth/trainer.py:598) before warping."""
+    h, dev = handle_and_device(backend)
+    inputs, t = make_photometric_inputs(2, 32, 48, seed=29, translation_scale=0.3)
+    d = lambda x: x.to(dev)
+    want = O.images_pred_ensemble(inputs, t[("cam_T_cam", 0, -1)], t[("cam_T_cam", 0, 1)],
+                                  (t[("mono_disp", 0)] + t[("multi_disp", 0)]) / 2.0, height=32, width=48)
+    out = raw.photo(h, target=d(inputs[("color", 0, 0)]), src=[d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])],
+                    depth=d(t[("mono_disp", 0)]), depth_b=d(t[("multi_disp", 0)]), K=d(inputs[("K", 0)]),
+                    inv_K=d(inputs[("inv_K", 0)]), T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])],
+                    want_selection=False)
+    assert torch.equal(out["min_reproj"].cpu(), want)

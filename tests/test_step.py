@@ -10,6 +10,7 @@ from mal_b200 import step as S
 from mal_b200.utils.synthetic import to_device
 from oracle import mal_oracle as O
 from oracle.step_oracle import oracle_step
+from tests.backends import BACKENDS, handle_and_device
 
 LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4
 
@@ -44,13 +45,31 @@ def test_step_losses_match_oracle(op_device):
     _check(total, loss_list, grads, outputs, want)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_fused_step_matches_oracle(backend):
+    """The libmal_b200-only schedule (24 launches, mal_step_combine tail) against the oracle."""
+    h, dev = handle_and_device(backend)
+    opt = S.default_opt(2, 32, 64, num_depth_bins=16, matching_channels=16)
+    b = S.synthetic_batch(opt, seed=5)
+    for w in ((0.5, 0.5), (0.3, 1.7)):
+        want = oracle_step(b, opt, w)
+        d = to_device(b, dev)
+        scalars, grads, outputs = S.fused_step(h, d, opt, torch.tensor(w, device=dev))
+        _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
+    # without loss balancing the total is the plain sum (loss_utils.py:271-275)
+    opt2 = S.default_opt(2, 32, 64, num_depth_bins=16, matching_channels=16, loss_blc=False)
+    scalars, _, _ = S.fused_step(h, to_device(b, dev), opt2)
+    assert abs(float(scalars[0]) - float(scalars[1] + scalars[2])) < 1e-6
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_malstep_graph_and_eager(use_graph):
+@pytest.mark.parametrize("fused", [False, True])
+def test_malstep_graph_and_eager(use_graph, fused):
     opt = S.default_opt(2, 64, 96, num_depth_bins=32, matching_channels=32)
     b = S.synthetic_batch(opt, seed=11)
     want = oracle_step(b, opt)
-    st = S.MalStep(opt, use_graph=use_graph)
+    st = S.MalStep(opt, use_graph=use_graph, fused=fused)
     st.load(b)
     for it in range(3):   # replays must reproduce the first run (weights start at 0.5, lambda 0 keeps them)
         scalars, grads, outputs = st(0, sync_weights=False)
