@@ -273,6 +273,34 @@ typedef struct mal_step_combine_args {
 
 int mal_step_combine(const mal_step_combine_args* args, mal_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 6. DynamicDepth forward warp: z-buffered splat of the (up-sampled) source depth into the target
+ *    view, then inverse warp of the image with the splatted depth.
+ *
+ * Replaces dynamicdepth/rigid_warp.forward_warp (:534-597) incl. pixel2cam (:34-50),
+ * cam2pix_trans (:513-530), torch_sparse.coalesce(op='max') (:577), inverse_warp (:337-373),
+ * cam2pixel (:54-83).  Forward only (the reference calls it under no_grad,
+ * dynamicdepth/trainer.py:494).  The small per-sample matrices are what the reference derives
+ * with torch on the way: Ku_inv = inverse([K[0:2]*upscale; K[2]]) (:562-564), K_inv =
+ * inverse(K) (:355), proj = K @ pose_vec2mat([t, mat2euler(R)] of inverse(pose)) (:585-589, :357-360).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_forward_warp_args {
+  int32_t batch, channels, height, width, upscale;
+  const float* img;      /* (B,C,H,W)                                                        */
+  const float* depth;    /* (B,1,H,W) depth of the source view                               */
+  const float* pose;     /* (B,3,4)   source -> target                                       */
+  const float* K;        /* (B,3,3)                                                          */
+  const float* Ku_inv;   /* (B,3,3)                                                          */
+  const float* K_inv;    /* (B,3,3)                                                          */
+  const float* proj;     /* (B,3,4)                                                          */
+  float* img_w;          /* (B,C,H,W) img warped, x valid                                    */
+  float* depth_w;        /* (B,1,H,W) splatted depth, x valid                                */
+  float* valid;          /* (B,1,H,W) fw_val * iw_val                                        */
+  void* zbuf;            /* workspace: B*H*W uint32                                          */
+} mal_forward_warp_args;
+
+int mal_forward_warp(const mal_forward_warp_args* args, mal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

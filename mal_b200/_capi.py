@@ -45,6 +45,13 @@ class StepCombineArgs(C.Structure):
     ]
 
 
+class ForwardWarpArgs(C.Structure):
+    """struct mal_forward_warp_args."""
+    _fields_ = [(n, C.c_int32) for n in ("batch", "channels", "height", "width", "upscale")] + \
+               [(n, C.c_void_p) for n in ("img", "depth", "pose", "K", "Ku_inv", "K_inv", "proj", "img_w",
+                                          "depth_w", "valid", "zbuf")]
+
+
 class CostVolumeArgs(C.Structure):
     """struct mal_cost_volume_args."""
     _fields_ = [
@@ -110,6 +117,7 @@ EXPORTS = {
     "mal_main_terms_forward": (C.c_int, [C.POINTER(MainTermsArgs), C.c_void_p]),
     "mal_matching_mask": (C.c_int, [C.POINTER(MatchingMaskArgs), C.c_void_p]),
     "mal_step_combine": (C.c_int, [C.POINTER(StepCombineArgs), C.c_void_p]),
+    "mal_forward_warp": (C.c_int, [C.POINTER(ForwardWarpArgs), C.c_void_p]),
     "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),

@@ -19,7 +19,7 @@ from torch import Tensor
 from . import _capi, raw
 
 __all__ = ["photo", "reprojection_loss_map", "smooth", "main_terms", "cost_volume", "matching_mask",
-           "backproject", "project3d", "ssim"]
+           "backproject", "project3d", "ssim", "forward_warp"]
 
 
 def _lib(t: Tensor):
@@ -447,3 +447,25 @@ _ssim_op.register_autograd(_ssim_backward, setup_context=_ssim_setup)
 def ssim(x, y):
     """SSIM.forward: clamp((1 - SSIM(x, y)) / 2, 0, 1), differentiable w.r.t. both images."""
     return _ssim_op(x, y)
+
+
+# --------------------------------------------------------------------------------------------
+# DynamicDepth forward warp (no gradient in the reference)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("mal_b200::forward_warp", mutates_args=())
+def _forward_warp_op(img: Tensor, depth: Tensor, pose: Tensor, K: Tensor, Ku_inv: Tensor, K_inv: Tensor,
+                     proj: Tensor, upscale: int) -> Tuple[Tensor, Tensor, Tensor]:
+    return raw.forward_warp(_lib(img), img=img, depth=depth, pose=pose, K=K, Ku_inv=Ku_inv, K_inv=K_inv, proj=proj,
+                            upscale=upscale)
+
+
+@_forward_warp_op.register_fake
+def _(img, depth, pose, K, Ku_inv, K_inv, proj, upscale):
+    return img.new_empty(img.shape), depth.new_empty(depth.shape), depth.new_empty(depth.shape)
+
+
+def forward_warp(img, depth, pose, K, Ku_inv, K_inv, proj, upscale=3):
+    """Z-buffered forward splat + inverse warp -> (img_w * valid, depth_w * valid, valid)."""
+    with torch.no_grad():
+        c = lambda t: t.detach().contiguous()
+        return _forward_warp_op(c(img), c(depth), c(pose), c(K), c(Ku_inv), c(K_inv), c(proj), int(upscale))

@@ -318,3 +318,23 @@ def step_combine(handle, *, batch, height, width, weights, sums_teacher, sums_st
     _capi.check(handle.mal_step_combine(C.byref(a), _stream(gd_teacher)), handle)
     LAUNCHES[0] += 1
     return out
+
+
+def forward_warp(handle, *, img, depth, pose, K, Ku_inv, K_inv, proj, upscale=3):
+    """mal_forward_warp -> (img_w * valid, depth_w * valid, valid)."""
+    B, Cn, H, W = img.shape
+    img, depth = _f32(img, "img", (B, Cn, H, W)), _f32(depth, "depth", (B, 1, H, W))
+    pose, proj = _f32(pose, "pose", (B, 3, 4)), _f32(proj, "proj", (B, 3, 4))
+    K, Ku_inv, K_inv = _f32(K, "K", (B, 3, 3)), _f32(Ku_inv, "Ku_inv", (B, 3, 3)), _f32(K_inv, "K_inv", (B, 3, 3))
+    dev = _same_device([img, depth, pose, K, Ku_inv, K_inv, proj])
+    img_w = torch.empty_like(img)
+    depth_w, valid = torch.empty_like(depth), torch.empty_like(depth)
+    zbuf = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    a = _capi.ForwardWarpArgs()
+    a.batch, a.channels, a.height, a.width, a.upscale = B, Cn, H, W, int(upscale)
+    a.img, a.depth, a.pose, a.K = _ptr(img), _ptr(depth), _ptr(pose), _ptr(K)
+    a.Ku_inv, a.K_inv, a.proj = _ptr(Ku_inv), _ptr(K_inv), _ptr(proj)
+    a.img_w, a.depth_w, a.valid, a.zbuf = _ptr(img_w), _ptr(depth_w), _ptr(valid), _ptr(zbuf)
+    _capi.check(handle.mal_forward_warp(C.byref(a), _stream(img)), handle)
+    LAUNCHES[0] += 2
+    return img_w, depth_w, valid

@@ -457,6 +457,104 @@ def cost_volume_head(current_feats, lookup_feats, relative_poses, K, invK, bins,
 
 
 # --------------------------------------------------------------------------
+# DynamicDepth forward warp (z-buffered splat + inverse warp)
+# --------------------------------------------------------------------------
+def _pixel2cam(depth, intrinsics_inv):
+    """dynamicdepth/rigid_warp.py:34-50 (set_id_grid :14-21)."""
+    b, h, w = depth.shape
+    i_range = torch.arange(0, h).view(1, h, 1).expand(1, h, w).type_as(depth)
+    j_range = torch.arange(0, w).view(1, 1, w).expand(1, h, w).type_as(depth)
+    ones = torch.ones(1, h, w).type_as(depth)
+    pix = torch.stack((j_range, i_range, ones), dim=1).expand(b, 3, h, w).reshape(b, 3, -1)
+    cam = (intrinsics_inv @ pix).reshape(b, 3, h, w)
+    return cam * depth.unsqueeze(1)
+
+
+def _euler2mat(angle):
+    """dynamicdepth/rigid_warp.py:204-241."""
+    B = angle.size(0)
+    x, y, z = angle[:, 0], angle[:, 1], angle[:, 2]
+    cosz, sinz = torch.cos(z), torch.sin(z)
+    zeros = z.detach() * 0
+    ones = zeros.detach() + 1
+    zmat = torch.stack([cosz, -sinz, zeros, sinz, cosz, zeros, zeros, zeros, ones], dim=1).reshape(B, 3, 3)
+    cosy, siny = torch.cos(y), torch.sin(y)
+    ymat = torch.stack([cosy, zeros, siny, zeros, ones, zeros, -siny, zeros, cosy], dim=1).reshape(B, 3, 3)
+    cosx, sinx = torch.cos(x), torch.sin(x)
+    xmat = torch.stack([ones, zeros, zeros, zeros, cosx, -sinx, zeros, sinx, cosx], dim=1).reshape(B, 3, 3)
+    return xmat @ ymat @ zmat
+
+
+def _mat2euler(R):
+    """dynamicdepth/rigid_warp.py:175-200."""
+    sy = torch.sqrt(R[:, 0, 0] * R[:, 0, 0] + R[:, 1, 0] * R[:, 1, 0])
+    singular = (sy < 1e-6).float()
+    x = torch.atan2(R[:, 2, 1], R[:, 2, 2])
+    y = torch.atan2(-R[:, 2, 0], sy)
+    z = torch.atan2(R[:, 1, 0], R[:, 0, 0])
+    xs = torch.atan2(-R[:, 1, 2], R[:, 1, 1])
+    ys = torch.atan2(-R[:, 2, 0], sy)
+    zs = R[:, 1, 0] * 0
+    return torch.stack([x * (1 - singular) + xs * singular, y * (1 - singular) + ys * singular,
+                        z * (1 - singular) + zs * singular], dim=-1)
+
+
+def forward_warp_matrices(pose, intrinsics, upscale):
+    """The (B,3,3)/(B,3,4) constants forward_warp derives on the way (rigid_warp.py:562-589,
+    inverse_warp :355-362): inverse of the up-scaled intrinsics, inverse intrinsics, and the
+    target->source projection K @ [R(euler(inv pose)) | t(inv pose)]."""
+    bs = pose.shape[0]
+    intrinsic_u = torch.cat((intrinsics[:, 0:2] * upscale, intrinsics[:, 2:]), dim=1)
+    aux = torch.tensor([0, 0, 0, 1]).type_as(pose).unsqueeze(0).unsqueeze(0).repeat(bs, 1, 1)
+    pose_inv_mat = torch.inverse(torch.cat([pose, aux], dim=1))
+    pose_inv = torch.cat([pose_inv_mat[:, :3, 3], _mat2euler(pose_inv_mat[:, :3, :3])], dim=1)
+    pose_mat = torch.cat([_euler2mat(pose_inv[:, 3:]), pose_inv[:, :3].unsqueeze(-1)], dim=2)
+    return intrinsic_u.inverse(), intrinsics.inverse(), intrinsics @ pose_mat
+
+
+def forward_warp(img, depth, pose, intrinsics, upscale=3, matrices=None):
+    """dynamicdepth/rigid_warp.forward_warp :534-597 (cam2pix_trans :513-530, inverse_warp
+    :337-373, cam2pixel :54-83).  torch_sparse.coalesce(op='max') (:577; third-party, version
+    unpinned, absent from the tree) is restated from its published semantics as a scatter-max of
+    1/z onto the (hh+1, ww+1) grid whose last row / column collect the out-of-range points."""
+    bs, _, hh, ww = depth.shape
+    Ku_inv, K_inv, proj = matrices if matrices is not None else forward_warp_matrices(pose, intrinsics, upscale)
+    depth_u = F.interpolate(depth, scale_factor=upscale).squeeze(1)
+    cam = _pixel2cam(depth_u, Ku_inv)
+    b, _, h, w = cam.shape
+    rot, tr = pose[:, :, :3], pose[:, :, -1:]
+    trans = rot @ cam.reshape(b, 3, -1) + tr
+    X, Y, Z = trans[:, 0], trans[:, 1], trans[:, 2].clamp(min=1e-3)
+    P_norm = torch.stack([X / Z, Y / Z, Z / Z], dim=1)
+    pcoords = (intrinsics @ P_norm).permute(0, 2, 1)[:, :, :2].reshape(b, h, w, 2)
+    depth_w, fw_val = [], []
+    for coo, z in zip(pcoords, Z.reshape(b, 1, h, w)):
+        idx = coo.reshape(-1, 2).permute(1, 0).long()[[1, 0]]
+        val = z.reshape(-1)
+        idx[0][idx[0] < 0] = hh
+        idx[0][idx[0] > hh - 1] = hh
+        idx[1][idx[1] < 0] = ww
+        idx[1][idx[1] > ww - 1] = ww
+        dense = torch.zeros((hh + 1) * (ww + 1)).scatter_reduce(0, idx[0] * (ww + 1) + idx[1], 1 / val, "amax",
+                                                                include_self=False)
+        dense = dense.view(hh + 1, ww + 1)[:-1, :-1]
+        depth_w.append(1 / dense)
+        fw_val.append(1 - (dense == 0).float())
+    depth_w, fw_val = torch.stack(depth_w, 0), torch.stack(fw_val, 0)
+    depth_w[fw_val == 0] = 0
+    # inverse_warp(img, depth_w, pose_inv, intrinsics) with zeros padding
+    cam2 = _pixel2cam(depth_w, K_inv)
+    pc = proj[:, :, :3] @ cam2.reshape(bs, 3, -1) + proj[:, :, -1:]
+    Xs, Ys, Zs = pc[:, 0], pc[:, 1], pc[:, 2].clamp(min=1e-3)
+    grid = torch.stack([2 * (Xs / Zs) / (ww - 1) - 1, 2 * (Ys / Zs) / (hh - 1) - 1], dim=2).reshape(bs, hh, ww, 2)
+    img_w = F.grid_sample(img, grid, padding_mode="zeros", align_corners=True)
+    iw_val = (grid.abs().max(dim=-1)[0] <= 1).float().unsqueeze(1)
+    depth_w = depth_w.unsqueeze(1)
+    valid = fw_val.unsqueeze(1) * iw_val
+    return img_w * valid, depth_w * valid, valid
+
+
+# --------------------------------------------------------------------------
 # host-side loss balancers (fp64 numpy state, as the reference)
 # --------------------------------------------------------------------------
 class LossBalancing:

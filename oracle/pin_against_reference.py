@@ -138,6 +138,37 @@ def _eq(name, a, b):
     return ok
 
 
+def reference_forward_warp():
+    """dynamicdepth.rigid_warp.forward_warp from the reference, with the one third-party call it
+    makes (torch_sparse.coalesce(op='max'), not installed, version unpinned) replaced by a
+    restatement of its published semantics: sort the (row, col) indices, reduce duplicates by max."""
+    load_reference()
+    rw = importlib.import_module("dynamicdepth.rigid_warp")
+
+    def coalesce(index, value, m, n, op="add"):
+        assert op == "max"
+        flat = index[0] * n + index[1]
+        uniq, inv = torch.unique(flat, sorted=True, return_inverse=True)
+        out = torch.full((uniq.numel(),), float("-inf"), dtype=value.dtype).scatter_reduce(0, inv, value, "amax")
+        return torch.stack([uniq // n, uniq % n]), out
+
+    rw.coalesce = coalesce
+    return rw.forward_warp
+
+
+def forward_warp_inputs(batch=2, height=24, width=64, seed=31):
+    from mal_b200.utils.synthetic import CITYSCAPES_K, make_photometric_inputs
+    from . import mal_oracle as O
+    inputs, t = make_photometric_inputs(batch, height, width, seed=seed, normalised_K=CITYSCAPES_K,
+                                        translation_scale=0.3)
+    img = inputs[("color", 0, 0)].clone()
+    img[:, :, : height // 3] = 0          # a "doj_mask"-like hole: forward_warp is fed masked images
+    depth = O.disp_to_depth(t[("mono_disp", 0)], 0.1, 100.0)[1]
+    pose = t[("cam_T_cam", 0, -1)][:, :3, :].clone()
+    K = inputs[("K", 0)][:, :3, :3].clone()
+    return img, depth, pose, K
+
+
 def run_pin(batch=2, height=96, width=160, seed=7):
     """Bitwise comparison of the restatement with the reference on one seeded batch."""
     from mal_b200.utils.synthetic import make_photometric_inputs, make_cost_volume_inputs
@@ -283,6 +314,17 @@ def run_pin(batch=2, height=96, width=160, seed=7):
         good &= lb_ref.update_weight(it, 0.3) == lb_ora.update_weight(it, 0.3)
     print(f"  {'OK ' if good else 'FAIL'} LossBalancing (6 iterations, weights + loss)")
     ok &= good
+
+    # ---- DynamicDepth forward_warp --------------------------------------------------------
+    import warnings
+    fw = reference_forward_warp()
+    img, depth_fw, pose, K3 = forward_warp_inputs()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = fw(img, depth_fw, pose, K3, upscale=3)
+    got = O.forward_warp(img, depth_fw, pose, K3, upscale=3)
+    for n, a, b in zip(("img_w", "depth_w", "valid"), got, want):
+        ok &= _eq("forward_warp " + n, a, b)
     return bool(ok)
 
 

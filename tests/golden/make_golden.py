@@ -22,7 +22,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle.pin_against_reference import (load_reference, reference_matcher,  # noqa: E402
+from oracle.pin_against_reference import (forward_warp_inputs, load_reference,  # noqa: E402
+                                          reference_forward_warp, reference_matcher,
                                           reference_trainer_shell, run_pin)
 from mal_b200.utils.synthetic import make_cost_volume_inputs, make_photometric_inputs  # noqa: E402
 
@@ -148,11 +149,29 @@ def cost_volume_case(name, batch, height, width, channels, bins, seed):
     print("wrote", name)
 
 
+def forward_warp_case(name):
+    """dynamicdepth/rigid_warp.forward_warp (coalesce restated, see pin_against_reference)."""
+    import warnings
+    from oracle import mal_oracle as O
+    fw = reference_forward_warp()
+    img, depth, pose, K = forward_warp_inputs()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        img_w, depth_w, valid = fw(img, depth, pose, K, upscale=3)
+    Ku_inv, K_inv, proj = O.forward_warp_matrices(pose, K, 3)
+    np.savez_compressed(os.path.join(HERE, name), in_img=_np(img), in_depth=_np(depth), in_pose=_np(pose),
+                        in_K=_np(K), in_Ku_inv=_np(Ku_inv), in_K_inv=_np(K_inv), in_proj=_np(proj),
+                        ref_img_w=_np(img_w), ref_depth_w=_np(depth_w), ref_valid=_np(valid).astype(np.uint8),
+                        meta_torch=np.array(torch.__version__))
+    print("wrote", name)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     photometric_case("photometric_smooth.npz", 2, 32, 48, seed=101, white_noise=False)
     photometric_case("photometric_noise.npz", 1, 24, 40, seed=202, white_noise=True)
     cost_volume_case("cost_volume.npz", 2, 32, 48, channels=8, bins=12, seed=303)
+    forward_warp_case("forward_warp.npz")
     ok = run_pin()
     print("oracle pinned:", ok)
     sys.exit(0 if ok else 1)

@@ -34,14 +34,16 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_the_c_compiler(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mal_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "mal_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(mal_photo_args),sizeof(mal_cost_volume_args),sizeof(mal_smooth_args),"
-                   "sizeof(mal_main_terms_args),sizeof(mal_matching_mask_args));return 0;}\n")
+                   "sizeof(mal_main_terms_args),sizeof(mal_matching_mask_args),sizeof(mal_step_combine_args),"
+                   "sizeof(mal_forward_warp_args));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(s) for s in (_capi.PhotoArgs, _capi.CostVolumeArgs, _capi.SmoothArgs,
-                                       _capi.MainTermsArgs, _capi.MatchingMaskArgs)]
+                                       _capi.MainTermsArgs, _capi.MatchingMaskArgs, _capi.StepCombineArgs,
+                                       _capi.ForwardWarpArgs)]
     assert got == want
 
 
