@@ -106,11 +106,14 @@ int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream);
  *    torch.no_grad(): manydepth/networks/resnet_encoder.py:292-307).
  *
  * Replaces ResnetEncoderMatching.match_features (manydepth/networks/resnet_encoder.py:151-233;
- * dualrefine/networks/resnet_encoder.py:163-245 with MAL_CONV_DUALREFINE) and, when the optional
+ * dualrefine/networks/resnet_encoder.py:163-245 with MAL_CONV_DUALREFINE;
+ * dynamicdepth/networks/resnet_encoder.py:148-249 with the cv_min / occ fields) and, when the optional
  * outputs are given, the head of forward(): compute_confidence_mask (:255-262), the "viz"
  * arg-min and indices_to_disparity (:247-253, :309-313) and cost_volume *= confidence (:317).
  * A lookup frame whose 4x4 pose sums to 0 is skipped on the device (:183-185, no host sync).
  * ------------------------------------------------------------------------------------------ */
+enum { MAL_CV_OCC_NONE = 0, MAL_CV_OCC_SET_1 = 1, MAL_CV_OCC_POOL = 2 };
+
 typedef struct mal_cost_volume_args {
   int32_t batch, channels, height, width; /* matching resolution (H/4, W/4)                  */
   int32_t num_lookup, num_bins;
@@ -133,6 +136,14 @@ typedef struct mal_cost_volume_args {
   int32_t* argmin;             /* (B,h,w) optional: arg-min bin of the 0->100 "viz" volume    */
   float* lowest_cost;          /* (B,h,w) optional: 1 / bins[argmin]                          */
   float* packed;               /* workspace, mal_cost_volume_workspace_floats() floats, 16-B aligned */
+
+  /* DynamicDepth variant (dynamicdepth/networks/resnet_encoder.py:148-249); all zero/NULL = off */
+  int32_t cv_min;              /* min over lookup frames instead of the mean (:163-166, :220-227)  */
+  int32_t occ_mode;            /* MAL_CV_OCC_*: what to do where the projected occlusion mask > pool_th */
+  int32_t pool_radius;         /* pool_r: (2r+1)^3 max-pool window over (bin, y, x) (:199)         */
+  float pool_th;               /* pool_th (:195)                                                   */
+  const float* occ;            /* (B,h,w) {0,1}: occ_batch > 0 at the matching resolution (:160, :194) */
+  const float* aug_mask;       /* (B) occlusion handling only where aug_mask == 0 (:192); NULL: all */
 } mal_cost_volume_args;
 
 size_t mal_cost_volume_workspace_floats(int batch, int channels, int height, int width, int num_lookup);

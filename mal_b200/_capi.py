@@ -63,6 +63,8 @@ class CostVolumeArgs(C.Structure):
         ("inv_K", C.c_void_p), ("bins", C.c_void_p),
         ("cost_volume", C.c_void_p), ("missing_mask", C.c_void_p), ("confidence", C.c_void_p),
         ("argmin", C.c_void_p), ("lowest_cost", C.c_void_p), ("packed", C.c_void_p),
+        ("cv_min", C.c_int32), ("occ_mode", C.c_int32), ("pool_radius", C.c_int32), ("pool_th", C.c_float),
+        ("occ", C.c_void_p), ("aug_mask", C.c_void_p),
     ]
 
 

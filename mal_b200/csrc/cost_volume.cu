@@ -107,7 +107,84 @@ __device__ __forceinline__ float quad_l1(float acc, const float4& a, const float
   return acc;
 }
 
-template <int CONV, int MINB>
+
+// ---- DynamicDepth extras (dynamicdepth/networks/resnet_encoder.py:191-202) ---------------------
+constexpr int CV_OCC_BIT = 1 << 30;   // descriptor flag: the projected occlusion mask exceeds pool_th
+
+// F.grid_sample(occ_mask, pix_locs, zeros, bilinear, align_corners) > pool_th at one location
+template <int CONV>
+__device__ __forceinline__ bool occluded_at(const float* __restrict__ occ, const GridPoint& gp, int h, int w,
+                                            float th) {
+  const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+  if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) return 0.0f > th;
+  Taps t = make_taps(ux, uy, h, w);
+  return bilinear(occ, t) > th;
+}
+
+// warped value of 4 channels at an arbitrary location, zeros padding
+__device__ __forceinline__ float4 bilinear4(const float4* __restrict__ plane, const Taps& t) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = t.v00 ? ldg4(plane + t.o00) : z, b = t.v01 ? ldg4(plane + t.o01) : z;
+  const float4 c = t.v10 ? ldg4(plane + t.o10) : z, d = t.v11 ? ldg4(plane + t.o11) : z;
+  float4 r;
+  r.x = xfma(d.x, t.se, xfma(c.x, t.sw, xfma(b.x, t.ne, xmul(a.x, t.nw))));
+  r.y = xfma(d.y, t.se, xfma(c.y, t.sw, xfma(b.y, t.ne, xmul(a.y, t.nw))));
+  r.z = xfma(d.z, t.se, xfma(c.z, t.sw, xfma(b.z, t.ne, xmul(a.z, t.nw))));
+  r.w = xfma(d.w, t.se, xfma(c.w, t.sw, xfma(b.w, t.ne, xmul(a.w, t.nw))));
+  return r;
+}
+
+__device__ __forceinline__ float quad_l1_vals(float acc, const float4& v, const float4& cur) {
+  acc = xadd(acc, fabsf(xsub(v.x, cur.x)));
+  acc = xadd(acc, fabsf(xsub(v.y, cur.y)));
+  acc = xadd(acc, fabsf(xsub(v.z, cur.z)));
+  acc = xadd(acc, fabsf(xsub(v.w, cur.w)));
+  return acc;
+}
+
+// "pool": an occluded sample takes, per channel, the max over its (2r+1)^3 neighbourhood in
+// (bin, y, x) of the warped features with occluded entries zeroed (F.max_pool3d, implicit -inf
+// padding).  Slow path: every neighbour is re-projected and re-sampled; only occluded samples pay.
+template <int CONV>
+__device__ __noinline__ float pooled_chunk_l1(const mal_cost_volume_args& a, const CvGeom* geom,
+                                              const float4* __restrict__ lqc, const float* __restrict__ occ,
+                                              const float4* cq, int k, int px, int py) {
+  const int h = a.height, w = a.width, hw = h * w, r = a.pool_radius;
+  float4 m[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) m[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
+  for (int dk = -r; dk <= r; dk++) {
+    const int kk = k + dk;
+    if (kk < 0 || kk >= a.num_bins) continue;
+    const float depth = __ldg(a.bins + kk);
+    for (int dy = -r; dy <= r; dy++) {
+      const int yy = py + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -r; dx <= r; dx++) {
+        const int xx = px + dx;
+        if (xx < 0 || xx >= w) continue;
+        const Ray ray = pixel_ray(geom->iK, (float)xx, (float)yy);
+        const GridPoint gp = project_grid<CONV>(geom->P, ray, depth, a.eps, h, w);
+        if (occluded_at<CONV>(occ, gp, h, w, a.pool_th)) continue;       // x[mask] = 0
+        const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+        if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
+        const Taps t = make_taps(ux, uy, h, w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 v = bilinear4(lqc + (size_t)j * hw, t);
+          m[j].x = fmaxf(m[j].x, v.x); m[j].y = fmaxf(m[j].y, v.y);
+          m[j].z = fmaxf(m[j].z, v.z); m[j].w = fmaxf(m[j].w, v.w);
+        }
+      }
+    }
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc = quad_l1_vals(acc, m[j], cq[j]);
+  return acc;
+}
+
+template <int CONV, int MINB, bool DYN>
 __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = a.height, w = a.width, hw = h * w;
@@ -128,7 +205,11 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
   float* cnt = cost + (size_t)nb * CV_PX;                // [nb][PX]
   float* scr = cnt + (size_t)nb * CV_PX;                 // [4][WARPS][PX]
 
-  for (int i = tid; i < nb * CV_PX; i += CV_NT) { cost[i] = 0.0f; cnt[i] = 0.0f; }
+  const bool cv_min = DYN && a.cv_min;
+  for (int i = tid; i < nb * CV_PX; i += CV_NT) { cost[i] = cv_min ? 1.0f : 0.0f; cnt[i] = 0.0f; }
+  // occlusion handling applies to samples whose matching augmentation is off (aug_mask == 0)
+  const float* occ = nullptr;
+  if (DYN && a.occ && a.occ_mode != 0 && !(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
 
   const float4* curq = reinterpret_cast<const float4*>(a.packed) + (size_t)b * nquads * hw;
   const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
@@ -178,6 +259,7 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
             off = yi * w + xi;
             tx = xsub(ux, x0);
             ty = xsub(uy, y0);
+            if (DYN && occ && occluded_at<CONV>(occ, gp, h, w, a.pool_th)) off |= CV_OCC_BIT;
           }
         }
         d_off[k * CV_PX + lane] = off;
@@ -200,8 +282,18 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
         const float* pty = d_ty + lane;
         float* pp = part + (size_t)ch * CV_BG * CV_PX + lane;
         for (int k = 0; k < gn; k++) {
-          const int off = po[k * CV_PX];
+          int off = po[k * CV_PX];
           float acc = 0.0f;
+          if (DYN && off >= 0 && (off & CV_OCC_BIT)) {
+            if (a.occ_mode == MAL_CV_OCC_SET_1) {            // warped[mask] = 1.0
+              const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+              for (int j = 0; j < 4; j++) acc = quad_l1_vals(acc, one, cq[j]);
+            } else {                                          // warped[mask] = max_pool3d(x)[mask]
+              acc = pooled_chunk_l1<CONV>(a, geom, lqc, occ, cq, g0 + k, px, py);
+            }
+            off = -1;
+          }
           if (off >= 0) {
             if (off != coff) {
               coff = off;
@@ -232,8 +324,13 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
           for (int ch = 1; ch < nchunks; ch++) s = xadd(s, part[((size_t)ch * CV_BG + k) * CV_PX + lane]);
           float diff = xdiv(s, (float)a.channels);                         // .mean(1), edge mask == 1
           int o = (g0 + k) * CV_PX + lane;
-          cost[o] = xadd(cost[o], diff);
-          if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+          if (cv_min) {   // diffs[diffs == 0] = 1.0; cost_volume = minimum(diffs, cost_volume)
+            if (diff == 0.0f) diff = 1.0f;
+            cost[o] = fminf(diff, cost[o]);
+          } else {
+            cost[o] = xadd(cost[o], diff);
+            if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+          }
         }
       }
       // the next group's P phase rewrites the descriptors only after the barrier below
@@ -249,7 +346,9 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
   float vmax = -INFINITY;
   for (int k = k0; k < k1; k++) {
     int o = k * CV_PX + lane;
-    float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));   // cost_volume / (counts + 1e-7)
+    float v;
+    if (cv_min) v = (cost[o] == 1.0f) ? 0.0f : cost[o];   // cost_volume[cost_volume == 1] = 0
+    else v = xdiv(cost[o], xadd(cnt[o], 1e-7f));         // cost_volume / (counts + 1e-7)
     cost[o] = v;
     vmax = fmaxf(vmax, v);
   }
@@ -328,6 +427,9 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
               a.channels);
   MAL_REQUIRE(a.convention == MAL_CONV_MANYDEPTH || a.convention == MAL_CONV_DUALREFINE,
               "mal_cost_volume_forward: bad convention %d", a.convention);
+  MAL_REQUIRE(a.occ_mode == MAL_CV_OCC_NONE || a.occ_mode == MAL_CV_OCC_SET_1 || a.occ_mode == MAL_CV_OCC_POOL,
+              "mal_cost_volume_forward: bad occ_mode %d", a.occ_mode);
+  if (a.occ_mode == MAL_CV_OCC_POOL) MAL_REQUIRE(a.pool_radius >= 0 && a.pool_radius <= 3, "mal_cost_volume_forward: pool_radius %d", a.pool_radius);
   MAL_REQUIRE(a.current && a.lookup && a.poses && a.K && a.inv_K && a.bins && a.cost_volume && a.packed,
               "mal_cost_volume_forward: current/lookup/poses/K/inv_K/bins/cost_volume/packed are required");
   cudaStream_t st = (cudaStream_t)stream;
@@ -352,11 +454,13 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   // environment override exists for tuning runs only
   int minb = CV_DEFAULT_MINB;
   if (const char* e = getenv("MAL_CV_MINB")) minb = atoi(e);
-#define MAL_CV_LAUNCH(CONV_)                                                                  \
-  do {                                                                                        \
-    if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3>, grid, dim3(CV_NT), smem, st, a, Cp);      \
-    else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4>, grid, dim3(CV_NT), smem, st, a, Cp); \
-    else launch(cv_sweep_kernel<CONV_, 5>, grid, dim3(CV_NT), smem, st, a, Cp);                \
+  const bool dyn = a.cv_min || (a.occ && a.occ_mode != MAL_CV_OCC_NONE);
+#define MAL_CV_LAUNCH(CONV_)                                                                         \
+  do {                                                                                               \
+    if (dyn) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp);             \
+    else if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
+    else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
+    else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp);                \
   } while (0)
   if (a.convention == MAL_CONV_MANYDEPTH) MAL_CV_LAUNCH(MAL_CONV_MANYDEPTH);
   else MAL_CV_LAUNCH(MAL_CONV_DUALREFINE);

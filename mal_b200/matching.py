@@ -87,6 +87,29 @@ class CostVolumeMatcher:
         return cv, low, conf
 
 
+class DynamicCostVolumeMatcher(CostVolumeMatcher):
+    """DynamicDepth's matcher (dynamicdepth/networks/resnet_encoder.py:148-249): `match_features`
+    takes the lookup image and the occlusion options; min over lookup frames (cv_min) and the
+    set-to-1 / 3-D max-pool fill of occluded warped features happen inside the sweep kernel."""
+
+    def occlusion_mask(self, lookup_images, h, w):
+        """(B,3,H,W) DOMD-processed lookup image -> (B,h,w) {0,1}: black pixels (< 0.15 summed RGB),
+        nearest-resized to the matching resolution (:160; the reference hard-codes 48x128)."""
+        occ = torch.nn.functional.interpolate((lookup_images.sum(1).unsqueeze(1) < 0.15).float(), [h, w])
+        return (occ[:, 0] > 0).float()
+
+    def match_features(self, current_feats, lookup_feats, relative_poses, K, invK, lookup_images=None, cv_min=False,
+                       aug_mask=None, set_1=False, pool=False, pool_r=1, pool_th=0.7):
+        h, w = current_feats.shape[-2:]
+        mode = raw.OCC_SET_1 if set_1 else (raw.OCC_POOL if pool else raw.OCC_NONE)
+        occ = self.occlusion_mask(lookup_images, h, w) if mode != raw.OCC_NONE else None
+        cv, missing, *_ = ops.cost_volume(current_feats, lookup_feats, relative_poses, K, invK,
+                                          self._bins_on(current_feats.device), convention=self.convention,
+                                          set_missing_to_max=self.set_missing_to_max, cv_min=bool(cv_min), occ=occ,
+                                          occ_mode=mode, pool_radius=pool_r, pool_th=pool_th, aug_mask=aug_mask)
+        return cv, missing
+
+
 class ResnetEncoderMatching(nn.Module, CostVolumeMatcher):
     """ResNet encoder with the cost volume after the 2nd block (reference constructor/forward)."""
 

@@ -271,16 +271,20 @@ def main_terms(multi, mono, pixel_mask, sample_mask, mono_reproj, ens_reproj, mu
 @torch.library.custom_op("mal_b200::cost_volume", mutates_args=())
 def _cost_volume_op(current: Tensor, lookup: Tensor, poses: Tensor, K: Tensor, inv_K: Tensor,
                     bins: Tensor, convention: int, set_missing_to_max: bool, apply_confidence: bool,
-                    num_bins_threshold: int, eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                    num_bins_threshold: int, eps: float, cv_min: bool, occ: Optional[Tensor], occ_mode: int,
+                    pool_radius: int, pool_th: float,
+                    aug_mask: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     out = raw.cost_volume(_lib(current), current=current, lookup=lookup, poses=poses, K=K, inv_K=inv_K,
                           bins=bins, convention=convention, set_missing_to_max=set_missing_to_max,
-                          apply_confidence=apply_confidence, num_bins_threshold=num_bins_threshold, eps=eps)
+                          apply_confidence=apply_confidence, num_bins_threshold=num_bins_threshold, eps=eps,
+                          cv_min=cv_min, occ=occ, occ_mode=occ_mode, pool_radius=pool_radius, pool_th=pool_th,
+                          aug_mask=aug_mask)
     return out["cost_volume"], out["missing_mask"], out["confidence"], out["argmin"], out["lowest_cost"]
 
 
 @_cost_volume_op.register_fake
 def _(current, lookup, poses, K, inv_K, bins, convention, set_missing_to_max, apply_confidence,
-      num_bins_threshold, eps):
+      num_bins_threshold, eps, cv_min, occ, occ_mode, pool_radius, pool_th, aug_mask):
     B, _, h, w = current.shape
     nb = bins.shape[0]
     f = lambda *s: current.new_empty(s)
@@ -288,13 +292,16 @@ def _(current, lookup, poses, K, inv_K, bins, convention, set_missing_to_max, ap
 
 
 def cost_volume(current, lookup, poses, K, inv_K, bins, *, convention=raw.CONV_MANYDEPTH,
-                set_missing_to_max=True, apply_confidence=False, num_bins_threshold=0, eps=1e-7):
+                set_missing_to_max=True, apply_confidence=False, num_bins_threshold=0, eps=1e-7,
+                cv_min=False, occ=None, occ_mode=raw.OCC_NONE, pool_radius=1, pool_th=0.7, aug_mask=None):
     """Plane-sweep cost volume + head.  Returns ``(cost_volume, missing_mask, confidence, argmin,
-    lowest_cost)``; inputs are detached (the reference builds the volume under no_grad)."""
+    lowest_cost)``; inputs are detached (the reference builds the volume under no_grad).
+    ``cv_min`` / ``occ`` / ``occ_mode`` select DynamicDepth's variant."""
     with torch.no_grad():
         return _cost_volume_op(current.detach(), lookup.detach(), poses.detach(), K, inv_K, bins, convention,
                                bool(set_missing_to_max), bool(apply_confidence), int(num_bins_threshold),
-                               float(eps))
+                               float(eps), bool(cv_min), occ, int(occ_mode), int(pool_radius), float(pool_th),
+                               None if aug_mask is None else aug_mask.reshape(-1).float())
 
 
 @torch.library.custom_op("mal_b200::matching_mask", mutates_args=())

@@ -18,6 +18,7 @@ CONV_MANYDEPTH, CONV_DUALREFINE = 0, 1
 # kernels launched through this module since the caller last reset it (bench.py's gpu_launches)
 LAUNCHES = [0]
 PHOTO_WARP, PHOTO_PRED = 0, 1
+OCC_NONE, OCC_SET_1, OCC_POOL = 0, 1, 2
 
 
 def _f32(t, name, shape=None):
@@ -114,7 +115,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
 
 def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CONV_MANYDEPTH,
                 set_missing_to_max=True, apply_confidence=False, num_bins_threshold=0, eps=1e-7,
-                want_missing=True, want_head=True):
+                want_missing=True, want_head=True, cv_min=False, occ=None, occ_mode=OCC_NONE, pool_radius=1,
+                pool_th=0.7, aug_mask=None):
     """mal_cost_volume_forward.  `want_head` adds confidence / argmin / lowest_cost."""
     B, Cn, h, w = current.shape
     F_ = lookup.shape[1]
@@ -124,7 +126,10 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     poses = _f32(poses, "poses", (B, F_, 4, 4))
     K, inv_K = _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
     bins = _f32(bins, "bins", (nb,))
-    dev = _same_device([current, lookup, poses, K, inv_K, bins])
+    occ = _f32(occ, "occ", (B, h, w))
+    if aug_mask is not None:
+        aug_mask = _f32(aug_mask.reshape(-1).float(), "aug_mask", (B,))
+    dev = _same_device([current, lookup, poses, K, inv_K, bins, occ, aug_mask])
     new = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
     out = {"cost_volume": new((B, nb, h, w))}
     out["missing_mask"] = new((B, nb, h, w)) if want_missing else None
@@ -141,6 +146,8 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     a.cost_volume, a.missing_mask = _ptr(out["cost_volume"]), _ptr(out["missing_mask"])
     a.confidence, a.argmin, a.lowest_cost = _ptr(out["confidence"]), _ptr(out["argmin"]), _ptr(out["lowest_cost"])
     a.packed = _ptr(packed)
+    a.cv_min, a.occ_mode, a.pool_radius, a.pool_th = int(bool(cv_min)), int(occ_mode), int(pool_radius), float(pool_th)
+    a.occ, a.aug_mask = _ptr(occ), _ptr(aug_mask)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
     LAUNCHES[0] += 3   # cv_pack_kernel x2 + cv_sweep_kernel
     out["_keepalive"] = (packed,)

@@ -148,6 +148,86 @@ def compute_losses(inputs, outputs, opt, is_multi=False, has_ins=False, noises=N
     return losses, []
 
 
+def generate_images_pred_dualrefine(inputs, outputs, opt):
+    """dualrefine/trainer.py generate_images_pred :395-455: one WarpSpec per (scale, deq_iter) with
+    DualRefine's convention (half-pixel Project3D, align_corners=False) and pose-detach rules."""
+    H, W = _o(opt, "height"), _o(opt, "width")
+    for scale in opt.scales:
+        n = getattr(opt, "n_losses", 1) + 1 if scale in (0, 1, 2) else 1
+        for it in range(n):
+            if scale == 1:
+                continue
+            disp = outputs[("disp", scale, it)]
+            if disp.shape[-2:] != (H, W):
+                disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+            _, depth = disp_to_depth(disp, _o(opt, "min_depth"), _o(opt, "max_depth"))
+            outputs[("depth", 0, scale, it)] = depth
+            Ts = []
+            for frame_id in (-1, 1):
+                if frame_id == 1:
+                    T = outputs[("cam_T_cam", 0, frame_id)]
+                    T = T.detach() if it > 0 else T
+                elif it > 0:
+                    T = (outputs[("cam_T_cam", 0, frame_id)].detach() if getattr(opt, "Dstar_T0_pair", False)
+                         else outputs[("cam_T_cam", 0, frame_id, 1)])
+                else:
+                    T = outputs[("cam_T_cam", 0, frame_id)]
+                Ts.append(T)
+            outputs[("warp_spec", scale, it)] = WarpSpec(disp, inputs[("K", 0)], inputs[("inv_K", 0)], Ts,
+                                                         raw.CONV_DUALREFINE, _o(opt, "min_depth"), _o(opt, "max_depth"))
+    return outputs
+
+
+def compute_losses_dualrefine(inputs, outputs, opt, noises=None):
+    """dualrefine/trainer.py compute_losses :530-697 (f_thres > 0 branch): per (scale, deq_iter)
+    fused photometric pass with automask x consistency mask, consistency towards the deq_iter-0
+    depth, smoothness.  Returns the losses dict."""
+    if getattr(opt, "avg_reprojection", False):
+        raise NotImplementedError("avg_reprojection (mean instead of min over frames) is not implemented")
+    losses, total_loss = {}, 0
+    target = inputs[("color", 0, 0)]
+    ssim = _Ssim(_o(opt, "no_ssim"))
+    automask = not _o(opt, "disable_automasking")
+    ident, draw = None, 0
+    for scale in opt.scales:
+        loss = 0
+        n = getattr(opt, "n_losses", 1) + 1 if scale in (0, 1, 2) else 1
+        for it in range(n):
+            if scale == 1:
+                continue
+            spec = outputs[("warp_spec", scale, it)]
+            kw = dict(src=[inputs[("color", f, 0)] for f in (-1, 1)], depth=spec.disp, K=spec.K, inv_K=spec.inv_K,
+                      T=spec.T, convention=spec.convention, depth_is_disp=True, min_depth=spec.min_depth,
+                      max_depth=spec.max_depth, no_ssim=ssim.no_ssim)
+            if automask:
+                ident = identity_reprojection(ssim, inputs) if ident is None else ident
+                kw.update(identity_min=ident,
+                          noise=_draw_noise(ident.shape, target.device, None if noises is None else noises[draw]))
+                draw += 1
+            pm = None
+            if it > 0 and not _o(opt, "disable_motion_masking"):
+                pm = outputs["consistency_mask"].reshape(target.shape[0], *target.shape[-2:])
+            sums, min_reproj, sel = ops.photo(target, pixel_mask=pm, **kw)
+            consistency_loss = 0
+            if it > 0:
+                # consistency_mask = 1 - (automask * consistency mask): the final per-pixel weight
+                weight = (sel >> 7).float()[:, 0] * (pm if pm is not None else 1.0)
+                consistency_loss, _, _, tgt = ops.main_terms(
+                    outputs[("depth", 0, scale, it)], outputs[("depth", 0, scale, 0)].detach(), weight.contiguous(),
+                    None, min_reproj, None, min_reproj)
+                outputs["consistency_target/{}_{}".format(scale, it)] = tgt
+                losses["consistency_loss/{}_{}".format(scale, it)] = consistency_loss
+            outputs[("mal_selection", scale, it)] = sel
+            losses["reproj_loss/{}".format(scale)] = sums[2]
+            loss = loss + sums[2] + consistency_loss
+            smooth_loss = ops.smooth(outputs[("disp", scale, it)], inputs[("color", 0, scale)], normalise=True)
+            loss = loss + _o(opt, "disparity_smoothness") * smooth_loss / (2 ** scale)
+            total_loss = total_loss + loss
+            losses["loss/{}_{}".format(scale, it)] = loss
+    losses["loss"] = total_loss / len(opt.scales)
+    return losses
+
+
 def process_batch_losses(inputs, mono_outputs, outputs, opt, *, has_ins=False, multi_has_ins=False,
                          loss_blc=None, index_iter=0, current_lambda_for_adjust=0.0, w_list=None,
                          noises=None, freeze_tp=False):

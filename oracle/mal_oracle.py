@@ -376,6 +376,84 @@ def trainer_compute_losses(inputs, outputs, *, num_scales=1, is_multi=False, tem
     return losses, aux
 
 
+def dualrefine_images_pred(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, height=192, width=640,
+                           min_depth=0.1, max_depth=100.0, Dstar_T0_pair=False):
+    """dualrefine/trainer.py generate_images_pred :395-455 (half-pixel Project3D,
+    align_corners=False; per (scale, deq_iter); scale 1 is skipped).  dualrefine.trainer cannot be
+    imported (networks/lib is missing), so this restatement is checked only through
+    the pinned primitives it is built from."""
+    for scale in scales:
+        n = n_losses + 1 if scale in (0, 1, 2) else 1
+        for it in range(n):
+            if scale == 1:
+                continue
+            disp = upsample_disp(outputs[("disp", scale, it)], height, width)
+            _, depth = disp_to_depth(disp, min_depth, max_depth)
+            outputs[("depth", 0, scale, it)] = depth
+            for fid in (-1, 1):
+                if fid == 1:
+                    T = outputs[("cam_T_cam", 0, fid)]
+                    if it > 0:
+                        T = T.detach()
+                elif it > 0:
+                    T = outputs[("cam_T_cam", 0, fid)].detach() if Dstar_T0_pair else outputs[("cam_T_cam", 0, fid, 1)]
+                else:
+                    T = outputs[("cam_T_cam", 0, fid)]
+                cam = backproject(depth, inputs[("inv_K", 0)])
+                grid = project3d(cam, inputs[("K", 0)], T, height, width, DUALREFINE)
+                outputs[("sample", fid, scale, it)] = grid
+                outputs[("color", fid, scale, it)] = warp(inputs[("color", fid, 0)], grid, DUALREFINE)
+    return outputs
+
+
+def dualrefine_compute_losses(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, automask=True,
+                              motion_masking=True, smoothness=1e-3, noises=None, no_ssim=False):
+    """dualrefine/trainer.py compute_losses :530-697, the f_thres > 0 branch (:543-626): per
+    (scale, deq_iter); for deq_iter > 0 the automask is multiplied by the consistency mask and the
+    consistency term pulls towards the deq_iter-0 depth; total / len(scales)."""
+    losses, total, aux = {}, 0, {}
+    target = inputs[("color", 0, 0)]
+    draw = 0
+    for scale in scales:
+        loss = 0
+        n = n_losses + 1 if scale in (0, 1, 2) else 1
+        for it in range(n):
+            if scale == 1:
+                continue
+            cands = torch.cat([reprojection_loss(outputs[("color", f, scale, it)], target, no_ssim) for f in (-1, 1)], 1)
+            ident = None
+            if automask:
+                ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, no_ssim) for f in (-1, 1)], 1)
+                ident, _ = torch.min(ident, dim=1, keepdim=True)
+            reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
+            if automask:
+                nz = noises[draw] if noises is not None else torch.randn(ident.shape)
+                draw += 1
+                ident = ident + nz * 0.00001
+            mask = loss_masks(reproj, ident)
+            if it > 0:
+                if motion_masking:
+                    mask = mask * outputs["consistency_mask"]
+                cons_mask = (1 - mask).float()
+            reproj_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+            cons = 0
+            if it > 0:
+                multi_depth = outputs[("depth", 0, scale, it)]
+                mono_depth = outputs[("depth", 0, scale, 0)].detach()
+                cons = (torch.abs(multi_depth - mono_depth) * cons_mask).mean()
+                losses[f"consistency_loss/{scale}_{it}"] = cons
+            losses[f"reproj_loss/{scale}"] = reproj_loss
+            loss = loss + reproj_loss + cons
+            loss = loss + smoothness * normalised_smooth_loss(outputs[("disp", scale, it)],
+                                                              inputs[("color", 0, scale)]) / (2 ** scale)
+            total = total + loss
+            losses[f"loss/{scale}_{it}"] = loss
+            aux[("frame_idx", scale, it)] = frame_idx
+            aux[("mask", scale, it)] = mask
+    losses["loss"] = total / len(scales)
+    return losses, aux
+
+
 # --------------------------------------------------------------------------
 # plane-sweep matching cost volume
 # --------------------------------------------------------------------------
@@ -423,6 +501,70 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, bins,
             cost = cost + diffs
             counts = counts + (diffs > 0).float()
         cost = cost / (counts + 1e-7)
+        missing = (cost == 0).float()
+        if set_missing_to_max:
+            cost = cost * (1 - missing) + cost.max(0)[0].unsqueeze(0) * missing
+        volumes.append(cost)
+        masks.append(missing)
+    return torch.stack(volumes, 0), torch.stack(masks, 0)
+
+
+def occlusion_batch(lookup_images, h, w):
+    """dynamicdepth/networks/resnet_encoder.py:160 (the reference hard-codes [48, 128], its
+    matching resolution): black (< 0.15 summed RGB) pixels of the DOMD-processed lookup image."""
+    return F.interpolate((lookup_images.sum(1).unsqueeze(1) < 0.15).float(), [h, w])
+
+
+def match_features_dynamic(current_feats, lookup_feats, relative_poses, K, invK, bins, lookup_images, cv_min,
+                           aug_mask, set_1, pool, pool_r, pool_th, set_missing_to_max=True):
+    """DynamicDepth's match_features, dynamicdepth/networks/resnet_encoder.py:148-249: min over
+    lookup frames (cv_min) and the occlusion fill of the warped features (set_1 / pool)."""
+    B, C, h, w = current_feats.shape
+    nb = len(bins)
+    planes = bins.view(nb, 1, 1, 1).float().expand(nb, 1, h, w).contiguous()
+    occ_batch = occlusion_batch(lookup_images, h, w)
+    volumes, masks = [], []
+    for b in range(B):
+        if cv_min:
+            cost = torch.ones(nb, h, w)
+        else:
+            cost, counts = torch.zeros(nb, h, w), torch.zeros(nb, h, w)
+        world = backproject(planes, invK[b:b + 1])
+        for li in range(lookup_feats.shape[1]):
+            pose = relative_poses[b:b + 1, li]
+            if pose.sum() == 0:
+                continue
+            feat = lookup_feats[b:b + 1, li].repeat([nb, 1, 1, 1])
+            locs = project3d(world, K[b:b + 1], pose, h, w)
+            warped = F.grid_sample(feat, locs, padding_mode="zeros", mode="bilinear", align_corners=True)
+            if aug_mask[b][0][0][0] == 0 and (set_1 or pool):
+                occ_mask = (occ_batch[b] > 0).unsqueeze(0).repeat([nb, C, 1, 1])
+                mask = (F.grid_sample(occ_mask.float(), locs, padding_mode="zeros", mode="bilinear",
+                                      align_corners=True) > pool_th).detach()
+                if set_1:
+                    warped[mask] = 1.0
+                elif pool:
+                    x = warped.clone()
+                    x[mask] = 0
+                    x = F.max_pool3d(x.permute(1, 0, 2, 3), pool_r * 2 + 1, stride=1, padding=pool_r).permute(1, 0, 2, 3)
+                    warped[mask] = x[mask]
+            xv = (locs[..., 0] / 2 + 0.5) * (w - 1)
+            yv = (locs[..., 1] / 2 + 0.5) * (h - 1)
+            edge = ((xv >= 2.0) * (xv <= w - 2) * (yv >= 2.0) * (yv <= h - 2)).float()
+            inner = torch.zeros_like(edge)
+            inner[:, 2:-2, 2:-2] = 1.0
+            edge = edge * inner
+            diffs = torch.abs(warped - current_feats[b:b + 1]).mean(1) * edge
+            if cv_min:
+                diffs[diffs == 0] = 1.0
+                cost = torch.minimum(diffs, cost)
+            else:
+                cost = cost + diffs
+                counts = counts + (diffs > 0).float()
+        if cv_min:
+            cost[cost == 1] = 0
+        else:
+            cost = cost / (counts + 1e-7)
         missing = (cost == 0).float()
         if set_missing_to_max:
             cost = cost * (1 - missing) + cost.max(0)[0].unsqueeze(0) * missing

@@ -328,8 +328,48 @@ def run_pin(batch=2, height=96, width=160, seed=7):
     return bool(ok)
 
 
+
+
+def pin_dynamicdepth_match_features(seed=77):
+    """dynamicdepth/networks/resnet_encoder.py:148-249 against O.match_features_dynamic.  The
+    reference hard-codes 96 bins x 64 channels at 48x128 (:160, :193), so this runs at full size."""
+    from mal_b200.utils.synthetic import CITYSCAPES_K, make_cost_volume_inputs
+    from . import mal_oracle as O
+    load_reference()
+    dd = importlib.import_module("dynamicdepth.networks.resnet_encoder")
+    dl = importlib.import_module("dynamicdepth.layers")
+    H, W = 192, 512
+    h, w = H // 4, W // 4
+    cv = make_cost_volume_inputs(2, H, W, channels=64, num_lookup=2, num_bins=96, seed=seed, normalised_K=CITYSCAPES_K,
+                                 min_bin=0.5, max_bin=6.0, translation_scale=0.5)
+    gen = torch.Generator().manual_seed(seed + 1)
+    look_img = torch.rand(2, 3, H, W, generator=gen)
+    look_img[:, :, 60:130, 100:260] = 0.0       # DOMD holes are black
+    look_img[:, :, 20:50, 300:420] = 0.01
+    aug = torch.zeros(2, 1, 1, 1)
+    aug[1] = 1
+    bins = cv["bins"]
+    enc = dd.ResnetEncoderMatching.__new__(dd.ResnetEncoderMatching)
+    torch.nn.Module.__init__(enc)
+    enc.num_depth_bins, enc.matching_height, enc.matching_width, enc.set_missing_to_max = len(bins), h, w, True
+    enc.depth_bins = bins
+    enc.warp_depths = torch.stack([torch.ones((1, h, w)) * d for d in bins], 0).float()
+    enc.backprojector, enc.projector = dl.BackprojectDepth(len(bins), h, w), dl.Project3D(len(bins), h, w)
+    ok = True
+    for cv_min, set_1, pool in ((True, False, True), (False, True, False), (True, False, False)):
+        want = enc.match_features(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"], cv["inv_K"],
+                                  look_img, cv_min, aug, set_1, pool, 1, 0.7)
+        got = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
+                                       cv["inv_K"], bins, look_img, cv_min, aug, set_1, pool, 1, 0.7)
+        tag = f"dynamicdepth match_features(cv_min={cv_min}, set_1={set_1}, pool={pool})"
+        ok &= _eq(tag + " volume", got[0], want[0])
+        ok &= _eq(tag + " missing", got[1], want[1])
+    return bool(ok)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     good = run_pin()
+    good &= pin_dynamicdepth_match_features()
     print("PINNED" if good else "PIN FAILED")
     sys.exit(0 if good else 1)

@@ -265,3 +265,64 @@ def test_operators_refuse_cpu_tensors():
     inputs, t = make_photometric_inputs(1, 16, 32, seed=1)
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA tensors only"):
         ops.smooth(t[("mono_disp", 0)], inputs[("color", 0, 0)])
+
+
+def test_dynamicdepth_matcher(op_device):
+    """matching.DynamicCostVolumeMatcher.match_features with the reference's DynamicDepth signature."""
+    dev = op_device
+    B, H, W = 1, 64, 96
+    cv = make_cost_volume_inputs(B, H, W, channels=16, num_lookup=1, num_bins=12, seed=19, min_bin=0.5, max_bin=6.0,
+                                 translation_scale=0.5)
+    look_img = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(3))
+    look_img[:, :, 16:48, 20:70] = 0.0
+    aug = torch.zeros(B, 1, 1, 1)
+    m = matching.DynamicCostVolumeMatcher(num_depth_bins=12, min_depth_bin=0.5, max_depth_bin=6.0)
+    d = to_device(cv, dev)
+    for cv_min, set_1, pool in ((True, False, True), (False, True, False)):
+        want = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
+                                        cv["inv_K"], cv["bins"], look_img, cv_min, aug, set_1, pool, 1, 0.7)
+        got = m.match_features(d["current_feats"], d["lookup_feats"], d["relative_poses"], d["K"], d["inv_K"],
+                               look_img.to(dev), cv_min, aug.to(dev), set_1, pool, 1, 0.7)
+        assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
+
+
+def test_dualrefine_losses_match_oracle(op_device):
+    """BASELINE config 4: DualRefine's per-(scale, deq_iter) losses with half-pixel sampling
+    (dualrefine/trainer.py:395-455, :530-626) - selections bit-exact, losses and gradients."""
+    dev = op_device
+    B, H, W = 1, 32, 64
+    scales = [0, 1, 2, 3]
+    inputs, t = make_photometric_inputs(B, H, W, num_scales=4, seed=61, translation_scale=0.3)
+    opt = SimpleNamespace(height=H, width=W, scales=scales, n_losses=1, min_depth=0.1, max_depth=100.0,
+                          disparity_smoothness=1e-3)
+    keys = [(s, it) for s in scales if s != 1 for it in range(2 if s in (0, 1, 2) else 1)]
+    noises = [torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(70 + i)) for i in range(len(keys))]
+    cmask = t["consistency_mask"].unsqueeze(1)
+
+    def build(dv):
+        d = lambda x: x.to(dv)
+        leaves = {(s, it): t[("mono_disp" if it == 0 else "multi_disp", s)].clone().to(dv).requires_grad_(True)
+                  for s, it in keys}
+        Ts = {k: t[("cam_T_cam", 0, f)].clone().to(dv).requires_grad_(True) for k, f in
+              (((0, -1), -1), ((0, 1), 1), ((0, -1, 1), -1))}
+        o = {("disp", s, it): leaves[(s, it)] for s, it in keys}
+        o[("cam_T_cam", 0, -1)], o[("cam_T_cam", 0, 1)], o[("cam_T_cam", 0, -1, 1)] = Ts[(0, -1)], Ts[(0, 1)], Ts[(0, -1, 1)]
+        o["consistency_mask"] = d(cmask)
+        return to_device(inputs, dv), o, list(leaves.values()) + list(Ts.values())
+
+    inp_c, o_c, leaves_c = build("cpu")
+    O.dualrefine_images_pred(inp_c, o_c, scales, 1, H, W)
+    want, aux = O.dualrefine_compute_losses(inp_c, o_c, scales, 1, noises=noises)
+    want_g = torch.autograd.grad(want["loss"], leaves_c)
+
+    inp_d, o_d, leaves_d = build(dev)
+    trainer_ops.generate_images_pred_dualrefine(inp_d, o_d, opt)
+    got = trainer_ops.compute_losses_dualrefine(inp_d, o_d, opt, noises=[n.to(dev) for n in noises])
+    for k in want:
+        assert _close(got[k], want[k]), k
+    for s, it in keys:
+        sel = o_d[("mal_selection", s, it)].cpu().numpy()
+        assert np.array_equal(sel & 0x7F, aux[("frame_idx", s, it)].numpy().astype(np.uint8)), (s, it)
+    g = torch.autograd.grad(got["loss"], leaves_d)
+    for a, b in zip(g, want_g):
+        assert _gerr(a, b) < GRAD_RTOL

@@ -75,3 +75,35 @@ def test_cost_volume_dualrefine_convention(backend):
     out = _run(h, dev, cv, convention=raw.CONV_DUALREFINE)
     assert torch.equal(out["missing_mask"].cpu(), miss)
     assert torch.equal(out["cost_volume"].cpu(), vol)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("cv_min,set_1,pool", [(True, False, True), (False, True, False), (True, False, False),
+                                               (False, False, True)])
+def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool):
+    """dynamicdepth/networks/resnet_encoder.py:148-249: min over lookup frames and the occlusion
+    fill (set_1 / 3-D max-pool) of the warped features, one sample with augmentation on (no fill)."""
+    h, dev = handle_and_device(backend)
+    B, H, W, C, nb = 2, 64, 96, 32, 20
+    cv = make_cost_volume_inputs(B, H, W, channels=C, num_lookup=2, num_bins=nb, seed=91, min_bin=0.5, max_bin=6.0,
+                                 translation_scale=0.5)
+    gen = torch.Generator().manual_seed(92)
+    look_img = torch.rand(B, 3, H, W, generator=gen)
+    look_img[:, :, 20:44, 24:64] = 0.0
+    look_img[:, :, 4:16, 70:90] = 0.01
+    aug = torch.zeros(B, 1, 1, 1)
+    aug[1] = 1
+    want_vol, want_miss = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"],
+                                                   cv["K"], cv["inv_K"], cv["bins"], look_img, cv_min, aug, set_1, pool,
+                                                   1, 0.7)
+    occ = (O.occlusion_batch(look_img, H // 4, W // 4)[:, 0] > 0).float()
+    assert 0.02 < float(occ.mean()) < 0.5
+    mode = raw.OCC_SET_1 if set_1 else (raw.OCC_POOL if pool else raw.OCC_NONE)
+    out = _run(h, dev, cv, cv_min=cv_min, occ=occ.to(dev), occ_mode=mode, pool_radius=1, pool_th=0.7,
+               aug_mask=aug.to(dev))
+    assert torch.equal(out["missing_mask"].cpu(), want_miss)
+    assert torch.equal(out["cost_volume"].cpu(), want_vol)
+    if mode != raw.OCC_NONE:   # the fill really changed something, and only on the un-augmented sample
+        plain, _ = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
+                                            cv["inv_K"], cv["bins"], look_img, cv_min, aug, False, False, 1, 0.7)
+        assert not torch.equal(plain[0], want_vol[0]) and torch.equal(plain[1], want_vol[1])
