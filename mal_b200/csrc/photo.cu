@@ -122,8 +122,21 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
   // ---- phase B: losses, selection, weights -----------------------------------------------
   const bool automask = a.identity_min != nullptr;
   float acc_loss = 0.0f, acc_w = 0.0f;
-  for (int i = tid; i < tl.LN; i += PH_NT) {
-    int ly = i / tl.LW, lx = i - ly * tl.LW;
+  // Work is handed out in warp-sized tasks so that the 32 lanes of a task read 32 consecutive
+  // words of a value-tile row (conflict-free): LH row tasks cover columns 0..31 of the loss
+  // region; the LW-32 leftover columns (the gradient halo) are packed column-major into extra tasks.
+  const int extra_items = (tl.LW - 32) * tl.LH;
+  const int ntasks = tl.LH + (extra_items + 31) / 32;
+  for (int task = tid >> 5; task < ntasks; task += PH_NT / 32) {
+    int ly, lx;
+    if (task < tl.LH) {
+      ly = task; lx = tid & 31;
+    } else {
+      const int j = (task - tl.LH) * 32 + (tid & 31);
+      if (j >= extra_items) continue;
+      ly = j % tl.LH; lx = 32 + j / tl.LH;
+    }
+    const int i = ly * tl.LW + lx;
     int gy = y0 - tl.HL + ly, gx = x0 - tl.HL + lx;
     bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
     if (!in_img) {
@@ -131,6 +144,11 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
       continue;
     }
     const int vc = (ly + tl.HV - tl.HL) * tl.VW + (lx + tl.HV - tl.HL);  // window centre in value tile
+    // per-pixel planes are fetched now so their latency hides behind the SSIM arithmetic
+    const size_t po = (size_t)b * HW + (size_t)gy * W + gx;
+    float p_ident = 0.0f, p_noise = 0.0f, p_mask = 1.0f;
+    if (automask) { p_ident = __ldg(a.identity_min + po); p_noise = __ldg(a.noise + po); }
+    if (a.pixel_mask) p_mask = __ldg(a.pixel_mask + po);
     float ssum[4], lsum[4];
     float cf0[9], cf1[9];
 #pragma unroll
@@ -183,14 +201,13 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
         if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
       }
     }
-    const size_t po = (size_t)b * HW + (size_t)gy * W + gx;
     int mbit = 1;
     if (automask) {
-      float ident = xadd(__ldg(a.identity_min + po), xmul(__ldg(a.noise + po), 0.00001f));
+      float ident = xadd(p_ident, xmul(p_noise, 0.00001f));
       mbit = (ident < rmin) ? 0 : 1;  // argmin([reproj, identity]) == 0, first index wins ties
     }
     float w = (float)mbit;
-    if (a.pixel_mask) w = xmul(w, __ldg(a.pixel_mask + po));
+    if (a.pixel_mask) w = xmul(w, p_mask);
     if (a.sample_mask) w = xmul(w, xsub(1.0f, __ldg(a.sample_mask + b)));
     const bool interior = ly >= tl.HL && ly < tl.HL + PH_TH && lx >= tl.HL && lx < tl.HL + PH_TW;
     if (interior) {
