@@ -46,7 +46,6 @@ constexpr int CV_WARPS = 4;    // channel chunks in flight
 constexpr int CV_NT = CV_PX * CV_WARPS;
 constexpr int CV_BG = 16;      // bins per group
 constexpr int CV_CHUNK = 16;   // channels per chunk (cascade_sum level step)
-constexpr int CV_MAXF = 8;     // lookup frames
 constexpr int CV_DEFAULT_MINB = 4;
 
 struct CvGeom {

@@ -65,6 +65,11 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
   float* lw = coef + 9 * tl.LN;                         // [LN] weights (GRAD)
   int* lsel = reinterpret_cast<int*>(lw + tl.LN);       // [LN] selected warped candidate or -1
 
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+    // the finalize kernel's ticket (see photo_finalize_kernel); it launches after this kernel ends
+    float* tail = a.partials + (size_t)gridDim.x * gridDim.y * gridDim.z * PH_NPART;
+    *reinterpret_cast<unsigned*>(tail + (size_t)gridDim.z * 2) = 0u;
+  }
   // ---- phase 0: camera constants --------------------------------------------------------
   if (WARP) {
     if (tid < 24) {
@@ -359,52 +364,48 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
 }
 
 // Deterministic reduction of the per-CTA partials: grad_P (B,2,12) and the masked mean.
-// One warp per (sample, value) pair, four pairs and eight tiles per lane in flight at a time so the
-// whole reduction is a handful of memory round trips; every sum is formed in a fixed order.
-constexpr int PF_PAIRS = 4, PF_TILES = 8;
-__global__ void __launch_bounds__(1024) photo_finalize_kernel(const float* __restrict__ partials, int batch,
-                                                             int tiles, float* __restrict__ sums,
-                                                             float* __restrict__ grad_P) {
-  double* per_sample = reinterpret_cast<double*>(dyn_smem());  // [batch][2]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int v0 = grad_P ? 0 : 24;                 // without gradients only the two loss sums are live
-  const int nv = PH_NPART - v0, npairs = batch * nv;
-  for (int base = warp * PF_PAIRS; base < npairs; base += nwarp * PF_PAIRS) {
-    double s[PF_PAIRS];
-#pragma unroll
-    for (int u = 0; u < PF_PAIRS; u++) s[u] = 0.0;
+// One CTA per sample, one warp per value, every lane keeps PF_TILES loads in flight, so the
+// whole reduction is one or two memory round trips spread over B SMs.  The cross-sample sum of the
+// two loss scalars is done by whichever CTA finishes last (ticket), in sample order, so the
+// result does not depend on scheduling.  The ticket word lives behind the partials and is
+// zeroed by photo_kernel's first CTA (stream order makes that visible here).
+constexpr int PF_TILES = 8;
+__global__ void __launch_bounds__(PH_NPART * 32) photo_finalize_kernel(float* __restrict__ partials, int batch,
+                                                                      int tiles, float* __restrict__ sums,
+                                                                      float* __restrict__ grad_P) {
+  const int b = blockIdx.x, v = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tail = partials + (size_t)batch * tiles * PH_NPART;       // [batch][2] per-sample sums, then the ticket
+  unsigned* ticket = reinterpret_cast<unsigned*>(tail + (size_t)batch * 2);
+  __shared__ bool last;
+  if (grad_P != nullptr || v >= 24) {   // without gradients only the two loss sums are live
+    double s = 0.0;
     for (int t0 = 0; t0 < tiles; t0 += 32 * PF_TILES) {
-      float x[PF_PAIRS][PF_TILES];
+      float x[PF_TILES];
 #pragma unroll
-      for (int u = 0; u < PF_PAIRS; u++) {
-        const int pair = base + u;
-        const int b = pair / nv, v = v0 + pair - b * nv;
-#pragma unroll
-        for (int k = 0; k < PF_TILES; k++) {
-          const int t = t0 + k * 32 + lane;
-          x[u][k] = (pair < npairs && t < tiles) ? __ldg(partials + ((size_t)b * tiles + t) * PH_NPART + v) : 0.0f;
-        }
+      for (int k = 0; k < PF_TILES; k++) {
+        const int t = t0 + k * 32 + lane;
+        x[k] = t < tiles ? partials[((size_t)b * tiles + t) * PH_NPART + v] : 0.0f;
       }
 #pragma unroll
-      for (int u = 0; u < PF_PAIRS; u++)
-#pragma unroll
-        for (int k = 0; k < PF_TILES; k++) s[u] += (double)x[u][k];
+      for (int k = 0; k < PF_TILES; k++) s += (double)x[k];
     }
-#pragma unroll
-    for (int u = 0; u < PF_PAIRS; u++) {
-      const int pair = base + u;
-      const double r = warp_sum(s[u]);
-      if (lane == 0 && pair < npairs) {
-        const int b = pair / nv, v = v0 + pair - b * nv;
-        if (v < 24) grad_P[b * 24 + v] = (float)r;
-        else per_sample[b * 2 + (v - 24)] = r;
-      }
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (v < 24) grad_P[b * 24 + v] = (float)s;
+      else tail[b * 2 + (v - 24)] = (float)s;
     }
   }
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == (unsigned)(batch - 1));
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
     double ls = 0.0, ws = 0.0;
-    for (int b = 0; b < batch; b++) { ls += per_sample[b * 2]; ws += per_sample[b * 2 + 1]; }
+    for (int i = 0; i < batch; i++) {
+      ls += (double)reinterpret_cast<volatile float*>(tail)[i * 2];
+      ws += (double)reinterpret_cast<volatile float*>(tail)[i * 2 + 1];
+    }
     float lf = (float)ls, wf = (float)ws;
     sums[0] = lf;
     sums[1] = wf;
@@ -428,7 +429,7 @@ using namespace mal;
 
 extern "C" size_t mal_photo_partials_floats(int batch, int height, int width) {
   size_t tiles = (size_t)((width + PH_TW - 1) / PH_TW) * ((height + PH_TH - 1) / PH_TH);
-  return (size_t)batch * tiles * PH_NPART;
+  return (size_t)batch * tiles * PH_NPART + (size_t)batch * 2 + 4;   // + per-sample sums + ticket
 }
 
 extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream) {
@@ -474,7 +475,7 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   }
   int rc = check_launch("photo_kernel");
   if (rc) return rc;
-  launch(photo_finalize_kernel, dim3(1), dim3(1024), (size_t)a.batch * 16 + 16, st, (const float*)a.partials,
-         a.batch, (int)(grid.x * grid.y), a.sums, (grad && a.mode == MAL_PHOTO_WARP) ? a.grad_P : (float*)nullptr);
+  launch(photo_finalize_kernel, dim3(a.batch), dim3(PH_NPART * 32), 0, st, a.partials, a.batch,
+         (int)(grid.x * grid.y), a.sums, (grad && a.mode == MAL_PHOTO_WARP) ? a.grad_P : (float*)nullptr);
   return check_launch("photo_finalize_kernel");
 }
