@@ -201,14 +201,14 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
     # algorithmic bytes per launch (fp32, every tensor once):
     cases = [
         # target 12 + src 24 + syn 24 + disp 4 + identity 4 + noise 4 read; min_reproj 4 + sel 1 + grad 4 written
-        ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass)", photo4, 81 * px),
+        ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass)", photo4, 81 * px, "photo_teacher"),
         # target 12 + src 24 + disp 4 + mask 4 read; min_reproj 4 + sel 1 + grad 4 written
-        ("photo_kernel<WARP,GRAD> 2 candidates + masks (student pass)", photo2, 53 * px),
+        ("photo_kernel<WARP,GRAD> 2 candidates + masks (student pass)", photo2, 53 * px, "photo_student"),
         # pack: 2*C*4 read + 2*C*4 written; sweep: 2*C*4 read, bins*4 + 12 written
-        ("cv_pack + cv_sweep_kernel (cost-volume head)", cv, (3 * 2 * C * 4 + nb * 4 + 12) * lowpx),
+        ("cv_pack x2 + cv_sweep_kernel (cost-volume head)", cv, (3 * 2 * C * 4 + nb * 4 + 12) * lowpx, "cost_volume"),
     ]
     out = []
-    for name, fn, nbytes in cases:
+    for name, fn, nbytes, key in cases:
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
@@ -220,8 +220,8 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / iters * 1e3
         gbs = nbytes / (us * 1e-6) / 1e9
-        out.append({"kernel": name, "us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_gbs": gbs,
-                    "frac": gbs / peak_gbs})
+        out.append({"kernel": name, "key": key, "us_per_launch": us, "algorithmic_bytes": nbytes,
+                    "achieved_gbs": gbs, "frac": gbs / peak_gbs})
     return out
 
 
@@ -315,7 +315,7 @@ def ours(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom["kernel"].split("<")[0].split(" ")[0])
+            traffic = json.load(open(tpath)).get(dom["key"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.batch),
@@ -325,7 +325,8 @@ def ours(args):
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs,
                              "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                              "us_per_launch": dom["us_per_launch"], "algorithmic_bytes": dom["algorithmic_bytes"],
-                             "limiter": "fp32 issue (exact-arithmetic SSIM / bilinear), see DESIGN.md"},
+                             "limiter": "fp32 issue, not HBM: bit-exact fp32 arithmetic (DESIGN.md section 4); ncu: "
+                                        "61% issue slots busy, 1.8% DRAM throughput (profiles/r1_notes.md)"},
                 "kernels": roof,
                 # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
                 "step_hbm": {"survey_bytes_per_frame": 20636160,

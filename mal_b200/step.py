@@ -112,10 +112,14 @@ def _head_op(cur, look, poses, K, inv_K, bins):
     return cv, low, conf
 
 
-def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False):
+def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None):
     """The same step as `step_losses` + backward, as 24 launches of libmal_b200 and nothing else:
     no autograd graph, no intermediate depth maps, no one-element torch kernels.  The scalar tail
     and the gradient hand-over are `mal_step_combine` (csrc/step.cu).  Needs opt.distil.
+
+    `side_streams` (two CUDA streams) lets the three independent chains of the step - the cost-volume
+    head, the teacher + ensemble passes, and the two smoothness terms - run as parallel branches
+    (of the captured graph), so the small kernels and the last waves of the big ones overlap.
 
     Returns (scalars, grads, outputs): scalars = [total, loss_list[0], loss_list[1], reproj_loss/0
     of the teacher, of the student, consistency, teacher loss, student loss]; grads follow LEAVES."""
@@ -128,41 +132,83 @@ def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False):
     T = [b["T_-1"], b["T_1"]]
     mono, multi = b["mono_disp"].detach(), b["multi_disp"].detach()
     geom = dict(K=b["K"], inv_K=b["inv_K"], T=[t.detach() for t in T], min_depth=lo, max_depth=hi)
-    head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"], poses=b["relative_poses"],
-                           K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"], apply_confidence=True, want_missing=False)
+
+    main = torch.cuda.current_stream(tgt.device) if tgt.is_cuda else None
+    branch = _Branches(main, side_streams)
+
+    with branch(0):   # cost-volume head
+        head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"],
+                               poses=b["relative_poses"], K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"],
+                               apply_confidence=True, want_missing=False)
+    with branch(1):   # smoothness of both disparities
+        sm_t = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True)
+        sm_s = raw.smooth(handle, disp=multi, img=tgt, normalise=True, with_grad=True)
+    # main chain: identity -> teacher -> ensemble
     ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
     teacher = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None, depth=mono,
                         identity_min=ident, noise=b["noise_mono"], with_grad=True, **geom)
-    sm_t = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True)
-    mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
-                             mono_is_disp=True, min_depth=lo, max_depth=hi)
     ens = None
     if not opt.no_ens:
         ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
                         **geom)["min_reproj"]
+    branch.join(0)
+    mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
+                             mono_is_disp=True, min_depth=lo, max_depth=hi)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
     student = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
                         depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, **geom)
     dual = bool(opt.dual_distil) and ens is None
-    main = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
-                          mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
-                          inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
-    sm_s = raw.smooth(handle, disp=multi, img=tgt, normalise=True, with_grad=True)
+    mt = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
+                        mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
+                        inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
+    branch.join(1)
     comb = raw.step_combine(handle, batch=B, height=H, width=W, weights=weights if opt.loss_blc else None,
                             sums_teacher=teacher["sums"], sums_student=student["sums"], smooth_teacher=sm_t["loss"],
-                            smooth_student=sm_s["loss"], main_sums=main["sums"], K=b["K"],
+                            smooth_student=sm_s["loss"], main_sums=mt["sums"], K=b["K"],
                             gd_teacher=teacher["grad_depth"], gs_teacher=sm_t["grad_disp"],
                             gP_teacher=teacher["grad_P"], gd_student=student["grad_depth"],
-                            gs_student=sm_s["grad_disp"], g_cons=main["grad_cons"], g_distil=main["grad_distil"],
-                            g_distil_mono=main["grad_distil_mono"])
+                            gs_student=sm_s["grad_disp"], g_cons=mt["grad_cons"], g_distil=mt["grad_distil"],
+                            g_distil_mono=mt["grad_distil_mono"])
     outputs = {"cost_volume": head["cost_volume"], "lowest_cost": head["lowest_cost"],
                "confidence_mask": head["confidence"], "consistency_mask": mask,
-               "mal_distil_index": main["distil_index"], "consistency_target/0": main["consistency_target"],
+               "mal_distil_index": mt["distil_index"], "consistency_target/0": mt["consistency_target"],
                ("mal_selection", 0): student["selection"], "mono_reproj": teacher["min_reproj"],
                "multi_reproj": student["min_reproj"], "ensemble_reproj": ens,
-               "_keepalive": (head, teacher, student, sm_t, sm_s, main, comb, ident)}
+               "_keepalive": (head, teacher, student, sm_t, sm_s, mt, comb, ident)}
     grads = (comb["grad_disp_teacher"], comb["grad_disp_student"], comb["grad_T"][0], comb["grad_T"][1])
     return comb["scalars"], grads, outputs
+
+
+class _Branches:
+    """Fork / join of side streams off the current stream (a no-op without side streams, e.g. on
+    the CPU twin used by the tests).  Works inside CUDA-graph capture: forks and joins are events."""
+
+    def __init__(self, main, side):
+        self.main, self.side = main, side if (side and main is not None) else None
+
+    def __call__(self, i):
+        return _Branch(self, i)
+
+    def join(self, i):
+        if self.side is not None:
+            self.main.wait_stream(self.side[i])
+
+
+class _Branch:
+    def __init__(self, owner, i):
+        self.o, self.i, self.ctx = owner, i, None
+
+    def __enter__(self):
+        if self.o.side is not None:
+            st = self.o.side[self.i]
+            st.wait_stream(self.o.main)
+            self.ctx = torch.cuda.stream(st)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 class MalStep:
@@ -173,7 +219,7 @@ class MalStep:
     input bytes than the L2 holds."""
 
     def __init__(self, opt, device="cuda:0", use_graph=True, slots=1, num_train_data=1 << 20,
-                 lambda_for_adjust=0.0, fused=True):
+                 lambda_for_adjust=0.0, fused=True, branches=True):
         self.opt, self.device, self.use_graph = opt, torch.device(device), use_graph
         self.fused = fused and opt.distil   # libmal_b200-only schedule; False: op-by-op through autograd
         self.slots = [dict(buf=None, graph=None, static=None) for _ in range(slots)]
@@ -185,6 +231,10 @@ class MalStep:
         self._scalars_host = torch.empty(8, dtype=torch.float32).pin_memory()
         self.launches_per_step = None
         self.copy_stream = torch.cuda.Stream(self.device)
+        # parallel branches only inside a captured graph: there every buffer is static, so tensors
+        # produced on one stream and consumed on another need no allocator bookkeeping
+        self.side_streams = ([torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+                             if (branches and use_graph) else None)
 
     # -- buffers -------------------------------------------------------------------------------
     def load_async(self, batch, slot=0):
@@ -224,7 +274,7 @@ class MalStep:
         if self.fused:
             from . import _capi
             with torch.no_grad():
-                return fused_step(_capi.lib(), buf, self.opt, self.weights)
+                return fused_step(_capi.lib(), buf, self.opt, self.weights, side_streams=self.side_streams)
         leaves = {k: buf[k] for k in LEAVES}
         total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights)
         grads = torch.autograd.grad(total, [leaves[k] for k in LEAVES])
