@@ -85,3 +85,16 @@ def test_cost_volume_matches_reference():
     low, idx = O.lowest_cost(vol, tt("in_bins"))
     assert np.array_equal(idx.numpy().astype(np.int32), g["ref_argmin"])
     assert rel_err(low, g["ref_lowest_cost"]) < 1e-6
+
+
+def test_forward_warp_matches_reference():
+    """dynamicdepth/rigid_warp.forward_warp (third-party coalesce restated, see make_golden.py)."""
+    g = load_npz("forward_warp.npz")
+    tt = lambda k: torch.from_numpy(g[k].copy())
+    img_w, depth_w, valid = O.forward_warp(tt("in_img"), tt("in_depth"), tt("in_pose"), tt("in_K"), 3)
+    assert np.array_equal(valid.numpy().astype(np.uint8), g["ref_valid"])
+    assert rel_err(depth_w, g["ref_depth_w"]) < 1e-6
+    assert rel_err(img_w, g["ref_img_w"]) < 1e-6
+    mats = O.forward_warp_matrices(tt("in_pose"), tt("in_K"), 3)
+    for m, k in zip(mats, ("in_Ku_inv", "in_K_inv", "in_proj")):
+        assert rel_err(m, g[k]) < 1e-6
