@@ -1,0 +1,123 @@
+"""Full-size (BASELINE.json configs[1]: batch 12, 192x640, 96 bins x 64 channels) checks on the GPU
+through properties that do not need the oracle to finish in seconds:
+
+  * batch sharding: a batch of 12 equals 12 batches of 1 (per-pixel outputs bit-exact; the masked
+    sums add up) - the property the data-parallel split relies on;
+  * the fused WARP kernel equals the PRED kernel fed with materialised warps (two code paths);
+  * cost-volume self-consistency: arg-min / lowest_cost / confidence / missing fill agree with the
+    volume they were derived from;
+  * linearity of the masked sums in the per-pixel weights;
+  * one oracle spot check on a single sample at full resolution.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mal_b200 import _capi, layers, raw, step as S
+from mal_b200.utils.synthetic import to_device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    opt = S.default_opt(12)
+    b = to_device(S.synthetic_batch(opt, seed=2024), torch.device("cuda:0"))
+    return opt, b, _capi.lib()
+
+
+def _teacher(h, b, sl=slice(None), **kw):
+    tgt, src = b["color_0"][sl], [b["color_-1"][sl], b["color_1"][sl]]
+    ident = raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+    return raw.photo(h, target=tgt, src=src, syn=[b["syn_-1"][sl], b["syn_1"][sl]], depth=b["mono_disp"][sl].detach(),
+                     K=b["K"][sl], inv_K=b["inv_K"][sl], T=[b["T_-1"][sl].detach(), b["T_1"][sl].detach()],
+                     identity_min=ident, noise=b["noise_mono"][sl], with_grad=True, **kw)
+
+
+def test_photo_batch_sharding(full):
+    opt, b, h = full
+    whole = _teacher(h, b)
+    S_sum, W_sum = 0.0, 0.0
+    for i in range(opt.batch_size):
+        one = _teacher(h, b, slice(i, i + 1))
+        for k in ("min_reproj", "selection", "grad_depth"):
+            assert torch.equal(one[k], whole[k][i:i + 1]), (k, i)
+        assert torch.allclose(one["grad_P"], whole["grad_P"][i:i + 1], rtol=1e-5, atol=1e-7)
+        S_sum += float(one["sums"][0])
+        W_sum += float(one["sums"][1])
+    assert abs(S_sum - float(whole["sums"][0])) <= 1e-5 * abs(S_sum)
+    assert W_sum == float(whole["sums"][1])
+
+
+def test_fused_warp_equals_materialised_warp(full):
+    opt, b, h = full
+    H, W, B = opt.height, opt.width, opt.batch_size
+    depth = layers.disp_to_depth(b["multi_disp"].detach(), opt.min_depth, opt.max_depth)[1]
+    cam = raw.backproject(h, depth, b["inv_K"])
+    preds = []
+    for f in (-1, 1):
+        grid, _ = raw.project3d(h, cam, b["K"], b["T_%d" % f].detach(), H, W)
+        preds.append(F.grid_sample(b["color_%d" % f], grid, padding_mode="border", align_corners=True))
+    mask = (b["noise_main"][:, 0] > 0).float()
+    fused = raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], depth=b["multi_disp"].detach(),
+                      K=b["K"], inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()], pixel_mask=mask)
+    classic = raw.photo(h, target=b["color_0"], src=preds, mode=raw.PHOTO_PRED, pixel_mask=mask)
+    # torch's CUDA grid_sample rounds differently from the CPU kernel the fused path reproduces:
+    # compare selections where the two candidates are not within rounding of each other
+    close = (fused["min_reproj"] - classic["min_reproj"]).abs() <= 1e-5
+    assert float(close.float().mean()) > 0.9999
+    agree = (fused["selection"] == classic["selection"]).float().mean()
+    assert float(agree) > 0.999
+    assert abs(float(fused["sums"][2]) - float(classic["sums"][2])) <= 1e-5 * float(classic["sums"][2])
+
+
+def test_sums_are_linear_in_the_pixel_weights(full):
+    opt, b, h = full
+    kw = dict(target=b["color_0"], src=[b["color_-1"], b["color_1"]], depth=b["multi_disp"].detach(), K=b["K"],
+              inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()])
+    m1 = (b["noise_main"][:, 0] > 0.3).float()
+    m2 = (b["noise_mono"][:, 0] < -0.2).float()
+    s1, s2 = raw.photo(h, pixel_mask=m1, **kw)["sums"], raw.photo(h, pixel_mask=m2, **kw)["sums"]
+    s12 = raw.photo(h, pixel_mask=m1 + 2 * m2, **kw)["sums"]
+    assert abs(float(s12[0]) - float(s1[0] + 2 * s2[0])) <= 2e-5 * float(s12[0])
+    assert abs(float(s12[1]) - float(s1[1] + 2 * s2[1])) <= 1e-6 * float(s12[1])
+
+
+def test_cost_volume_self_consistency_and_sharding(full):
+    opt, b, h = full
+    kw = lambda sl: dict(current=b["current_feats"][sl], lookup=b["lookup_feats"][sl], poses=b["relative_poses"][sl],
+                         K=b["K2"][sl], inv_K=b["inv_K2"][sl], bins=b["bins"])
+    out = raw.cost_volume(h, **kw(slice(None)))
+    cv, miss, conf, idx, low = (out[k] for k in ("cost_volume", "missing_mask", "confidence", "argmin", "lowest_cost"))
+    assert cv.shape == (12, 96, 48, 160)
+    viz = torch.where(cv == 0, torch.full_like(cv, 100.0), cv)
+    mn, am = viz.min(1)
+    assert torch.equal(am.int(), idx)                                     # first-index arg-min
+    assert torch.equal(low, 1 / b["bins"][idx.long()])
+    assert torch.equal(conf, ((cv * (1 - miss)) > 0).sum(1).eq(96).float())
+    mx = (cv * (1 - miss)).max(1, keepdim=True)[0]
+    assert torch.equal(torch.where(miss > 0, mx.expand_as(cv), cv), cv)   # missing entries hold the per-pixel max
+    assert 0.3 < float(conf.mean()) < 0.95
+    for i in (0, 7, 11):
+        one = raw.cost_volume(h, **kw(slice(i, i + 1)))
+        for k in ("cost_volume", "missing_mask", "confidence", "argmin", "lowest_cost"):
+            assert torch.equal(one[k], out[k][i:i + 1]), (k, i)
+    masked = raw.cost_volume(h, apply_confidence=True, want_missing=False, **kw(slice(None)))["cost_volume"]
+    assert torch.equal(masked, cv * conf.unsqueeze(1))
+
+
+def test_full_resolution_sample_against_oracle(full):
+    """One sample at 192x640 / 96 bins x 64 channels through the whole step oracle (a few seconds)."""
+    from oracle.step_oracle import oracle_step
+    opt1 = S.default_opt(1)
+    b1 = S.synthetic_batch(opt1, seed=77)
+    total, loss_list, grads, aux = oracle_step(b1, opt1)
+    scalars, g, outputs = S.fused_step(_capi.lib(), to_device(b1, torch.device("cuda:0")), opt1,
+                                       torch.tensor([0.5, 0.5], device="cuda:0"))
+    assert abs(float(scalars[0]) - float(total)) <= 1e-5 * abs(float(total))
+    assert torch.equal(outputs["cost_volume"].cpu(), aux["cv"])
+    assert torch.equal(outputs["consistency_mask"].cpu(), aux["mask"])
+    assert np.array_equal(outputs["mal_distil_index"].cpu().numpy(), aux["distil_idx"].numpy().astype(np.uint8))
+    for a, bb in zip(g, grads):
+        assert float((a.cpu() - bb).abs().max()) <= 1e-4 * float(bb.abs().max())
