@@ -312,6 +312,34 @@ typedef struct mal_forward_warp_args {
 
 int mal_forward_warp(const mal_forward_warp_args* args, mal_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MAL temporal hint: synthesis of the motion-compensated source images from matched instance
+ * masks.
+ *
+ * mal_dynamic_instance replaces generate_dynamic_instance (manydepth/dyn_utils.py:38-119):
+ * mask extents (:52-78), half displacement with round-half-even and the `replace` dead zone
+ * (:80-100), background swap (:102-112), fill_dynamic_obj for both frames (:114-118).
+ * mal_fill_dynamic_obj replaces fill_dynamic_obj (:5-36) with caller-given displacements.
+ * Masks are bool tensors (1 byte per element).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_dynamic_instance_args {
+  int32_t num, channels, height, width; /* N matched instances, image (C,H,W), C <= 4          */
+  int32_t replace;
+  const uint8_t* mask_last;  /* (N,H,W) instance masks in the warped frame -1                  */
+  const uint8_t* mask_next;  /* (N,H,W) ... frame +1, same instance order                      */
+  const float* img_last;     /* (C,H,W) outputs[("color", -1, scale)][b]                       */
+  const float* img_next;     /* (C,H,W) outputs[("color", +1, scale)][b]                       */
+  float* ori_last;           /* (C,H,W) -> outputs[("syn", -1, scale)][b]                      */
+  float* ori_next;           /* (C,H,W) -> outputs[("syn", +1, scale)][b]                      */
+  int32_t* workspace;        /* 12 * N ints: extents [N][2][4] = (low, top, right, left), then
+                                deltas [4][N] = (dx_last, dy_last, dx_next, dy_next)            */
+} mal_dynamic_instance_args;
+
+int mal_dynamic_instance(const mal_dynamic_instance_args* args, mal_stream_t stream);
+int mal_fill_dynamic_obj(const uint8_t* mask, const int32_t* delta_x, const int32_t* delta_y, const float* source,
+                         const float* img, int num, int channels, int height, int width, float* out,
+                         mal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,13 @@ class ForwardWarpArgs(C.Structure):
                                           "depth_w", "valid", "zbuf")]
 
 
+class DynamicInstanceArgs(C.Structure):
+    """struct mal_dynamic_instance_args."""
+    _fields_ = [(n, C.c_int32) for n in ("num", "channels", "height", "width", "replace")] + \
+               [(n, C.c_void_p) for n in ("mask_last", "mask_next", "img_last", "img_next", "ori_last", "ori_next",
+                                          "workspace")]
+
+
 class CostVolumeArgs(C.Structure):
     """struct mal_cost_volume_args."""
     _fields_ = [
@@ -120,6 +127,8 @@ EXPORTS = {
     "mal_matching_mask": (C.c_int, [C.POINTER(MatchingMaskArgs), C.c_void_p]),
     "mal_step_combine": (C.c_int, [C.POINTER(StepCombineArgs), C.c_void_p]),
     "mal_forward_warp": (C.c_int, [C.POINTER(ForwardWarpArgs), C.c_void_p]),
+    "mal_dynamic_instance": (C.c_int, [C.POINTER(DynamicInstanceArgs), C.c_void_p]),
+    "mal_fill_dynamic_obj": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),

@@ -19,7 +19,7 @@ from torch import Tensor
 from . import _capi, raw
 
 __all__ = ["photo", "reprojection_loss_map", "smooth", "main_terms", "cost_volume", "matching_mask",
-           "backproject", "project3d", "ssim", "forward_warp"]
+           "backproject", "project3d", "ssim", "forward_warp", "dynamic_instance", "fill_dynamic_obj"]
 
 
 def _lib(t: Tensor):
@@ -476,3 +476,43 @@ def forward_warp(img, depth, pose, K, Ku_inv, K_inv, proj, upscale=3):
     with torch.no_grad():
         c = lambda t: t.detach().contiguous()
         return _forward_warp_op(c(img), c(depth), c(pose), c(K), c(Ku_inv), c(K_inv), c(proj), int(upscale))
+
+
+# --------------------------------------------------------------------------------------------
+# MAL temporal hint (integer / byte work, no gradient)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("mal_b200::dynamic_instance", mutates_args=())
+def _dynamic_instance_op(mask_last: Tensor, mask_next: Tensor, img_last: Tensor, img_next: Tensor,
+                         replace: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    a, b, d = raw.dynamic_instance(_lib(img_last), mask_last=mask_last, mask_next=mask_next, img_last=img_last,
+                                   img_next=img_next, replace=replace)
+    return a, b, d.clone()
+
+
+@_dynamic_instance_op.register_fake
+def _(mask_last, mask_next, img_last, img_next, replace):
+    return (img_last.new_empty(img_last.shape), img_next.new_empty(img_next.shape),
+            img_last.new_empty((4, mask_last.shape[0]), dtype=torch.int32))
+
+
+def dynamic_instance(mask_last, mask_next, img_last, img_next, replace=False):
+    """-> (ori_last, ori_next, deltas (4,N) int32 = dx_last, dy_last, dx_next, dy_next)."""
+    with torch.no_grad():
+        return _dynamic_instance_op(mask_last.contiguous(), mask_next.contiguous(), img_last.detach().contiguous(),
+                                    img_next.detach().contiguous(), bool(replace))
+
+
+@torch.library.custom_op("mal_b200::fill_dynamic_obj", mutates_args=())
+def _fill_dynamic_obj_op(mask: Tensor, delta_x: Tensor, delta_y: Tensor, source: Tensor, img: Tensor) -> Tensor:
+    return raw.fill_dynamic_obj(_lib(img), mask=mask, delta_x=delta_x, delta_y=delta_y, source=source, img=img)
+
+
+@_fill_dynamic_obj_op.register_fake
+def _(mask, delta_x, delta_y, source, img):
+    return img.new_empty(img.shape)
+
+
+def fill_dynamic_obj(mask, delta_x, delta_y, source, img):
+    with torch.no_grad():
+        return _fill_dynamic_obj_op(mask.contiguous(), delta_x, delta_y, source.detach().contiguous(),
+                                    img.detach().contiguous())

@@ -345,3 +345,45 @@ def forward_warp(handle, *, img, depth, pose, K, Ku_inv, K_inv, proj, upscale=3)
     _capi.check(handle.mal_forward_warp(C.byref(a), _stream(img)), handle)
     LAUNCHES[0] += 2
     return img_w, depth_w, valid
+
+
+def _mask_u8(m, name, shape):
+    if m.dtype not in (torch.bool, torch.uint8):
+        raise TypeError(f"{name}: expected a bool mask, got {m.dtype}")
+    if tuple(m.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(m.shape)}")
+    return m.contiguous().view(torch.uint8)
+
+
+def dynamic_instance(handle, *, mask_last, mask_next, img_last, img_next, replace=False):
+    """mal_dynamic_instance -> (ori_last, ori_next, deltas (4,N) int32)."""
+    N, H, W = mask_last.shape
+    Cn = img_last.shape[0]
+    ml, mn = _mask_u8(mask_last, "mask_last", (N, H, W)), _mask_u8(mask_next, "mask_next", (N, H, W))
+    il, inx = _f32(img_last, "img_last", (Cn, H, W)), _f32(img_next, "img_next", (Cn, H, W))
+    dev = _same_device([ml, mn, il, inx])
+    ol, on = torch.empty_like(il), torch.empty_like(inx)
+    ws = torch.empty((12 * N,), dtype=torch.int32, device=dev)
+    a = _capi.DynamicInstanceArgs()
+    a.num, a.channels, a.height, a.width, a.replace = N, Cn, H, W, int(bool(replace))
+    a.mask_last, a.mask_next, a.img_last, a.img_next = _ptr(ml), _ptr(mn), _ptr(il), _ptr(inx)
+    a.ori_last, a.ori_next, a.workspace = _ptr(ol), _ptr(on), _ptr(ws)
+    _capi.check(handle.mal_dynamic_instance(C.byref(a), _stream(il)), handle)
+    LAUNCHES[0] += 3
+    return ol, on, ws[8 * N:].view(4, N)
+
+
+def fill_dynamic_obj(handle, *, mask, delta_x, delta_y, source, img):
+    """mal_fill_dynamic_obj -> (C,H,W)."""
+    N, H, W = mask.shape
+    Cn = img.shape[0]
+    m = _mask_u8(mask, "mask", (N, H, W))
+    src, im = _f32(source, "source", (Cn, H, W)), _f32(img, "img", (Cn, H, W))
+    dx = delta_x.to(torch.int32).contiguous()
+    dy = delta_y.to(torch.int32).contiguous()
+    _same_device([m, src, im, dx, dy])
+    out = torch.empty_like(im)
+    _capi.check(handle.mal_fill_dynamic_obj(_vp(m), _vp(dx), _vp(dy), _vp(src), _vp(im), N, Cn, H, W, _vp(out),
+                                            _stream(im)), handle)
+    LAUNCHES[0] += 1
+    return out

@@ -118,6 +118,33 @@ def make_cost_volume_inputs(batch=2, height=192, width=640, channels=64, num_loo
             "inv_K": inv_K, "bins": bins}
 
 
+def make_instance_masks(num=6, height=192, width=640, seed=99, max_shift=12, empty=None):
+    """Synthetic Mask2Former-shaped matched instance masks: `num` random
+    rectangles / ellipses in the "last" frame and the same shapes shifted by up to `max_shift`
+    pixels in the "next" frame; instance `empty` (if given) is absent from the next frame."""
+    gen = torch.Generator().manual_seed(seed)
+    ys = torch.arange(height).view(-1, 1).float()
+    xs = torch.arange(width).view(1, -1).float()
+    last = torch.zeros(num, height, width, dtype=torch.bool)
+    nxt = torch.zeros(num, height, width, dtype=torch.bool)
+    for n in range(num):
+        cy = float(torch.randint(0, height, (1,), generator=gen))
+        cx = float(torch.randint(0, width, (1,), generator=gen))
+        ry = float(torch.randint(3, max(4, height // 4), (1,), generator=gen))
+        rx = float(torch.randint(3, max(4, width // 6), (1,), generator=gen))
+        dy = float(torch.randint(-max_shift, max_shift + 1, (1,), generator=gen))
+        dx = float(torch.randint(-max_shift, max_shift + 1, (1,), generator=gen))
+        if n % 2 == 0:
+            shape = lambda oy, ox: ((ys - cy - oy).abs() <= ry) & ((xs - cx - ox).abs() <= rx)
+        else:
+            shape = lambda oy, ox: ((ys - cy - oy) / ry) ** 2 + ((xs - cx - ox) / rx) ** 2 <= 1.0
+        last[n] = shape(0.0, 0.0)
+        nxt[n] = shape(dy, dx)
+    if empty is not None:
+        nxt[empty] = False
+    return last, nxt
+
+
 def warp_by_depth(feat, depth, K, inv_K, T):
     """Sample `feat` (B,C,h,w) where the pixels of a view with `depth` (B,1,h,w) land after the
     rigid motion T: plain-torch pinhole geometry, used only to make synthetic feature pairs

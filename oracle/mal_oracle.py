@@ -697,6 +697,93 @@ def forward_warp(img, depth, pose, intrinsics, upscale=3, matrices=None):
 
 
 # --------------------------------------------------------------------------
+# MAL temporal hint: image synthesis from matched instance masks
+# --------------------------------------------------------------------------
+def fill_dynamic_obj(mask, delta_x, delta_y, source, img):
+    """manydepth/dyn_utils.py:5-36 (TorchScript in the reference; same tensor ops here)."""
+    N, H, W = mask.shape
+    start_hl = torch.max(torch.zeros_like(delta_x), delta_x)
+    end_hl = torch.min(torch.ones_like(delta_x) * H, H + delta_x)
+    start_hr = torch.max(torch.zeros_like(delta_x), -delta_x)
+    end_hr = torch.min(torch.ones_like(delta_x) * H, H - delta_x)
+    start_wl = torch.max(torch.zeros_like(delta_y), delta_y)
+    end_wl = torch.min(torch.ones_like(delta_y) * W, W + delta_y)
+    start_wr = torch.max(torch.zeros_like(delta_y), -delta_y)
+    end_wr = torch.min(W - delta_y, torch.ones_like(delta_y) * W)
+    chn = img.shape[0]
+    source_mv = torch.zeros((N, chn, H, W))
+    mask_mv = torch.zeros(mask.shape, dtype=torch.bool)
+    for i in range(len(mask)):
+        a, b, c, d = int(start_hl[i]), int(end_hl[i]), int(start_wl[i]), int(end_wl[i])
+        e, f, g, h = int(start_hr[i]), int(end_hr[i]), int(start_wr[i]), int(end_wr[i])
+        if b > a and d > c:
+            source_mv[i, :, a:b, c:d] = source[:, e:f, g:h]
+            mask_mv[i, a:b, c:d] = mask[i, e:f, g:h]
+    img_mv = mask_mv.unsqueeze(1).repeat(1, chn, 1, 1) * source_mv
+    img_sum = img_mv.sum(dim=0)
+    mask_or = torch.zeros((H, W), dtype=torch.bool)
+    for m in mask_mv:
+        mask_or = mask_or | m
+    return torch.where(mask_or, img_sum, img)
+
+
+def _extents(mask, grid, axis_sum, idx):
+    """low/top (or right/left) of one set of masks, manydepth/dyn_utils.py:56-78."""
+    inf = (mask.shape[1] + 1) * (mask.shape[2] + 1)
+    s = (mask * grid).sum(dim=axis_sum)
+    nz = torch.where(s == 0, 0, idx)
+    hi = nz.argmax(dim=1)
+    nz = torch.where(nz == 0, inf, nz)
+    lo = nz.argmin(dim=1)
+    return hi, lo
+
+
+def generate_dynamic_instance(mask_last, mask_next, img_last, img_next, replace=False):
+    """manydepth/dyn_utils.py:38-119 -> (ori_last, ori_next, (dx_last, dy_last, dx_next, dy_next))."""
+    mask_or = mask_last | mask_next
+    mask_or_ = torch.zeros_like(mask_or[0])
+    for m in mask_or:
+        mask_or_ = mask_or_ | m
+    num, H, W = mask_last.shape
+    x, y = torch.arange(H), torch.arange(W)
+    grid_h, grid_w = torch.meshgrid(x, y, indexing="ij")
+    grid_h, grid_w = grid_h.repeat(num, 1, 1), grid_w.repeat(num, 1, 1)
+    low_last, top_last = _extents(mask_last, grid_h, 2, x)
+    right_last, left_last = _extents(mask_last, grid_w, 1, y)
+    low_next, top_next = _extents(mask_next, grid_h, 2, x)
+    right_next, left_next = _extents(mask_next, grid_w, 1, y)
+    sl = torch.arange(num)
+    delta_x = torch.stack([low_next - low_last, top_next - top_last], dim=1)
+    delta_x_sel = delta_x[sl, delta_x.abs().argmax(dim=1)]
+    delta_y = torch.stack([right_next - right_last, left_next - left_last], dim=1)
+    delta_y_sel = delta_y[sl, delta_y.abs().argmax(dim=1)]
+    disp_x = torch.round(delta_x_sel / 2).long()
+    disp_y = torch.round(delta_y_sel / 2).long()
+    if replace:
+        dxl = torch.where(disp_x.abs() < 3, 0, disp_x)
+        dyl = torch.where(disp_y.abs() < 3, 0, disp_y)
+        dxn = torch.where(disp_x.abs() < 3, 0, -disp_x)
+        dyn = torch.where(disp_y.abs() < 3, 0, -disp_y)
+    else:
+        dxl, dyl, dxn, dyn = disp_x, disp_y, -disp_x, -disp_y
+    mask = mask_last & (~mask_next)
+    mask_bg = torch.zeros_like(mask[0])
+    for ms in mask:
+        mask_bg = mask_bg | ms
+    img_bg = torch.where(mask_bg, img_next, img_last)
+    mask2 = mask_next & (~mask_last)
+    mask_bg2 = torch.zeros_like(mask2[0])
+    for ms in mask2:
+        mask_bg2 = mask_bg2 | ms
+    img_bg2 = torch.where(mask_bg2, img_last, img_next)
+    syn_last = fill_dynamic_obj(mask_last, dxl, dyl, img_last, img_bg)
+    ori_last = torch.where(mask_or_, syn_last, img_last)
+    syn_next = fill_dynamic_obj(mask_next, dxn, dyn, img_next, img_bg2)
+    ori_next = torch.where(mask_or_, syn_next, img_next)
+    return ori_last, ori_next, (dxl, dyl, dxn, dyn)
+
+
+# --------------------------------------------------------------------------
 # host-side loss balancers (fp64 numpy state, as the reference)
 # --------------------------------------------------------------------------
 class LossBalancing:

@@ -367,9 +367,33 @@ def pin_dynamicdepth_match_features(seed=77):
     return bool(ok)
 
 
+def pin_image_synthesis():
+    """manydepth/dyn_utils.py generate_dynamic_instance / fill_dynamic_obj (TorchScript) against the
+    oracle restatement, on synthetic Mask2Former-shaped matched masks."""
+    from mal_b200.utils.synthetic import make_instance_masks
+    from . import mal_oracle as O
+    load_reference()
+    du = importlib.import_module("manydepth.dyn_utils")
+    ok = True
+    for N, H, W, seed, empty, replace in ((6, 48, 96, 1, None, False), (5, 40, 64, 2, 1, True),
+                                          (17, 32, 48, 3, None, False), (3, 24, 40, 4, 0, False)):
+        ml, mn = make_instance_masks(N, H, W, seed=seed, max_shift=9, empty=empty)
+        g = torch.Generator().manual_seed(seed)
+        il, inx = torch.rand(3, H, W, generator=g), torch.rand(3, H, W, generator=g)
+        gh, gw = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        want = du.generate_dynamic_instance(gh, gw, ml, mn, il, inx, replace)
+        got = O.generate_dynamic_instance(ml, mn, il, inx, replace)
+        ok &= _eq(f"generate_dynamic_instance N={N} last", got[0], want[0])
+        ok &= _eq(f"generate_dynamic_instance N={N} next", got[1], want[1])
+        dx, dy = torch.randint(-5, 6, (N,), generator=g), torch.randint(-7, 8, (N,), generator=g)
+        ok &= _eq(f"fill_dynamic_obj N={N}", O.fill_dynamic_obj(ml, dx, dy, il, inx), du.fill_dynamic_obj(ml, dx, dy, il, inx))
+    return bool(ok)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     good = run_pin()
     good &= pin_dynamicdepth_match_features()
+    good &= pin_image_synthesis()
     print("PINNED" if good else "PIN FAILED")
     sys.exit(0 if good else 1)
