@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 2
+#define MAL_ABI_VERSION 3
 
 enum {
   MAL_OK = 0,
@@ -96,6 +96,8 @@ typedef struct mal_photo_args {
   float* grad_P;            /* (B,2,12) WARP+grad: d(sum w*reproj)/d (K@T)[:3,:] per frame   */
   const float* depth_b;     /* (B,1,H,W) optional: the kernel uses (depth + depth_b) / 2, the
                                ensemble disparity of manydepth/trainer.py:598; no gradient      */
+  float* grad_syn[2];       /* (B,3,H,W) optional, PRED+grad with syn: d(sum w*reproj)/d syn(f); in
+                               WARP mode the temporal-hint candidates are data                   */
 } mal_photo_args;
 
 size_t mal_photo_partials_floats(int batch, int height, int width);
@@ -336,6 +338,12 @@ typedef struct mal_dynamic_instance_args {
 } mal_dynamic_instance_args;
 
 int mal_dynamic_instance(const mal_dynamic_instance_args* args, mal_stream_t stream);
+/* Backward of mal_dynamic_instance (the reference's copies keep autograd history to the warped
+ * images): `deltas` is the (4,N) block the forward left in its workspace (+ 8*N ints);
+ * `flags` is an H*W byte workspace.  Uses args->mask_*, num, channels, height, width only. */
+int mal_dynamic_instance_backward(const mal_dynamic_instance_args* args, const int32_t* deltas,
+                                  const float* grad_ori_last, const float* grad_ori_next, float* grad_img_last,
+                                  float* grad_img_next, uint8_t* flags, mal_stream_t stream);
 int mal_fill_dynamic_obj(const uint8_t* mask, const int32_t* delta_x, const int32_t* delta_y, const float* source,
                          const float* img, int num, int channels, int height, int width, float* out,
                          mal_stream_t stream);

@@ -29,6 +29,7 @@ class PhotoArgs(C.Structure):
         ("min_reproj", C.c_void_p), ("selection", C.c_void_p), ("weight", C.c_void_p),
         ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
         ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
+        ("grad_syn", C.c_void_p * 2),
     ]
 
 
@@ -128,6 +129,7 @@ EXPORTS = {
     "mal_step_combine": (C.c_int, [C.POINTER(StepCombineArgs), C.c_void_p]),
     "mal_forward_warp": (C.c_int, [C.POINTER(ForwardWarpArgs), C.c_void_p]),
     "mal_dynamic_instance": (C.c_int, [C.POINTER(DynamicInstanceArgs), C.c_void_p]),
+    "mal_dynamic_instance_backward": (C.c_int, [C.POINTER(DynamicInstanceArgs)] + [C.c_void_p] * 7),
     "mal_fill_dynamic_obj": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -138,7 +140,7 @@ EXPORTS = {
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def bind(handle):

@@ -144,6 +144,78 @@ __global__ void __launch_bounds__(DS_NT) dyn_fill_kernel(const uint8_t* __restri
   }
 }
 
+// ---- backward of the composition (the reference's copies keep autograd history) --------------------
+// pass 1: per-pixel selection flags of the forward: bit0 mask_or, bit1 any_last, bit2 any_next, bit3 bg, bit4 bg2
+__global__ void __launch_bounds__(DS_NT) dyn_flags_kernel(const mal_dynamic_instance_args a,
+                                                         const int* __restrict__ delta, uint8_t* __restrict__ flags) {
+  const int N = a.num, H = a.height, W = a.width;
+  const size_t hw = (size_t)H * W;
+  for (size_t p = (size_t)blockIdx.x * DS_NT + threadIdx.x; p < hw; p += (size_t)gridDim.x * DS_NT) {
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    unsigned f = 0;
+    for (int n = 0; n < N; n++) {
+      const bool ml = a.mask_last[(size_t)n * hw + p] != 0, mn = a.mask_next[(size_t)n * hw + p] != 0;
+      if (ml | mn) f |= 1u;
+      if (ml & !mn) f |= 8u;
+      if (mn & !ml) f |= 16u;
+      int sy = y - delta[n], sx = x - delta[N + n];
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W && a.mask_last[(size_t)n * hw + (size_t)sy * W + sx]) f |= 2u;
+      sy = y - delta[2 * N + n]; sx = x - delta[3 * N + n];
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W && a.mask_next[(size_t)n * hw + (size_t)sy * W + sx]) f |= 4u;
+    }
+    flags[p] = (uint8_t)f;
+  }
+}
+
+// pass 2: gather.  ori_last(q) = !or ? last(q) : any_l ? sum_n [mask_last_n(q-d)] last(q-d) : bg ? next(q) : last(q)
+//                  ori_next(q) = !or ? next(q) : any_n ? sum_n [mask_next_n(q-d)] next(q-d) : bg2 ? last(q) : next(q)
+__global__ void __launch_bounds__(DS_NT) dyn_backward_kernel(const mal_dynamic_instance_args a,
+                                                            const int* __restrict__ delta,
+                                                            const uint8_t* __restrict__ flags,
+                                                            const float* __restrict__ g_ol,
+                                                            const float* __restrict__ g_on, float* __restrict__ g_last,
+                                                            float* __restrict__ g_next) {
+  const int N = a.num, C = a.channels, H = a.height, W = a.width;
+  const size_t hw = (size_t)H * W;
+  for (size_t p = (size_t)blockIdx.x * DS_NT + threadIdx.x; p < hw; p += (size_t)gridDim.x * DS_NT) {
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    const unsigned f = flags[p];
+    float gl[4] = {0.f, 0.f, 0.f, 0.f}, gn[4] = {0.f, 0.f, 0.f, 0.f};
+    // pass-through terms at this pixel
+    const bool l_self = !(f & 1u) || (!(f & 2u) && !(f & 8u));    // ori_last(p) reads last(p)
+    const bool l_from_next = (f & 1u) && !(f & 2u) && (f & 8u);   // ori_last(p) reads next(p)
+    const bool n_self = !(f & 1u) || (!(f & 4u) && !(f & 16u));
+    const bool n_from_last = (f & 1u) && !(f & 4u) && (f & 16u);
+    for (int c = 0; c < C; c++) {
+      const float a_l = g_ol[c * hw + p], a_n = g_on[c * hw + p];
+      if (l_self) gl[c] += a_l;
+      if (l_from_next) gn[c] += a_l;
+      if (n_self) gn[c] += a_n;
+      if (n_from_last) gl[c] += a_n;
+    }
+    // shifted copies that read this pixel
+    for (int n = 0; n < N; n++) {
+      if (a.mask_last[(size_t)n * hw + p]) {
+        const int qy = y + delta[n], qx = x + delta[N + n];
+        if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+          const size_t q = (size_t)qy * W + qx;
+          if (flags[q] & 1u)
+            for (int c = 0; c < C; c++) gl[c] += g_ol[c * hw + q];
+        }
+      }
+      if (a.mask_next[(size_t)n * hw + p]) {
+        const int qy = y + delta[2 * N + n], qx = x + delta[3 * N + n];
+        if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+          const size_t q = (size_t)qy * W + qx;
+          if (flags[q] & 1u)
+            for (int c = 0; c < C; c++) gn[c] += g_on[c * hw + q];
+        }
+      }
+    }
+    for (int c = 0; c < C; c++) { g_last[c * hw + p] = gl[c]; g_next[c * hw + p] = gn[c]; }
+  }
+}
+
 inline unsigned ds_blocks(size_t n) {
   size_t b = (n + DS_NT - 1) / DS_NT;
   return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -183,4 +255,25 @@ extern "C" int mal_fill_dynamic_obj(const uint8_t* mask, const int32_t* delta_x,
   launch(dyn_fill_kernel, dim3(ds_blocks((size_t)height * width)), dim3(DS_NT), 0, (cudaStream_t)stream, mask, delta_x,
          delta_y, source, img, num, channels, height, width, out);
   return check_launch("dyn_fill_kernel");
+}
+
+extern "C" int mal_dynamic_instance_backward(const mal_dynamic_instance_args* args, const int32_t* deltas,
+                                             const float* grad_ori_last, const float* grad_ori_next,
+                                             float* grad_img_last, float* grad_img_next, uint8_t* flags,
+                                             mal_stream_t stream) {
+  MAL_REQUIRE(args != nullptr, "mal_dynamic_instance_backward: args is NULL");
+  const mal_dynamic_instance_args& a = *args;
+  MAL_REQUIRE(a.num > 0 && a.num < 256 && a.channels > 0 && a.channels <= 4 && a.height > 0 && a.width > 0,
+              "mal_dynamic_instance_backward: bad shape");
+  MAL_REQUIRE(a.mask_last && a.mask_next && deltas && grad_ori_last && grad_ori_next && grad_img_last &&
+                  grad_img_next && flags,
+              "mal_dynamic_instance_backward: a required pointer is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned nb = ds_blocks((size_t)a.height * a.width);
+  launch(dyn_flags_kernel, dim3(nb), dim3(DS_NT), 0, st, a, deltas, flags);
+  int rc = check_launch("dyn_flags_kernel");
+  if (rc) return rc;
+  launch(dyn_backward_kernel, dim3(nb), dim3(DS_NT), 0, st, a, deltas, (const uint8_t*)flags, grad_ori_last,
+         grad_ori_next, grad_img_last, grad_img_next);
+  return check_launch("dyn_backward_kernel");
 }

@@ -223,13 +223,38 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
       acc_w += w;
     }
     if (GRAD) {
-      const bool live = idx < 2 && w != 0.0f;
+      // warped candidates always carry a gradient; the temporal-hint candidates only in PRED mode
+      // when the caller asked for d/d syn (they are data for the fused WARP path)
+      const bool syn_grad = !WARP && a.grad_syn[0] != nullptr;
+      const bool live = (idx < 2 || syn_grad) && w != 0.0f;
       lsel[i] = live ? idx : -1;
       lw[i] = w;
       if (live && !a.no_ssim) {
         const float sc = w * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
+        if (idx < 2) {
 #pragma unroll
-        for (int j = 0; j < 9; j++) coef[j * tl.LN + i] = (idx == 0 ? cf0[j] : cf1[j]) * sc;
+          for (int j = 0; j < 9; j++) coef[j * tl.LN + i] = (idx == 0 ? cf0[j] : cf1[j]) * sc;
+        } else {
+          // rare path: re-derive the SSIM terms of the selected temporal-hint candidate
+          for (int c = 0; c < 3; c++) {
+            float yw[9], xw[9];
+            const float* X = sx + (idx * 3 + c) * tl.VN + vc;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+              for (int dx = 0; dx < 3; dx++) {
+                yw[dy * 3 + dx] = sy[c * tl.VN + vc + (dy - 1) * tl.VW + dx - 1];
+                xw[dy * 3 + dx] = X[(dy - 1) * tl.VW + dx - 1];
+              }
+            SsimTerms t = ssim_terms(xdivc<9>(sum9(xw)), xdivc<9>(sum9(yw)), xdivc<9>(sum9_prod(xw, xw)),
+                                     xdivc<9>(sum9_prod(yw, yw)), xdivc<9>(sum9_prod(xw, yw)));
+            float al, be, ga;
+            ssim_coefs(t, al, be, ga);
+            coef[(c * 3) * tl.LN + i] = al * sc;
+            coef[(c * 3 + 1) * tl.LN + i] = be * sc;
+            coef[(c * 3 + 2) * tl.LN + i] = ga * sc;
+          }
+        }
       }
     }
   }
@@ -246,6 +271,47 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
       if (gy >= H || gx >= W) continue;
       const int lc = (qy + tl.HL) * tl.LW + qx + tl.HL;
       const int vc = (qy + tl.HV) * tl.VW + qx + tl.HV;
+      if (!WARP) {
+        // PRED mode: d S / d prediction for every candidate that can be selected, one at a time
+        const size_t pq = (size_t)gy * W + gx;
+        for (int k = 0; k < ncand; k++) {
+          float* out = k < 2 ? a.grad_pred[k] : a.grad_syn[k - 2];
+          if (out == nullptr) continue;
+          float g[3] = {0.f, 0.f, 0.f};
+          float xq[3], yq[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { xq[c] = sx[(k * 3 + c) * tl.VN + vc]; yq[c] = sy[c * tl.VN + vc]; }
+          if (!a.no_ssim) {
+            for (int dy = -1; dy <= 1; dy++) {
+              int py = gy + dy;
+              if (py < 0 || py >= H) continue;
+              float my = ((py == 0 && dy == -1) || (py == H - 1 && dy == 1)) ? 2.0f : 1.0f;
+              for (int dx = -1; dx <= 1; dx++) {
+                int px = gx + dx;
+                if (px < 0 || px >= W) continue;
+                float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
+                int li = lc + dy * tl.LW + dx;
+                if (lsel[li] != k) continue;
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                  g[c] += m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq[c] * coef[(c * 3 + 1) * tl.LN + li] +
+                               yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
+              }
+            }
+          }
+          if (lsel[lc] == k) {
+            float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float d = yq[c] - xq[c];
+              g[c] += d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; c++) out[((size_t)b * 3 + c) * HW + pq] = g[c];
+        }
+        continue;
+      }
       float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
       float xq0[3], xq1[3], yq[3];
 #pragma unroll
@@ -293,13 +359,7 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
         }
       }
       const size_t po = (size_t)gy * W + gx;
-      if (!WARP) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          a.grad_pred[0][((size_t)b * 3 + c) * HW + po] = g0[c];
-          if (ncand > 1) a.grad_pred[1][((size_t)b * 3 + c) * HW + po] = g1[c];
-        }
-      } else {
+      {
         float dv_in = __ldg(a.depth + (size_t)b * HW + po);
         float dv = a.depth_is_disp ? xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv_in))) : dv_in;
         Ray ray = pixel_ray(geom->iK, (float)gx, (float)gy);

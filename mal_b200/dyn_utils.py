@@ -12,8 +12,9 @@ segmenter (`ins_model`, Mask2Former in the reference) and the Hungarian `matcher
 caller's - they are out of scope here - and any callable with the same
 interface works (tests use synthetic Mask2Former-shaped masks).
 
-The synthesised images are data for the loss (no gradient flows through them here; the
-reference's copies keep autograd history to the warped source images - DESIGN.md section 9).
+Like the reference's copies, the synthesised images keep autograd history to the warped source
+images (mal_dynamic_instance_backward); the classic loss path (PRED mode) returns d loss / d syn.
+The fused WARP path treats them as data.
 """
 from __future__ import annotations
 
@@ -47,17 +48,17 @@ def image_synthesis(inputs, outputs, scale, thres, ins_model, matcher):
     """Fill outputs[("syn", -1/+1, scale)] from the warped images; returns has_ins."""
     bs = inputs[("color", 0, 0)].shape[0]
     instances = generate_instances(inputs[("color", 0, 0)], ins_model)
-    syn_last = outputs[("color", -1, scale)].detach().clone()
-    syn_next = outputs[("color", 1, scale)].detach().clone()
+    syn_last = outputs[("color", -1, scale)].clone()
+    syn_next = outputs[("color", 1, scale)].clone()
     has_ins = False
     for b in range(bs):
         cur = instances[b]["instances"]
         instances_cur = cur[cur.scores > thres]
         if len(instances_cur) == 0:
             continue
-        img_last = outputs[("color", -1, scale)][b].detach().clone()
-        img_next = outputs[("color", 1, scale)][b].detach().clone()
-        both = generate_instances(torch.stack([img_last, img_next], 0), ins_model)
+        img_last = outputs[("color", -1, scale)][b].clone()
+        img_next = outputs[("color", 1, scale)][b].clone()
+        both = generate_instances(torch.stack([img_last, img_next], 0).detach(), ins_model)
         ins_last, ins_next = both[0]["instances"], both[1]["instances"]
         slice_last, slice_next = matcher(ins_last, ins_next, instances_cur)
         if len(slice_last) + len(slice_next) == 0:

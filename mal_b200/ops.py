@@ -30,6 +30,16 @@ def _lib(t: Tensor):
     return _capi.lib()
 
 
+_warned = set()
+
+
+def _warn_once(msg):
+    if msg not in _warned:
+        _warned.add(msg)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
+
+
 def _empty(ref: Tensor) -> Tensor:
     return torch.empty(0, device=ref.device, dtype=torch.float32)
 
@@ -48,7 +58,7 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
               identity_min: Optional[Tensor], noise: Optional[Tensor], pixel_mask: Optional[Tensor],
               sample_mask: Optional[Tensor], mode: int, convention: int, depth_is_disp: bool,
               no_ssim: bool, min_depth: float, max_depth: float, eps: float,
-              need_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+              need_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     h = _lib(target)
     src = [src0] if src1 is None else [src0, src1]
     out = raw.photo(h, target=target, src=src, syn=None if syn0 is None else [syn0, syn1],
@@ -56,11 +66,13 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
                     identity_min=identity_min, noise=noise, pixel_mask=pixel_mask,
                     sample_mask=sample_mask, mode=mode, convention=convention,
                     depth_is_disp=depth_is_disp, no_ssim=no_ssim, with_grad=need_grad,
-                    min_depth=min_depth, max_depth=max_depth, eps=eps)
+                    min_depth=min_depth, max_depth=max_depth, eps=eps,
+                    want_grad_syn=need_grad and mode == raw.PHOTO_PRED and syn0 is not None)
     gp = out.get("grad_pred", [None, None])
+    gs = out.get("grad_syn", [None, None])
     pick = lambda v: v if v is not None else _empty(target)   # a fresh tensor each: outputs may not alias
     return (out["sums"], out["min_reproj"], out["selection"], pick(out.get("grad_depth")),
-            pick(out.get("grad_P")), pick(gp[0]), pick(gp[1]))
+            pick(out.get("grad_P")), pick(gp[0]), pick(gp[1]), pick(gs[0]), pick(gs[1]))
 
 
 @_photo_op.register_fake
@@ -72,20 +84,22 @@ def _(target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noi
     return (f(4), f(B, 1, H, W), target.new_empty((B, 1, H, W), dtype=torch.uint8),
             f(B, 1, H, W) if need_grad and warp else f(0), f(B, 2, 12) if need_grad and warp else f(0),
             f(B, 3, H, W) if need_grad and not warp else f(0),
-            f(B, 3, H, W) if need_grad and not warp and src1 is not None else f(0))
+            f(B, 3, H, W) if need_grad and not warp and src1 is not None else f(0),
+            f(B, 3, H, W) if need_grad and not warp and syn0 is not None else f(0),
+            f(B, 3, H, W) if need_grad and not warp and syn0 is not None else f(0))
 
 
 def _photo_setup(ctx, inputs, output):
     (target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noise, pixel_mask,
      sample_mask, mode, *_rest) = inputs
-    sums, _, _, g_depth, g_P, g_p0, g_p1 = output
+    sums, _, _, g_depth, g_P, g_p0, g_p1, g_s0, g_s1 = output
     ctx.mode = mode
     ctx.need_grad = inputs[-1]
-    ctx.save_for_backward(sums, g_depth, g_P, g_p0, g_p1, K if K is not None else sums)
+    ctx.save_for_backward(sums, g_depth, g_P, g_p0, g_p1, K if K is not None else sums, g_s0, g_s1)
 
 
 def _photo_backward(ctx, g_sums, *_unused):
-    sums, g_depth, g_P, g_p0, g_p1, K = ctx.saved_tensors
+    sums, g_depth, g_P, g_p0, g_p1, K, g_s0, g_s1 = ctx.saved_tensors
     if not ctx.need_grad:
         raise RuntimeError("mal_b200::photo was run with need_grad=False but a gradient is requested")
     # sums = [S, W, S / (W + 1e-7), 0]; the planes hold d S / d input
@@ -101,6 +115,8 @@ def _photo_backward(ctx, g_sums, *_unused):
         grads[1] = coef * g_p0
         if g_p1.numel():
             grads[2] = coef * g_p1
+        if g_s0.numel():
+            grads[3], grads[4] = coef * g_s0, coef * g_s1
     return tuple(grads)
 
 
@@ -118,8 +134,12 @@ def photo(target, src, *, syn=None, depth=None, K=None, inv_K=None, T=None, iden
     ``min_reproj`` (B,1,H,W) and ``selection`` (uint8: arg-min candidate | automask << 7) are not.
     """
     src = list(src)
-    diff = [depth, *(T or [])] if mode == raw.PHOTO_WARP else src
+    diff = [depth, *(T or [])] if mode == raw.PHOTO_WARP else src + list(syn or [])
     need_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in diff)
+    if mode == raw.PHOTO_WARP and syn and torch.is_grad_enabled() and any(t.requires_grad for t in syn):
+        _warn_once("mal_b200.ops.photo: in the fused WARP mode the temporal-hint candidates `syn` are data; their "
+                   "gradient (which the reference propagates into the warped images) is dropped.  Use the "
+                   "classic path (materialised warps, PRED mode) to keep it.")
     sample_mask = None if sample_mask is None else sample_mask.reshape(-1)
     out = _photo_op(target, src[0], src[1] if len(src) > 1 else None,
                     syn[0] if syn else None, syn[1] if syn else None, depth, K, inv_K,
@@ -495,11 +515,36 @@ def _(mask_last, mask_next, img_last, img_next, replace):
             img_last.new_empty((4, mask_last.shape[0]), dtype=torch.int32))
 
 
+@torch.library.custom_op("mal_b200::dynamic_instance_backward", mutates_args=())
+def _dynamic_instance_bwd_op(mask_last: Tensor, mask_next: Tensor, deltas: Tensor, g_last: Tensor,
+                             g_next: Tensor) -> Tuple[Tensor, Tensor]:
+    return raw.dynamic_instance_backward(_lib(g_last), mask_last=mask_last, mask_next=mask_next, deltas=deltas,
+                                         grad_ori_last=g_last, grad_ori_next=g_next)
+
+
+@_dynamic_instance_bwd_op.register_fake
+def _(mask_last, mask_next, deltas, g_last, g_next):
+    return g_last.new_empty(g_last.shape), g_next.new_empty(g_next.shape)
+
+
+def _dynamic_instance_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], output[2])
+
+
+def _dynamic_instance_backward(ctx, g_last, g_next, _g_delta):
+    mask_last, mask_next, deltas = ctx.saved_tensors
+    gl, gn = _dynamic_instance_bwd_op(mask_last, mask_next, deltas, g_last.contiguous(), g_next.contiguous())
+    return None, None, gl, gn, None
+
+
+_dynamic_instance_op.register_autograd(_dynamic_instance_backward, setup_context=_dynamic_instance_setup)
+
+
 def dynamic_instance(mask_last, mask_next, img_last, img_next, replace=False):
-    """-> (ori_last, ori_next, deltas (4,N) int32 = dx_last, dy_last, dx_next, dy_next)."""
-    with torch.no_grad():
-        return _dynamic_instance_op(mask_last.contiguous(), mask_next.contiguous(), img_last.detach().contiguous(),
-                                    img_next.detach().contiguous(), bool(replace))
+    """-> (ori_last, ori_next, deltas (4,N) int32 = dx_last, dy_last, dx_next, dy_next).  The two
+    images are differentiable w.r.t. img_last / img_next (pure copies and selections)."""
+    return _dynamic_instance_op(mask_last.contiguous(), mask_next.contiguous(), img_last.contiguous(),
+                                img_next.contiguous(), bool(replace))
 
 
 @torch.library.custom_op("mal_b200::fill_dynamic_obj", mutates_args=())

@@ -59,7 +59,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           identity_min=None, noise=None, pixel_mask=None, sample_mask=None,
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
-          want_min_reproj=True, want_selection=True, want_weight=False):
+          want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h)."""
     B, C3, H, W = target.shape
     if C3 != 3:
@@ -90,6 +90,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
         out["grad_depth"], out["grad_P"] = new(plane), new((B, 2, 12))
     if with_grad and mode == PHOTO_PRED:
         out["grad_pred"] = [new(img), new(img) if src[1] is not None else None]
+        if want_grad_syn and syn[0] is not None:
+            out["grad_syn"] = [new(img), new(img)]
     partials = new((handle.mal_photo_partials_floats(B, H, W),))
 
     a = _capi.PhotoArgs()
@@ -101,6 +103,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     for i in range(2):
         a.src[i], a.syn[i], a.T[i] = _ptr(src[i]), _ptr(syn[i]), _ptr(T[i])
         a.grad_pred[i] = _ptr(out["grad_pred"][i]) if "grad_pred" in out else None
+        a.grad_syn[i] = _ptr(out["grad_syn"][i]) if "grad_syn" in out else None
     a.depth, a.depth_b, a.K, a.inv_K = _ptr(depth), _ptr(depth_b), _ptr(K), _ptr(inv_K)
     a.identity_min, a.noise = _ptr(identity_min), _ptr(noise)
     a.pixel_mask, a.sample_mask = _ptr(pixel_mask), _ptr(sample_mask)
@@ -387,3 +390,22 @@ def fill_dynamic_obj(handle, *, mask, delta_x, delta_y, source, img):
                                             _stream(im)), handle)
     LAUNCHES[0] += 1
     return out
+
+
+def dynamic_instance_backward(handle, *, mask_last, mask_next, deltas, grad_ori_last, grad_ori_next):
+    """mal_dynamic_instance_backward -> (grad_img_last, grad_img_next)."""
+    N, H, W = mask_last.shape
+    Cn = grad_ori_last.shape[0]
+    ml, mn = _mask_u8(mask_last, "mask_last", (N, H, W)), _mask_u8(mask_next, "mask_next", (N, H, W))
+    gol, gon = _f32(grad_ori_last, "grad_ori_last", (Cn, H, W)), _f32(grad_ori_next, "grad_ori_next", (Cn, H, W))
+    d = deltas.to(torch.int32).contiguous()
+    dev = _same_device([ml, mn, gol, gon, d])
+    gl, gn = torch.empty_like(gol), torch.empty_like(gon)
+    flags = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    a = _capi.DynamicInstanceArgs()
+    a.num, a.channels, a.height, a.width, a.replace = N, Cn, H, W, 0
+    a.mask_last, a.mask_next = _ptr(ml), _ptr(mn)
+    _capi.check(handle.mal_dynamic_instance_backward(C.byref(a), _vp(d), _vp(gol), _vp(gon), _vp(gl), _vp(gn),
+                                                     _vp(flags), _stream(gol)), handle)
+    LAUNCHES[0] += 2
+    return gl, gn

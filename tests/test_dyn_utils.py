@@ -80,3 +80,69 @@ def test_image_synthesis_orchestration(op_device):
     none = dyn_utils.image_synthesis(inputs, {k: v for k, v in outputs.items() if k[0] == "color"}, 0, 0.99,
                                      ins_model, matcher)
     assert none is False
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("N,H,W,seed,empty,replace", CASES[:4])
+def test_dynamic_instance_backward(backend, N, H, W, seed, empty, replace):
+    """The composition is copies and selections: its backward is exact (autograd on the oracle)."""
+    h, dev = handle_and_device(backend)
+    ml, mn = make_instance_masks(N, H, W, seed=seed, max_shift=9, empty=empty)
+    g = torch.Generator().manual_seed(seed)
+    il = torch.rand(3, H, W, generator=g).requires_grad_(True)
+    inx = torch.rand(3, H, W, generator=g).requires_grad_(True)
+    gl, gn = torch.rand(3, H, W, generator=g), torch.rand(3, H, W, generator=g)
+    want_l, want_n, deltas = O.generate_dynamic_instance(ml, mn, il, inx, replace)
+    want = torch.autograd.grad((want_l * gl).sum() + (want_n * gn).sum(), [il, inx])
+    got = raw.dynamic_instance_backward(h, mask_last=ml.to(dev), mask_next=mn.to(dev),
+                                        deltas=torch.stack(deltas, 0).to(dev), grad_ori_last=gl.to(dev),
+                                        grad_ori_next=gn.to(dev))
+    for a, b in zip(got, want):
+        assert torch.allclose(a.cpu(), b, rtol=1e-6, atol=1e-7)
+
+
+def test_temporal_hint_gradient_reaches_the_warped_images(op_device):
+    """Classic path: warped images -> image synthesis -> compute_mono_losses (PRED mode, 4 candidates):
+    d loss / d warped image matches autograd on the oracle, including pixels whose min is a syn candidate."""
+    from mal_b200 import loss_utils, layers
+    dev = op_device
+    B, H, W = 1, 32, 64
+    inputs, t = make_photometric_inputs(B, H, W, seed=13, translation_scale=0.3)
+    ml, mn = make_instance_masks(5, H, W, seed=14, max_shift=6)
+    # moving objects: painted at their "last" position in the warped frame -1, at their "next"
+    # position in frame +1 and half-way in the target, so the synthesised candidates win there
+    base = {f: (inputs[("color", 0, 0)] + 0.05 * (inputs[("color", f, 0)] - 0.5)).clamp(0, 1) for f in (-1, 1)}
+    inputs[("color", 0, 0)] = inputs[("color", 0, 0)].clone()
+    _, _, d = O.generate_dynamic_instance(ml, mn, base[-1][0], base[1][0], False)
+    gen = torch.Generator().manual_seed(15)
+    for n in range(ml.shape[0]):
+        col = torch.rand(3, 1, generator=gen)
+        base[-1][0][:, ml[n]] = col
+        base[1][0][:, mn[n]] = col
+        mid = torch.roll(ml[n], shifts=(int(d[0][n]), int(d[1][n])), dims=(0, 1))
+        inputs[("color", 0, 0)][0][:, mid] = col
+    res = []
+    for mode, dv in (("oracle", torch.device("cpu")), ("ours", dev)):
+        warped = {f: base[f].clone().to(dv).requires_grad_(True) for f in (-1, 1)}
+        inp = {k: v.to(dv) for k, v in inputs.items()}
+        if mode == "oracle":
+            sl, sn, _ = O.generate_dynamic_instance(ml, mn, warped[-1][0], warped[1][0], False)
+            out = {("color", -1, 0): warped[-1], ("color", 1, 0): warped[1], ("syn", -1, 0): sl.unsqueeze(0),
+                   ("syn", 1, 0): sn.unsqueeze(0), ("disp", 0): t[("mono_disp", 0)]}
+            losses, mono_reproj, aux = O.mono_losses(inp, out, True, True, noise=t["noise"][0])
+            frame_idx = aux["frame_idx"]
+        else:
+            sl, sn = dyn_utils.generate_dynamic_instance(None, None, ml.to(dv), mn.to(dv), warped[-1][0], warped[1][0], False)
+            out = {("color", -1, 0): warped[-1], ("color", 1, 0): warped[1], ("syn", -1, 0): sl.unsqueeze(0),
+                   ("syn", 1, 0): sn.unsqueeze(0), ("disp", 0): t[("mono_disp", 0)].to(dv)}
+            losses, mono_reproj = loss_utils.compute_mono_losses(layers.SSIM(), inp, out, True, True,
+                                                                 noise=t["noise"][0].to(dv))
+            frame_idx = out[("mal_selection", 0)] & 0x7F
+        grads = torch.autograd.grad(losses["reproj_loss/0"], [warped[-1], warped[1]])
+        res.append((float(losses["reproj_loss/0"].detach()), frame_idx.cpu(), [g.cpu() for g in grads]))
+    (l0, idx0, g0), (l1, idx1, g1) = res
+    assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    assert torch.equal(idx0.to(torch.uint8), idx1.to(torch.uint8))
+    assert float((idx0 >= 2).float().mean()) > 0.02          # some pixels do select a temporal-hint candidate
+    for a, b in zip(g1, g0):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
