@@ -228,6 +228,82 @@ def compute_losses_dualrefine(inputs, outputs, opt, noises=None):
     return losses
 
 
+def compute_reprojection_loss_dynamicdepth(pred, target, zero_img=True, no_ssim=False):
+    """dynamicdepth/trainer.py compute_reprojection_loss :958-975: with zero_img the dark pixels of
+    `pred` (DOMD warping holes, RGB sum < 0.1) are zeroed in a copy of pred and IN PLACE in `target`
+    (the reference mutates the caller's target image; so do we)."""
+    if zero_img:
+        mask = (pred.sum(1) < 0.1).unsqueeze(1).repeat([1, 3, 1, 1]).detach()
+        pred = pred.clone()
+        pred[mask] = 0
+        target[mask] = 0
+        # later calls keep zeroing `target` in place: hand the kernel (which keeps its inputs for the
+        # backward) a snapshot of the image as this call saw it
+        return ops.reprojection_loss_map(pred, target.detach().clone(), no_ssim=no_ssim)
+    return ops.reprojection_loss_map(pred, target, no_ssim=no_ssim)
+
+
+def compute_losses_dynamicdepth(inputs, outputs, opt, is_multi=False, noises=None):
+    """dynamicdepth/trainer.py compute_losses :1006-1128 over opt.scales, with `selec_reproj`
+    (:1058-1064), `zero_img` (:961-965), `avg_reprojection` and `no_teacher_warp`.
+
+    zero_img makes every candidate's loss depend on the order of the calls before it (each call
+    zeroes more of the shared target), so this trainer variant scores one materialised warp at a
+    time (`generate_images_pred(..., materialize=True)`) instead of using the fused multi-candidate
+    pass; the SSIM+L1 maps and their gradients still come from the photometric kernel (PRED mode)."""
+    if str(getattr(opt, "feat_loss", "false")) == "true":
+        raise NotImplementedError("feat_loss (get_feature_metric_loss) is outside the hot path")
+    zero_img, no_ssim = getattr(opt, "zero_img", True), str(_o(opt, "no_ssim")) in ("True", "true")
+    rl = lambda p, t: compute_reprojection_loss_dynamicdepth(p, t, zero_img, no_ssim)
+    avg = getattr(opt, "avg_reprojection", False)
+    losses, total_loss = {}, 0
+    scales = list(opt.scales)
+    for si, scale in enumerate(scales):
+        disp, color, target = outputs[("disp", scale)], inputs[("color", 0, scale)], inputs[("color", 0, 0)]
+        cands = torch.cat([rl(outputs[("color", f, scale)], target) for f in (-1, 1)], 1)
+        ident = None
+        if not _o(opt, "disable_automasking"):
+            use_ori = (not is_multi) and getattr(opt, "no_teacher_warp", False) and not getattr(opt, "train_teacher_only", False)
+            preds = [inputs[("ori_color" if use_ori else "color", f, 0)] for f in (-1, 1)]
+            ident = torch.cat([rl(p, target) for p in preds], 1)
+            ident = ident.mean(1, keepdim=True) if avg else torch.min(ident, dim=1, keepdim=True)[0]
+        reproj = cands.mean(1, keepdim=True) if avg else torch.min(cands, dim=1, keepdim=True)[0]
+        if getattr(opt, "selec_reproj", True):
+            maskm1 = (outputs[("color", -1, scale)].sum(1) < 0.1).detach()
+            maskp1 = (outputs[("color", 1, scale)].sum(1) < 0.1).detach()
+            maskand = (maskm1 * maskp1).detach()
+            reproj = reproj.clone()
+            reproj[maskm1.unsqueeze(1)] = (cands[:, 1, :, :])[maskm1]
+            reproj[maskp1.unsqueeze(1)] = (cands[:, 0, :, :])[maskp1]
+            reproj[maskand.unsqueeze(1)] = 0
+        if ident is not None:
+            ident = ident + _draw_noise(ident.shape, target.device, None if noises is None else noises[si]) * 0.00001
+        mask = (~(ident < reproj)).float() if ident is not None else torch.ones_like(reproj)
+        consistency_loss = 0
+        if is_multi:
+            mask = torch.ones_like(mask)
+            if not _o(opt, "disable_motion_masking"):
+                mask = mask * outputs["consistency_mask"].unsqueeze(1)
+            if not str(_o(opt, "no_matching_augmentation")) == "true":
+                mask = mask * (1 - outputs["augmentation_mask"])
+            consistency_mask = (1 - mask).float()
+        reprojection_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+        if is_multi:
+            multi_depth, mono_depth = outputs[("depth", 0, scale)], outputs[("mono_depth", 0, scale)].detach()
+            consistency_loss = (torch.abs(multi_depth - mono_depth) * consistency_mask).mean()
+            outputs["consistency_target/{}".format(scale)] = 1 / (mono_depth * consistency_mask +
+                                                                  multi_depth.detach() * (1 - consistency_mask))
+            losses["consistency_loss/{}".format(scale)] = consistency_loss
+        losses["reproj_loss/{}".format(scale)] = reprojection_loss
+        loss = reprojection_loss + consistency_loss
+        loss = loss + _o(opt, "disparity_smoothness") * ops.smooth(disp, color, normalise=True) / (2 ** scale)
+        total_loss = total_loss + loss
+        losses["loss/{}".format(scale)] = loss
+        outputs[("mal_mask", scale)] = mask
+    losses["loss"] = total_loss / len(scales)
+    return losses
+
+
 def process_batch_losses(inputs, mono_outputs, outputs, opt, *, has_ins=False, multi_has_ins=False,
                          loss_blc=None, index_iter=0, current_lambda_for_adjust=0.0, w_list=None,
                          noises=None, freeze_tp=False):

@@ -454,6 +454,75 @@ def dualrefine_compute_losses(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, 
     return losses, aux
 
 
+def dynamicdepth_reprojection_loss(pred, target, zero_img=True, no_ssim=False):
+    """dynamicdepth/trainer.py compute_reprojection_loss :958-975.  With zero_img the dark pixels
+    of `pred` (DOMD warping holes) are zeroed in a copy of pred AND IN PLACE in `target`."""
+    if zero_img:
+        mask = (pred.sum(1) < 0.1).unsqueeze(1).repeat([1, 3, 1, 1]).detach()
+        pred = pred.clone()
+        pred[mask] = 0
+        target[mask] = 0
+    l1 = torch.abs(target - pred).mean(1, True)
+    if no_ssim:
+        return l1
+    return 0.85 * ssim(pred, target).mean(1, True) + 0.15 * l1
+
+
+def dynamicdepth_compute_losses(inputs, outputs, scales=(0, 1, 2, 3), is_multi=False, automask=True,
+                                avg_reprojection=False, selec_reproj=True, zero_img=True, motion_masking=True,
+                                matching_augmentation=True, no_teacher_warp=False, train_teacher_only=False,
+                                smoothness=1e-3, noises=None, no_ssim=False):
+    """dynamicdepth/trainer.py compute_losses :1006-1128 (feat_loss off).  NOTE: mutates
+    inputs[("color", 0, 0)] in place when zero_img is set, exactly like the reference."""
+    losses, total, aux = {}, 0, {}
+    rl = lambda p, t: dynamicdepth_reprojection_loss(p, t, zero_img, no_ssim)
+    for si, scale in enumerate(scales):
+        loss = 0
+        disp, color, target = outputs[("disp", scale)], inputs[("color", 0, scale)], inputs[("color", 0, 0)]
+        cands = torch.cat([rl(outputs[("color", f, scale)], target) for f in (-1, 1)], 1)
+        ident = None
+        if automask:
+            preds = [(inputs[("ori_color", f, 0)] if ((not is_multi) and no_teacher_warp and not train_teacher_only)
+                      else inputs[("color", f, 0)]) for f in (-1, 1)]
+            ident = torch.cat([rl(p, target) for p in preds], 1)
+            ident = ident.mean(1, keepdim=True) if avg_reprojection else torch.min(ident, dim=1, keepdim=True)[0]
+        reproj = cands.mean(1, keepdim=True) if avg_reprojection else torch.min(cands, dim=1, keepdim=True)[0]
+        if selec_reproj:
+            maskm1 = (outputs[("color", -1, scale)].sum(1) < 0.1).detach()
+            maskp1 = (outputs[("color", 1, scale)].sum(1) < 0.1).detach()
+            maskand = (maskm1 * maskp1).detach()
+            reproj[maskm1.unsqueeze(1)] = (cands[:, 1, :, :])[maskm1]
+            reproj[maskp1.unsqueeze(1)] = (cands[:, 0, :, :])[maskp1]
+            reproj[maskand.unsqueeze(1)] = 0
+        if automask:
+            nz = noises[si] if noises is not None else torch.randn(ident.shape)
+            ident = ident + nz * 0.00001
+        mask = loss_masks(reproj, ident)
+        if is_multi:
+            mask = torch.ones_like(mask)
+            if motion_masking:
+                mask = mask * outputs["consistency_mask"].unsqueeze(1)
+            if matching_augmentation:
+                mask = mask * (1 - outputs["augmentation_mask"])
+            cons_mask = (1 - mask).float()
+        reproj_loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+        cons = 0
+        if is_multi:
+            multi_depth = outputs[("depth", 0, scale)]
+            mono_depth = outputs[("mono_depth", 0, scale)].detach()
+            cons = (torch.abs(multi_depth - mono_depth) * cons_mask).mean()
+            losses[f"consistency_loss/{scale}"] = cons
+        losses[f"reproj_loss/{scale}"] = reproj_loss
+        loss = loss + reproj_loss + cons
+        loss = loss + smoothness * normalised_smooth_loss(disp, color) / (2 ** scale)
+        total = total + loss
+        losses[f"loss/{scale}"] = loss
+        aux[("mask", scale)] = mask
+        aux[("reproj", scale)] = reproj
+    losses["loss"] = total / len(scales)
+    return losses, aux
+
+
 # --------------------------------------------------------------------------
 # plane-sweep matching cost volume
 # --------------------------------------------------------------------------

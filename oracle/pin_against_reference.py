@@ -367,6 +367,68 @@ def pin_dynamicdepth_match_features(seed=77):
     return bool(ok)
 
 
+def dynamicdepth_loss_case(batch=1, height=32, width=64, seed=55, holes=True):
+    """Inputs for DynamicDepth's compute_losses: 4-scale disparities, materialised warps with black
+    DOMD-style holes, identity frames."""
+    from mal_b200.utils.synthetic import make_photometric_inputs
+    from . import mal_oracle as O
+    inputs, t = make_photometric_inputs(batch, height, width, num_scales=4, seed=seed, translation_scale=0.3)
+    outs = {}
+    for name in ("mono", "multi"):
+        o = {("disp", s): t[(name + "_disp", s)] for s in range(4)}
+        for f in (-1, 1):
+            o[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+        O.images_pred(inputs, o, num_scales=4, height=height, width=width, is_multi=(name == "multi"))
+        if holes:
+            for s in range(4):
+                o[("color", -1, s)] = o[("color", -1, s)].clone()
+                o[("color", 1, s)] = o[("color", 1, s)].clone()
+                o[("color", -1, s)][:, :, 4:12, 6:30] = 0.0
+                o[("color", 1, s)][:, :, 8:20, 20:44] = 0.0
+        outs[name] = o
+    outs["multi"]["consistency_mask"] = t["consistency_mask"]
+    outs["multi"]["augmentation_mask"] = t["augmentation_mask"]
+    for s in range(4):
+        outs["multi"][("mono_depth", 0, s)] = outs["mono"][("depth", 0, s)]
+    return inputs, t, outs
+
+
+def pin_dynamicdepth_losses():
+    """dynamicdepth/trainer.py Trainer.compute_losses (:1006-1128) called unbound on a shell `self`."""
+    from . import mal_oracle as O
+    load_reference()
+    tr = importlib.import_module("dynamicdepth.trainer")
+    dl = importlib.import_module("dynamicdepth.layers")
+    ok = True
+    for is_multi, selec, zero in ((False, True, True), (True, True, True), (False, False, False)):
+        res = []
+        for who in ("ref", "oracle"):
+            inputs, t, outs = dynamicdepth_loss_case()
+            o = outs["multi" if is_multi else "mono"]
+            noises = t["noise"] + t["noise"]
+            if who == "ref":
+                opt = SimpleNamespace(scales=[0, 1, 2, 3], v1_multiscale=False, frame_ids=[0, -1, 1],
+                                      disable_automasking=False, no_teacher_warp=False, train_teacher_only=False,
+                                      avg_reprojection=False, selec_reproj=selec, zero_img=zero, no_ssim="false",
+                                      disable_motion_masking=False, no_matching_augmentation="false",
+                                      disparity_smoothness=1e-3, feat_loss="false")
+                shell = SimpleNamespace(opt=opt, ssim=dl.SSIM(), device=torch.device("cpu"), num_scales=4)
+                shell.compute_reprojection_loss = lambda p, tg: tr.Trainer.compute_reprojection_loss(shell, p, tg)
+                shell.compute_loss_masks = tr.Trainer.compute_loss_masks
+                it = iter(noises)
+                with mock.patch.object(torch, "randn", lambda *a, **k: next(it)):
+                    losses = tr.Trainer.compute_losses(shell, inputs, o, is_multi=is_multi)
+            else:
+                losses, _ = O.dynamicdepth_compute_losses(inputs, o, (0, 1, 2, 3), is_multi=is_multi,
+                                                          selec_reproj=selec, zero_img=zero, noises=noises)
+            res.append((losses, inputs[("color", 0, 0)].clone()))
+        tag = f"dynamicdepth compute_losses(multi={is_multi}, selec={selec}, zero={zero})"
+        for k in res[0][0]:
+            ok &= _eq(f"{tag} {k}", res[1][0][k].detach(), res[0][0][k].detach())
+        ok &= _eq(tag + " mutated target", res[1][1], res[0][1])
+    return bool(ok)
+
+
 def pin_image_synthesis():
     """manydepth/dyn_utils.py generate_dynamic_instance / fill_dynamic_obj (TorchScript) against the
     oracle restatement, on synthetic Mask2Former-shaped matched masks."""
@@ -395,5 +457,6 @@ if __name__ == "__main__":
     good = run_pin()
     good &= pin_dynamicdepth_match_features()
     good &= pin_image_synthesis()
+    good &= pin_dynamicdepth_losses()
     print("PINNED" if good else "PIN FAILED")
     sys.exit(0 if good else 1)

@@ -326,3 +326,51 @@ def test_dualrefine_losses_match_oracle(op_device):
     g = torch.autograd.grad(got["loss"], leaves_d)
     for a, b in zip(g, want_g):
         assert _gerr(a, b) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("is_multi,selec,zero", [(False, True, True), (True, True, True), (False, False, False)])
+def test_dynamicdepth_losses_match_oracle(op_device, is_multi, selec, zero):
+    """BASELINE config 5: DynamicDepth's 4-scale losses with `selec_reproj` and `zero_img`
+    (dynamicdepth/trainer.py:958-975, :1006-1128), incl. the in-place zeroing of the target image;
+    the oracle side is pinned bitwise against the reference's Trainer.compute_losses."""
+    from oracle.pin_against_reference import dynamicdepth_loss_case
+    dev = op_device
+    H, W = 32, 64
+    name = "multi" if is_multi else "mono"
+    res = []
+    for who, dv in (("oracle", torch.device("cpu")), ("ours", dev)):
+        inputs, t, outs = dynamicdepth_loss_case(1, H, W)
+        inputs = {k: v.to(dv) for k, v in inputs.items()}
+        o = {k: (v.to(dv) if torch.is_tensor(v) else v) for k, v in outs[name].items()}
+        preds = []
+        for s in range(4):
+            for f in (-1, 1):
+                o[("color", f, s)] = o[("color", f, s)].detach().clone().requires_grad_(True)
+                preds.append(o[("color", f, s)])
+        disps = [o[("disp", s)].detach().clone().requires_grad_(True) for s in range(4)]
+        for s in range(4):
+            o[("disp", s)] = disps[s]
+        if is_multi:
+            for s in range(4):
+                o[("depth", 0, s)] = o[("depth", 0, s)].detach().clone().requires_grad_(True)
+                preds.append(o[("depth", 0, s)])
+        noises = [n.to(dv) for n in (t["noise"] + t["noise"])]
+        if who == "oracle":
+            losses, aux = O.dynamicdepth_compute_losses(inputs, o, (0, 1, 2, 3), is_multi=is_multi, selec_reproj=selec,
+                                                        zero_img=zero, noises=noises)
+            masks = [aux[("mask", s)] for s in range(4)]
+        else:
+            opt = SimpleNamespace(scales=[0, 1, 2, 3], selec_reproj=selec, zero_img=zero, no_ssim="false",
+                                  no_matching_augmentation="false", disparity_smoothness=1e-3)
+            losses = trainer_ops.compute_losses_dynamicdepth(inputs, o, opt, is_multi=is_multi, noises=noises)
+            masks = [o[("mal_mask", s)] for s in range(4)]
+        grads = torch.autograd.grad(losses["loss"], preds + disps)
+        res.append((losses, [m.cpu() for m in masks], [g.cpu() for g in grads], inputs[("color", 0, 0)].cpu()))
+    (lo, mo, go, to_), (lk, mk, gk, tk) = res
+    for k in lo:
+        assert _close(lk[k], lo[k]), k
+    for a, b in zip(mk, mo):
+        assert torch.equal(a, b)
+    assert torch.equal(tk, to_)                      # the target image was mutated identically
+    for a, b in zip(gk, go):
+        assert _gerr(a, b) < GRAD_RTOL
