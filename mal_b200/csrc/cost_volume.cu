@@ -408,6 +408,178 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
   }
 }
 
+
+// ---- sweep, variant Q: four lanes per pixel ------------------------------------------------------
+// A warp owns 8 consecutive pixels; the 4 lanes of a pixel own the four 16-channel chunks (C <= 64).
+// Per group of 4 depth planes each lane projects ONE plane, the descriptors travel by shuffle, and
+// each lane then sweeps the 4 planes for its chunk with the 2x2x16 register cache.  The four chunk
+// sums of a plane are gathered by shuffle and added in the reference's order.  Compared with the
+// one-pixel-per-lane kernel above: no descriptor / partial-sum arrays in shared memory, no block
+// barrier inside the sweep, and only 8 (not 32) pixels share a warp's re-fetch decision, so a texel
+// block is re-fetched in ~20% instead of ~57% of the warp iterations (profiles/r1_notes.md).
+constexpr int CQ_NT = 128;                 // 4 warps = 32 pixels per CTA
+inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * num_bins * CV_PX + 64) * 4; }
+
+template <int CONV, int MINB>
+__global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp) {
+  __shared__ CvGeom geom;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane & 3, col = warp * 8 + (lane >> 2);   // chunk of this lane, pixel column in the tile
+  const int qbase = lane & ~3;                               // first lane of this pixel's quad
+  const int h = a.height, w = a.width, hw = h * w;
+  const int nb = a.num_bins, nchunks = Cp / CV_CHUNK, nquads = Cp / 4;
+  const int tiles = (hw + CV_PX - 1) / CV_PX;
+  const int b = blockIdx.x / tiles;
+  const int p = (blockIdx.x - b * tiles) * CV_PX + col;
+  const bool pix_ok = p < hw;
+  const int py = pix_ok ? p / w : 0, px = pix_ok ? p - py * w : 0;
+  const bool inner = pix_ok && py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
+  const bool active = sub < nchunks;       // lanes beyond the last chunk still project their plane
+
+  float* cost = reinterpret_cast<float*>(dyn_smem());   // [nb][CV_PX]
+  float* cnt = cost + (size_t)nb * CV_PX;                // [nb][CV_PX]
+  for (int k = sub; k < nb; k += 4) { cost[k * CV_PX + col] = 0.0f; cnt[k * CV_PX + col] = 0.0f; }
+
+  const float4* curq = reinterpret_cast<const float4*>(a.packed) + (size_t)b * nquads * hw;
+  const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
+  float4 cq[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    cq[j] = (pix_ok && active) ? ldg4(curq + (size_t)(sub * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int f = 0; f < a.num_lookup; f++) {
+    __syncthreads();
+    if (tid < 12) {
+      geom.P[tid] = kt_entry(a.K + b * 16, a.poses + ((size_t)b * a.num_lookup + f) * 16, tid / 4, tid % 4);
+    } else if (tid < 21) {
+      int e = tid - 12;
+      geom.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
+    } else if (tid == 21) {
+      const float* T = a.poses + ((size_t)b * a.num_lookup + f) * 16;
+      float s = 0.0f;
+      for (int e = 0; e < 16; e++) s += T[e];
+      geom.live = (s != 0.0f) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!geom.live) continue;
+    const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
+    const float4* lqc = lookq + ((size_t)b * a.num_lookup + f) * nquads * hw + (size_t)sub * 4 * hw;
+    float4 t00[4], t01[4], t10[4], t11[4];
+    int coff = -1;
+
+    for (int k0 = 0; k0 < nb; k0 += 4) {
+      // ---- this lane's plane of the group: projection descriptor --------------------------------
+      const int kk = k0 + sub;
+      int off = -1;
+      float tx = 0.0f, ty = 0.0f;
+      if (inner && kk < nb) {
+        const float depth = __ldg(a.bins + kk);
+        GridPoint gp = project_grid<CONV>(geom.P, ray, depth, a.eps, h, w);
+        const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
+        const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
+        if (xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2)) {
+          const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+          const float x0 = floorf(ux), y0 = floorf(uy);
+          const int xi = min(max((int)x0, 0), w - 2), yi = min(max((int)y0, 0), h - 2);
+          off = yi * w + xi;
+          tx = xsub(ux, x0);
+          ty = xsub(uy, y0);
+        }
+      }
+      // ---- the four planes of the group, this lane's chunk -------------------------------------
+      float s_mine = 0.0f;
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        const int o = __shfl_sync(0xffffffffu, off, qbase | j);
+        const float txj = __shfl_sync(0xffffffffu, tx, qbase | j);
+        const float tyj = __shfl_sync(0xffffffffu, ty, qbase | j);
+        float acc = 0.0f;
+        if (o >= 0 && active) {
+          if (o != coff) {
+            coff = o;
+            const float4* base = lqc + o;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              t00[q] = ldg4(base); t01[q] = ldg4(base + 1);
+              const float4* row1 = base + w;
+              t10[q] = ldg4(row1); t11[q] = ldg4(row1 + 1);
+              base += hw;
+            }
+          }
+          const float e = xsub(1.0f, txj), sy_ = xsub(1.0f, tyj);
+          const float nw = xmul(sy_, e), ne = xmul(sy_, txj), sw = xmul(tyj, e), se = xmul(tyj, txj);
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc = quad_l1(acc, t00[q], t01[q], t10[q], t11[q], cq[q], nw, ne, sw, se);
+        }
+        // chunk sums of plane j in the reference's order; inactive / masked lanes contribute +0
+        const float c0 = __shfl_sync(0xffffffffu, acc, qbase);
+        const float c1 = __shfl_sync(0xffffffffu, acc, qbase | 1);
+        const float c2 = __shfl_sync(0xffffffffu, acc, qbase | 2);
+        const float c3 = __shfl_sync(0xffffffffu, acc, qbase | 3);
+        const float sj = xadd(xadd(xadd(c0, c1), c2), c3);
+        if (sub == j) s_mine = sj;
+      }
+      if (off >= 0) {
+        const float diff = xdiv(s_mine, (float)a.channels);   // .mean(1); edge mask == 1
+        const int o = kk * CV_PX + col;
+        cost[o] = xadd(cost[o], diff);
+        if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue: lane `sub` of a pixel owns planes sub, sub+4, ... ---------------------------------
+  float vmax = -INFINITY;
+  for (int k = sub; k < nb; k += 4) {
+    const int o = k * CV_PX + col;
+    const float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));
+    cost[o] = v;
+    vmax = fmaxf(vmax, v);
+  }
+  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
+  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
+  float npos = 0.0f, best = INFINITY;
+  int besti = 0x7fffffff;
+  for (int k = sub; k < nb; k += 4) {
+    const int o = k * CV_PX + col;
+    const float v = cost[o];
+    const float miss = (v == 0.0f) ? 1.0f : 0.0f;
+    float out = v;
+    if (a.set_missing_to_max) out = xadd(xmul(v, xsub(1.0f, miss)), xmul(vmax, miss));
+    cost[o] = out;
+    cnt[o] = miss;
+    if (xmul(out, xsub(1.0f, miss)) > 0.0f) npos += 1.0f;
+    const float viz = (out == 0.0f) ? 100.0f : out;
+    if (viz < best) { best = viz; besti = k; }
+  }
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    npos += __shfl_xor_sync(0xffffffffu, npos, m);
+    const float ov = __shfl_xor_sync(0xffffffffu, best, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, m);
+    if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  const int thr = a.num_bins_threshold > 0 ? a.num_bins_threshold : nb;
+  const float conf = (npos == (float)thr) ? 1.0f : 0.0f;
+  if (pix_ok) {
+    const size_t vol = (size_t)b * nb * hw;
+    for (int k = sub; k < nb; k += 4) {
+      const int o = k * CV_PX + col;
+      float out = cost[o];
+      if (a.apply_confidence) out = xmul(out, conf);
+      a.cost_volume[vol + (size_t)k * hw + p] = out;
+      if (a.missing_mask) a.missing_mask[vol + (size_t)k * hw + p] = cnt[o];
+    }
+    if (sub == 0) {
+      const size_t po = (size_t)b * hw + p;
+      if (a.confidence) a.confidence[po] = conf;
+      if (a.argmin) a.argmin[po] = besti;
+      if (a.lowest_cost) a.lowest_cost[po] = xdiv(1.0f, __ldg(a.bins + besti));
+    }
+  }
+}
+
 }  // namespace mal
 
 using namespace mal;
@@ -461,6 +633,23 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
     else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp);                \
   } while (0)
+  // kernel choice: the four-lanes-per-pixel sweep handles up to 4 chunks (C <= 64) and no
+  // DynamicDepth extras; MAL_CV_KERNEL=lane forces the one-pixel-per-lane kernel (tuning only)
+  bool quad = !dyn && Cp / CV_CHUNK <= 4;
+  if (const char* e = getenv("MAL_CV_KERNEL")) quad = quad && e[0] != 'l';
+  if (quad) {
+    const size_t qsmem = cq_smem_bytes(a.num_bins);
+#define MAL_CQ_LAUNCH(CONV_)                                                                              \
+  do {                                                                                                    \
+    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp);            \
+    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp);       \
+    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp);                      \
+  } while (0)
+    if (a.convention == MAL_CONV_MANYDEPTH) MAL_CQ_LAUNCH(MAL_CONV_MANYDEPTH);
+    else MAL_CQ_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_CQ_LAUNCH
+    return check_launch("cv_sweep_quad_kernel");
+  }
   if (a.convention == MAL_CONV_MANYDEPTH) MAL_CV_LAUNCH(MAL_CONV_MANYDEPTH);
   else MAL_CV_LAUNCH(MAL_CONV_DUALREFINE);
 #undef MAL_CV_LAUNCH

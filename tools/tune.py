@@ -43,10 +43,13 @@ def main():
         os.environ["MAL_CV_MINB"] = only[2:] or "4"
         print("cv", timeit(cv, iters=3, warm=1))
         return
-    for minb in ("3", "4", "5"):
-        os.environ["MAL_CV_MINB"] = minb
-        res["cost_volume minb=" + minb] = timeit(cv)
+    for kern in ("quad", "lane"):
+        os.environ["MAL_CV_KERNEL"] = kern
+        for minb in ("3", "4", "5"):
+            os.environ["MAL_CV_MINB"] = minb
+            res["cost_volume %s minb=%s" % (kern, minb)] = timeit(cv)
     os.environ.pop("MAL_CV_MINB")
+    os.environ.pop("MAL_CV_KERNEL")
 
     def k_ident(i):
         b = bufs[i % 3]
