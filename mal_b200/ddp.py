@@ -23,7 +23,6 @@ import os
 import torch
 import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import loss_utils, ops, trainer_ops
 from .pose import transformation_from_parameters

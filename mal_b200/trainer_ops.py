@@ -24,8 +24,7 @@ import torch.nn.functional as F
 
 from . import ops, raw
 from .layers import disp_to_depth
-from .loss_utils import (WarpSpec, _draw_noise, _no_ssim, compute_main_losses, compute_mono_losses,
-                         identity_reprojection)
+from .loss_utils import WarpSpec, _draw_noise, compute_main_losses, compute_mono_losses, identity_reprojection
 
 _DEFAULTS = dict(height=192, width=640, min_depth=0.1, max_depth=100.0, frame_ids=[0, -1, 1], sclm=0,
                  temporal=False, main_temporal=False, distil=False, no_ens=False, loss_blc=False,

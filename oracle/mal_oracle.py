@@ -28,8 +28,6 @@ restated from its published semantics (duplicate-index max reduction).
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 import torch
 import torch.nn.functional as F

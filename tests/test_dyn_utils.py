@@ -1,8 +1,6 @@
 """MAL temporal hint (mal_dynamic_instance / mal_fill_dynamic_obj) against the oracle restatement
 of manydepth/dyn_utils.py (pinned bitwise against the reference's TorchScript by
 oracle/pin_against_reference.py).  Integer / byte work: everything must be bit-exact."""
-from types import SimpleNamespace
-
 import pytest
 import torch
 

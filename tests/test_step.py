@@ -4,7 +4,6 @@ reference functions, and the CUDA-graph replay against the eager run."""
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
 from mal_b200 import step as S
 from mal_b200.utils.synthetic import to_device
