@@ -247,6 +247,15 @@ int mal_project3d(const float* points, const float* K, const float* T, int batch
 int mal_project3d_backward(const float* points, const float* K, const float* T, const float* grad_pix,
                            const float* grad_z, int batch, int height, int width, int convention, float eps,
                            float* grad_points, float* grad_P, float* partials, mal_stream_t stream);
+/* F.grid_sample(img, grid, mode="bilinear", padding_mode=border?"border":"zeros", align_corners) as the
+ * reference calls it (manydepth/trainer.py:1122-1125, dualrefine/trainer.py:444-447,
+ * networks/resnet_encoder.py:189, dynamicdepth/rigid_warp.py:367), with the rounding of ATen's CPU
+ * kernel; the backward is w.r.t. the grid (B,Ho,Wo,2) only. */
+int mal_grid_sample(const float* img, const float* grid, int batch, int channels, int height, int width,
+                    int out_height, int out_width, int align_corners, int border, float* out, mal_stream_t stream);
+int mal_grid_sample_backward(const float* img, const float* grid, const float* grad_out, int batch, int channels,
+                             int height, int width, int out_height, int out_width, int align_corners, int border,
+                             float* grad_grid, mal_stream_t stream);
 int mal_ssim(const float* x, const float* y, int planes, int height, int width, float* out, mal_stream_t stream);
 /* workspace: 4 * planes * height * width floats; grad_y may be NULL */
 int mal_ssim_backward(const float* x, const float* y, const float* grad_out, int planes, int height, int width,

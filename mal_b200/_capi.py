@@ -136,6 +136,8 @@ EXPORTS = {
     "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_project3d": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_project3d_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 4),
+    "mal_grid_sample": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
+    "mal_grid_sample_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
     "mal_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }

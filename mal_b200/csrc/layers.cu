@@ -240,6 +240,65 @@ __global__ void __launch_bounds__(LY_NT) ssim_bwd_gather_kernel(const float* __r
   }
 }
 
+// ---- F.grid_sample (bilinear; border or zeros padding) ------------------------------------------------
+// Forward with the arithmetic of ATen's vectorised CPU kernel (so a materialised warp is bit-identical
+// to the reference's), backward w.r.t. the grid (source images are data at every reference call site).
+template <int CONV>
+__device__ __forceinline__ Taps grid_taps(float gx, float gy, int H, int W, int border, float* gmx, float* gmy) {
+  float ux = unnormalize<CONV>(gx, W), uy = unnormalize<CONV>(gy, H);
+  *gmx = *gmy = 1.0f;
+  if (border) {   // clip_coordinates_set_grad: the coordinate gradient vanishes where clamped
+    *gmx = (ux <= 0.0f || ux >= (float)(W - 1)) ? 0.0f : 1.0f;
+    *gmy = (uy <= 0.0f || uy >= (float)(H - 1)) ? 0.0f : 1.0f;
+    ux = fminf((float)(W - 1), fmaxf(ux, 0.0f));
+    uy = fminf((float)(H - 1), fmaxf(uy, 0.0f));
+  }
+  Taps t = make_taps(ux, uy, H, W);
+  if (!(ux > -2.0f && ux < (float)W + 1.0f && uy > -2.0f && uy < (float)H + 1.0f)) t.v00 = t.v01 = t.v10 = t.v11 = false;
+  return t;
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(LY_NT) grid_sample_kernel(const float* __restrict__ img,
+                                                           const float2* __restrict__ grid, int B, int C, int H, int W,
+                                                           int Ho, int Wo, int border, float* __restrict__ out) {
+  const size_t hwo = (size_t)Ho * Wo, hw = (size_t)H * W, total = (size_t)B * hwo;
+  for (size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x; i < total; i += (size_t)gridDim.x * LY_NT) {
+    const size_t b = i / hwo, p = i - b * hwo;
+    const float2 g = grid[i];
+    float mx, my;
+    const Taps t = grid_taps<CONV>(g.x, g.y, H, W, border, &mx, &my);
+    for (int c = 0; c < C; c++) out[(b * C + c) * hwo + p] = bilinear(img + (b * C + c) * hw, t);
+  }
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(LY_NT) grid_sample_bwd_kernel(const float* __restrict__ img,
+                                                               const float2* __restrict__ grid,
+                                                               const float* __restrict__ g_out, int B, int C, int H,
+                                                               int W, int Ho, int Wo, int border,
+                                                               float2* __restrict__ g_grid) {
+  const size_t hwo = (size_t)Ho * Wo, hw = (size_t)H * W, total = (size_t)B * hwo;
+  // d(unnormalised)/d(grid): (size-1)/2 with align_corners, size/2 without
+  const float sx = CONV == MAL_CONV_MANYDEPTH ? (float)(W - 1) * 0.5f : (float)W * 0.5f;
+  const float sy = CONV == MAL_CONV_MANYDEPTH ? (float)(H - 1) * 0.5f : (float)H * 0.5f;
+  for (size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x; i < total; i += (size_t)gridDim.x * LY_NT) {
+    const size_t b = i / hwo, p = i - b * hwo;
+    const float2 g = grid[i];
+    float mx, my;
+    const Taps t = grid_taps<CONV>(g.x, g.y, H, W, border, &mx, &my);
+    float gix = 0.0f, giy = 0.0f;
+    for (int c = 0; c < C; c++) {
+      float v00, v01, v10, v11;
+      bilinear(img + (b * C + c) * hw, t, &v00, &v01, &v10, &v11);
+      const float go = __ldg(g_out + (b * C + c) * hwo + p);
+      gix += go * ((v01 - v00) * (1.0f - t.ty) + (v11 - v10) * t.ty);
+      giy += go * ((v10 - v00) * (1.0f - t.tx) + (v11 - v01) * t.tx);
+    }
+    g_grid[i] = make_float2(gix * mx * sx, giy * my * sy);
+  }
+}
+
 }  // namespace mal
 
 using namespace mal;
@@ -328,4 +387,38 @@ extern "C" int mal_ssim_backward(const float* x, const float* y, const float* gr
   launch(ssim_bwd_gather_kernel, dim3(nb), dim3(LY_NT), 0, st, x, y, (const float*)workspace, planes, height, width,
          grad_x, grad_y);
   return check_launch("ssim_bwd_gather_kernel");
+}
+
+extern "C" int mal_grid_sample(const float* img, const float* grid, int batch, int channels, int height, int width,
+                               int out_height, int out_width, int align_corners, int border, float* out,
+                               mal_stream_t stream) {
+  MAL_REQUIRE(img && grid && out && batch > 0 && channels > 0 && height > 1 && width > 1 && out_height > 0 &&
+                  out_width > 0,
+              "mal_grid_sample: bad arguments");
+  const unsigned nb = ly_blocks((size_t)batch * out_height * out_width);
+  if (align_corners)
+    launch(grid_sample_kernel<MAL_CONV_MANYDEPTH>, dim3(nb), dim3(LY_NT), 0, (cudaStream_t)stream, img,
+           reinterpret_cast<const float2*>(grid), batch, channels, height, width, out_height, out_width, border, out);
+  else
+    launch(grid_sample_kernel<MAL_CONV_DUALREFINE>, dim3(nb), dim3(LY_NT), 0, (cudaStream_t)stream, img,
+           reinterpret_cast<const float2*>(grid), batch, channels, height, width, out_height, out_width, border, out);
+  return check_launch("grid_sample_kernel");
+}
+
+extern "C" int mal_grid_sample_backward(const float* img, const float* grid, const float* grad_out, int batch,
+                                        int channels, int height, int width, int out_height, int out_width,
+                                        int align_corners, int border, float* grad_grid, mal_stream_t stream) {
+  MAL_REQUIRE(img && grid && grad_out && grad_grid && batch > 0 && channels > 0 && height > 1 && width > 1 &&
+                  out_height > 0 && out_width > 0,
+              "mal_grid_sample_backward: bad arguments");
+  const unsigned nb = ly_blocks((size_t)batch * out_height * out_width);
+  if (align_corners)
+    launch(grid_sample_bwd_kernel<MAL_CONV_MANYDEPTH>, dim3(nb), dim3(LY_NT), 0, (cudaStream_t)stream, img,
+           reinterpret_cast<const float2*>(grid), grad_out, batch, channels, height, width, out_height, out_width,
+           border, reinterpret_cast<float2*>(grad_grid));
+  else
+    launch(grid_sample_bwd_kernel<MAL_CONV_DUALREFINE>, dim3(nb), dim3(LY_NT), 0, (cudaStream_t)stream, img,
+           reinterpret_cast<const float2*>(grid), grad_out, batch, channels, height, width, out_height, out_width,
+           border, reinterpret_cast<float2*>(grad_grid));
+  return check_launch("grid_sample_bwd_kernel");
 }

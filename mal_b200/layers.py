@@ -76,6 +76,11 @@ class SSIM(nn.Module):
         return ops.ssim(x, y)
 
 
+def grid_sample(img, grid, padding_mode="border", align_corners=True):
+    """Bilinear F.grid_sample with the reference's CPU rounding (differentiable w.r.t. the grid)."""
+    return ops.grid_sample(img, grid, padding_mode=padding_mode, align_corners=align_corners)
+
+
 def get_smooth_loss(disp, img):
     """Edge-aware smoothness of a disparity image."""
     return ops.smooth(disp, img, normalise=False)

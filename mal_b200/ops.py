@@ -19,7 +19,8 @@ from torch import Tensor
 from . import _capi, raw
 
 __all__ = ["photo", "reprojection_loss_map", "smooth", "main_terms", "cost_volume", "matching_mask",
-           "backproject", "project3d", "ssim", "forward_warp", "dynamic_instance", "fill_dynamic_obj"]
+           "backproject", "project3d", "ssim", "forward_warp", "dynamic_instance", "fill_dynamic_obj",
+           "grid_sample"]
 
 
 def _lib(t: Tensor):
@@ -561,3 +562,48 @@ def fill_dynamic_obj(mask, delta_x, delta_y, source, img):
     with torch.no_grad():
         return _fill_dynamic_obj_op(mask.contiguous(), delta_x, delta_y, source.detach().contiguous(),
                                     img.detach().contiguous())
+
+
+# --------------------------------------------------------------------------------------------
+# grid_sample with the reference's (CPU) rounding
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("mal_b200::grid_sample", mutates_args=())
+def _grid_sample_op(img: Tensor, grid: Tensor, align_corners: bool, border: bool) -> Tensor:
+    return raw.grid_sample(_lib(img), img, grid, align_corners, border)
+
+
+@_grid_sample_op.register_fake
+def _(img, grid, align_corners, border):
+    return img.new_empty((img.shape[0], img.shape[1], grid.shape[1], grid.shape[2]))
+
+
+@torch.library.custom_op("mal_b200::grid_sample_backward", mutates_args=())
+def _grid_sample_bwd_op(img: Tensor, grid: Tensor, grad_out: Tensor, align_corners: bool, border: bool) -> Tensor:
+    return raw.grid_sample_backward(_lib(img), img, grid, grad_out, align_corners, border)
+
+
+@_grid_sample_bwd_op.register_fake
+def _(img, grid, grad_out, align_corners, border):
+    return grid.new_empty(grid.shape)
+
+
+def _grid_sample_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.flags = (inputs[2], inputs[3])
+
+
+def _grid_sample_backward(ctx, g):
+    img, grid = ctx.saved_tensors
+    return None, _grid_sample_bwd_op(img, grid, g.contiguous(), ctx.flags[0], ctx.flags[1]), None, None
+
+
+_grid_sample_op.register_autograd(_grid_sample_backward, setup_context=_grid_sample_setup)
+
+
+def grid_sample(img, grid, padding_mode="border", align_corners=True):
+    """F.grid_sample(img, grid, mode="bilinear", ...) bit-identical to torch's CPU kernel (which the
+    reference's golden outputs come from); differentiable w.r.t. `grid` (the image is data)."""
+    if padding_mode not in ("border", "zeros"):
+        raise NotImplementedError("padding_mode must be 'border' or 'zeros'")
+    return _grid_sample_op(img.detach().contiguous(), grid.contiguous(), bool(align_corners),
+                           padding_mode == "border")

@@ -409,3 +409,25 @@ def dynamic_instance_backward(handle, *, mask_last, mask_next, deltas, grad_ori_
                                                      _vp(flags), _stream(gol)), handle)
     LAUNCHES[0] += 2
     return gl, gn
+
+
+def grid_sample(handle, img, grid, align_corners=True, border=True):
+    B, Cn, H, W = img.shape
+    Ho, Wo = grid.shape[1:3]
+    img, grid = _f32(img, "img"), _f32(grid, "grid", (B, Ho, Wo, 2))
+    _same_device([img, grid])
+    out = torch.empty((B, Cn, Ho, Wo), dtype=torch.float32, device=img.device)
+    _capi.check(handle.mal_grid_sample(_vp(img), _vp(grid), B, Cn, H, W, Ho, Wo, int(align_corners), int(border),
+                                       _vp(out), _stream(img)), handle)
+    return out
+
+
+def grid_sample_backward(handle, img, grid, grad_out, align_corners=True, border=True):
+    B, Cn, H, W = img.shape
+    Ho, Wo = grid.shape[1:3]
+    img, grid = _f32(img, "img"), _f32(grid, "grid", (B, Ho, Wo, 2))
+    grad_out = _f32(grad_out, "grad_out", (B, Cn, Ho, Wo))
+    g = torch.empty_like(grid)
+    _capi.check(handle.mal_grid_sample_backward(_vp(img), _vp(grid), _vp(grad_out), B, Cn, H, W, Ho, Wo,
+                                                int(align_corners), int(border), _vp(g), _stream(img)), handle)
+    return g

@@ -72,7 +72,7 @@ def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False
                 cam = back(depth, inputs[("inv_K", 0)])
                 pix = proj(cam, inputs[("K", 0)], T)
                 outputs[("sample", frame_id, scale)] = pix
-                outputs[("color", frame_id, scale)] = F.grid_sample(
+                outputs[("color", frame_id, scale)] = ops.grid_sample(
                     inputs[("color", frame_id, 0)], pix, padding_mode="border",
                     align_corners=_o(opt, "convention") == raw.CONV_MANYDEPTH)
     return outputs

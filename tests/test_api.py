@@ -374,3 +374,21 @@ def test_dynamicdepth_losses_match_oracle(op_device, is_multi, selec, zero):
     assert torch.equal(tk, to_)                      # the target image was mutated identically
     for a, b in zip(gk, go):
         assert _gerr(a, b) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("padding,align", [("border", True), ("border", False), ("zeros", True), ("zeros", False)])
+def test_grid_sample_matches_torch_cpu(op_device, padding, align):
+    """layers.grid_sample: forward bit-identical to torch's CPU F.grid_sample, backward w.r.t. the grid."""
+    dev = op_device
+    gen = torch.Generator().manual_seed(11)
+    img = torch.rand(2, 3, 24, 40, generator=gen)
+    grid = (torch.rand(2, 20, 36, 2, generator=gen) * 2.4 - 1.2)
+    w = torch.rand(2, 3, 20, 36, generator=gen)
+    g_c = grid.clone().requires_grad_(True)
+    want = F.grid_sample(img, g_c, padding_mode=padding, align_corners=align)
+    want_g, = torch.autograd.grad((want * w).sum(), g_c)
+    g_d = grid.clone().to(dev).requires_grad_(True)
+    got = layers.grid_sample(img.to(dev), g_d, padding_mode=padding, align_corners=align)
+    assert torch.equal(got.detach().cpu(), want.detach())
+    got_g, = torch.autograd.grad((got * w.to(dev)).sum(), g_d)
+    assert _gerr(got_g, want_g) < GRAD_RTOL

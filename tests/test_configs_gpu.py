@@ -69,12 +69,12 @@ def test_config3_cityscapes_temporal_hint_step():
                     [x.cpu() for x in g]))
     (l0, i0, r0, g0), (l1, i1, r1, g1) = res
     assert abs(l0 - l1) <= 1e-5 * abs(l0)
-    # torch's CUDA grid_sample rounds differently from the CPU one: selections agree except at near-ties
-    assert float((i0 == i1).float().mean()) > 0.999
-    assert float(((r0 - r1).abs() <= 1e-5).float().mean()) > 0.9999
+    # the materialised warps come from mal_b200's own grid_sample (CPU rounding): everything is exact
+    assert torch.equal(i0, i1)
+    assert torch.equal(r0, r1)
     assert float((i0 >= 2).float().mean()) > 1e-4
     for a, b in zip(g1, g0):
-        assert _gerr(a, b) < 2e-3      # two different bilinear-sampling implementations upstream
+        assert _gerr(a, b) < 1e-4
 
 
 def test_config4_dualrefine_full_size():
