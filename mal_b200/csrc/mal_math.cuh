@@ -10,7 +10,8 @@
 //   * grid_sample bilinear   nw*a, then 3 FMAs        (GridSamplerKernel.cpp, contracted)
 //   * avg_pool2d 3x3         row-major running sum, then /9   (AvgPoolKernel.cpp)
 //   * SSIM formula, mean over channels ((c0+c1)+c2)/3, 0.85*s+0.15*l: one rounding per op
-// tests/test_bitexact_model.py replays this contract on the host against torch.
+// The contract is replayed on the host against torch by the CPU twin (tests/emu): the golden and
+// oracle tests demand torch.equal on every selection, min-reprojection and cost-volume value.
 #pragma once
 #include "mal_common.cuh"
 
