@@ -39,6 +39,10 @@ def _ptr(t):
 
 def _stream(t):
     if t.is_cuda:
+        if t.device.index != torch.cuda.current_device():
+            # kernels are launched into the calling thread's current CUDA context
+            raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               "call torch.cuda.set_device() (one process per GPU) first")
         return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     return C.c_void_p(0)
 
