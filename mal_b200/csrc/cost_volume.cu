@@ -411,21 +411,39 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 
 // ---- sweep, variant Q: four lanes per pixel ------------------------------------------------------
 // A warp owns 8 consecutive pixels; the 4 lanes of a pixel own the four 16-channel chunks (C <= 64).
-// Per group of 4 depth planes each lane projects ONE plane, the descriptors travel by shuffle, and
-// each lane then sweeps the 4 planes for its chunk with the 2x2x16 register cache.  The four chunk
-// sums of a plane are gathered by shuffle and added in the reference's order.  Compared with the
-// one-pixel-per-lane kernel above: no descriptor / partial-sum arrays in shared memory, no block
-// barrier inside the sweep, and only 8 (not 32) pixels share a warp's re-fetch decision, so a texel
-// block is re-fetched in ~20% instead of ~57% of the warp iterations (profiles/r1_notes.md).
+// Per group of 4 depth planes each lane projects ONE plane; descriptors and chunk sums are exchanged
+// through a per-warp shared-memory scratch (one 128-bit store + broadcast loads: half the L1
+// wavefronts of the equivalent shuffles), and each lane then sweeps the 4 planes for its chunk with
+// the 2x2x16 register cache.  No block barrier inside the sweep, and only 8 (not 32) pixels share a
+// warp's re-fetch decision, so a texel block is re-fetched in ~20% instead of ~57% of the warp
+// iterations (profiles/r1_notes.md).
+// The bilinear blend and the subtraction run on packed fp32 pairs (FFMA2 / FADD2: two channels per
+// instruction, same IEEE results, mal_common.cuh); only the sequential |.| accumulation is scalar:
+// 3.5 instead of 6 issue slots per (pixel, plane, channel).
 constexpr int CQ_NT = 128;                 // 4 warps = 32 pixels per CTA
-inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * num_bins * CV_PX + 64) * 4; }
+inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * ((num_bins + 3) / 4 * 4) * CV_PX + 64) * 4; }
+// cost / count accumulators: [plane group][pixel][plane & 3] so that the 32 lanes of a warp
+// (8 pixels x 4 planes of a group) hit 32 different banks
+__device__ __forceinline__ int cq_idx(int k, int col) { return (k >> 2) * (4 * CV_PX) + col * 4 + (k & 3); }
+
+struct CqTaps { pk2 v[4][2]; };   // one tap of a 16-channel chunk: 4 channel quads x {xy, zw}
+
+__device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
+  const float4 v = ldg4(reinterpret_cast<const float4*>(p));
+  dst[0] = pack2(v.x, v.y);
+  dst[1] = pack2(v.z, v.w);
+}
 
 template <int CONV, int MINB>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp) {
   __shared__ CvGeom geom;
+  __shared__ float s_tx[4][4][8], s_ty[4][4][8];     // [warp][plane][pixel] bilinear fractions
+  __shared__ int s_o[4][4][8];                         // [warp][plane][pixel] tap origin or -1
+  __shared__ __align__(16) float4 s_part[4][4][8];    // [warp][plane][pixel] chunk sums c0..c3
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sub = lane & 3, col = warp * 8 + (lane >> 2);   // chunk of this lane, pixel column in the tile
-  const int qbase = lane & ~3;                               // first lane of this pixel's quad
+  // chunk of this lane, pixel column in the tile.  A quarter-warp (the unit a 128-bit load is
+  // processed in) holds 8 consecutive pixels of ONE chunk: its 8 taps are 128 contiguous bytes.
+  const int sub = lane >> 3, pl = lane & 7, col = warp * 8 + pl;
   const int h = a.height, w = a.width, hw = h * w;
   const int nb = a.num_bins, nchunks = Cp / CV_CHUNK, nquads = Cp / 4;
   const int tiles = (hw + CV_PX - 1) / CV_PX;
@@ -437,15 +455,19 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   const bool active = sub < nchunks;       // lanes beyond the last chunk still project their plane
 
   float* cost = reinterpret_cast<float*>(dyn_smem());   // [nb][CV_PX]
-  float* cnt = cost + (size_t)nb * CV_PX;                // [nb][CV_PX]
-  for (int k = sub; k < nb; k += 4) { cost[k * CV_PX + col] = 0.0f; cnt[k * CV_PX + col] = 0.0f; }
+  float* cnt = cost + (size_t)((nb + 3) / 4 * 4) * CV_PX;
+  for (int k = sub; k < nb; k += 4) { cost[cq_idx(k, col)] = 0.0f; cnt[cq_idx(k, col)] = 0.0f; }
 
   const float4* curq = reinterpret_cast<const float4*>(a.packed) + (size_t)b * nquads * hw;
   const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
-  float4 cq[4];
+  pk2 ncur[4][2];   // -current features of this lane's chunk (w - cur == w + (-cur))
 #pragma unroll
-  for (int j = 0; j < 4; j++)
-    cq[j] = (pix_ok && active) ? ldg4(curq + (size_t)(sub * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < 4; j++) {
+    const float4 v = (pix_ok && active) ? ldg4(curq + (size_t)(sub * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ncur[j][0] = pack2(-v.x, -v.y);
+    ncur[j][1] = pack2(-v.z, -v.w);
+  }
+  const pk2 one2 = dup2(1.0f), mone2 = dup2(-1.0f);
 
   for (int f = 0; f < a.num_lookup; f++) {
     __syncthreads();
@@ -464,7 +486,9 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     if (!geom.live) continue;
     const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
     const float4* lqc = lookq + ((size_t)b * a.num_lookup + f) * nquads * hw + (size_t)sub * 4 * hw;
-    float4 t00[4], t01[4], t10[4], t11[4];
+    const char* lbase = reinterpret_cast<const char*>(lqc);
+    const size_t row_stride = (size_t)w * 16, quad_stride = (size_t)hw * 16;
+    CqTaps t00, t01, t10, t11;
     int coff = -1;
 
     for (int k0 = 0; k0 < nb; k0 += 4) {
@@ -486,42 +510,57 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
           ty = xsub(uy, y0);
         }
       }
+      if (!__any_sync(0xffffffffu, off >= 0)) continue;   // the warp's 8 pixels x 4 planes are all masked
+      s_tx[warp][sub][pl] = tx;
+      s_ty[warp][sub][pl] = ty;
+      s_o[warp][sub][pl] = off;
+      __syncwarp();
       // ---- the four planes of the group, this lane's chunk -------------------------------------
-      float s_mine = 0.0f;
-#pragma unroll 1
+      float acc[4];
+#pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int o = __shfl_sync(0xffffffffu, off, qbase | j);
-        const float txj = __shfl_sync(0xffffffffu, tx, qbase | j);
-        const float tyj = __shfl_sync(0xffffffffu, ty, qbase | j);
-        float acc = 0.0f;
+        const int o = s_o[warp][j][pl];
+        acc[j] = 0.0f;
         if (o >= 0 && active) {
           if (o != coff) {
             coff = o;
-            const float4* base = lqc + o;
+            // two 64-bit pointer increments per channel quad; the taps are fixed offsets from them
+            const char* r0 = lbase + (size_t)(unsigned)o * 16;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              t00[q] = ldg4(base); t01[q] = ldg4(base + 1);
-              const float4* row1 = base + w;
-              t10[q] = ldg4(row1); t11[q] = ldg4(row1 + 1);
-              base += hw;
+              const char* r1 = r0 + row_stride;
+              cq_ld(t00.v[q], r0); cq_ld(t01.v[q], r0 + 16);
+              cq_ld(t10.v[q], r1); cq_ld(t11.v[q], r1 + 16);
+              r0 += quad_stride;
             }
           }
-          const float e = xsub(1.0f, txj), sy_ = xsub(1.0f, tyj);
-          const float nw = xmul(sy_, e), ne = xmul(sy_, txj), sw = xmul(tyj, e), se = xmul(tyj, txj);
+          const pk2 tx2 = dup2(s_tx[warp][j][pl]), ty2 = dup2(s_ty[warp][j][pl]);
+          const pk2 e2 = x2fma(tx2, mone2, one2), s2 = x2fma(ty2, mone2, one2);   // 1 - tx, 1 - ty
+          const pk2 nw = x2mul(s2, e2), ne = x2mul(s2, tx2), sw = x2mul(ty2, e2), se = x2mul(ty2, tx2);
+          float s = 0.0f;
 #pragma unroll
-          for (int q = 0; q < 4; q++) acc = quad_l1(acc, t00[q], t01[q], t10[q], t11[q], cq[q], nw, ne, sw, se);
+          for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+              const pk2 wq = x2fma(t11.v[q][hh], se, x2fma(t10.v[q][hh], sw, x2fma(t01.v[q][hh], ne, x2mul(t00.v[q][hh], nw))));
+              const pk2 d = x2add(wq, ncur[q][hh]);
+              s = xadd(s, fabsf(lo2(d)));
+              s = xadd(s, fabsf(hi2(d)));
+            }
+          }
+          acc[j] = s;
         }
-        // chunk sums of plane j in the reference's order; inactive / masked lanes contribute +0
-        const float c0 = __shfl_sync(0xffffffffu, acc, qbase);
-        const float c1 = __shfl_sync(0xffffffffu, acc, qbase | 1);
-        const float c2 = __shfl_sync(0xffffffffu, acc, qbase | 2);
-        const float c3 = __shfl_sync(0xffffffffu, acc, qbase | 3);
-        const float sj = xadd(xadd(xadd(c0, c1), c2), c3);
-        if (sub == j) s_mine = sj;
       }
+      // ---- chunk sums of each plane, gathered in the reference's order ------------------------
+      float* part = reinterpret_cast<float*>(&s_part[warp][0][0]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) part[(j * 8 + pl) * 4 + sub] = acc[j];   // inactive / masked lanes contribute +0
+      __syncwarp();
       if (off >= 0) {
+        const float4 c = s_part[warp][sub][pl];
+        const float s_mine = xadd(xadd(xadd(c.x, c.y), c.z), c.w);
         const float diff = xdiv(s_mine, (float)a.channels);   // .mean(1); edge mask == 1
-        const int o = kk * CV_PX + col;
+        const int o = cq_idx(kk, col);
         cost[o] = xadd(cost[o], diff);
         if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
       }
@@ -532,17 +571,17 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   // ---- epilogue: lane `sub` of a pixel owns planes sub, sub+4, ... ---------------------------------
   float vmax = -INFINITY;
   for (int k = sub; k < nb; k += 4) {
-    const int o = k * CV_PX + col;
+    const int o = cq_idx(k, col);
     const float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));
     cost[o] = v;
     vmax = fmaxf(vmax, v);
   }
-  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
-  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
+  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
+  vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
   float npos = 0.0f, best = INFINITY;
   int besti = 0x7fffffff;
   for (int k = sub; k < nb; k += 4) {
-    const int o = k * CV_PX + col;
+    const int o = cq_idx(k, col);
     const float v = cost[o];
     const float miss = (v == 0.0f) ? 1.0f : 0.0f;
     float out = v;
@@ -554,7 +593,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     if (viz < best) { best = viz; besti = k; }
   }
 #pragma unroll
-  for (int m = 1; m <= 2; m <<= 1) {
+  for (int m = 8; m <= 16; m <<= 1) {
     npos += __shfl_xor_sync(0xffffffffu, npos, m);
     const float ov = __shfl_xor_sync(0xffffffffu, best, m);
     const int oi = __shfl_xor_sync(0xffffffffu, besti, m);
@@ -565,7 +604,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   if (pix_ok) {
     const size_t vol = (size_t)b * nb * hw;
     for (int k = sub; k < nb; k += 4) {
-      const int o = k * CV_PX + col;
+      const int o = cq_idx(k, col);
       float out = cost[o];
       if (a.apply_confidence) out = xmul(out, conf);
       a.cost_volume[vol + (size_t)k * hw + p] = out;

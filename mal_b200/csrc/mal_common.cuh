@@ -87,6 +87,55 @@ __device__ __forceinline__ float xdivc(float x) {
   return __fmaf_rn(rem, r, q);
 }
 
+// ------------------------------------------------------------------ packed exact fp32 (f32x2)
+// sm_100a issues two independent IEEE round-to-nearest fp32 operations per lane with one
+// instruction (FFMA2 / FADD2 / FMUL2 on a 64-bit register pair).  Each half is the same
+// correctly-rounded operation as its scalar x* counterpart, so the arithmetic contract is
+// unchanged; what changes is the issue-slot cost (tools/ubench/f32x2.cu: an FFMA2 holds the fma
+// pipe for two cycles but one issue slot, so loads, shuffles and integer work issue beside it).
+typedef unsigned long long pk2;   // {lo, hi} fp32 pair in an aligned register pair
+#ifdef MAL_EMU
+__device__ __forceinline__ pk2 pack2(float lo, float hi) {
+  pk2 r; float v[2] = {lo, hi}; memcpy(&r, v, 8); return r;
+}
+__device__ __forceinline__ void unpack2(pk2 p, float& lo, float& hi) {
+  float v[2]; memcpy(v, &p, 8); lo = v[0]; hi = v[1];
+}
+__device__ __forceinline__ pk2 x2mul(pk2 a, pk2 b) {
+  float a0, a1, b0, b1; unpack2(a, a0, a1); unpack2(b, b0, b1);
+  return pack2(xmul(a0, b0), xmul(a1, b1));
+}
+__device__ __forceinline__ pk2 x2add(pk2 a, pk2 b) {
+  float a0, a1, b0, b1; unpack2(a, a0, a1); unpack2(b, b0, b1);
+  return pack2(xadd(a0, b0), xadd(a1, b1));
+}
+__device__ __forceinline__ pk2 x2fma(pk2 a, pk2 b, pk2 c) {
+  float a0, a1, b0, b1, c0, c1; unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
+  return pack2(xfma(a0, b0, c0), xfma(a1, b1, c1));
+}
+#else
+__device__ __forceinline__ pk2 pack2(float lo, float hi) {
+  pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(pk2 p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ pk2 x2mul(pk2 a, pk2 b) {
+  pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ pk2 x2add(pk2 a, pk2 b) {
+  pk2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ pk2 x2fma(pk2 a, pk2 b, pk2 c) {
+  pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+#endif
+__device__ __forceinline__ pk2 dup2(float v) { return pack2(v, v); }
+__device__ __forceinline__ float lo2(pk2 p) { float a, b; unpack2(p, a, b); return a; }
+__device__ __forceinline__ float hi2(pk2 p) { float a, b; unpack2(p, a, b); return b; }
+// a - b per half (RN(a + (-b)) == RN(a - b))
+__device__ __forceinline__ pk2 x2sub(pk2 a, pk2 b) { return x2add(a, b ^ 0x8000000080000000ull); }
+
 // ------------------------------------------------------------------ reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
