@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 // instruction, same IEEE results, mal_common.cuh); only the sequential |.| accumulation is scalar:
 // 3.5 instead of 6 issue slots per (pixel, plane, channel).
 constexpr int CQ_NT = 128;                 // 4 warps = 32 pixels per CTA
+constexpr int CQ_G = 8;                    // depth planes per group: every lane projects two of them
 inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * ((num_bins + 3) / 4 * 4) * CV_PX + 64) * 4; }
 // cost / count accumulators: [plane group][pixel][plane & 3] so that the 32 lanes of a warp
 // (8 pixels x 4 planes of a group) hit 32 different banks
@@ -437,9 +438,9 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
 template <int CONV, int MINB>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp) {
   __shared__ CvGeom geom;
-  __shared__ float s_tx[4][4][8], s_ty[4][4][8];     // [warp][plane][pixel] bilinear fractions
-  __shared__ int s_o[4][4][8];                         // [warp][plane][pixel] tap origin or -1
-  __shared__ __align__(16) float4 s_part[4][4][8];    // [warp][plane][pixel] chunk sums c0..c3
+  __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
+  __shared__ int s_o[4][CQ_G][8];                          // [warp][plane][pixel] tap origin or -1
+  __shared__ __align__(16) float4 s_part[4][CQ_G][8];     // [warp][plane][pixel] chunk sums c0..c3
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // chunk of this lane, pixel column in the tile.  A quarter-warp (the unit a 128-bit load is
   // processed in) holds 8 consecutive pixels of ONE chunk: its 8 taps are 128 contiguous bytes.
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     ncur[j][1] = pack2(-v.z, -v.w);
   }
   const pk2 one2 = dup2(1.0f), mone2 = dup2(-1.0f);
+  const float inv_channels = (a.channels & (a.channels - 1)) == 0 ? 1.0f / (float)a.channels : 0.0f;
 
   for (int f = 0; f < a.num_lookup; f++) {
     __syncthreads();
@@ -491,78 +493,92 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     CqTaps t00, t01, t10, t11;
     int coff = -1;
 
-    for (int k0 = 0; k0 < nb; k0 += 4) {
-      // ---- this lane's plane of the group: projection descriptor --------------------------------
-      const int kk = k0 + sub;
-      int off = -1;
-      float tx = 0.0f, ty = 0.0f;
-      if (inner && kk < nb) {
-        const float depth = __ldg(a.bins + kk);
-        GridPoint gp = project_grid<CONV>(geom.P, ray, depth, a.eps, h, w);
+    for (int k0 = 0; k0 < nb; k0 += CQ_G) {
+      // ---- this lane's two planes of the group: projection descriptors --------------------------
+      // branch-free, so that the two dependent chains (each ends in four IEEE divisions) interleave
+      int off[2];
+      float tx[2], ty[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int kk = k0 + sub + 4 * u;
+        const float depth = __ldg(a.bins + min(kk, nb - 1));
+        const GridPoint gp = project_grid<CONV>(geom.P, ray, depth, a.eps, h, w);
         const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
         const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
-        if (xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2)) {
-          const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
-          const float x0 = floorf(ux), y0 = floorf(uy);
-          const int xi = min(max((int)x0, 0), w - 2), yi = min(max((int)y0, 0), h - 2);
-          off = yi * w + xi;
-          tx = xsub(ux, x0);
-          ty = xsub(uy, y0);
-        }
+        const bool ok = inner && kk < nb && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2);
+        const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+        const float x0 = floorf(ux), y0 = floorf(uy);
+        // with the edge mask on, all four taps are inside the image; the clamp guards pathological inputs
+        const int xi = min(max((int)x0, 0), w - 2), yi = min(max((int)y0, 0), h - 2);
+        off[u] = ok ? yi * w + xi : -1;
+        tx[u] = xsub(ux, x0);
+        ty[u] = xsub(uy, y0);
       }
-      if (!__any_sync(0xffffffffu, off >= 0)) continue;   // the warp's 8 pixels x 4 planes are all masked
-      s_tx[warp][sub][pl] = tx;
-      s_ty[warp][sub][pl] = ty;
-      s_o[warp][sub][pl] = off;
-      __syncwarp();
-      // ---- the four planes of the group, this lane's chunk -------------------------------------
-      float acc[4];
+      if (!__any_sync(0xffffffffu, (off[0] & off[1]) >= 0)) continue;   // 8 pixels x 8 planes all masked
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int o = s_o[warp][j][pl];
-        acc[j] = 0.0f;
-        if (o >= 0 && active) {
-          if (o != coff) {
-            coff = o;
-            // two 64-bit pointer increments per channel quad; the taps are fixed offsets from them
-            const char* r0 = lbase + (size_t)(unsigned)o * 16;
+      for (int u = 0; u < 2; u++) {
+        s_tx[warp][sub + 4 * u][pl] = tx[u];
+        s_ty[warp][sub + 4 * u][pl] = ty[u];
+        s_o[warp][sub + 4 * u][pl] = off[u];
+      }
+      __syncwarp();
+      // ---- the planes of the group, this lane's chunk ------------------------------------------
+      float* part = reinterpret_cast<float*>(&s_part[warp][0][0]);
+#pragma unroll 1
+      for (int j0 = 0; j0 < CQ_G; j0 += 4) {
+        float acc[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int j = j0 + jj;
+          const int o = s_o[warp][j][pl];
+          acc[jj] = 0.0f;
+          if (o >= 0 && active) {
+            if (o != coff) {
+              coff = o;
+              // two 64-bit pointer increments per channel quad; the taps are fixed offsets from them
+              const char* r0 = lbase + (size_t)(unsigned)o * 16;
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const char* r1 = r0 + row_stride;
+                cq_ld(t00.v[q], r0); cq_ld(t01.v[q], r0 + 16);
+                cq_ld(t10.v[q], r1); cq_ld(t11.v[q], r1 + 16);
+                r0 += quad_stride;
+              }
+            }
+            const pk2 tx2 = dup2(s_tx[warp][j][pl]), ty2 = dup2(s_ty[warp][j][pl]);
+            const pk2 e2 = x2fma(tx2, mone2, one2), s2 = x2fma(ty2, mone2, one2);   // 1 - tx, 1 - ty
+            const pk2 nw = x2mul(s2, e2), ne = x2mul(s2, tx2), sw = x2mul(ty2, e2), se = x2mul(ty2, tx2);
+            float s = 0.0f;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              const char* r1 = r0 + row_stride;
-              cq_ld(t00.v[q], r0); cq_ld(t01.v[q], r0 + 16);
-              cq_ld(t10.v[q], r1); cq_ld(t11.v[q], r1 + 16);
-              r0 += quad_stride;
-            }
-          }
-          const pk2 tx2 = dup2(s_tx[warp][j][pl]), ty2 = dup2(s_ty[warp][j][pl]);
-          const pk2 e2 = x2fma(tx2, mone2, one2), s2 = x2fma(ty2, mone2, one2);   // 1 - tx, 1 - ty
-          const pk2 nw = x2mul(s2, e2), ne = x2mul(s2, tx2), sw = x2mul(ty2, e2), se = x2mul(ty2, tx2);
-          float s = 0.0f;
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-              const pk2 wq = x2fma(t11.v[q][hh], se, x2fma(t10.v[q][hh], sw, x2fma(t01.v[q][hh], ne, x2mul(t00.v[q][hh], nw))));
-              const pk2 d = x2add(wq, ncur[q][hh]);
-              s = xadd(s, fabsf(lo2(d)));
-              s = xadd(s, fabsf(hi2(d)));
+              for (int hh = 0; hh < 2; hh++) {
+                const pk2 wq = x2fma(t11.v[q][hh], se, x2fma(t10.v[q][hh], sw, x2fma(t01.v[q][hh], ne, x2mul(t00.v[q][hh], nw))));
+                const pk2 d = x2add(wq, ncur[q][hh]);
+                s = xadd(s, fabsf(lo2(d)));
+                s = xadd(s, fabsf(hi2(d)));
+              }
             }
+            acc[jj] = s;
           }
-          acc[j] = s;
         }
-      }
-      // ---- chunk sums of each plane, gathered in the reference's order ------------------------
-      float* part = reinterpret_cast<float*>(&s_part[warp][0][0]);
+        // chunk sums of each plane; inactive / masked lanes contribute +0
 #pragma unroll
-      for (int j = 0; j < 4; j++) part[(j * 8 + pl) * 4 + sub] = acc[j];   // inactive / masked lanes contribute +0
+        for (int jj = 0; jj < 4; jj++) part[((j0 + jj) * 8 + pl) * 4 + sub] = acc[jj];
+      }
       __syncwarp();
-      if (off >= 0) {
-        const float4 c = s_part[warp][sub][pl];
-        const float s_mine = xadd(xadd(xadd(c.x, c.y), c.z), c.w);
-        const float diff = xdiv(s_mine, (float)a.channels);   // .mean(1); edge mask == 1
-        const int o = cq_idx(kk, col);
-        cost[o] = xadd(cost[o], diff);
-        if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+      // ---- gather the chunk sums in the reference's order, mean over channels, accumulate -------
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (off[u] >= 0) {
+          const float4 c = s_part[warp][sub + 4 * u][pl];
+          const float s_mine = xadd(xadd(xadd(c.x, c.y), c.z), c.w);
+          // .mean(1); edge mask == 1.  A power-of-two channel count divides exactly by multiplying.
+          const float diff = inv_channels != 0.0f ? xmul(s_mine, inv_channels) : xdiv(s_mine, (float)a.channels);
+          const int o = cq_idx(k0 + sub + 4 * u, col);
+          cost[o] = xadd(cost[o], diff);
+          if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+        }
       }
     }
   }
