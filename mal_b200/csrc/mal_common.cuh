@@ -93,6 +93,13 @@ __device__ __forceinline__ float xdivc(float x) {
 // correctly-rounded operation as its scalar x* counterpart, so the arithmetic contract is
 // unchanged; what changes is the issue-slot cost (tools/ubench/f32x2.cu: an FFMA2 holds the fma
 // pipe for two cycles but one issue slot, so loads, shuffles and integer work issue beside it).
+//
+// HAZARD (ptxas 12.9, measured: tools/ubench/x2check.cu): unlike the scalar forms, ptxas contracts an
+// explicit mul.rn.f32x2 whose result feeds an add.rn/sub.rn.f32x2 into ONE FFMA2 (single rounding),
+// with or without --fmad=false, and it sees through fma(p, 1, s) and fma(a, b, -0) rewrites.  A
+// product that feeds a packed add or subtract must therefore use x2mul_nf (".ftz" on the multiply
+// blocks the contraction; it differs from IEEE only when an operand or the product is subnormal).
+// x2mul feeding x2fma's addend, or a store, is safe: there is nothing to contract.
 typedef unsigned long long pk2;   // {lo, hi} fp32 pair in an aligned register pair
 #ifdef MAL_EMU
 __device__ __forceinline__ pk2 pack2(float lo, float hi) {
@@ -113,6 +120,11 @@ __device__ __forceinline__ pk2 x2fma(pk2 a, pk2 b, pk2 c) {
   float a0, a1, b0, b1, c0, c1; unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
   return pack2(xfma(a0, b0, c0), xfma(a1, b1, c1));
 }
+__device__ __forceinline__ pk2 x2sub(pk2 a, pk2 b) {
+  float a0, a1, b0, b1; unpack2(a, a0, a1); unpack2(b, b0, b1);
+  return pack2(xsub(a0, b0), xsub(a1, b1));
+}
+__device__ __forceinline__ pk2 x2mul_nf(pk2 a, pk2 b) { return x2mul(a, b); }
 #else
 __device__ __forceinline__ pk2 pack2(float lo, float hi) {
   pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
@@ -129,12 +141,26 @@ __device__ __forceinline__ pk2 x2add(pk2 a, pk2 b) {
 __device__ __forceinline__ pk2 x2fma(pk2 a, pk2 b, pk2 c) {
   pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
+__device__ __forceinline__ pk2 x2sub(pk2 a, pk2 b) {
+  pk2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ pk2 x2mul_nf(pk2 a, pk2 b) {
+  pk2 d; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 #endif
 __device__ __forceinline__ pk2 dup2(float v) { return pack2(v, v); }
 __device__ __forceinline__ float lo2(pk2 p) { float a, b; unpack2(p, a, b); return a; }
 __device__ __forceinline__ float hi2(pk2 p) { float a, b; unpack2(p, a, b); return b; }
-// a - b per half (RN(a + (-b)) == RN(a - b))
-__device__ __forceinline__ pk2 x2sub(pk2 a, pk2 b) { return x2add(a, b ^ 0x8000000080000000ull); }
+// |p| per half (folds into the abs modifier of the consuming FADD2)
+__device__ __forceinline__ pk2 abs2(pk2 p) { float a, b; unpack2(p, a, b); return pack2(fabsf(a), fabsf(b)); }
+// packed form of xdivc: correctly rounded p / C per half
+template <int C>
+__device__ __forceinline__ pk2 x2divc(pk2 x) {
+  const pk2 r = dup2(1.0f / (float)C);
+  const pk2 q = x2mul(x, r);
+  const pk2 rem = x2fma(dup2(-(float)C), q, x);
+  return x2fma(rem, r, q);
+}
 
 // ------------------------------------------------------------------ reductions
 __device__ __forceinline__ float warp_sum(float v) {

@@ -144,6 +144,20 @@ __device__ __forceinline__ float sum9_prod(const float* a, const float* b) {
   return s;
 }
 
+// packed forms: two predictions (the halves of each pair) against the same target window
+__device__ __forceinline__ pk2 sum9(const pk2* w) {
+  pk2 s = w[0];
+#pragma unroll
+  for (int i = 1; i < 9; i++) s = x2add(s, w[i]);
+  return s;
+}
+__device__ __forceinline__ pk2 sum9_prod(const pk2* a, const pk2* b) {
+  pk2 s = x2mul_nf(a[0], b[0]);   // also feeds an add: see the contraction hazard in mal_common.cuh
+#pragma unroll
+  for (int i = 1; i < 9; i++) s = x2add(s, x2mul_nf(a[i], b[i]));
+  return s;
+}
+
 struct SsimTerms { float mu_x, mu_y, A, Bq, Cq, D, n, d, v; };
 
 #define MAL_C1 0.0001f   /* 0.01**2 */
@@ -164,6 +178,26 @@ __device__ __forceinline__ SsimTerms ssim_terms(float mu_x, float mu_y, float ex
   t.d = xmul(t.Cq, t.D);
   t.v = xmul(xsub(1.0f, xdiv(t.n, t.d)), 0.5f);   // (1 - n/d) / 2, /2 is exact as *0.5
   return t;
+}
+// Two predictions at once (halves of each pair) against one target: same operations as ssim_terms,
+// the target-only products are passed in (mu_y*mu_y and sig_y are shared by every candidate).
+__device__ __forceinline__ void ssim_terms2(pk2 mu_x, float mu_y, float mu_yy, float sig_y, pk2 exx, pk2 exy,
+                                            SsimTerms& t0, SsimTerms& t1) {
+  const pk2 my = dup2(mu_y), two = dup2(2.0f), c1 = dup2(MAL_C1), c2 = dup2(MAL_C2);
+  const pk2 mxx = x2mul_nf(mu_x, mu_x);
+  const pk2 sig_x = x2sub(exx, mxx);
+  const pk2 sig_xy = x2sub(exy, x2mul_nf(mu_x, my));
+  const pk2 A = x2add(x2mul_nf(x2mul(two, mu_x), my), c1);
+  const pk2 Bq = x2add(x2mul_nf(two, sig_xy), c2);
+  const pk2 Cq = x2add(x2add(mxx, dup2(mu_yy)), c1);
+  const pk2 D = x2add(x2add(sig_x, dup2(sig_y)), c2);
+  const pk2 n = x2mul(A, Bq), d = x2mul(Cq, D);
+  unpack2(mu_x, t0.mu_x, t1.mu_x);
+  t0.mu_y = t1.mu_y = mu_y;
+  unpack2(A, t0.A, t1.A); unpack2(Bq, t0.Bq, t1.Bq); unpack2(Cq, t0.Cq, t1.Cq); unpack2(D, t0.D, t1.D);
+  unpack2(n, t0.n, t1.n); unpack2(d, t0.d, t1.d);
+  t0.v = xmul(xsub(1.0f, xdiv(t0.n, t0.d)), 0.5f);
+  t1.v = xmul(xsub(1.0f, xdiv(t1.n, t1.d)), 0.5f);
 }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 

@@ -18,3 +18,20 @@ def test_division_by_constant_is_exact(tmp_path):
     res = subprocess.run([str(exe), stride], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     assert res.stdout.count("mismatches=0") == 2, res.stdout
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_packed_fp32_helpers_are_bit_exact_on_the_gpu(tmp_path):
+    """FFMA2 / FADD2 / FMUL2 helpers == their scalar counterparts on sm_100a, including the ptxas
+    mul+add contraction hazard documented in mal_common.cuh (tools/ubench/x2check.cu)."""
+    import shutil
+    here = os.path.dirname(os.path.abspath(__file__))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(os.path.dirname(here), "tools", "ubench", "x2check.cu")
+    exe = str(tmp_path / "x2check")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", exe, src], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout
