@@ -98,6 +98,12 @@ typedef struct mal_photo_args {
                                ensemble disparity of manydepth/trainer.py:598; no gradient      */
   float* grad_syn[2];       /* (B,3,H,W) optional, PRED+grad with syn: d(sum w*reproj)/d syn(f); in
                                WARP mode the temporal-hint candidates are data                   */
+  int32_t depth_height, depth_width; /* 0,0: `depth`/`depth_b` are (B,1,H,W).  Otherwise they are
+                               (B,1,depth_height,depth_width) and the kernel reads them through
+                               F.interpolate(.., [H,W], mode="bilinear", align_corners=False)
+                               (manydepth/trainer.py:1093-1094): the full-resolution disparity never
+                               exists.  grad_depth stays (B,1,H,W) = d/d(up-sampled value); take it to
+                               the low resolution with mal_upsample_bilinear_backward              */
 } mal_photo_args;
 
 size_t mal_photo_partials_floats(int batch, int height, int width);
@@ -256,6 +262,15 @@ int mal_grid_sample(const float* img, const float* grid, int batch, int channels
 int mal_grid_sample_backward(const float* img, const float* grid, const float* grad_out, int batch, int channels,
                              int height, int width, int out_height, int out_width, int align_corners, int border,
                              float* grad_grid, mal_stream_t stream);
+
+/* F.interpolate(x, [out_height, out_width], mode="bilinear", align_corners=False) of `planes` planes with
+ * the arithmetic of ATen's CPU kernel (manydepth/trainer.py:1093-1094 and :1176-1177, dualrefine/trainer.py:412-413,
+ * dynamicdepth/trainer.py:915-916: every low-resolution disparity goes through it before disp_to_depth),
+ * and its adjoint (deterministic gather, no atomics). */
+int mal_upsample_bilinear(const float* in, int planes, int in_height, int in_width, int out_height, int out_width,
+                          float* out, mal_stream_t stream);
+int mal_upsample_bilinear_backward(const float* grad_out, int planes, int in_height, int in_width, int out_height,
+                                   int out_width, float* grad_in, mal_stream_t stream);
 int mal_ssim(const float* x, const float* y, int planes, int height, int width, float* out, mal_stream_t stream);
 /* workspace: 4 * planes * height * width floats; grad_y may be NULL */
 int mal_ssim_backward(const float* x, const float* y, const float* grad_out, int planes, int height, int width,

@@ -30,6 +30,7 @@ class PhotoArgs(C.Structure):
         ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
         ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
         ("grad_syn", C.c_void_p * 2),
+        ("depth_height", C.c_int32), ("depth_width", C.c_int32),
     ]
 
 
@@ -138,6 +139,8 @@ EXPORTS = {
     "mal_project3d_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 4),
     "mal_grid_sample": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
     "mal_grid_sample_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
+    "mal_upsample_bilinear": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "mal_upsample_bilinear_backward": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "mal_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }

@@ -299,6 +299,56 @@ __global__ void __launch_bounds__(LY_NT) grid_sample_bwd_kernel(const float* __r
   }
 }
 
+
+// ---- F.interpolate(x, [H, W], mode="bilinear", align_corners=False) ---------------------------------
+// (manydepth/trainer.py:1093-1094, dualrefine/trainer.py:412-413, dynamicdepth/trainer.py:915-916:
+// every trainer brings the low-resolution disparities to full resolution before the warp).
+// Forward: one thread per output pixel, ATen's CPU arithmetic (mal_math.cuh).  Backward: the adjoint as a
+// gather - one thread per INPUT pixel visits the few output pixels whose 2x2 footprint contains it -
+// so the gradient is deterministic and needs no atomics.
+__global__ void __launch_bounds__(LY_NT) upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                  int planes, int ih, int iw, int oh, int ow) {
+  const size_t n = (size_t)planes * oh * ow;
+  const size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x;
+  if (i >= n) return;
+  const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+  const size_t pl = i / ((size_t)ow * oh);
+  if (ih == oh && iw == ow) { out[i] = __ldg(in + i); return; }
+  const UpAxis ay = up_axis(oy, ih, up_scale(ih, oh)), ax = up_axis(ox, iw, up_scale(iw, ow));
+  out[i] = upsample_at(in + pl * ih * iw, iw, ay, ax);
+}
+
+__global__ void __launch_bounds__(LY_NT) upsample_bilinear_bwd_kernel(const float* __restrict__ gout,
+                                                                      float* __restrict__ gin, int planes, int ih,
+                                                                      int iw, int oh, int ow) {
+  const size_t n = (size_t)planes * ih * iw;
+  const size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x;
+  if (i >= n) return;
+  const int ix = (int)(i % iw), iy = (int)((i / iw) % ih);
+  const size_t pl = i / ((size_t)iw * ih);
+  if (ih == oh && iw == ow) { gin[i] = __ldg(gout + i); return; }
+  const float sy = up_scale(ih, oh), sx = up_scale(iw, ow);
+  const float ry = (float)oh / (float)ih, rx = (float)ow / (float)iw;
+  // output rows / columns whose source index can fall in [i-1, i+1]
+  const int y_lo = max(0, (int)floorf((iy - 1) * ry) - 1), y_hi = min(oh - 1, (int)ceilf((iy + 2) * ry) + 1);
+  const int x_lo = max(0, (int)floorf((ix - 1) * rx) - 1), x_hi = min(ow - 1, (int)ceilf((ix + 2) * rx) + 1);
+  const float* g = gout + pl * oh * ow;
+  float acc = 0.0f;
+  for (int oy = y_lo; oy <= y_hi; oy++) {
+    const UpAxis ay = up_axis(oy, ih, sy);
+    const float wy = (ay.i0 == iy ? ay.l0 : 0.0f) + (ay.i1 == iy ? ay.l1 : 0.0f);
+    if (wy == 0.0f) continue;
+    float row = 0.0f;
+    for (int ox = x_lo; ox <= x_hi; ox++) {
+      const UpAxis ax = up_axis(ox, iw, sx);
+      const float wx = (ax.i0 == ix ? ax.l0 : 0.0f) + (ax.i1 == ix ? ax.l1 : 0.0f);
+      if (wx != 0.0f) row += wx * __ldg(g + (size_t)oy * ow + ox);
+    }
+    acc += wy * row;
+  }
+  gin[i] = acc;
+}
+
 }  // namespace mal
 
 using namespace mal;
@@ -421,4 +471,22 @@ extern "C" int mal_grid_sample_backward(const float* img, const float* grid, con
            reinterpret_cast<const float2*>(grid), grad_out, batch, channels, height, width, out_height, out_width,
            border, reinterpret_cast<float2*>(grad_grid));
   return check_launch("grid_sample_bwd_kernel");
+}
+
+extern "C" int mal_upsample_bilinear(const float* in, int planes, int in_height, int in_width, int out_height,
+                                     int out_width, float* out, mal_stream_t stream) {
+  MAL_REQUIRE(in && out && planes > 0 && in_height > 0 && in_width > 0 && out_height > 0 && out_width > 0,
+              "mal_upsample_bilinear: bad arguments");
+  launch(upsample_bilinear_kernel, dim3(ly_blocks((size_t)planes * out_height * out_width)), dim3(LY_NT), 0,
+         (cudaStream_t)stream, in, out, planes, in_height, in_width, out_height, out_width);
+  return check_launch("upsample_bilinear_kernel");
+}
+
+extern "C" int mal_upsample_bilinear_backward(const float* grad_out, int planes, int in_height, int in_width,
+                                              int out_height, int out_width, float* grad_in, mal_stream_t stream) {
+  MAL_REQUIRE(grad_out && grad_in && planes > 0 && in_height > 0 && in_width > 0 && out_height > 0 && out_width > 0,
+              "mal_upsample_bilinear_backward: bad arguments");
+  launch(upsample_bilinear_bwd_kernel, dim3(ly_blocks((size_t)planes * in_height * in_width)), dim3(LY_NT), 0,
+         (cudaStream_t)stream, grad_out, grad_in, planes, in_height, in_width, out_height, out_width);
+  return check_launch("upsample_bilinear_bwd_kernel");
 }

@@ -129,6 +129,32 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ plane, const
   return xfma(v11, t.se, xfma(v10, t.sw, xfma(v01, t.ne, xmul(v00, t.nw))));
 }
 
+// ---- bilinear up-sampling of a plane (F.interpolate(mode="bilinear", align_corners=False)) ------
+// ATen's vectorised CPU kernel (UpSampleKernel.cpp, cpu_upsample_linear), measured against torch 2.11:
+//   source index  s = fma(in/out, o + 0.5, -0.5), clamped at 0;  i0 = min(int(s), in-1), i1 = i0 + (i0 < in-1)
+//   l1 = clamp(s - i0, 0, 1), l0 = 1 - l1
+//   value         fma(ly0, fma(lx0, v00, lx1*v01), ly1 * fma(lx0, v10, lx1*v11))
+// ATen uses this kernel when out_h + out_w > 128 (_use_vectorized_kernel_cond_2d); every disparity on the
+// reference's path is up-sampled to the full image (192 + 640), smaller outputs are only within ~1 ulp.
+struct UpAxis { int i0, i1; float l0, l1; };
+__device__ __forceinline__ UpAxis up_axis(int o, int in_size, float scale) {
+  float s = xfma(scale, xadd((float)o, 0.5f), -0.5f);
+  if (s < 0.0f) s = 0.0f;
+  UpAxis a;
+  a.i0 = min((int)s, in_size - 1);
+  a.i1 = a.i0 + (a.i0 < in_size - 1 ? 1 : 0);
+  a.l1 = fminf(fmaxf(xsub(s, (float)a.i0), 0.0f), 1.0f);
+  a.l0 = xsub(1.0f, a.l1);
+  return a;
+}
+__device__ __forceinline__ float up_scale(int in_size, int out_size) { return xdiv((float)in_size, (float)out_size); }
+__device__ __forceinline__ float upsample_at(const float* __restrict__ plane, int w, const UpAxis& ay, const UpAxis& ax) {
+  const float v00 = __ldg(plane + ay.i0 * w + ax.i0), v01 = __ldg(plane + ay.i0 * w + ax.i1);
+  const float v10 = __ldg(plane + ay.i1 * w + ax.i0), v11 = __ldg(plane + ay.i1 * w + ax.i1);
+  const float t0 = xfma(ax.l0, v00, xmul(ax.l1, v01)), t1 = xfma(ax.l0, v10, xmul(ax.l1, v11));
+  return xfma(ay.l0, t0, xmul(ay.l1, t1));
+}
+
 // ---- SSIM ------------------------------------------------------------------------------
 // running row-major sum of a 3x3 window, as avg_pool2d accumulates it
 __device__ __forceinline__ float sum9(const float* w) {

@@ -55,6 +55,10 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
   const int x0 = blockIdx.x * PH_TW, y0 = blockIdx.y * PH_TH;
   const int H = a.height, W = a.width;
   const size_t HW = (size_t)H * W;
+  // low-resolution disparity, up-sampled on the fly (mal_photo_args.depth_height / depth_width)
+  const bool lowres = WARP && a.depth_height > 0;
+  const size_t dhw = (size_t)a.depth_height * a.depth_width;
+  const float up_sy = lowres ? up_scale(a.depth_height, H) : 1.0f, up_sx = lowres ? up_scale(a.depth_width, W) : 1.0f;
 
   float* smem = reinterpret_cast<float*>(dyn_smem());
   Geom* geom = reinterpret_cast<Geom*>(smem);
@@ -100,8 +104,15 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
           sx[((2 + k) * 3 + c) * tl.VN + i] = __ldg(a.syn[k] + ((size_t)b * 3 + c) * HW + o);
     }
     if (WARP) {
-      float dv = __ldg(a.depth + (size_t)b * HW + o);
-      if (a.depth_b) dv = xmul(xadd(dv, __ldg(a.depth_b + (size_t)b * HW + o)), 0.5f);   // (a + b) / 2.0
+      float dv;
+      if (lowres) {   // F.interpolate(disp, [H, W], bilinear) read straight from the low-resolution plane
+        const UpAxis ay = up_axis(ry, a.depth_height, up_sy), ax = up_axis(rx, a.depth_width, up_sx);
+        dv = upsample_at(a.depth + (size_t)b * dhw, a.depth_width, ay, ax);
+        if (a.depth_b) dv = xmul(xadd(dv, upsample_at(a.depth_b + (size_t)b * dhw, a.depth_width, ay, ax)), 0.5f);
+      } else {
+        dv = __ldg(a.depth + (size_t)b * HW + o);
+        if (a.depth_b) dv = xmul(xadd(dv, __ldg(a.depth_b + (size_t)b * HW + o)), 0.5f);   // (a + b) / 2.0
+      }
       if (a.depth_is_disp) dv = xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv)));
       Ray ray = pixel_ray(geom->iK, (float)rx, (float)ry);
 #pragma unroll
@@ -360,7 +371,13 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
       }
       const size_t po = (size_t)gy * W + gx;
       {
-        float dv_in = __ldg(a.depth + (size_t)b * HW + po);
+        float dv_in;
+        if (lowres) {
+          const UpAxis ay = up_axis(gy, a.depth_height, up_sy), ax = up_axis(gx, a.depth_width, up_sx);
+          dv_in = upsample_at(a.depth + (size_t)b * dhw, a.depth_width, ay, ax);
+        } else {
+          dv_in = __ldg(a.depth + (size_t)b * HW + po);
+        }
         float dv = a.depth_is_disp ? xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv_in))) : dv_in;
         Ray ray = pixel_ray(geom->iK, (float)gx, (float)gy);
         float cam[3] = {dv * ray.x, dv * ray.y, dv * ray.z};
@@ -514,6 +531,8 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     if (a.with_grad) MAL_REQUIRE(a.grad_depth && a.grad_P, "mal_photo_forward: WARP+grad needs grad_depth, grad_P");
     if (a.with_grad) MAL_REQUIRE(!a.depth_b, "mal_photo_forward: the averaged (ensemble) disparity carries no gradient");
     if (a.depth_is_disp) MAL_REQUIRE(a.min_depth > 0 && a.max_depth > a.min_depth, "mal_photo_forward: bad depth range");
+    MAL_REQUIRE((a.depth_height > 0) == (a.depth_width > 0) && a.depth_height >= 0,
+                "mal_photo_forward: depth_height / depth_width must both be set (or both 0)");
   } else if (a.with_grad) {
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }

@@ -20,7 +20,7 @@ from . import _capi, raw
 
 __all__ = ["photo", "reprojection_loss_map", "smooth", "main_terms", "cost_volume", "matching_mask",
            "backproject", "project3d", "ssim", "forward_warp", "dynamic_instance", "fill_dynamic_obj",
-           "grid_sample"]
+           "grid_sample", "upsample_bilinear"]
 
 
 def _lib(t: Tensor):
@@ -96,6 +96,7 @@ def _photo_setup(ctx, inputs, output):
     sums, _, _, g_depth, g_P, g_p0, g_p1, g_s0, g_s1 = output
     ctx.mode = mode
     ctx.need_grad = inputs[-1]
+    ctx.depth_size = None if depth is None else tuple(depth.shape[-2:])
     ctx.save_for_backward(sums, g_depth, g_P, g_p0, g_p1, K if K is not None else sums, g_s0, g_s1)
 
 
@@ -108,6 +109,8 @@ def _photo_backward(ctx, g_sums, *_unused):
     grads = [None] * 22
     if ctx.mode == raw.PHOTO_WARP:
         grads[5] = coef * g_depth
+        if ctx.depth_size != tuple(g_depth.shape[-2:]):   # the kernel up-sampled a low-resolution disparity
+            grads[5] = _upsample_bwd_op(grads[5], ctx.depth_size[0], ctx.depth_size[1])
         gP = (coef * g_P).view(-1, 2, 3, 4)
         Kt = K[:, :3, :].transpose(1, 2)      # P = (K @ T)[:3]  =>  dT = K[:3]^T @ dP
         grads[8] = Kt @ gP[:, 0]
@@ -607,3 +610,44 @@ def grid_sample(img, grid, padding_mode="border", align_corners=True):
         raise NotImplementedError("padding_mode must be 'border' or 'zeros'")
     return _grid_sample_op(img.detach().contiguous(), grid.contiguous(), bool(align_corners),
                            padding_mode == "border")
+
+
+# --------------------------------------------------------------------------------------------
+# bilinear up-sampling with the reference's (CPU) rounding
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("mal_b200::upsample_bilinear", mutates_args=())
+def _upsample_op(x: Tensor, out_height: int, out_width: int) -> Tensor:
+    return raw.upsample_bilinear(_lib(x), x, (out_height, out_width))
+
+
+@_upsample_op.register_fake
+def _(x, out_height, out_width):
+    return x.new_empty(tuple(x.shape[:-2]) + (out_height, out_width))
+
+
+@torch.library.custom_op("mal_b200::upsample_bilinear_backward", mutates_args=())
+def _upsample_bwd_op(grad_out: Tensor, in_height: int, in_width: int) -> Tensor:
+    return raw.upsample_bilinear_backward(_lib(grad_out), grad_out, (in_height, in_width))
+
+
+@_upsample_bwd_op.register_fake
+def _(grad_out, in_height, in_width):
+    return grad_out.new_empty(tuple(grad_out.shape[:-2]) + (in_height, in_width))
+
+
+def _upsample_setup(ctx, inputs, output):
+    ctx.in_size = tuple(inputs[0].shape[-2:])
+
+
+def _upsample_backward(ctx, g):
+    return _upsample_bwd_op(g.contiguous(), ctx.in_size[0], ctx.in_size[1]), None, None
+
+
+_upsample_op.register_autograd(_upsample_backward, setup_context=_upsample_setup)
+
+
+def upsample_bilinear(x, size):
+    """F.interpolate(x, size, mode="bilinear", align_corners=False) bit-identical to torch's CPU kernel
+    (torch's CUDA kernel rounds differently, which can flip a min-reprojection selection at scales > 0);
+    differentiable (deterministic gather adjoint)."""
+    return _upsample_op(x.contiguous(), int(size[0]), int(size[1]))

@@ -75,7 +75,12 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
         src = [src[0], None]
     syn = [_f32(s, f"syn[{i}]", img) for i, s in enumerate(syn)] if syn is not None else [None, None]
     plane = (B, 1, H, W)
-    depth, depth_b = _f32(depth, "depth", plane), _f32(depth_b, "depth_b", plane)
+    # a low-resolution disparity is up-sampled inside the kernel (trainer.py:1093-1094 fused away)
+    dplane, dh, dw = plane, 0, 0
+    if depth is not None and tuple(depth.shape[-2:]) != (H, W):
+        dh, dw = int(depth.shape[-2]), int(depth.shape[-1])
+        dplane = (B, 1, dh, dw)
+    depth, depth_b = _f32(depth, "depth", dplane), _f32(depth_b, "depth_b", dplane)
     K, inv_K = _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
     T = [_f32(t, f"T[{i}]", (B, 4, 4)) for i, t in enumerate(T)] if T is not None else [None, None]
     identity_min, noise = _f32(identity_min, "identity_min", plane), _f32(noise, "noise", plane)
@@ -109,6 +114,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
         a.grad_pred[i] = _ptr(out["grad_pred"][i]) if "grad_pred" in out else None
         a.grad_syn[i] = _ptr(out["grad_syn"][i]) if "grad_syn" in out else None
     a.depth, a.depth_b, a.K, a.inv_K = _ptr(depth), _ptr(depth_b), _ptr(K), _ptr(inv_K)
+    a.depth_height, a.depth_width = dh, dw
     a.identity_min, a.noise = _ptr(identity_min), _ptr(noise)
     a.pixel_mask, a.sample_mask = _ptr(pixel_mask), _ptr(sample_mask)
     a.min_reproj, a.selection, a.weight = _ptr(out["min_reproj"]), _ptr(out["selection"]), _ptr(out["weight"])
@@ -435,3 +441,27 @@ def grid_sample_backward(handle, img, grid, grad_out, align_corners=True, border
     _capi.check(handle.mal_grid_sample_backward(_vp(img), _vp(grid), _vp(grad_out), B, Cn, H, W, Ho, Wo,
                                                 int(align_corners), int(border), _vp(g), _stream(img)), handle)
     return g
+
+
+def upsample_bilinear(handle, x, size):
+    """mal_upsample_bilinear: F.interpolate(x, size, mode="bilinear", align_corners=False), CPU-kernel rounding."""
+    x = _f32(x, "x", None)
+    oh, ow = int(size[0]), int(size[1])
+    out = torch.empty(tuple(x.shape[:-2]) + (oh, ow), dtype=torch.float32, device=x.device)
+    planes = x.numel() // (x.shape[-2] * x.shape[-1])
+    _capi.check(handle.mal_upsample_bilinear(_vp(x), planes, x.shape[-2], x.shape[-1], oh, ow, _vp(out), _stream(x)),
+                handle)
+    LAUNCHES[0] += 1
+    return out
+
+
+def upsample_bilinear_backward(handle, grad_out, in_size):
+    """mal_upsample_bilinear_backward: the adjoint of upsample_bilinear (deterministic gather)."""
+    g = _f32(grad_out, "grad_out", None)
+    ih, iw = int(in_size[0]), int(in_size[1])
+    gin = torch.empty(tuple(g.shape[:-2]) + (ih, iw), dtype=torch.float32, device=g.device)
+    planes = g.numel() // (g.shape[-2] * g.shape[-1])
+    _capi.check(handle.mal_upsample_bilinear_backward(_vp(g), planes, ih, iw, g.shape[-2], g.shape[-1], _vp(gin),
+                                                      _stream(g)), handle)
+    LAUNCHES[0] += 1
+    return gin

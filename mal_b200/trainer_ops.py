@@ -20,7 +20,6 @@ materialize=True to also get outputs[("sample", f, s)] / ("color", f, s) like th
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import ops, raw
 from .layers import disp_to_depth
@@ -52,9 +51,10 @@ def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False
         raise NotImplementedError("v1_multiscale (per-scale source images) is not on the MAL path")
     for scale in range(_o(opt, "sclm") + 1):
         disp = outputs[("disp", scale)]
-        if disp.shape[-2:] != (H, W):
-            disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
-        _, depth = disp_to_depth(disp, _o(opt, "min_depth"), _o(opt, "max_depth"))
+        # trainer.py:1093-1097.  The fused kernels read the low-resolution disparity directly
+        # (mal_photo_args.depth_height); the full-resolution depth map is only built for the dict.
+        disp_full = disp if disp.shape[-2:] == (H, W) else ops.upsample_bilinear(disp, (H, W))
+        _, depth = disp_to_depth(disp_full, _o(opt, "min_depth"), _o(opt, "max_depth"))
         outputs[("depth", 0, scale)] = depth
         Ts = []
         for frame_id in _o(opt, "frame_ids")[1:]:
@@ -80,9 +80,7 @@ def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False
 
 def generate_images_pred_ensemble(inputs, T_l, T_n, disp, opt):
     """min over the two source frames of the reprojection loss under `disp` (no gradient)."""
-    H, W = _o(opt, "height"), _o(opt, "width")
-    if disp.shape[-2:] != (H, W):
-        disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+    # trainer.py:1176-1177: a low-resolution disparity is up-sampled inside the kernel
     with torch.no_grad():
         _, min_reproj, _ = ops.photo(inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in (-1, 1)],
                                      depth=disp.detach(), K=inputs[("K", 0)], inv_K=inputs[("inv_K", 0)],
@@ -157,9 +155,9 @@ def generate_images_pred_dualrefine(inputs, outputs, opt):
             if scale == 1:
                 continue
             disp = outputs[("disp", scale, it)]
-            if disp.shape[-2:] != (H, W):
-                disp = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
-            _, depth = disp_to_depth(disp, _o(opt, "min_depth"), _o(opt, "max_depth"))
+            # dualrefine/trainer.py:412-413: the fused kernels read the low-resolution disparity directly
+            disp_full = disp if disp.shape[-2:] == (H, W) else ops.upsample_bilinear(disp, (H, W))
+            _, depth = disp_to_depth(disp_full, _o(opt, "min_depth"), _o(opt, "max_depth"))
             outputs[("depth", 0, scale, it)] = depth
             Ts = []
             for frame_id in (-1, 1):
