@@ -372,6 +372,36 @@ int mal_fill_dynamic_obj(const uint8_t* mask, const int32_t* delta_x, const int3
                          const float* img, int num, int channels, int height, int width, float* out,
                          mal_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DualRefine epipolar correlation lookup, forward and backward.
+ *
+ * Replaces dualrefine/networks/corr.py CoordSampler: register (:11-22, the 2x2 average-pooled pyramid
+ * of the source-frame features), __call__ (:24-50, used inside every DEQ iteration,
+ * dualrefine/networks/depth_pose.py:433-435) and __corr__ (:52-76, num_head == 1).  For every pixel,
+ * level l and epipolar candidate d the pyramid level is sampled at coords[b, :, l, d, y, x] (pixel
+ * units of the level-0 map) with F.grid_sample(align_corners=False, zeros padding) and
+ * out[b, (l*heads + head)*D + d, y, x] = mean over the head's channels of |fmap1 - sample|.
+ * The (B, C, h, w, D) intermediates of the reference never exist.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_corr_args {
+  int32_t batch, channels, height, width;  /* fmap1 / level-0 resolution                          */
+  int32_t num_levels, num_samples, num_head;
+  const float* fmap1;     /* (B,C,h,w)                                                            */
+  const float* pyramid;   /* mal_corr_pyramid() output: level l is (B,C,h>>l,w>>l), levels back to back */
+  const float* coords;    /* (B,2,L,D,h,w): x then y                                              */
+  float* out;             /* (B, L*heads*D, h, w)                     [mal_corr_lookup]           */
+  const float* grad_out;  /* (B, L*heads*D, h, w)                     [mal_corr_lookup_backward]  */
+  float* grad_coords;     /* (B,2,L,D,h,w) optional, written                                       */
+  float* grad_fmap1;      /* (B,C,h,w) optional, ACCUMULATED into: zero it first                   */
+  float* grad_pyramid;    /* pyramid layout, optional, ACCUMULATED into: zero it first             */
+} mal_corr_args;
+
+size_t mal_corr_pyramid_floats(int batch, int channels, int height, int width, int num_levels);
+int mal_corr_pyramid(const float* fmap2, int batch, int channels, int height, int width, int num_levels,
+                     float* pyramid, mal_stream_t stream);
+int mal_corr_lookup(const mal_corr_args* args, mal_stream_t stream);
+int mal_corr_lookup_backward(const mal_corr_args* args, mal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

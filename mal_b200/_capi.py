@@ -77,6 +77,14 @@ class CostVolumeArgs(C.Structure):
     ]
 
 
+class CorrArgs(C.Structure):
+    """struct mal_corr_args."""
+    _fields_ = [(n, C.c_int32) for n in ("batch", "channels", "height", "width", "num_levels", "num_samples",
+                                          "num_head")] + \
+               [(n, C.c_void_p) for n in ("fmap1", "pyramid", "coords", "out", "grad_out", "grad_coords",
+                                          "grad_fmap1", "grad_pyramid")]
+
+
 class SmoothArgs(C.Structure):
     """struct mal_smooth_args."""
     _fields_ = [
@@ -139,6 +147,10 @@ EXPORTS = {
     "mal_project3d_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 4),
     "mal_grid_sample": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
     "mal_grid_sample_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
+    "mal_corr_pyramid_floats": (C.c_size_t, [C.c_int] * 5),
+    "mal_corr_pyramid": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "mal_corr_lookup": (C.c_int, [C.POINTER(CorrArgs), C.c_void_p]),
+    "mal_corr_lookup_backward": (C.c_int, [C.POINTER(CorrArgs), C.c_void_p]),
     "mal_upsample_bilinear": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "mal_upsample_bilinear_backward": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "mal_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

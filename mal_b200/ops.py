@@ -20,7 +20,7 @@ from . import _capi, raw
 
 __all__ = ["photo", "reprojection_loss_map", "smooth", "main_terms", "cost_volume", "matching_mask",
            "backproject", "project3d", "ssim", "forward_warp", "dynamic_instance", "fill_dynamic_obj",
-           "grid_sample", "upsample_bilinear"]
+           "grid_sample", "upsample_bilinear", "corr_pyramid", "corr_lookup"]
 
 
 def _lib(t: Tensor):
@@ -651,3 +651,99 @@ def upsample_bilinear(x, size):
     (torch's CUDA kernel rounds differently, which can flip a min-reprojection selection at scales > 0);
     differentiable (deterministic gather adjoint)."""
     return _upsample_op(x.contiguous(), int(size[0]), int(size[1]))
+
+
+# --------------------------------------------------------------------------------------------
+# DualRefine epipolar correlation lookup (dualrefine/networks/corr.py)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("mal_b200::corr_pyramid", mutates_args=())
+def _corr_pyramid_op(fmap2: Tensor, num_levels: int) -> Tensor:
+    return raw.corr_pyramid(_lib(fmap2), fmap2, num_levels)
+
+
+@_corr_pyramid_op.register_fake
+def _(fmap2, num_levels):
+    B, C, h, w = fmap2.shape
+    n = 0
+    for _ in range(num_levels):
+        n += B * C * h * w
+        h, w = h // 2, w // 2
+    return fmap2.new_empty((n,))
+
+
+def _corr_pyramid_setup(ctx, inputs, output):
+    ctx.shape = tuple(inputs[0].shape)
+    ctx.levels = inputs[1]
+
+
+def _corr_pyramid_backward(ctx, g):
+    # adjoint of the chain of 2x2 average pools: level l+1's gradient is spread over its 2x2 parents / 4
+    B, C, h, w = ctx.shape
+    parts = raw.pyramid_levels(g, B, C, h, w, ctx.levels)
+    total = None
+    for gl in reversed(parts):
+        if total is not None:
+            up = torch.zeros_like(gl)
+            hh, ww = total.shape[-2:]
+            up[..., :2 * hh, :2 * ww] = total.repeat_interleave(2, -2).repeat_interleave(2, -1) * 0.25
+            total = gl + up
+        else:
+            total = gl.clone()
+    return total, None
+
+
+_corr_pyramid_op.register_autograd(_corr_pyramid_backward, setup_context=_corr_pyramid_setup)
+
+
+@torch.library.custom_op("mal_b200::corr_lookup", mutates_args=())
+def _corr_lookup_op(fmap1: Tensor, pyramid: Tensor, coords: Tensor, num_head: int) -> Tensor:
+    return raw.corr_lookup(_lib(fmap1), fmap1, pyramid, coords, num_head)
+
+
+@_corr_lookup_op.register_fake
+def _(fmap1, pyramid, coords, num_head):
+    B, _, L, D, h, w = coords.shape
+    return fmap1.new_empty((B, L * num_head * D, h, w))
+
+
+@torch.library.custom_op("mal_b200::corr_lookup_backward", mutates_args=())
+def _corr_lookup_bwd_op(fmap1: Tensor, pyramid: Tensor, coords: Tensor, grad_out: Tensor, num_head: int,
+                        want_coords: bool, want_fmap1: bool, want_pyramid: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    gc, g1, gp = raw.corr_lookup_backward(_lib(fmap1), fmap1, pyramid, coords, grad_out, num_head, want_coords,
+                                          want_fmap1, want_pyramid)
+    pick = lambda v: v if v is not None else _empty(fmap1)
+    return pick(gc), pick(g1), pick(gp)
+
+
+@_corr_lookup_bwd_op.register_fake
+def _(fmap1, pyramid, coords, grad_out, num_head, want_coords, want_fmap1, want_pyramid):
+    e = lambda t, w: t.new_empty(t.shape) if w else t.new_empty((0,))
+    return e(coords, want_coords), e(fmap1, want_fmap1), e(pyramid, want_pyramid)
+
+
+def _corr_lookup_setup(ctx, inputs, output):
+    fmap1, pyramid, coords, num_head = inputs
+    ctx.save_for_backward(fmap1, pyramid, coords)
+    ctx.num_head = num_head
+
+
+def _corr_lookup_backward(ctx, g):
+    fmap1, pyramid, coords = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    gc, g1, gp = _corr_lookup_bwd_op(fmap1, pyramid, coords, g.contiguous(), ctx.num_head, need[2], need[0], need[1])
+    return (g1 if need[0] else None, gp if need[1] else None, gc if need[2] else None, None)
+
+
+_corr_lookup_op.register_autograd(_corr_lookup_backward, setup_context=_corr_lookup_setup)
+
+
+def corr_pyramid(fmap2, num_levels):
+    """fmap2 and its (num_levels - 1) 2x2 average-pooled levels as one flat differentiable buffer
+    (CoordSampler.register, dualrefine/networks/corr.py:11-22)."""
+    return _corr_pyramid_op(fmap2.contiguous(), int(num_levels))
+
+
+def corr_lookup(fmap1, pyramid, coords, num_head=1):
+    """CoordSampler.__call__ (dualrefine/networks/corr.py:24-50): mean_c |fmap1 - grid_sample(level l, coords)|
+    for every level and epipolar candidate -> (B, L*heads*D, h, w); differentiable w.r.t. all three."""
+    return _corr_lookup_op(fmap1.contiguous(), pyramid, coords.contiguous(), int(num_head))

@@ -465,3 +465,63 @@ def upsample_bilinear_backward(handle, grad_out, in_size):
                                                       _stream(g)), handle)
     LAUNCHES[0] += 1
     return gin
+
+
+def corr_pyramid(handle, fmap2, num_levels):
+    """mal_corr_pyramid: fmap2 and its 2x2 average-pooled levels in one flat buffer (corr.py:11-22)."""
+    fmap2 = _f32(fmap2, "fmap2", None)
+    B, Cn, h, w = fmap2.shape
+    out = torch.empty((handle.mal_corr_pyramid_floats(B, Cn, h, w, num_levels),), dtype=torch.float32,
+                      device=fmap2.device)
+    _capi.check(handle.mal_corr_pyramid(_vp(fmap2), B, Cn, h, w, num_levels, _vp(out), _stream(fmap2)), handle)
+    LAUNCHES[0] += num_levels - 1
+    return out
+
+
+def pyramid_levels(pyramid, B, Cn, h, w, num_levels):
+    """Views of the levels inside a flat pyramid buffer."""
+    out, off = [], 0
+    for _ in range(num_levels):
+        n = B * Cn * h * w
+        out.append(pyramid[off:off + n].view(B, Cn, h, w))
+        off += n
+        h, w = h // 2, w // 2
+    return out
+
+
+def _corr_args(fmap1, pyramid, coords, num_head):
+    B, Cn, h, w = fmap1.shape
+    _, two, L, D, h1, w1 = coords.shape
+    if two != 2 or (h1, w1) != (h, w) or coords.shape[0] != B:
+        raise ValueError(f"coords must be (B,2,L,D,{h},{w}), got {tuple(coords.shape)}")
+    a = _capi.CorrArgs()
+    a.batch, a.channels, a.height, a.width = B, Cn, h, w
+    a.num_levels, a.num_samples, a.num_head = L, D, num_head
+    a.fmap1, a.pyramid, a.coords = _ptr(fmap1), _ptr(pyramid), _ptr(coords)
+    return a, (B, L * num_head * D, h, w)
+
+
+def corr_lookup(handle, fmap1, pyramid, coords, num_head=1):
+    """mal_corr_lookup -> (B, L*heads*D, h, w)."""
+    fmap1, pyramid, coords = _f32(fmap1, "fmap1"), _f32(pyramid, "pyramid"), _f32(coords, "coords")
+    a, oshape = _corr_args(fmap1, pyramid, coords, num_head)
+    out = torch.empty(oshape, dtype=torch.float32, device=fmap1.device)
+    a.out = _ptr(out)
+    _capi.check(handle.mal_corr_lookup(C.byref(a), _stream(fmap1)), handle)
+    LAUNCHES[0] += 1
+    return out
+
+
+def corr_lookup_backward(handle, fmap1, pyramid, coords, grad_out, num_head=1, want_coords=True, want_fmap1=True,
+                         want_pyramid=True):
+    """mal_corr_lookup_backward -> (grad_coords, grad_fmap1, grad_pyramid) (None where not wanted)."""
+    fmap1, pyramid, coords = _f32(fmap1, "fmap1"), _f32(pyramid, "pyramid"), _f32(coords, "coords")
+    a, oshape = _corr_args(fmap1, pyramid, coords, num_head)
+    grad_out = _f32(grad_out, "grad_out", oshape)
+    gc = torch.empty_like(coords) if want_coords else None
+    g1 = torch.zeros_like(fmap1) if want_fmap1 else None
+    gp = torch.zeros_like(pyramid) if want_pyramid else None
+    a.grad_out, a.grad_coords, a.grad_fmap1, a.grad_pyramid = _ptr(grad_out), _ptr(gc), _ptr(g1), _ptr(gp)
+    _capi.check(handle.mal_corr_lookup_backward(C.byref(a), _stream(fmap1)), handle)
+    LAUNCHES[0] += 1
+    return gc, g1, gp

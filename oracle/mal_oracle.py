@@ -894,3 +894,39 @@ class LossBalancing:
         self.previous_total_loss = np.sum(mean * self.w_list)
         self.previous_loss = mean
         return self.w_list[0], self.w_list[1]
+
+
+# --------------------------------------------------------------------------
+# DualRefine epipolar correlation lookup
+def corr_pyramid(fmap2, num_levels):
+    """dualrefine/networks/corr.py:11-22 (CoordSampler.register): fmap2 and its avg-pooled levels."""
+    levels = [fmap2]
+    f2 = fmap2
+    for _ in range(num_levels - 1):
+        f2 = F.avg_pool2d(f2, 2, stride=2)
+        levels.append(f2)
+    return levels
+
+
+def corr_lookup(fmap1, pyramid, coords, num_head=1):
+    """dualrefine/networks/corr.py:24-50 (CoordSampler.__call__; __corr__ :52-76 is num_head == 1).
+
+    fmap1 (B,C,h,w), pyramid = corr_pyramid(fmap2, L), coords (B,2,L,D,h,w) -> (B, L*heads*D, h, w)."""
+    batch, _, n1, d1, h1, w1 = coords.shape
+    c = coords.permute(2, 0, 4, 5, 3, 1).reshape(n1, batch, h1 * w1, d1, 2)
+    f1 = fmap1[..., None]
+    out_pyramid = []
+    for i in range(n1):
+        f2 = pyramid[i]
+        xgrid, ygrid = c[i].split([1, 1], dim=-1)
+        xgrid = 2 * (xgrid + 0.5) / (w1) - 1
+        ygrid = 2 * (ygrid + 0.5) / (h1) - 1
+        grid = torch.cat([xgrid, ygrid], dim=-1)
+        f2 = F.grid_sample(f2, grid, align_corners=False)
+        f2 = f2.view(batch, -1, h1, w1, d1)
+        corr = torch.abs(f1 - f2)
+        corr = corr.view(batch, num_head, -1, h1, w1, d1).mean(2)
+        corr = corr.permute(0, 2, 3, 1, 4).reshape(batch, h1, w1, -1)
+        out_pyramid.append(corr)
+    out = torch.cat(out_pyramid, dim=-1)
+    return out.permute(0, 3, 1, 2).contiguous().float()

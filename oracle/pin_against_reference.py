@@ -452,11 +452,47 @@ def pin_image_synthesis():
     return bool(ok)
 
 
+def corr_case(batch=2, channels=64, height=12, width=24, levels=3, samples=5, seed=91, spread=2.5):
+    """Seeded inputs for the DualRefine correlation lookup: features >= 0 and epipolar candidates scattered
+    around each pixel (some leave the map: zeros padding is exercised)."""
+    g = torch.Generator().manual_seed(seed)
+    fmap1 = torch.rand(batch, channels, height, width, generator=g)
+    fmap2 = torch.rand(batch, channels, height, width, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(height).float(), torch.arange(width).float(), indexing="ij")
+    base = torch.stack([xs, ys])[None, :, None, None]
+    coords = base + spread * torch.randn(batch, 2, levels, samples, height, width, generator=g)
+    return fmap1, fmap2, coords
+
+
+def pin_corr_lookup():
+    """dualrefine/networks/corr.py CoordSampler (imported by file path: its own imports are torch-only,
+    SURVEY.md 8c) against the oracle restatement, with and without ATen's reduction tail (h*w*D % 32)."""
+    import importlib.util
+    from . import mal_oracle as O
+    spec = importlib.util.spec_from_file_location("ref_dualrefine_corr", os.path.join(REFERENCE_ROOT, "dualrefine", "networks", "corr.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ok = True
+    for (B, Cn, h, w, L, D, heads) in ((2, 64, 12, 24, 3, 5, 1), (1, 64, 8, 16, 2, 17, 1), (2, 32, 12, 20, 3, 4, 2)):
+        fmap1, fmap2, coords = corr_case(B, Cn, h, w, L, D)
+        cs = mod.CoordSampler(None)
+        cs.register(fmap1, fmap2, num_levels=L)
+        want = cs(coords, num_levels=L, num_head=heads)
+        pyr = O.corr_pyramid(fmap2, L)
+        ok &= _eq(f"corr pyramid {h}x{w}", torch.cat([p.reshape(-1) for p in pyr]),
+                  torch.cat([p.reshape(-1) for p in cs.f2_pyramid]))
+        ok &= _eq(f"corr_lookup {Cn}ch {h}x{w} L={L} D={D} heads={heads}", O.corr_lookup(fmap1, pyr, coords, heads), want)
+        if heads == 1:
+            ok &= _eq(f"__corr__ {h}x{w}", O.corr_lookup(fmap1, pyr, coords, 1), cs.__corr__(coords, num_levels=L))
+    return bool(ok)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     good = run_pin()
     good &= pin_dynamicdepth_match_features()
     good &= pin_image_synthesis()
     good &= pin_dynamicdepth_losses()
+    good &= pin_corr_lookup()
     print("PINNED" if good else "PIN FAILED")
     sys.exit(0 if good else 1)

@@ -166,12 +166,34 @@ def forward_warp_case(name):
     print("wrote", name)
 
 
+def corr_lookup_case(name):
+    """dualrefine/networks/corr.py CoordSampler.register + __call__, imported by file path."""
+    import importlib.util
+    from oracle.pin_against_reference import REFERENCE_ROOT, corr_case
+    spec = importlib.util.spec_from_file_location(
+        "ref_dualrefine_corr", os.path.join(REFERENCE_ROOT, "dualrefine", "networks", "corr.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for tag, (B, Cn, h, w, L, D, heads) in {"a": (2, 64, 12, 24, 3, 5, 1), "b": (2, 32, 12, 20, 3, 4, 2)}.items():
+        fmap1, fmap2, coords = corr_case(B, Cn, h, w, L, D)
+        cs = mod.CoordSampler(None)
+        cs.register(fmap1, fmap2, num_levels=L)
+        out[f"{tag}_in_fmap1"], out[f"{tag}_in_fmap2"], out[f"{tag}_in_coords"] = _np(fmap1), _np(fmap2), _np(coords)
+        out[f"{tag}_heads"] = np.int32(heads)
+        out[f"{tag}_ref_corr"] = _np(cs(coords, num_levels=L, num_head=heads))
+        out[f"{tag}_ref_pyramid"] = _np(torch.cat([p.reshape(-1) for p in cs.f2_pyramid]))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     photometric_case("photometric_smooth.npz", 2, 32, 48, seed=101, white_noise=False)
     photometric_case("photometric_noise.npz", 1, 24, 40, seed=202, white_noise=True)
     cost_volume_case("cost_volume.npz", 2, 32, 48, channels=8, bins=12, seed=303)
     forward_warp_case("forward_warp.npz")
+    corr_lookup_case("corr_lookup.npz")
     ok = run_pin()
     print("oracle pinned:", ok)
     sys.exit(0 if ok else 1)
