@@ -12,6 +12,8 @@ maps.  One fused kernel (mal_b200/csrc/corr.cu) replaces the per-level grid_samp
 """
 from __future__ import annotations
 
+import torch
+
 from . import ops
 
 
@@ -52,3 +54,26 @@ class CoordSampler:
 
     def _update_fmap1(self, fmap1):
         self.fmap1 = fmap1
+
+
+def sample_tgt(tgt_feat, p2, tgt_w):
+    """PoseUpdate.sample_tgt (dualrefine/networks/utils/utils.py:383-404): target features at the projected
+    point and its +-1 pixel neighbours (p2: (B,2,1,5,h,w) from depth2gradcoords :213-231) ->
+    (warped_tgt_feat (B,C,h,w), warped_tgt_gradients (B,C,h,w,2), warped_tgt_w (B,1,h,w)).
+
+    The reference stores the third result in self.warped_tgt_w.  The sampler is mal_b200's grid_sample
+    kernel with ATen's CPU rounding (zeros padding, align_corners=False); gradients reach p2."""
+    batch, _, n1, d1, h1, w1 = p2.shape
+    p2 = p2.permute(2, 0, 4, 5, 3, 1).reshape(batch, h1 * w1, d1, 2)
+    xgrid, ygrid = p2.split([1, 1], dim=-1)
+    xgrid = 2 * (xgrid + 0.5) / (w1) - 1
+    ygrid = 2 * (ygrid + 0.5) / (h1) - 1
+    grid = torch.cat([xgrid, ygrid], dim=-1)
+    f = ops.grid_sample(tgt_feat, grid, padding_mode="zeros", align_corners=False)
+    f = f.view(batch, -1, h1, w1, d1)
+    warped_tgt_feat = f[..., 0]
+    warped_tgt_gradients = torch.stack([(f[..., 1] - f[..., 2]) / 2, (f[..., 3] - f[..., 4]) / 2], dim=-1)
+    grid_0 = grid[:, :, :1]
+    warped_tgt_w = ops.grid_sample(tgt_w.type(grid_0.dtype), grid_0, padding_mode="zeros",
+                                   align_corners=False).reshape(batch, 1, h1, w1)
+    return warped_tgt_feat, warped_tgt_gradients, warped_tgt_w

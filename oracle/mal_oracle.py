@@ -930,3 +930,22 @@ def corr_lookup(fmap1, pyramid, coords, num_head=1):
         out_pyramid.append(corr)
     out = torch.cat(out_pyramid, dim=-1)
     return out.permute(0, 3, 1, 2).contiguous().float()
+
+
+def sample_tgt(tgt_feat, p2, tgt_w):
+    """dualrefine/networks/utils/utils.py:383-404 (PoseUpdate.sample_tgt): the target features at the
+    projected point and its +-1 pixel neighbours -> warped features, central-difference gradients, and the
+    warped confidence weight.  p2 is (B, 2, 1, 5, h, w) from depth2gradcoords (:213-231)."""
+    batch, _, n1, d1, h1, w1 = p2.shape
+    p2 = p2.permute(2, 0, 4, 5, 3, 1).reshape(batch, h1 * w1, d1, 2)
+    xgrid, ygrid = p2.split([1, 1], dim=-1)
+    xgrid = 2 * (xgrid + 0.5) / (w1) - 1
+    ygrid = 2 * (ygrid + 0.5) / (h1) - 1
+    grid = torch.cat([xgrid, ygrid], dim=-1)
+    f = F.grid_sample(tgt_feat, grid, align_corners=False)
+    f = f.view(batch, -1, h1, w1, d1)
+    warped_tgt_feat = f[..., 0]
+    warped_tgt_gradients = torch.stack([(f[..., 1] - f[..., 2]) / 2, (f[..., 3] - f[..., 4]) / 2], dim=-1)
+    grid_0 = grid[:, :, :1]
+    warped_tgt_w = F.grid_sample(tgt_w.type(grid_0.dtype), grid_0, align_corners=False).reshape(batch, 1, h1, w1)
+    return warped_tgt_feat, warped_tgt_gradients, warped_tgt_w

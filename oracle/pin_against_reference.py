@@ -487,6 +487,36 @@ def pin_corr_lookup():
     return bool(ok)
 
 
+def pin_sample_tgt():
+    """PoseUpdate.sample_tgt: dualrefine/networks/utils/utils.py does not import outside its package
+    (SURVEY.md 8c), so the method's own source lines are cut out of the file and executed as they are."""
+    import ast
+    import textwrap
+    import types
+    import torch.nn.functional as F
+    from . import mal_oracle as O
+    path = os.path.join(REFERENCE_ROOT, "dualrefine", "networks", "utils", "utils.py")
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "sample_tgt")
+    code = textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno]))
+    ns = {"torch": torch, "F": F}
+    exec(compile(code, path, "exec"), ns)
+    g = torch.Generator().manual_seed(23)
+    B, Cn, h, w = 2, 16, 10, 14
+    feat, wmap = torch.rand(B, Cn, h, w, generator=g), torch.rand(B, 1, h, w, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    c1 = torch.stack([xs, ys])[None, :, None, None] + 1.5 * torch.randn(B, 2, 1, 1, h, w, generator=g)
+    delta = torch.tensor([[0., 1., -1., 0., 0.], [0., 0., 0., 1., -1.]]).reshape(1, 2, 1, 5, 1, 1)
+    p2 = c1 + delta
+    shell = types.SimpleNamespace(tgt_w=wmap)
+    want_feat, want_grad = ns["sample_tgt"](shell, feat, p2)
+    got = O.sample_tgt(feat, p2, wmap)
+    ok = _eq("sample_tgt feat", got[0], want_feat)
+    ok &= _eq("sample_tgt gradients", got[1], want_grad)
+    ok &= _eq("sample_tgt weight", got[2], shell.warped_tgt_w)
+    return bool(ok)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     good = run_pin()
@@ -494,5 +524,6 @@ if __name__ == "__main__":
     good &= pin_image_synthesis()
     good &= pin_dynamicdepth_losses()
     good &= pin_corr_lookup()
+    good &= pin_sample_tgt()
     print("PINNED" if good else "PIN FAILED")
     sys.exit(0 if good else 1)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from mal_b200 import raw
-from mal_b200.corr import CoordSampler
+from mal_b200.corr import CoordSampler, sample_tgt
 from oracle import mal_oracle as O
 from tests.backends import BACKENDS, handle_and_device
 from tests.helpers import load_npz
@@ -96,3 +96,23 @@ def test_sampler_interface(op_device):
     assert not torch.equal(s(c.to(dev), num_levels=2), out)
     with pytest.raises(ValueError):
         s(c.to(dev), num_levels=3)
+
+
+def test_sample_tgt_matches_the_oracle(op_device):
+    """PoseUpdate.sample_tgt (dualrefine/networks/utils/utils.py:383-404): bit-exact values, gradient to p2."""
+    dev = op_device
+    B, C, hh, ww = 2, 16, 10, 14
+    g = torch.Generator().manual_seed(23)
+    feat, wmap = torch.rand(B, C, hh, ww, generator=g), torch.rand(B, 1, hh, ww, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(hh).float(), torch.arange(ww).float(), indexing="ij")
+    c1 = torch.stack([xs, ys])[None, :, None, None] + 1.5 * torch.randn(B, 2, 1, 1, hh, ww, generator=g)
+    delta = torch.tensor([[0., 1., -1., 0., 0.], [0., 0., 0., 1., -1.]]).reshape(1, 2, 1, 5, 1, 1)   # utils.py:220-226
+    p2 = (c1 + delta).requires_grad_(True)
+    want = O.sample_tgt(feat, p2, wmap)
+    gw = torch.autograd.grad(want[0].sum() + (want[1] ** 2).sum() + want[2].sum(), p2)[0]
+    p2d = p2.detach().clone().to(dev).requires_grad_(True)
+    got = sample_tgt(feat.to(dev), p2d, wmap.to(dev))
+    for a, b in zip(got, want):
+        assert torch.equal(a.detach().cpu(), b.detach())
+    gg = torch.autograd.grad(got[0].sum() + (got[1] ** 2).sum() + got[2].sum(), p2d)[0]
+    assert _rel(gg.cpu(), gw) < GRAD_RTOL
