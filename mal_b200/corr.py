@@ -66,8 +66,12 @@ def sample_tgt(tgt_feat, p2, tgt_w):
     batch, _, n1, d1, h1, w1 = p2.shape
     p2 = p2.permute(2, 0, 4, 5, 3, 1).reshape(batch, h1 * w1, d1, 2)
     xgrid, ygrid = p2.split([1, 1], dim=-1)
-    xgrid = 2 * (xgrid + 0.5) / (w1) - 1
-    ygrid = 2 * (ygrid + 0.5) / (h1) - 1
+    # a device tensor as divisor: torch's CUDA kernels turn division by a host scalar into a multiplication
+    # by its reciprocal, which is not the IEEE division the reference's CPU path performs
+    wdiv = torch.full((), float(w1), device=p2.device, dtype=p2.dtype)
+    hdiv = torch.full((), float(h1), device=p2.device, dtype=p2.dtype)
+    xgrid = 2 * (xgrid + 0.5) / wdiv - 1
+    ygrid = 2 * (ygrid + 0.5) / hdiv - 1
     grid = torch.cat([xgrid, ygrid], dim=-1)
     f = ops.grid_sample(tgt_feat, grid, padding_mode="zeros", align_corners=False)
     f = f.view(batch, -1, h1, w1, d1)

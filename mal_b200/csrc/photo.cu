@@ -46,8 +46,8 @@ inline size_t photo_smem_bytes(bool grad, int ncand) {
   return fl * 4 + 16;
 }
 
-template <bool WARP, bool GRAD, int CONV>
-__global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, const int ncand,
+template <bool WARP, bool GRAD, int CONV, bool LOWRES>
+__global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_photo_args a, const int ncand,
                                                      const float min_disp, const float disp_range) {
   const PhotoTile tl = photo_tile(GRAD);
   const int tid = threadIdx.x;
@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(PH_NT) photo_kernel(const mal_photo_args a, co
   const int H = a.height, W = a.width;
   const size_t HW = (size_t)H * W;
   // low-resolution disparity, up-sampled on the fly (mal_photo_args.depth_height / depth_width)
-  const bool lowres = WARP && a.depth_height > 0;
+  // (a template parameter: the extra addressing costs registers - 97 instead of 79 with gradients -
+  // and with them the third resident CTA of the full-resolution case)
+  constexpr bool lowres = WARP && LOWRES;
   const size_t dhw = (size_t)a.depth_height * a.depth_width;
   const float up_sy = lowres ? up_scale(a.depth_height, H) : 1.0f, up_sx = lowres ? up_scale(a.depth_width, W) : 1.0f;
 
@@ -494,10 +496,14 @@ __global__ void __launch_bounds__(PH_NPART * 32) photo_finalize_kernel(float* __
 template <bool WARP, bool GRAD>
 static void photo_dispatch(const mal_photo_args& a, int ncand, float min_disp, float range, dim3 grid,
                            size_t smem, cudaStream_t st) {
-  if (a.convention == MAL_CONV_MANYDEPTH)
-    launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
-  else
-    launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+  const bool lowres = WARP && a.depth_height > 0;
+  if (a.convention == MAL_CONV_MANYDEPTH) {
+    if (lowres) launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH, WARP>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+    else launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH, false>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+  } else {
+    if (lowres) launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE, WARP>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+    else launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE, false>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
+  }
 }
 
 }  // namespace mal
