@@ -327,8 +327,10 @@ def ours(args):
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs,
                              "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                              "us_per_launch": dom["us_per_launch"], "algorithmic_bytes": dom["algorithmic_bytes"],
-                             "limiter": "fp32 issue, not HBM: bit-exact fp32 arithmetic (DESIGN.md section 4); ncu: "
-                                        "61% issue slots busy, 1.8% DRAM throughput (profiles/r1_notes.md)"},
+                             "limiter": "fp32 pipe / issue latency, not HBM: bit-exact fp32 arithmetic (DESIGN.md section 4); "
+                                        "ncu: fma pipe busy 49% of cycles (packed FFMA2), 56% issue slots, 38% L1 "
+                                        "data pipe, 16 warps/SM at 128 registers, <2% DRAM throughput "
+                                        "(profiles/r1_notes.md)"},
                 "kernels": roof,
                 # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
                 "step_hbm": {"survey_bytes_per_frame": 20636160,
