@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 3
+#define MAL_ABI_VERSION 4
 
 enum {
   MAL_OK = 0,

@@ -157,7 +157,7 @@ EXPORTS = {
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def bind(handle):
