@@ -162,7 +162,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -348,10 +348,26 @@ def ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_RESULT = None   # the process's real stdout, kept for the one JSON line
+
+
+def emit(line):
+    out = _RESULT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # Exactly ONE line may reach stdout.  Libraries write there too (NCCL prints its version banner on the
+    # first communicator), so file descriptor 1 is pointed at stderr for the whole run and the JSON line
+    # goes to a duplicate of the original stdout.
+    global _RESULT
+    _RESULT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         reference_arm(args)

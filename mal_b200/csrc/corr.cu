@@ -16,14 +16,28 @@
 //                    sequentially; for the tail columns (j >= floor(N/32)*32) row_sum: four interleaved
 //                    partial sums (channel % 4), each cascaded in 16s, then ((p0+p1)+p2)+p3; then / Cg.
 //
+// Layout: the pyramid buffer holds every level channel-quad interleaved, [B][C/4][h>>l][w>>l] float4, so
+// one 128-bit load fetches four channels of a bilinear tap and the blend runs on packed fp32 pairs
+// (FFMA2, mal_common.cuh); fmap1 stays NCHW (its loads are coalesced across the pixels of a warp).
+//
 // Backward (torch.abs -> sign, grid_sample's zero-padded bilinear adjoint): d/d coords is gathered per
-// thread; d/d fmap1 and d/d pyramid are scatter-adds (red.global.add.f32, fire-and-forget in L2) - the
-// same atomics ATen's grid_sampler_2d_backward issues, without the (B, C, h, w, D) intermediates.
+// thread; d/d fmap1 and d/d pyramid are scatter-adds (red.global.add, fire-and-forget in L2; 128-bit
+// vector reductions into the quad-interleaved pyramid gradient: one per tap and channel quad) - the same
+// atomics ATen's grid_sampler_2d_backward issues, a quarter as many, without the (B, C, h, w, D)
+// intermediates.
 #include "mal_math.cuh"
 
 namespace mal {
 
 constexpr int CR_NT = 128;
+
+__device__ __forceinline__ float4 ldg4c(const float4* p) {
+#ifdef MAL_EMU
+  return *p;
+#else
+  return __ldg(p);
+#endif
+}
 
 __host__ __device__ inline size_t corr_level_offset(int batch, int channels, int h, int w, int level) {
   size_t off = 0;
@@ -31,8 +45,25 @@ __host__ __device__ inline size_t corr_level_offset(int batch, int channels, int
   return off;
 }
 
-// level l+1 = F.avg_pool2d(level l, 2, stride=2); one thread per output element
-__global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict__ in, float* __restrict__ out,
+// level 0: NCHW -> [C/4][h][w] float4; one thread per (quad, pixel)
+__global__ void __launch_bounds__(256) corr_pack_kernel(const float* __restrict__ src, float4* __restrict__ dst,
+                                                        int C, int hw, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int p = (int)(i % hw);
+  const size_t r = i / hw;
+  const int q = (int)(r % (C / 4));
+  const size_t img = r / (C / 4);
+  const float* sp = src + (img * C + (size_t)q * 4) * hw + p;
+  dst[i] = make_float4(__ldg(sp), __ldg(sp + hw), __ldg(sp + 2 * (size_t)hw), __ldg(sp + 3 * (size_t)hw));
+}
+
+__device__ __forceinline__ float pool4(float a, float b, float c, float d) {
+  return xdiv(xadd(xadd(xadd(a, b), c), d), 4.0f);   // ATen avg_pool2d: row-major running sum / 4
+}
+
+// level l+1 = F.avg_pool2d(level l, 2, stride=2) on the packed planes; one thread per output float4
+__global__ void __launch_bounds__(256) corr_pool_kernel(const float4* __restrict__ in, float4* __restrict__ out,
                                                         size_t planes, int ih, int iw) {
   const int oh = ih / 2, ow = iw / 2;
   const size_t n = planes * oh * ow;
@@ -40,9 +71,10 @@ __global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict_
   if (i >= n) return;
   const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
   const size_t pl = i / ((size_t)ow * oh);
-  const float* p = in + pl * ih * iw + (size_t)(2 * oy) * iw + 2 * ox;
-  const float s = xadd(xadd(xadd(__ldg(p), __ldg(p + 1)), __ldg(p + iw)), __ldg(p + iw + 1));
-  out[i] = xdiv(s, 4.0f);
+  const float4* p = in + pl * ih * iw + (size_t)(2 * oy) * iw + 2 * ox;
+  const float4 a = p[0], b = p[1], c = p[iw], d = p[iw + 1];
+  out[i] = make_float4(pool4(a.x, b.x, c.x, d.x), pool4(a.y, b.y, c.y, d.y), pool4(a.z, b.z, c.z, d.z),
+                       pool4(a.w, b.w, c.w, d.w));
 }
 
 struct CorrSite {
@@ -80,51 +112,65 @@ __device__ __forceinline__ Taps corr_taps(const mal_corr_args& a, const CorrSite
   return make_taps(fminf(fmaxf(ix, -lim), lim), fminf(fmaxf(iy, -lim), lim), s.lh, s.lw);
 }
 
+// the four channels of one quad at a sampling point: zeros padding, nw*a then three FMAs per channel,
+// two channels per instruction
+struct Quad { pk2 lo, hi; };
+__device__ __forceinline__ float4 tap4(const float4* __restrict__ plane, bool ok, int o) {
+  return ok ? ldg4c(plane + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ Quad blend4(const float4* __restrict__ plane, const Taps& t, pk2 nw, pk2 ne, pk2 sw, pk2 se) {
+  const float4 a = tap4(plane, t.v00, t.o00), b = tap4(plane, t.v01, t.o01);
+  const float4 c = tap4(plane, t.v10, t.o10), d = tap4(plane, t.v11, t.o11);
+  Quad q;
+  q.lo = x2fma(pack2(d.x, d.y), se, x2fma(pack2(c.x, c.y), sw, x2fma(pack2(b.x, b.y), ne, x2mul(pack2(a.x, a.y), nw))));
+  q.hi = x2fma(pack2(d.z, d.w), se, x2fma(pack2(c.z, c.w), sw, x2fma(pack2(b.z, b.w), ne, x2mul(pack2(a.z, a.w), nw))));
+  return q;
+}
+
 __global__ void __launch_bounds__(CR_NT) corr_lookup_kernel(const mal_corr_args a) {
   CorrSite s;
   if (!corr_site(a, (size_t)blockIdx.x * CR_NT + threadIdx.x, s)) return;
-  const int h = a.height, w = a.width, C = a.channels, Cg = C / a.num_head;
+  const int h = a.height, w = a.width, C = a.channels, Cg = C / a.num_head, Qg = Cg / 4;
   const size_t hw = (size_t)h * w, lhw = (size_t)s.lh * s.lw;
   const size_t cbase = (((size_t)s.b * 2) * a.num_levels + s.l) * a.num_samples + s.d;
   const float cx = __ldg(a.coords + cbase * hw + (size_t)s.y * w + s.x);
   const float cy = __ldg(a.coords + (cbase + (size_t)a.num_levels * a.num_samples) * hw + (size_t)s.y * w + s.x);
   const Taps t = corr_taps(a, s, cx, cy);
+  const pk2 nw = dup2(t.nw), ne = dup2(t.ne), sw = dup2(t.sw), se = dup2(t.se);
   const float* f1 = a.fmap1 + (size_t)s.b * C * hw + (size_t)s.y * w + s.x;
-  const float* f2 = a.pyramid + corr_level_offset(a.batch, C, h, w, s.l) + (size_t)s.b * C * lhw;
+  const float4* f2 = reinterpret_cast<const float4*>(a.pyramid + corr_level_offset(a.batch, C, h, w, s.l)) +
+                     (size_t)s.b * (C / 4) * lhw;
   for (int hd = 0; hd < a.num_head; hd++) {
-    float total = 0.0f;   // acc[1] of the cascade
+    float total = 0.0f;   // acc[1] of ATen's cascade
     if (!s.tail) {
-      for (int c0 = 0; c0 < Cg; c0 += 16) {
-        float acc = 0.0f;
-        const int c1 = min(Cg, c0 + 16);
-        for (int c = c0; c < c1; c++) {
-          const int ch = hd * Cg + c;
-          acc = xadd(acc, fabsf(xsub(__ldg(f1 + ch * hw), bilinear(f2 + ch * lhw, t))));
-        }
-        // a trailing partial chunk stays in acc[0] and is added last: same sequence
-        total = xadd(total, acc);
+      float acc = 0.0f;
+      for (int q = 0; q < Qg; q++) {
+        const int qq = hd * Qg + q;
+        const Quad v = blend4(f2 + (size_t)qq * lhw, t, nw, ne, sw, se);
+        const float* f = f1 + (size_t)qq * 4 * hw;
+        const pk2 dlo = x2sub(pack2(__ldg(f), __ldg(f + hw)), v.lo);
+        const pk2 dhi = x2sub(pack2(__ldg(f + 2 * hw), __ldg(f + 3 * hw)), v.hi);
+        acc = xadd(acc, fabsf(lo2(dlo)));
+        acc = xadd(acc, fabsf(hi2(dlo)));
+        acc = xadd(acc, fabsf(lo2(dhi)));
+        acc = xadd(acc, fabsf(hi2(dhi)));
+        if ((q & 3) == 3) { total = xadd(total, acc); acc = 0.0f; }   // every 16 channels
       }
+      total = xadd(acc, total);   // a trailing partial chunk (acc[0]) joins last
     } else {
-      float part[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const int rows = Cg / 4;
-      for (int r = 0; r < rows; r++) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int ch = hd * Cg + r * 4 + k;
-          acc[k] = xadd(acc[k], fabsf(xsub(__ldg(f1 + ch * hw), bilinear(f2 + ch * lhw, t))));
-        }
-        if ((r & 15) == 15) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) { part[k] = xadd(part[k], acc[k]); acc[k] = 0.0f; }
-        }
+      // four interleaved partial sums (channel % 4 == component), cascaded every 16 rows
+      pk2 plo = dup2(0.0f), phi = dup2(0.0f), alo = dup2(0.0f), ahi = dup2(0.0f);
+      for (int q = 0; q < Qg; q++) {
+        const int qq = hd * Qg + q;
+        const Quad v = blend4(f2 + (size_t)qq * lhw, t, nw, ne, sw, se);
+        const float* f = f1 + (size_t)qq * 4 * hw;
+        alo = x2add(alo, abs2(x2sub(pack2(__ldg(f), __ldg(f + hw)), v.lo)));
+        ahi = x2add(ahi, abs2(x2sub(pack2(__ldg(f + 2 * hw), __ldg(f + 3 * hw)), v.hi)));
+        if ((q & 15) == 15) { plo = x2add(plo, alo); phi = x2add(phi, ahi); alo = dup2(0.0f); ahi = dup2(0.0f); }
       }
-#pragma unroll
-      for (int k = 0; k < 4; k++) part[k] = xadd(acc[k], part[k]);   // acc[0] += acc[1]
-      for (int c = rows * 4; c < Cg; c++) {                          // leftover channels go to partial 0
-        const int ch = hd * Cg + c;
-        part[0] = xadd(part[0], fabsf(xsub(__ldg(f1 + ch * hw), bilinear(f2 + ch * lhw, t))));
-      }
-      total = xadd(xadd(xadd(part[0], part[1]), part[2]), part[3]);
+      plo = x2add(alo, plo);
+      phi = x2add(ahi, phi);
+      total = xadd(xadd(xadd(lo2(plo), hi2(plo)), lo2(phi)), hi2(phi));
     }
     a.out[s.out_index + (size_t)hd * a.num_samples * hw] = xdiv(total, (float)Cg);
   }
@@ -138,10 +184,18 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 #endif
 }
 
+__device__ __forceinline__ void red_add4(float4* p, float x, float y, float z, float w) {
+#ifdef MAL_EMU
+  p->x += x; p->y += y; p->z += z; p->w += w;
+#else
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+#endif
+}
+
 __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_args a) {
   CorrSite s;
   if (!corr_site(a, (size_t)blockIdx.x * CR_NT + threadIdx.x, s)) return;
-  const int h = a.height, w = a.width, C = a.channels, Cg = C / a.num_head;
+  const int h = a.height, w = a.width, C = a.channels, Cg = C / a.num_head, Qg = Cg / 4;
   const size_t hw = (size_t)h * w, lhw = (size_t)s.lh * s.lw;
   const size_t cbase = (((size_t)s.b * 2) * a.num_levels + s.l) * a.num_samples + s.d;
   const size_t pix = (size_t)s.y * w + s.x;
@@ -150,28 +204,43 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
   const Taps t = corr_taps(a, s, cx, cy);
   const size_t loff = corr_level_offset(a.batch, C, h, w, s.l) + (size_t)s.b * C * lhw;
   const float* f1 = a.fmap1 + (size_t)s.b * C * hw + pix;
-  const float* f2 = a.pyramid + loff;
+  const float4* f2 = reinterpret_cast<const float4*>(a.pyramid + loff);
+  float4* gp = a.grad_pyramid ? reinterpret_cast<float4*>(a.grad_pyramid + loff) : nullptr;
   float gix = 0.0f, giy = 0.0f;
+  const float ex = 1.0f - t.tx, ey = 1.0f - t.ty;
   for (int hd = 0; hd < a.num_head; hd++) {
     const float g = __ldg(a.grad_out + s.out_index + (size_t)hd * a.num_samples * hw) / (float)Cg;
     if (g == 0.0f) continue;
-    for (int c = 0; c < Cg; c++) {
-      const int ch = hd * Cg + c;
-      float v00, v01, v10, v11;
-      const float sv = bilinear(f2 + ch * lhw, t, &v00, &v01, &v10, &v11);
-      const float df = __ldg(f1 + ch * hw) - sv;
-      const float sg = df > 0.0f ? g : (df < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1
-      if (sg == 0.0f) continue;
-      if (a.grad_fmap1) red_add(a.grad_fmap1 + ((size_t)s.b * C + ch) * hw + pix, sg);
-      if (a.grad_pyramid) {
-        float* gp = a.grad_pyramid + loff + ch * lhw;
-        if (t.v00) red_add(gp + t.o00, -sg * t.nw);
-        if (t.v01) red_add(gp + t.o01, -sg * t.ne);
-        if (t.v10) red_add(gp + t.o10, -sg * t.sw);
-        if (t.v11) red_add(gp + t.o11, -sg * t.se);
+    for (int q = 0; q < Qg; q++) {
+      const int qq = hd * Qg + q;
+      const float4* plane = f2 + (size_t)qq * lhw;
+      const float4 va = tap4(plane, t.v00, t.o00), vb = tap4(plane, t.v01, t.o01);
+      const float4 vc = tap4(plane, t.v10, t.o10), vd = tap4(plane, t.v11, t.o11);
+      const float* f = f1 + (size_t)qq * 4 * hw;
+      float sg[4];
+      const float av[4] = {va.x, va.y, va.z, va.w}, bv[4] = {vb.x, vb.y, vb.z, vb.w};
+      const float cv[4] = {vc.x, vc.y, vc.z, vc.w}, dv[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float sv = xfma(dv[k], t.se, xfma(cv[k], t.sw, xfma(bv[k], t.ne, xmul(av[k], t.nw))));
+        const float df = __ldg(f + k * hw) - sv;
+        sg[k] = df > 0.0f ? g : (df < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1
+        gix -= sg[k] * ((bv[k] - av[k]) * ey + (dv[k] - cv[k]) * t.ty);
+        giy -= sg[k] * ((cv[k] - av[k]) * ex + (dv[k] - bv[k]) * t.tx);
       }
-      gix -= sg * ((v01 - v00) * (1.0f - t.ty) + (v11 - v10) * t.ty);
-      giy -= sg * ((v10 - v00) * (1.0f - t.tx) + (v11 - v01) * t.tx);
+      if (a.grad_fmap1) {
+        float* g1 = a.grad_fmap1 + ((size_t)s.b * C + (size_t)qq * 4) * hw + pix;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (sg[k] != 0.0f) red_add(g1 + k * hw, sg[k]);
+      }
+      if (gp && (sg[0] != 0.0f || sg[1] != 0.0f || sg[2] != 0.0f || sg[3] != 0.0f)) {
+        float4* gq = gp + (size_t)qq * lhw;
+        if (t.v00) red_add4(gq + t.o00, -sg[0] * t.nw, -sg[1] * t.nw, -sg[2] * t.nw, -sg[3] * t.nw);
+        if (t.v01) red_add4(gq + t.o01, -sg[0] * t.ne, -sg[1] * t.ne, -sg[2] * t.ne, -sg[3] * t.ne);
+        if (t.v10) red_add4(gq + t.o10, -sg[0] * t.sw, -sg[1] * t.sw, -sg[2] * t.sw, -sg[3] * t.sw);
+        if (t.v11) red_add4(gq + t.o11, -sg[0] * t.se, -sg[1] * t.se, -sg[2] * t.se, -sg[3] * t.se);
+      }
     }
   }
   if (a.grad_coords) {
@@ -193,20 +262,21 @@ extern "C" int mal_corr_pyramid(const float* fmap2, int batch, int channels, int
                                 float* pyramid, mal_stream_t stream) {
   MAL_REQUIRE(fmap2 && pyramid && batch > 0 && channels > 0 && height > 0 && width > 0 && num_levels > 0,
               "mal_corr_pyramid: bad arguments");
+  MAL_REQUIRE(channels % 4 == 0, "mal_corr_pyramid: %d channels (the packed layout holds channel quads)", channels);
   MAL_REQUIRE((height >> (num_levels - 1)) > 0 && (width >> (num_levels - 1)) > 0,
               "mal_corr_pyramid: %d levels do not fit a %dx%d map", num_levels, height, width);
+  MAL_REQUIRE(((uintptr_t)pyramid & 15) == 0, "mal_corr_pyramid: the pyramid buffer must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t planes = (size_t)batch * channels;
-#ifdef MAL_EMU
-  memcpy(pyramid, fmap2, planes * height * width * sizeof(float));
-#else
-  cudaError_t e = cudaMemcpyAsync(pyramid, fmap2, planes * height * width * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  if (e != cudaSuccess) return fail(MAL_ERR_LAUNCH, "mal_corr_pyramid: %s", cudaGetErrorString(e));
-#endif
+  const size_t planes = (size_t)batch * (channels / 4);
+  {
+    const size_t total = planes * height * width;
+    launch(corr_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, fmap2,
+           reinterpret_cast<float4*>(pyramid), channels, height * width, total);
+  }
   int h = height, w = width;
   for (int l = 1; l < num_levels; l++) {
-    const float* in = pyramid + corr_level_offset(batch, channels, height, width, l - 1);
-    float* out = pyramid + corr_level_offset(batch, channels, height, width, l);
+    const float4* in = reinterpret_cast<const float4*>(pyramid + corr_level_offset(batch, channels, height, width, l - 1));
+    float4* out = reinterpret_cast<float4*>(pyramid + corr_level_offset(batch, channels, height, width, l));
     const size_t n = planes * (h / 2) * (w / 2);
     launch(corr_pool_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, in, out, planes, h, w);
     h /= 2; w /= 2;
@@ -218,7 +288,9 @@ static int corr_check(const mal_corr_args& a, const char* who) {
   MAL_REQUIRE(a.batch > 0 && a.channels > 0 && a.height > 0 && a.width > 0 && a.num_levels > 0 && a.num_samples > 0 &&
                   a.num_head > 0,
               "%s: bad shape", who);
-  MAL_REQUIRE(a.channels % a.num_head == 0, "%s: %d channels do not split into %d heads", who, a.channels, a.num_head);
+  MAL_REQUIRE(a.channels % a.num_head == 0 && (a.channels / a.num_head) % 4 == 0,
+              "%s: %d channels must split into %d heads of a multiple of 4 channels", who, a.channels, a.num_head);
+  MAL_REQUIRE(a.channels / a.num_head <= 256, "%s: more than 256 channels per head changes ATen's summation tree", who);
   MAL_REQUIRE((a.height >> (a.num_levels - 1)) > 0 && (a.width >> (a.num_levels - 1)) > 0, "%s: too many levels", who);
   MAL_REQUIRE(a.fmap1 && a.pyramid && a.coords, "%s: fmap1 / pyramid / coords are required", who);
   return MAL_OK;

@@ -479,11 +479,12 @@ def corr_pyramid(handle, fmap2, num_levels):
 
 
 def pyramid_levels(pyramid, B, Cn, h, w, num_levels):
-    """Views of the levels inside a flat pyramid buffer."""
+    """The levels of a flat pyramid buffer as (B, C, h>>l, w>>l) tensors.  The buffer stores every level
+    channel-quad interleaved ([B][C/4][h][w][4], csrc/corr.cu); this undoes the interleave (a copy)."""
     out, off = [], 0
     for _ in range(num_levels):
         n = B * Cn * h * w
-        out.append(pyramid[off:off + n].view(B, Cn, h, w))
+        out.append(pyramid[off:off + n].view(B, Cn // 4, h, w, 4).permute(0, 1, 4, 2, 3).reshape(B, Cn, h, w))
         off += n
         h, w = h // 2, w // 2
     return out
