@@ -227,6 +227,81 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
     return out
 
 
+def next_row_kernels(dev, batch, peak_gbs, iters=10):
+    """CUDA-event timing of the C-ABI calls that serve SURVEY.md section 8's "next" rows and the other
+    trainers (not part of the ManyDepth+MAL step above, so outside its timed region): DualRefine's
+    correlation lookup, the fused low-resolution disparity read, DynamicDepth's forward warp and the
+    temporal-hint image synthesis, each at its reference shape with synthetic inputs.  Bytes are the
+    algorithmic bytes (every tensor of the call once, fp32)."""
+    from mal_b200 import _capi, raw, rigid_warp
+    from mal_b200.utils.synthetic import make_instance_masks, make_photometric_inputs, to_device
+    h = _capi.lib()
+    g = torch.Generator().manual_seed(5)
+    B, C, hh, ww, L, D = batch, 64, HEIGHT // 4, WIDTH // 4, 3, 17
+    f1, f2 = torch.rand(B, C, hh, ww, generator=g).to(dev), torch.rand(B, C, hh, ww, generator=g).to(dev)
+    ys, xs = torch.meshgrid(torch.arange(hh).float(), torch.arange(ww).float(), indexing="ij")
+    dx = torch.linspace(-8, 8, D)[None, None, None, :, None, None] * \
+        torch.tensor([1.0, 2.0, 4.0])[None, None, :, None, None, None] * 0.4
+    coords = (torch.stack([xs, ys])[None, :, None, None] +
+              dx * torch.tensor([1.0, 0.15])[None, :, None, None, None, None]).repeat(B, 1, 1, 1, 1, 1).to(dev)
+    pyr = raw.corr_pyramid(h, f2, L)
+    go = torch.randn(B, L * D, hh, ww, generator=g).to(dev)
+    lpx = B * hh * ww
+    pyr_floats = pyr.numel()
+
+    inputs, t = make_photometric_inputs(B, HEIGHT, WIDTH, seed=77)
+    inputs, t = to_device(inputs, dev), to_device(t, dev)
+    lo = torch.nn.functional.avg_pool2d(t[("mono_disp", 0)], 4)
+    src = [inputs[("color", -1, 0)], inputs[("color", 1, 0)]]
+    Ts = [t[("cam_T_cam", 0, -1)], t[("cam_T_cam", 0, 1)]]
+    px = B * HEIGHT * WIDTH
+
+    Wc = 512   # CityScapes width (configs[2], configs[4])
+    img = torch.rand(B, 3, HEIGHT, Wc, generator=g).to(dev)
+    depth = (1.0 + 9.0 * torch.rand(B, 1, HEIGHT, Wc, generator=g)).to(dev)
+    pose = torch.cat([torch.eye(3)[None].repeat(B, 1, 1), 0.05 * torch.randn(B, 3, 1, generator=g)], 2).to(dev)
+    Kc = torch.tensor([[0.58 * Wc, 0, 0.5 * Wc], [0, 1.92 * HEIGHT, 0.5 * HEIGHT], [0, 0, 1.0]])[None].repeat(B, 1, 1).to(dev)
+    mats = rigid_warp.forward_warp_matrices(pose, Kc, 3)
+    cpx = B * HEIGHT * Wc
+
+    ml, mn = make_instance_masks(12, HEIGHT, Wc, seed=3)
+    ml, mn = ml.to(dev), mn.to(dev)
+    il, inx = torch.rand(3, HEIGHT, Wc, generator=g).to(dev), torch.rand(3, HEIGHT, Wc, generator=g).to(dev)
+
+    cases = [
+        ("f.2", "corr_lookup_kernel: DualRefine epipolar lookup, 64 ch, 48x160, 3 levels x 17 candidates",
+         lambda: raw.corr_lookup(h, f1, pyr, coords), 4 * (B * C * hh * ww + pyr_floats + 3 * L * D * lpx)),
+        ("f.2", "corr_lookup_bwd_kernel: gradients to coords, fmap1 and the pyramid",
+         lambda: raw.corr_lookup_backward(h, f1, pyr, coords, go), 4 * (2 * B * C * hh * ww + 2 * pyr_floats + 5 * L * D * lpx)),
+        ("f.3", "photo_kernel<WARP,GRAD,LOWRES>: student pass reading the scale-2 disparity in place",
+         lambda: raw.photo(h, target=inputs[("color", 0, 0)], src=src, depth=lo, K=inputs[("K", 0)],
+                           inv_K=inputs[("inv_K", 0)], T=Ts, with_grad=True), 49 * px),
+        ("a19", "fw_splat + fw_gather: DynamicDepth forward_warp, 192x512, upscale 3",
+         lambda: raw.forward_warp(h, img=img, depth=depth, pose=pose, K=Kc, Ku_inv=mats[0], K_inv=mats[1],
+                                  proj=mats[2], upscale=3), (4 * 9 + 4 + 8 * 3 + 8) * cpx),
+        ("f.1", "dynamic_instance: temporal-hint synthesis, 12 instances, one 192x512 frame pair",
+         lambda: raw.dynamic_instance(h, mask_last=ml, mask_next=mn, img_last=il, img_next=inx),
+         (2 * 12 + 4 * 12) * HEIGHT * Wc),
+    ]
+    out = []
+    with torch.no_grad():
+        for row, name, fn, nbytes in cases:
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / iters * 1e3
+            gbs = nbytes / (us * 1e-6) / 1e9
+            out.append({"row": row, "kernel": name, "us_per_call": us, "algorithmic_bytes": int(nbytes),
+                        "achieved_gbs": gbs, "frac": gbs / peak_gbs})
+    return out
+
+
 def ours(args):
     import torch.distributed as dist
     from mal_b200 import _capi, step as S
@@ -335,6 +410,9 @@ def ours(args):
                 # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
                 "step_hbm": {"survey_bytes_per_frame": 20636160,
                              "frac_of_peak": value / world * 20636160 / (peak_gbs * 1e9)}}
+        if world == 1:
+            # measured after the timed region; not part of `value`
+            line["next_rows"] = next_row_kernels(dev, args.batch, peak_gbs)
         if not args.skip_cpu_baseline and world == 1:
             r = time_cpu(args.cpu_frames, steps=8, warmup=1, budget_s=25.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
