@@ -104,10 +104,17 @@ typedef struct mal_photo_args {
                                (manydepth/trainer.py:1093-1094): the full-resolution disparity never
                                exists.  grad_depth stays (B,1,H,W) = d/d(up-sampled value); take it to
                                the low resolution with mal_upsample_bilinear_backward              */
+  int32_t skip_finalize;    /* 1: only the tile kernel runs; `sums` / `grad_P` are produced later by
+                               mal_photo_finalize(args, stream) - lets a scheduler keep the tiny
+                               reduction off the critical path between two heavy kernels           */
 } mal_photo_args;
 
 size_t mal_photo_partials_floats(int batch, int height, int width);
 int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream);
+/* The deterministic reduction of the per-tile partials that mal_photo_forward normally ends with;
+ * same args as the forward call it completes (only batch/height/width/mode/with_grad/partials/sums/grad_P
+ * are read). */
+int mal_photo_finalize(const mal_photo_args* args, mal_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Plane-sweep matching cost volume, forward only (the reference builds it under

@@ -30,7 +30,7 @@ class PhotoArgs(C.Structure):
         ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
         ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
         ("grad_syn", C.c_void_p * 2),
-        ("depth_height", C.c_int32), ("depth_width", C.c_int32),
+        ("depth_height", C.c_int32), ("depth_width", C.c_int32), ("skip_finalize", C.c_int32),
     ]
 
 
@@ -127,6 +127,7 @@ EXPORTS = {
     "mal_last_error": (C.c_char_p, []),
     "mal_check_device": (C.c_int, [C.c_int]),
     "mal_photo_partials_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mal_photo_finalize": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_cost_volume_workspace_floats": (C.c_size_t, [C.c_int] * 5),
     "mal_cost_volume_forward": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),

@@ -559,8 +559,18 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     else photo_dispatch<false, false>(a, ncand, min_disp, range, grid, smem, st);
   }
   int rc = check_launch("photo_kernel");
-  if (rc) return rc;
-  launch(photo_finalize_kernel, dim3(a.batch), dim3(PH_NPART * 32), 0, st, a.partials, a.batch,
-         (int)(grid.x * grid.y), a.sums, (grad && a.mode == MAL_PHOTO_WARP) ? a.grad_P : (float*)nullptr);
+  if (rc || a.skip_finalize) return rc;
+  return mal_photo_finalize(args, stream);
+}
+
+extern "C" int mal_photo_finalize(const mal_photo_args* args, mal_stream_t stream) {
+  MAL_REQUIRE(args != nullptr, "mal_photo_finalize: args is NULL");
+  const mal_photo_args& a = *args;
+  MAL_REQUIRE(a.batch > 0 && a.height >= 3 && a.width >= 3 && a.partials && a.sums, "mal_photo_finalize: bad arguments");
+  const bool grad = a.with_grad != 0 && a.mode == MAL_PHOTO_WARP;
+  if (grad) MAL_REQUIRE(a.grad_P, "mal_photo_finalize: WARP+grad needs grad_P");
+  const int tiles = ((a.width + PH_TW - 1) / PH_TW) * ((a.height + PH_TH - 1) / PH_TH);
+  launch(photo_finalize_kernel, dim3(a.batch), dim3(PH_NPART * 32), 0, (cudaStream_t)stream, a.partials, a.batch,
+         tiles, a.sums, grad ? a.grad_P : (float*)nullptr);
   return check_launch("photo_finalize_kernel");
 }

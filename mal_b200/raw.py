@@ -63,8 +63,12 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           identity_min=None, noise=None, pixel_mask=None, sample_mask=None,
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
-          want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False):
-    """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h)."""
+          want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True):
+    """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
+
+    finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
+    stream ordered after this call): a scheduler uses it to keep the tiny reduction kernel off the critical
+    path between two heavy kernels."""
     B, C3, H, W = target.shape
     if C3 != 3:
         raise ValueError("target must be (B,3,H,W)")
@@ -120,9 +124,18 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.min_reproj, a.selection, a.weight = _ptr(out["min_reproj"]), _ptr(out["selection"]), _ptr(out["weight"])
     a.grad_depth, a.grad_P = _ptr(out.get("grad_depth")), _ptr(out.get("grad_P"))
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
+    a.skip_finalize = 0 if finalize else 1
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
-    LAUNCHES[0] += 2   # photo_kernel + photo_finalize_kernel
+    LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
     out["_keepalive"] = (partials,)
+    out["_args"] = a
+    return out
+
+
+def photo_finalize(handle, out):
+    """mal_photo_finalize for a photo(..., finalize=False) result, on the current stream."""
+    _capi.check(handle.mal_photo_finalize(C.byref(out["_args"]), _stream(out["sums"])), handle)
+    LAUNCHES[0] += 1
     return out
 
 

@@ -113,7 +113,7 @@ def _head_op(cur, look, poses, K, inv_K, bins):
 
 
 def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None):
-    """The same step as `step_losses` + backward, as 24 launches of libmal_b200 and nothing else:
+    """The same step as `step_losses` + backward, as 21 launches of libmal_b200 and nothing else:
     no autograd graph, no intermediate depth maps, no one-element torch kernels.  The scalar tail
     and the gradient hand-over are `mal_step_combine` (csrc/step.cu).  Needs opt.distil.
 
@@ -136,27 +136,38 @@ def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, 
     main = torch.cuda.current_stream(tgt.device) if tgt.is_cuda else None
     branch = _Branches(main, side_streams)
 
-    with branch(0):   # cost-volume head
+    with branch(0):   # cost-volume head and the matching mask that only depends on it and the teacher disparity
         head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"],
                                poses=b["relative_poses"], K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"],
                                apply_confidence=True, want_missing=False)
+        mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
+                                 mono_is_disp=True, min_depth=lo, max_depth=hi)
     with branch(1):   # smoothness of both disparities
         sm_t = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True)
         sm_s = raw.smooth(handle, disp=multi, img=tgt, normalise=True, with_grad=True)
-    # main chain: identity -> teacher -> ensemble
-    ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
-    teacher = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None, depth=mono,
-                        identity_min=ident, noise=b["noise_mono"], with_grad=True, **geom)
+    # main chain: identity -> teacher -> ensemble.  The per-pass reductions (photo_finalize_kernel: 12 CTAs,
+    # ~6 us) are not needed before step_combine, so each is forked onto the smoothness branch, where it runs
+    # in the tail of the next heavy kernel instead of between two of them.
+    def later(out):
+        with branch(1):
+            raw.photo_finalize(handle, out)
+        return out
+
+    # (the identity and ensemble passes only feed their per-pixel maps forward: their sums are never read)
+    ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
+                      finalize=False)["min_reproj"]
+    teacher = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None,
+                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, finalize=False,
+                              **geom))
     ens = None
     if not opt.no_ens:
         ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
-                        **geom)["min_reproj"]
+                        finalize=False, **geom)["min_reproj"]
     branch.join(0)
-    mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
-                             mono_is_disp=True, min_depth=lo, max_depth=hi)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
-    student = raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
-                        depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, **geom)
+    student = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
+                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, finalize=False,
+                              **geom))
     dual = bool(opt.dual_distil) and ens is None
     mt = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
                         mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
