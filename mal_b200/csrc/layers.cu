@@ -309,44 +309,45 @@ __global__ void __launch_bounds__(LY_NT) grid_sample_bwd_kernel(const float* __r
 __global__ void __launch_bounds__(LY_NT) upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                   int planes, int ih, int iw, int oh, int ow) {
   const size_t n = (size_t)planes * oh * ow;
-  const size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x;
-  if (i >= n) return;
-  const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
-  const size_t pl = i / ((size_t)ow * oh);
-  if (ih == oh && iw == ow) { out[i] = __ldg(in + i); return; }
-  const UpAxis ay = up_axis(oy, ih, up_scale(ih, oh)), ax = up_axis(ox, iw, up_scale(iw, ow));
-  out[i] = upsample_at(in + pl * ih * iw, iw, ay, ax);
+  const float sy = up_scale(ih, oh), sx = up_scale(iw, ow);
+  for (size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x; i < n; i += (size_t)gridDim.x * LY_NT) {   // grid-stride
+    const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+    const size_t pl = i / ((size_t)ow * oh);
+    if (ih == oh && iw == ow) { out[i] = __ldg(in + i); continue; }
+    const UpAxis ay = up_axis(oy, ih, sy), ax = up_axis(ox, iw, sx);
+    out[i] = upsample_at(in + pl * ih * iw, iw, ay, ax);
+  }
 }
 
 __global__ void __launch_bounds__(LY_NT) upsample_bilinear_bwd_kernel(const float* __restrict__ gout,
                                                                       float* __restrict__ gin, int planes, int ih,
                                                                       int iw, int oh, int ow) {
   const size_t n = (size_t)planes * ih * iw;
-  const size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x;
-  if (i >= n) return;
-  const int ix = (int)(i % iw), iy = (int)((i / iw) % ih);
-  const size_t pl = i / ((size_t)iw * ih);
-  if (ih == oh && iw == ow) { gin[i] = __ldg(gout + i); return; }
   const float sy = up_scale(ih, oh), sx = up_scale(iw, ow);
   const float ry = (float)oh / (float)ih, rx = (float)ow / (float)iw;
-  // output rows / columns whose source index can fall in [i-1, i+1]
-  const int y_lo = max(0, (int)floorf((iy - 1) * ry) - 1), y_hi = min(oh - 1, (int)ceilf((iy + 2) * ry) + 1);
-  const int x_lo = max(0, (int)floorf((ix - 1) * rx) - 1), x_hi = min(ow - 1, (int)ceilf((ix + 2) * rx) + 1);
-  const float* g = gout + pl * oh * ow;
-  float acc = 0.0f;
-  for (int oy = y_lo; oy <= y_hi; oy++) {
-    const UpAxis ay = up_axis(oy, ih, sy);
-    const float wy = (ay.i0 == iy ? ay.l0 : 0.0f) + (ay.i1 == iy ? ay.l1 : 0.0f);
-    if (wy == 0.0f) continue;
-    float row = 0.0f;
-    for (int ox = x_lo; ox <= x_hi; ox++) {
-      const UpAxis ax = up_axis(ox, iw, sx);
-      const float wx = (ax.i0 == ix ? ax.l0 : 0.0f) + (ax.i1 == ix ? ax.l1 : 0.0f);
-      if (wx != 0.0f) row += wx * __ldg(g + (size_t)oy * ow + ox);
+  for (size_t i = (size_t)blockIdx.x * LY_NT + threadIdx.x; i < n; i += (size_t)gridDim.x * LY_NT) {   // grid-stride
+    const int ix = (int)(i % iw), iy = (int)((i / iw) % ih);
+    const size_t pl = i / ((size_t)iw * ih);
+    if (ih == oh && iw == ow) { gin[i] = __ldg(gout + i); continue; }
+    // output rows / columns whose source index can fall in [i-1, i+1]
+    const int y_lo = max(0, (int)floorf((iy - 1) * ry) - 1), y_hi = min(oh - 1, (int)ceilf((iy + 2) * ry) + 1);
+    const int x_lo = max(0, (int)floorf((ix - 1) * rx) - 1), x_hi = min(ow - 1, (int)ceilf((ix + 2) * rx) + 1);
+    const float* g = gout + pl * oh * ow;
+    float acc = 0.0f;
+    for (int oy = y_lo; oy <= y_hi; oy++) {
+      const UpAxis ay = up_axis(oy, ih, sy);
+      const float wy = (ay.i0 == iy ? ay.l0 : 0.0f) + (ay.i1 == iy ? ay.l1 : 0.0f);
+      if (wy == 0.0f) continue;
+      float row = 0.0f;
+      for (int ox = x_lo; ox <= x_hi; ox++) {
+        const UpAxis ax = up_axis(ox, iw, sx);
+        const float wx = (ax.i0 == ix ? ax.l0 : 0.0f) + (ax.i1 == ix ? ax.l1 : 0.0f);
+        if (wx != 0.0f) row += wx * __ldg(g + (size_t)oy * ow + ox);
+      }
+      acc += wy * row;
     }
-    acc += wy * row;
+    gin[i] = acc;
   }
-  gin[i] = acc;
 }
 
 }  // namespace mal

@@ -117,3 +117,60 @@ def test_full_resolution_sample_against_oracle(full):
     assert np.array_equal(outputs["mal_distil_index"].cpu().numpy(), aux["distil_idx"].numpy().astype(np.uint8))
     for a, bb in zip(g, grads):
         assert float((a.cpu() - bb).abs().max()) <= 1e-4 * float(bb.abs().max())
+
+
+def test_low_resolution_disparity_full_size(full):
+    """SURVEY.md 8 f.3 at 192x640: the teacher pass reading the scale-1..3 disparity in place equals the same
+    pass on F.interpolate(disp) computed on the CPU (selection, min-reprojection and gradient planes bit for
+    bit), and the gradient handed to the low resolution is the adjoint of the full-resolution one."""
+    import torch.nn.functional as F
+    opt, b, h = full
+    for s in (1, 2, 3):
+        lo = F.avg_pool2d(b["mono_disp"].detach(), 2 ** s)
+        up_cpu = F.interpolate(lo.cpu(), [opt.height, opt.width], mode="bilinear", align_corners=False)
+        up = raw.upsample_bilinear(h, lo, (opt.height, opt.width))
+        assert torch.equal(up.cpu(), up_cpu)
+        bb = dict(b)
+        bb["mono_disp"] = up
+        want = _teacher(h, bb)
+        bb["mono_disp"] = lo
+        got = _teacher(h, bb)
+        for k in ("min_reproj", "selection", "grad_depth", "grad_P", "sums"):
+            assert torch.equal(got[k], want[k]), (s, k)
+        g_lo = raw.upsample_bilinear_backward(h, got["grad_depth"], lo.shape[-2:])
+        lo_leaf = lo.cpu().clone().requires_grad_(True)
+        (ref,) = torch.autograd.grad(F.interpolate(lo_leaf, [opt.height, opt.width], mode="bilinear", align_corners=False),
+                                     lo_leaf, got["grad_depth"].cpu())
+        assert float((g_lo.cpu() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_correlation_lookup_full_size_against_the_oracle():
+    """SURVEY.md 8 f.2 at DualRefine's training shape (64 channels, 48x160, 3 levels x 17 candidates, two
+    samples): bit-exact forward against the CPU oracle; gradients within 1e-4."""
+    from oracle import mal_oracle as O
+    h = _capi.lib()
+    dev = torch.device("cuda:0")
+    B, C, hh, ww, L, D = 2, 64, 48, 160, 3, 17
+    g = torch.Generator().manual_seed(99)
+    f1, f2 = torch.rand(B, C, hh, ww, generator=g), torch.rand(B, C, hh, ww, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(hh).float(), torch.arange(ww).float(), indexing="ij")
+    dx = torch.linspace(-8, 8, D)[None, None, None, :, None, None] * torch.tensor([1.0, 2.0, 4.0])[None, None, :, None, None, None]
+    coords = torch.stack([xs, ys])[None, :, None, None] + 0.4 * dx * torch.tensor([1.0, 0.2])[None, :, None, None, None, None] \
+        + 0.3 * torch.randn(B, 2, L, D, hh, ww, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (f1, f2, coords)]
+    want = O.corr_lookup(leaves[0], O.corr_pyramid(leaves[1], L), leaves[2])
+    go = torch.randn(want.shape, generator=g)
+    want_g = torch.autograd.grad(want, leaves, go)
+    pyr = raw.corr_pyramid(h, f2.to(dev), L)
+    got = raw.corr_lookup(h, f1.to(dev), pyr, coords.to(dev))
+    assert torch.equal(got.cpu(), want.detach())
+    gc, g1, gp = raw.corr_lookup_backward(h, f1.to(dev), pyr, coords.to(dev), go.to(dev))
+    rel = lambda a, b_: float((a - b_).abs().max()) / float(b_.abs().max())
+    assert rel(gc.cpu(), want_g[2]) < 1e-4
+    assert rel(g1.cpu(), want_g[0]) < 1e-4
+    # gradient with respect to fmap2 = adjoint of the pooling chain applied to the pyramid gradient
+    from mal_b200 import ops
+    f2d = f2.to(dev).requires_grad_(True)
+    out = ops.corr_lookup(f1.to(dev), ops.corr_pyramid(f2d, L), coords.to(dev))
+    (g2,) = torch.autograd.grad(out, f2d, go.to(dev))
+    assert rel(g2.cpu(), want_g[1]) < 1e-4
