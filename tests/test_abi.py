@@ -33,18 +33,18 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_the_c_compiler(tmp_path):
+    pairs = [("mal_photo_args", _capi.PhotoArgs), ("mal_cost_volume_args", _capi.CostVolumeArgs),
+             ("mal_smooth_args", _capi.SmoothArgs), ("mal_main_terms_args", _capi.MainTermsArgs),
+             ("mal_matching_mask_args", _capi.MatchingMaskArgs), ("mal_step_combine_args", _capi.StepCombineArgs),
+             ("mal_forward_warp_args", _capi.ForwardWarpArgs), ("mal_corr_args", _capi.CorrArgs),
+             ("mal_dynamic_instance_args", _capi.DynamicInstanceArgs)]
+    body = "".join('printf("%%zu\\n", sizeof(%s));' % name for name, _ in pairs)
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mal_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
-                   "sizeof(mal_photo_args),sizeof(mal_cost_volume_args),sizeof(mal_smooth_args),"
-                   "sizeof(mal_main_terms_args),sizeof(mal_matching_mask_args),sizeof(mal_step_combine_args),"
-                   "sizeof(mal_forward_warp_args));return 0;}\n")
+    src.write_text('#include <stdio.h>\n#include "mal_b200.h"\nint main(void){' + body + "return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [ctypes.sizeof(s) for s in (_capi.PhotoArgs, _capi.CostVolumeArgs, _capi.SmoothArgs,
-                                       _capi.MainTermsArgs, _capi.MatchingMaskArgs, _capi.StepCombineArgs,
-                                       _capi.ForwardWarpArgs)]
-    assert got == want
+    assert got == [ctypes.sizeof(s) for _, s in pairs]
 
 
 def test_missing_library_is_an_error(monkeypatch):
@@ -52,3 +52,30 @@ def test_missing_library_is_an_error(monkeypatch):
     monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libmal_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _capi.lib()
+
+
+def test_bad_arguments_come_back_as_error_codes():
+    """No exception or crash crosses the C boundary: a bad call returns a status and leaves a message
+    (argument validation happens before any launch, so the host-emulated twin exercises the same code)."""
+    import torch
+    from mal_b200 import raw
+    from tests.emu.emu_lib import emu
+    h = emu()
+    f = torch.rand(1, 6, 8, 8)            # 6 channels: not a multiple of 4
+    with pytest.raises(RuntimeError, match="channel quads"):
+        raw.corr_pyramid(h, f, 2)
+    with pytest.raises(RuntimeError, match="levels do not fit"):
+        raw.corr_pyramid(h, torch.rand(1, 8, 4, 4), 4)
+    pyr = raw.corr_pyramid(h, torch.rand(1, 8, 8, 8), 2)
+    with pytest.raises(RuntimeError, match="heads"):
+        raw.corr_lookup(h, torch.rand(1, 8, 8, 8), pyr, torch.zeros(1, 2, 2, 3, 8, 8), num_head=3)
+    with pytest.raises(ValueError, match="coords must be"):
+        raw.corr_lookup(h, torch.rand(1, 8, 8, 8), pyr, torch.zeros(1, 2, 2, 3, 8, 9))
+    tgt = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="WARP mode needs"):
+        raw.photo(h, target=tgt, src=[tgt, tgt])                       # no depth / K / T
+    with pytest.raises(RuntimeError, match="bad shape"):
+        raw.photo(h, target=torch.rand(1, 3, 2, 2), src=[torch.rand(1, 3, 2, 2)] * 2, mode=raw.PHOTO_PRED)
+    a = _capi.PhotoArgs()
+    assert h.mal_photo_finalize(ctypes.byref(a), None) != 0 and b"mal_photo_finalize" in h.mal_last_error()
+    assert h.mal_upsample_bilinear(None, 1, 4, 4, 8, 8, None, None) != 0
