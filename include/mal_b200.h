@@ -96,8 +96,9 @@ typedef struct mal_photo_args {
   float* grad_P;            /* (B,2,12) WARP+grad: d(sum w*reproj)/d (K@T)[:3,:] per frame   */
   const float* depth_b;     /* (B,1,H,W) optional: the kernel uses (depth + depth_b) / 2, the
                                ensemble disparity of manydepth/trainer.py:598; no gradient      */
-  float* grad_syn[2];       /* (B,3,H,W) optional, PRED+grad with syn: d(sum w*reproj)/d syn(f); in
-                               WARP mode the temporal-hint candidates are data                   */
+  float* grad_syn[2];       /* (B,3,H,W) optional, with_grad and syn given (either mode):
+                               d(sum w*reproj)/d syn(f), non-zero where a temporal-hint candidate is
+                               the per-pixel minimum; NULL: the candidates are treated as data     */
   int32_t depth_height, depth_width; /* 0,0: `depth`/`depth_b` are (B,1,H,W).  Otherwise they are
                                (B,1,depth_height,depth_width) and the kernel reads them through
                                F.interpolate(.., [H,W], mode="bilinear", align_corners=False)

@@ -46,7 +46,7 @@ inline size_t photo_smem_bytes(bool grad, int ncand) {
   return fl * 4 + 16;
 }
 
-template <bool WARP, bool GRAD, int CONV, bool LOWRES>
+template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC>
 __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_photo_args a, const int ncand,
                                                      const float min_disp, const float disp_range) {
   const PhotoTile tl = photo_tile(GRAD);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
     size_t o = (size_t)ry * W + rx;
 #pragma unroll
     for (int c = 0; c < 3; c++) sy[c * tl.VN + i] = __ldg(tgt + c * HW + o);
-    if (ncand > 2) {
+    if (NC > 2 && ncand > 2) {
 #pragma unroll
       for (int k = 0; k < 2; k++)
 #pragma unroll
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
     float p_ident = 0.0f, p_noise = 0.0f, p_mask = 1.0f;
     if (automask) { p_ident = __ldg(a.identity_min + po); p_noise = __ldg(a.noise + po); }
     if (a.pixel_mask) p_mask = __ldg(a.pixel_mask + po);
-    float ssum[4], lsum[4];
+    float ssum[NC], lsum[NC];   // NC: compiled-in candidate capacity (2 or 4); ncand <= NC are live
     float cf0[9], cf1[9];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
         eyy = xdivc<9>(sum9_prod(yw, yw));
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < NC; k++) {
         if (k < ncand) {
           const float* X = sx + (k * 3 + c) * tl.VN + vc;
           float xw[9];
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
     float rmin = 0.f;
     int idx = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NC; k++) {
       if (k < ncand) {
         float l1m = xdivc<3>(lsum[k]);
         float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
@@ -236,15 +236,15 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
       acc_w += w;
     }
     if (GRAD) {
-      // warped candidates always carry a gradient; the temporal-hint candidates only in PRED mode
-      // when the caller asked for d/d syn (they are data for the fused WARP path)
-      const bool syn_grad = !WARP && a.grad_syn[0] != nullptr;
+      // warped candidates always carry a gradient; the temporal-hint candidates when the caller asked
+      // for d/d syn (autograd then carries it into the warped images image_synthesis copied from)
+      const bool syn_grad = (SYNG || !WARP) && a.grad_syn[0] != nullptr;
       const bool live = (idx < 2 || syn_grad) && w != 0.0f;
       lsel[i] = live ? idx : -1;
       lw[i] = w;
       if (live && !a.no_ssim) {
         const float sc = w * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
-        if (idx < 2) {
+        if (NC <= 2 || idx < 2) {
 #pragma unroll
           for (int j = 0; j < 9; j++) coef[j * tl.LN + i] = (idx == 0 ? cf0[j] : cf1[j]) * sc;
         } else {
@@ -284,47 +284,55 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
       if (gy >= H || gx >= W) continue;
       const int lc = (qy + tl.HL) * tl.LW + qx + tl.HL;
       const int vc = (qy + tl.HV) * tl.VW + qx + tl.HV;
+      // d S / d (candidate image k) at this pixel, for a candidate that is given as an image: the
+      // predictions of PRED mode, and the temporal-hint candidates (k >= 2) of either mode
+      auto image_grad = [&](int k, float* out) {
+        const size_t pq = (size_t)gy * W + gx;
+        float g[3] = {0.f, 0.f, 0.f};
+        float xq[3], yq[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { xq[c] = sx[(k * 3 + c) * tl.VN + vc]; yq[c] = sy[c * tl.VN + vc]; }
+        if (!a.no_ssim) {
+          for (int dy = -1; dy <= 1; dy++) {
+            int py = gy + dy;
+            if (py < 0 || py >= H) continue;
+            float my = ((py == 0 && dy == -1) || (py == H - 1 && dy == 1)) ? 2.0f : 1.0f;
+            for (int dx = -1; dx <= 1; dx++) {
+              int px = gx + dx;
+              if (px < 0 || px >= W) continue;
+              float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
+              int li = lc + dy * tl.LW + dx;
+              if (lsel[li] != k) continue;
+#pragma unroll
+              for (int c = 0; c < 3; c++)
+                g[c] += m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq[c] * coef[(c * 3 + 1) * tl.LN + li] +
+                             yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
+            }
+          }
+        }
+        if (lsel[lc] == k) {
+          float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            float d = yq[c] - xq[c];
+            g[c] += d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[((size_t)b * 3 + c) * HW + pq] = g[c];
+      };
       if (!WARP) {
         // PRED mode: d S / d prediction for every candidate that can be selected, one at a time
-        const size_t pq = (size_t)gy * W + gx;
         for (int k = 0; k < ncand; k++) {
           float* out = k < 2 ? a.grad_pred[k] : a.grad_syn[k - 2];
-          if (out == nullptr) continue;
-          float g[3] = {0.f, 0.f, 0.f};
-          float xq[3], yq[3];
-#pragma unroll
-          for (int c = 0; c < 3; c++) { xq[c] = sx[(k * 3 + c) * tl.VN + vc]; yq[c] = sy[c * tl.VN + vc]; }
-          if (!a.no_ssim) {
-            for (int dy = -1; dy <= 1; dy++) {
-              int py = gy + dy;
-              if (py < 0 || py >= H) continue;
-              float my = ((py == 0 && dy == -1) || (py == H - 1 && dy == 1)) ? 2.0f : 1.0f;
-              for (int dx = -1; dx <= 1; dx++) {
-                int px = gx + dx;
-                if (px < 0 || px >= W) continue;
-                float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
-                int li = lc + dy * tl.LW + dx;
-                if (lsel[li] != k) continue;
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                  g[c] += m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq[c] * coef[(c * 3 + 1) * tl.LN + li] +
-                               yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
-              }
-            }
-          }
-          if (lsel[lc] == k) {
-            float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              float d = yq[c] - xq[c];
-              g[c] += d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 3; c++) out[((size_t)b * 3 + c) * HW + pq] = g[c];
+          if (out != nullptr) image_grad(k, out);
         }
         continue;
       }
+      // (SYNG is a template parameter: the extra code costs the plain teacher pass 3% through the
+      // instruction cache even when it never runs)
+      if (SYNG && a.grad_syn[0] != nullptr)
+        for (int k = 2; k < ncand; k++) image_grad(k, a.grad_syn[k - 2]);
       float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
       float xq0[3], xq1[3], yq[3];
 #pragma unroll
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
             float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
             int li = lc + dy * tl.LW + dx;
             int s = lsel[li];
-            if (s < 0) continue;
+            if (s < 0 || (SYNG && s > 1)) continue;   // only the warped candidates chain into depth / pose here
 #pragma unroll
             for (int c = 0; c < 3; c++) {
               float al = coef[(c * 3) * tl.LN + li], be = coef[(c * 3 + 1) * tl.LN + li],
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4) photo_kernel(const mal_ph
       }
       {
         int s = lsel[lc];
-        if (s >= 0) {
+        if (s >= 0 && (!SYNG || s <= 1)) {
           float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
 #pragma unroll
           for (int c = 0; c < 3; c++) {
@@ -497,13 +505,25 @@ template <bool WARP, bool GRAD>
 static void photo_dispatch(const mal_photo_args& a, int ncand, float min_disp, float range, dim3 grid,
                            size_t smem, cudaStream_t st) {
   const bool lowres = WARP && a.depth_height > 0;
-  if (a.convention == MAL_CONV_MANYDEPTH) {
-    if (lowres) launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH, WARP>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
-    else launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH, false>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
-  } else {
-    if (lowres) launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE, WARP>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
-    else launch(photo_kernel<WARP, GRAD, MAL_CONV_DUALREFINE, false>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);
-  }
+  const bool syng = WARP && GRAD && a.grad_syn[0] != nullptr;   // PRED mode handles grad_syn in its own branch
+#define MAL_PHOTO_LAUNCH2(CONV_, NC_)                                                                        \
+  do {                                                                                                      \
+    if (lowres && syng) launch(photo_kernel<WARP, GRAD, CONV_, WARP, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range); \
+    else if (lowres) launch(photo_kernel<WARP, GRAD, CONV_, WARP, false, NC_>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);          \
+    else if (syng) launch(photo_kernel<WARP, GRAD, CONV_, false, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);    \
+    else launch(photo_kernel<WARP, GRAD, CONV_, false, false, NC_>, grid, dim3(PH_NT), smem, st, a, ncand, min_disp, range);                     \
+  } while (0)
+  // the candidate loops are compiled for 2 or 4 candidates: the 2-candidate passes (identity, ensemble,
+  // student) run a kernel half the size of the 4-candidate teacher pass (instruction-cache pressure)
+#define MAL_PHOTO_LAUNCH(CONV_)                  \
+  do {                                           \
+    if (ncand > 2) MAL_PHOTO_LAUNCH2(CONV_, 4);  \
+    else MAL_PHOTO_LAUNCH2(CONV_, 2);            \
+  } while (0)
+  if (a.convention == MAL_CONV_MANYDEPTH) MAL_PHOTO_LAUNCH(MAL_CONV_MANYDEPTH);
+  else MAL_PHOTO_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_PHOTO_LAUNCH2
+#undef MAL_PHOTO_LAUNCH
 }
 
 }  // namespace mal

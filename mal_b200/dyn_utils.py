@@ -13,8 +13,8 @@ caller's - they are out of scope here - and any callable w
 interface works (tests use synthetic Mask2Former-shaped masks).
 
 Like the reference's copies, the synthesised images keep autograd history to the warped source
-images (mal_dynamic_instance_backward); the classic loss path (PRED mode) returns d loss / d syn.
-The fused WARP path treats them as data.
+images (mal_dynamic_instance_backward); both loss paths (PRED mode and the fused WARP mode) return
+d loss / d syn when the candidates require grad.
 """
 from __future__ import annotations
 

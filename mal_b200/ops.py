@@ -59,7 +59,7 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
               identity_min: Optional[Tensor], noise: Optional[Tensor], pixel_mask: Optional[Tensor],
               sample_mask: Optional[Tensor], mode: int, convention: int, depth_is_disp: bool,
               no_ssim: bool, min_depth: float, max_depth: float, eps: float,
-              need_grad: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+              need_grad: bool, need_grad_syn: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     h = _lib(target)
     src = [src0] if src1 is None else [src0, src1]
     out = raw.photo(h, target=target, src=src, syn=None if syn0 is None else [syn0, syn1],
@@ -68,7 +68,7 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
                     sample_mask=sample_mask, mode=mode, convention=convention,
                     depth_is_disp=depth_is_disp, no_ssim=no_ssim, with_grad=need_grad,
                     min_depth=min_depth, max_depth=max_depth, eps=eps,
-                    want_grad_syn=need_grad and mode == raw.PHOTO_PRED and syn0 is not None)
+                    want_grad_syn=need_grad and need_grad_syn and syn0 is not None)
     gp = out.get("grad_pred", [None, None])
     gs = out.get("grad_syn", [None, None])
     pick = lambda v: v if v is not None else _empty(target)   # a fresh tensor each: outputs may not alias
@@ -78,7 +78,7 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
 
 @_photo_op.register_fake
 def _(target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noise, pixel_mask,
-      sample_mask, mode, convention, depth_is_disp, no_ssim, min_depth, max_depth, eps, need_grad):
+      sample_mask, mode, convention, depth_is_disp, no_ssim, min_depth, max_depth, eps, need_grad, need_grad_syn):
     B, _, H, W = target.shape
     f = lambda *s: target.new_empty(s)
     warp = mode == raw.PHOTO_WARP
@@ -86,8 +86,8 @@ def _(target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noi
             f(B, 1, H, W) if need_grad and warp else f(0), f(B, 2, 12) if need_grad and warp else f(0),
             f(B, 3, H, W) if need_grad and not warp else f(0),
             f(B, 3, H, W) if need_grad and not warp and src1 is not None else f(0),
-            f(B, 3, H, W) if need_grad and not warp and syn0 is not None else f(0),
-            f(B, 3, H, W) if need_grad and not warp and syn0 is not None else f(0))
+            f(B, 3, H, W) if need_grad and need_grad_syn and syn0 is not None else f(0),
+            f(B, 3, H, W) if need_grad and need_grad_syn and syn0 is not None else f(0))
 
 
 def _photo_setup(ctx, inputs, output):
@@ -95,7 +95,7 @@ def _photo_setup(ctx, inputs, output):
      sample_mask, mode, *_rest) = inputs
     sums, _, _, g_depth, g_P, g_p0, g_p1, g_s0, g_s1 = output
     ctx.mode = mode
-    ctx.need_grad = inputs[-1]
+    ctx.need_grad = inputs[-2]
     ctx.depth_size = None if depth is None else tuple(depth.shape[-2:])
     ctx.save_for_backward(sums, g_depth, g_P, g_p0, g_p1, K if K is not None else sums, g_s0, g_s1)
 
@@ -106,7 +106,9 @@ def _photo_backward(ctx, g_sums, *_unused):
         raise RuntimeError("mal_b200::photo was run with need_grad=False but a gradient is requested")
     # sums = [S, W, S / (W + 1e-7), 0]; the planes hold d S / d input
     coef = g_sums[0] + g_sums[2] / (sums[1] + 1e-7)
-    grads = [None] * 22
+    grads = [None] * 23
+    if g_s0.numel():   # temporal-hint candidates, either mode
+        grads[3], grads[4] = coef * g_s0, coef * g_s1
     if ctx.mode == raw.PHOTO_WARP:
         grads[5] = coef * g_depth
         if ctx.depth_size != tuple(g_depth.shape[-2:]):   # the kernel up-sampled a low-resolution disparity
@@ -119,8 +121,6 @@ def _photo_backward(ctx, g_sums, *_unused):
         grads[1] = coef * g_p0
         if g_p1.numel():
             grads[2] = coef * g_p1
-        if g_s0.numel():
-            grads[3], grads[4] = coef * g_s0, coef * g_s1
     return tuple(grads)
 
 
@@ -134,22 +134,21 @@ def photo(target, src, *, syn=None, depth=None, K=None, inv_K=None, T=None, iden
     """Fused photometric loss.  Returns ``(sums, min_reproj, selection)``.
 
     ``sums = [sum(w*reproj), sum(w), sum(w*reproj)/(sum(w)+1e-7), 0]`` is differentiable with
-    respect to ``depth`` and ``T`` (WARP mode) or the predictions in ``src`` (PRED mode);
+    respect to ``depth`` and ``T`` (WARP mode) or the predictions in ``src`` (PRED mode), and in either mode
+    to the temporal-hint candidates ``syn`` when they require grad (autograd then carries that gradient
+    into the warped images ``image_synthesis`` copied them from, as in the reference);
     ``min_reproj`` (B,1,H,W) and ``selection`` (uint8: arg-min candidate | automask << 7) are not.
     """
     src = list(src)
-    diff = [depth, *(T or [])] if mode == raw.PHOTO_WARP else src + list(syn or [])
+    syn_grad = torch.is_grad_enabled() and bool(syn) and any(t.requires_grad for t in syn)
+    diff = ([depth, *(T or [])] if mode == raw.PHOTO_WARP else src) + (list(syn) if syn_grad else [])
     need_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in diff)
-    if mode == raw.PHOTO_WARP and syn and torch.is_grad_enabled() and any(t.requires_grad for t in syn):
-        _warn_once("mal_b200.ops.photo: in the fused WARP mode the temporal-hint candidates `syn` are data; their "
-                   "gradient (which the reference propagates into the warped images) is dropped.  Use the "
-                   "classic path (materialised warps, PRED mode) to keep it.")
     sample_mask = None if sample_mask is None else sample_mask.reshape(-1)
     out = _photo_op(target, src[0], src[1] if len(src) > 1 else None,
                     syn[0] if syn else None, syn[1] if syn else None, depth, K, inv_K,
                     T[0] if T else None, T[1] if T else None, identity_min, noise, pixel_mask,
                     sample_mask, mode, convention, depth_is_disp, no_ssim, float(min_depth),
-                    float(max_depth), float(eps), need_grad)
+                    float(max_depth), float(eps), need_grad, syn_grad)
     return out[0], out[1], out[2]
 
 

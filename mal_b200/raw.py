@@ -103,8 +103,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
         out["grad_depth"], out["grad_P"] = new(plane), new((B, 2, 12))
     if with_grad and mode == PHOTO_PRED:
         out["grad_pred"] = [new(img), new(img) if src[1] is not None else None]
-        if want_grad_syn and syn[0] is not None:
-            out["grad_syn"] = [new(img), new(img)]
+    if with_grad and want_grad_syn and syn[0] is not None:   # either mode
+        out["grad_syn"] = [new(img), new(img)]
     partials = new((handle.mal_photo_partials_floats(B, H, W),))
 
     a = _capi.PhotoArgs()

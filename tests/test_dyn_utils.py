@@ -144,3 +144,40 @@ def test_temporal_hint_gradient_reaches_the_warped_images(op_device):
     assert float((idx0 >= 2).float().mean()) > 0.02          # some pixels do select a temporal-hint candidate
     for a, b in zip(g1, g0):
         assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
+
+
+def test_fused_warp_path_returns_the_temporal_hint_gradient(op_device):
+    """Fused WARP mode (no materialised warps inside the loss kernel): the gradient with respect to the
+    temporal-hint candidates equals autograd on the oracle, so autograd can carry it into the warped images
+    image_synthesis copied them from - the reference's behaviour (manydepth/loss_utils.py:84-88)."""
+    from mal_b200 import ops
+    dev = op_device
+    B, H, W = 1, 32, 64
+    inputs, t = make_photometric_inputs(B, H, W, seed=21, translation_scale=0.3)
+    # candidates that win on a good share of the pixels: the target, slightly perturbed
+    gen = torch.Generator().manual_seed(22)
+    syn = {f: (inputs[("color", 0, 0)] + 0.02 * torch.randn(B, 3, H, W, generator=gen)).clamp(0, 1) for f in (-1, 1)}
+    # oracle: syn as leaves
+    leaves = {f: syn[f].clone().requires_grad_(True) for f in (-1, 1)}
+    disp = t[("mono_disp", 0)].clone().requires_grad_(True)
+    out = {("disp", 0): disp, ("syn", -1, 0): leaves[-1], ("syn", 1, 0): leaves[1]}
+    for f in (-1, 1):
+        out[("cam_T_cam", 0, f)] = t[("cam_T_cam", 0, f)]
+    O.images_pred(inputs, out, height=H, width=W)
+    losses, _, aux = O.mono_losses(inputs, out, True, True, noise=t["noise"][0])
+    want = torch.autograd.grad(losses["reproj_loss/0"], [leaves[-1], leaves[1], disp])
+    assert float((aux["frame_idx"] >= 2).float().mean()) > 0.1
+    # ours: one fused call
+    d = lambda x: x.to(dev)
+    tgt, src = d(inputs[("color", 0, 0)]), [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])]
+    ident = ops.photo(tgt, src, mode=raw.PHOTO_PRED)[1]
+    syn_d = [d(syn[f]).requires_grad_(True) for f in (-1, 1)]
+    disp_d = d(t[("mono_disp", 0)]).requires_grad_(True)
+    sums, _, sel = ops.photo(tgt, src, syn=syn_d, depth=disp_d, K=d(inputs[("K", 0)]), inv_K=d(inputs[("inv_K", 0)]),
+                             T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])], identity_min=ident.detach(),
+                             noise=d(t["noise"][0]))
+    assert abs(float(sums[2]) - float(losses["reproj_loss/0"])) <= 1e-5 * abs(float(losses["reproj_loss/0"]))
+    assert torch.equal((sel.cpu() & 0x7F)[:, 0].long(), aux["frame_idx"].reshape(B, H, W).long())
+    got = torch.autograd.grad(sums[2], [syn_d[0], syn_d[1], disp_d])
+    for name, a, b in zip(("syn -1", "syn +1", "disp"), got, want):
+        assert float((a.cpu() - b).abs().max()) <= 1e-4 * float(b.abs().max()), name
