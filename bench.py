@@ -323,11 +323,11 @@ def ours(args):
         peak_gbs, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
     opt = S.default_opt(args.batch, HEIGHT, WIDTH)
+    st = S.MalStep(opt, device=dev, use_graph=not args.no_graph, slots=args.sets)
     host = []
     for i in range(args.sets):
-        b = S.synthetic_batch(opt, seed=1234 + 17 * i + 1000 * rank)
-        host.append({k: v.pin_memory() for k, v in b.items()})
-    st = S.MalStep(opt, device=dev, use_graph=not args.no_graph, slots=args.sets)
+        # pinned host batches in the slot layout: each goes up as one contiguous copy
+        host.append(st.staging(S.synthetic_batch(opt, seed=1234 + 17 * i + 1000 * rank)))
     h2d = 0
     for i in range(args.sets):
         h2d = st.load(host[i], slot=i)

@@ -222,6 +222,31 @@ class _Branch:
         return False
 
 
+class StagedBatch(dict):
+    """A batch whose tensors are views of one flat (pinned) buffer `flat` (MalStep.staging)."""
+    flat = None
+
+
+def _flat_layout(batch, align=256):
+    off, items = 0, {}
+    for k in INPUT_KEYS:
+        t = batch[k]
+        items[k] = (off, tuple(t.shape), t.dtype)
+        off += (t.numel() * t.element_size() + align - 1) // align * align
+    return {"items": items, "bytes": off}
+
+
+def _flat_views(flat, layout):
+    out = {}
+    for k, (off, shape, dtype) in layout["items"].items():
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        out[k] = flat[off:off + nbytes].view(dtype).view(shape)
+    return out
+
+
 class MalStep:
     """Static-buffer, graph-captured MAL step for one GPU.
 
@@ -241,6 +266,7 @@ class MalStep:
         self._w_host = torch.empty(2, dtype=torch.float32).pin_memory()
         self._scalars_host = torch.empty(8, dtype=torch.float32).pin_memory()
         self.launches_per_step = None
+        self._layout = None
         self.copy_stream = torch.cuda.Stream(self.device)
         # parallel branches only inside a captured graph: there every buffer is static, so tensors
         # produced on one stream and consumed on another need no allocator bookkeeping
@@ -261,8 +287,11 @@ class MalStep:
         else:
             self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream), torch.no_grad():
-            for k in INPUT_KEYS:
-                sl["buf"][k].copy_(batch[k], non_blocking=True)
+            if isinstance(batch, StagedBatch) and batch.flat.numel() == sl["flat"].numel():
+                sl["flat"].copy_(batch.flat, non_blocking=True)
+            else:
+                for k in INPUT_KEYS:
+                    sl["buf"][k].copy_(batch[k], non_blocking=True)
             sl["ready"] = torch.cuda.Event()
             sl["ready"].record(self.copy_stream)
         return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
@@ -272,13 +301,31 @@ class MalStep:
         Returns the bytes copied."""
         sl = self.slots[slot]
         if sl["buf"] is None:
-            sl["buf"] = {k: torch.empty_like(batch[k], device=self.device) for k in INPUT_KEYS}
+            # every input of the slot lives in ONE device allocation (256-byte aligned views), so that a
+            # batch staged with `staging()` goes up as a single host->device copy
+            self._layout = self._layout or _flat_layout(batch)
+            sl["flat"] = torch.empty(self._layout["bytes"], dtype=torch.uint8, device=self.device)
+            sl["buf"] = _flat_views(sl["flat"], self._layout)
             for k in LEAVES:
                 sl["buf"][k].requires_grad_(True)
         with torch.no_grad():
-            for k in INPUT_KEYS:
-                sl["buf"][k].copy_(batch[k], non_blocking=non_blocking)
+            if isinstance(batch, StagedBatch) and batch.flat.numel() == sl["flat"].numel():
+                sl["flat"].copy_(batch.flat, non_blocking=non_blocking)
+            else:
+                for k in INPUT_KEYS:
+                    sl["buf"][k].copy_(batch[k], non_blocking=non_blocking)
         return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
+
+    def staging(self, like):
+        """A pinned host batch with the slot layout: fill its tensors (same keys / shapes as `like`) and hand
+        it to load() / load_async(); it then travels as one contiguous copy instead of one per tensor."""
+        self._layout = self._layout or _flat_layout(like)
+        flat = torch.empty(self._layout["bytes"], dtype=torch.uint8).pin_memory()
+        staged = StagedBatch(_flat_views(flat, self._layout))
+        staged.flat = flat
+        for k in INPUT_KEYS:
+            staged[k].copy_(like[k])
+        return staged
 
     # -- one step ------------------------------------------------------------------------------
     def _run(self, buf):
