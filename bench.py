@@ -206,8 +206,10 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
         ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass)", photo4, 81 * px, "photo_teacher"),
         # target 12 + src 24 + disp 4 + mask 4 read; min_reproj 4 + sel 1 + grad 4 written
         ("photo_kernel<WARP,GRAD> 2 candidates + masks (student pass)", photo2, 53 * px, "photo_student"),
-        # pack: 2*C*4 read + 2*C*4 written; sweep: 2*C*4 read, bins*4 + 12 written
-        ("cv_pack x2 + cv_sweep_kernel (cost-volume head)", cv, (3 * 2 * C * 4 + nb * 4 + 12) * lowpx, "cost_volume"),
+        # SURVEY.md 8(d) A_cv without the missing mask (not requested here): current + lookup features read,
+        # cost volume + confidence / arg-min / lowest-cost planes written.  The lookup packing pass is the
+        # implementation's own traffic, not algorithmic bytes.
+        ("cv_pack (lookup) + cv_sweep_quad_kernel (cost-volume head)", cv, (2 * C * 4 + nb * 4 + 12) * lowpx, "cost_volume"),
     ]
     out = []
     for name, fn, nbytes, key in cases:

@@ -10,9 +10,10 @@
 // three times over); here nothing larger than the inputs and the (B, bins, h, w) result touches HBM.
 //
 // Work decomposition
-//   kernel 1  cv_pack_kernel: current/lookup features NCHW -> channel-quad interleaved float4
-//             planes [C/4][h][w] (zero padded to a multiple of 16 channels) so that one 128-bit load
-//             fetches 4 channels of one bilinear tap.
+//   kernel 1  cv_pack_kernel: lookup features NCHW -> channel-quad interleaved float4 planes
+//             [C/4][h][w] (zero padded to a multiple of 16 channels) so that one 128-bit load fetches 4
+//             channels of one bilinear tap.  (The quad sweep reads the current features in place; the
+//             general kernel below packs them too.)
 //   kernel 2  cv_sweep_kernel: one CTA = 32 consecutive pixels of one sample x all bins.
 //             warp  <-> a 16-channel chunk (the cascade-sum granule of the reference, see below)
 //             lane  <-> pixel
@@ -459,14 +460,23 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   float* cnt = cost + (size_t)((nb + 3) / 4 * 4) * CV_PX;
   for (int k = sub; k < nb; k += 4) { cost[cq_idx(k, col)] = 0.0f; cnt[cq_idx(k, col)] = 0.0f; }
 
-  const float4* curq = reinterpret_cast<const float4*>(a.packed) + (size_t)b * nquads * hw;
   const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
   pk2 ncur[4][2];   // -current features of this lane's chunk (w - cur == w + (-cur))
+  {
+    // read straight from the NCHW input (once per lane: 16 scalar loads; channels beyond C are zero
+    // padding): the current features need no packing pass
+    const float* cur = a.current + (size_t)b * a.channels * hw + p;
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const float4 v = (pix_ok && active) ? ldg4(curq + (size_t)(sub * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-    ncur[j][0] = pack2(-v.x, -v.y);
-    ncur[j][1] = pack2(-v.z, -v.w);
+    for (int j = 0; j < 4; j++) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int ch = sub * 16 + j * 4 + e;
+        v[e] = (pix_ok && active && ch < a.channels) ? __ldg(cur + (size_t)ch * hw) : 0.0f;
+      }
+      ncur[j][0] = pack2(-v[0], -v[1]);
+      ncur[j][1] = pack2(-v[2], -v[3]);
+    }
   }
   const pk2 one2 = dup2(1.0f), mone2 = dup2(-1.0f);
   const float inv_channels = (a.channels & (a.channels - 1)) == 0 ? 1.0f / (float)a.channels : 0.0f;
@@ -661,10 +671,16 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   cudaStream_t st = (cudaStream_t)stream;
   const int Cp = cv_padded_channels(a.channels);
   const int hw = a.height * a.width;
+  const bool dyn = a.cv_min || (a.occ && a.occ_mode != MAL_CV_OCC_NONE);
+  // kernel choice: the four-lanes-per-pixel sweep handles up to 4 chunks (C <= 64) and no
+  // DynamicDepth extras; MAL_CV_KERNEL=lane forces the one-pixel-per-lane kernel (tuning only)
+  bool quad = !dyn && Cp / CV_CHUNK <= 4;
+  if (const char* e = getenv("MAL_CV_KERNEL")) quad = quad && e[0] != 'l';
   {
     long long total = (long long)a.batch * (Cp / 4) * hw;
-    launch(cv_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a.current,
-           reinterpret_cast<float4*>(a.packed), a.channels, Cp, hw, total);
+    if (!quad)   // the quad sweep reads the current features in place (NCHW)
+      launch(cv_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a.current,
+             reinterpret_cast<float4*>(a.packed), a.channels, Cp, hw, total);
     long long total_l = total * a.num_lookup;
     launch(cv_pack_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
            reinterpret_cast<float4*>(a.packed) + total, a.channels, Cp, hw, total_l);
@@ -680,7 +696,6 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   // environment override exists for tuning runs only
   int minb = CV_DEFAULT_MINB;
   if (const char* e = getenv("MAL_CV_MINB")) minb = atoi(e);
-  const bool dyn = a.cv_min || (a.occ && a.occ_mode != MAL_CV_OCC_NONE);
 #define MAL_CV_LAUNCH(CONV_)                                                                         \
   do {                                                                                               \
     if (dyn) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp);             \
@@ -688,10 +703,6 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
     else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp);                \
   } while (0)
-  // kernel choice: the four-lanes-per-pixel sweep handles up to 4 chunks (C <= 64) and no
-  // DynamicDepth extras; MAL_CV_KERNEL=lane forces the one-pixel-per-lane kernel (tuning only)
-  bool quad = !dyn && Cp / CV_CHUNK <= 4;
-  if (const char* e = getenv("MAL_CV_KERNEL")) quad = quad && e[0] != 'l';
   if (quad) {
     const size_t qsmem = cq_smem_bytes(a.num_bins);
 #define MAL_CQ_LAUNCH(CONV_)                                                                              \

@@ -175,7 +175,12 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     a.cv_min, a.occ_mode, a.pool_radius, a.pool_th = int(bool(cv_min)), int(occ_mode), int(pool_radius), float(pool_th)
     a.occ, a.aug_mask = _ptr(occ), _ptr(aug_mask)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
-    LAUNCHES[0] += 3   # cv_pack_kernel x2 + cv_sweep_kernel
+    # the four-lanes-per-pixel sweep (C <= 64, no DynamicDepth extras) reads the current features in place:
+    # lookup pack + sweep; the general kernel packs both operands first
+    import os
+    dyn = bool(cv_min) or (occ is not None and occ_mode != OCC_NONE)
+    quad = not dyn and (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
+    LAUNCHES[0] += 2 if quad else 3
     out["_keepalive"] = (packed,)
     return out
 

@@ -113,7 +113,7 @@ def _head_op(cur, look, poses, K, inv_K, bins):
 
 
 def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None):
-    """The same step as `step_losses` + backward, as 21 launches of libmal_b200 and nothing else:
+    """The same step as `step_losses` + backward, as 20 launches of libmal_b200 and nothing else:
     no autograd graph, no intermediate depth maps, no one-element torch kernels.  The scalar tail
     and the gradient hand-over are `mal_step_combine` (csrc/step.cu).  Needs opt.distil.
 
