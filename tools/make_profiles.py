@@ -84,23 +84,24 @@ def main():
     pick = lambda pat, idx=0: next((v[min(idx, len(v) - 1)] for k, v in traffic.items() if pat in k), None)
     photo = lambda pat: [v for k, v in traffic.items() if pat in k]
     dram = {"_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, {tag} "
-                     f"(profiles/{tag}_ncu_full_summary.txt); cost_volume = 2 x cv_pack_kernel + cv_sweep_quad_kernel"}
+                     f"(profiles/{tag}_ncu_full_summary.txt); cost_volume = cv_pack_kernel (lookup) + cv_sweep_quad_kernel"}
     old = {}
     if os.path.exists(os.path.join(PROF, "dram_traffic.json")):
         old = json.load(open(os.path.join(PROF, "dram_traffic.json")))
     # cv_pack_kernel is a plain transpose whose traffic does not change: keep the last captured value
     sweep, pack = pick("cv_sweep"), pick("cv_pack") or old.get("cv_pack_kernel")
     if sweep and pack:
-        dram.update(cost_volume=int(round(sweep + 2 * pack, -5)), cv_sweep_quad_kernel=int(round(sweep, -5)),
+        dram.update(cost_volume=int(round(sweep + pack, -5)), cv_sweep_quad_kernel=int(round(sweep, -5)),
                     cv_pack_kernel=int(round(pack, -5)))
-    # photo_kernel<WARP, GRAD, CONV, LOWRES>: launch order inside a step is identity, teacher, ensemble, student
-    g = photo("photo_kernel<1, 1")
-    if g:
-        dram["photo_teacher"] = int(round(g[0][0], -5))
-        dram["photo_student"] = int(round(g[0][-1], -5))
-    for key, pat in (("photo_ensemble", "photo_kernel<1, 0"), ("photo_identity", "photo_kernel<0, 0"),
-                     ("smooth_main_kernel", "smooth_main")):
-        v = pick(pat)
+    # photo_kernel<WARP, GRAD, CONV, LOWRES, SYNG, NC>: the teacher pass is the 4-candidate gradient kernel, the
+    # student the 2-candidate one; ensemble = WARP without gradient, identity = PRED without gradient
+    import re
+    def first(rx):
+        return next((v[0] for k, v in traffic.items() if re.search(rx, k)), None)
+    for key, rx in (("photo_teacher", r"photo_kernel<1, 1, \d, \d, \d, 4>"), ("photo_student", r"photo_kernel<1, 1, \d, \d, \d, 2>"),
+                    ("photo_ensemble", r"photo_kernel<1, 0,"), ("photo_identity", r"photo_kernel<0, 0,"),
+                    ("smooth_main_kernel", r"smooth_main")):
+        v = first(rx)
         if v:
             dram[key] = int(round(v, -5))
     json.dump(dram, open(os.path.join(PROF, "dram_traffic.json"), "w"), indent=1)
