@@ -92,18 +92,19 @@ __device__ __forceinline__ float4 ldg4(const float4* p) {
 #endif
 }
 
-// sum_{c in quad} |bilinear(c) - cur(c)|, continuing the sequential chain in `acc`
+// sum_{c in quad} |bilinear(c) - cur(c)|, continuing the sequential chain in `acc`.  The blend and the
+// subtraction run two channels per instruction (FFMA2 / FADD2, same IEEE results: mal_common.cuh).
 __device__ __forceinline__ float quad_l1(float acc, const float4& a, const float4& b, const float4& c,
-                                         const float4& d, const float4& cur, float nw, float ne, float sw,
-                                         float se) {
-  float w0 = xfma(d.x, se, xfma(c.x, sw, xfma(b.x, ne, xmul(a.x, nw))));
-  float w1 = xfma(d.y, se, xfma(c.y, sw, xfma(b.y, ne, xmul(a.y, nw))));
-  float w2 = xfma(d.z, se, xfma(c.z, sw, xfma(b.z, ne, xmul(a.z, nw))));
-  float w3 = xfma(d.w, se, xfma(c.w, sw, xfma(b.w, ne, xmul(a.w, nw))));
-  acc = xadd(acc, fabsf(xsub(w0, cur.x)));
-  acc = xadd(acc, fabsf(xsub(w1, cur.y)));
-  acc = xadd(acc, fabsf(xsub(w2, cur.z)));
-  acc = xadd(acc, fabsf(xsub(w3, cur.w)));
+                                         const float4& d, const float4& cur, float nw_, float ne_, float sw_,
+                                         float se_) {
+  const pk2 nw = dup2(nw_), ne = dup2(ne_), sw = dup2(sw_), se = dup2(se_);
+  const pk2 lo = x2fma(pack2(d.x, d.y), se, x2fma(pack2(c.x, c.y), sw, x2fma(pack2(b.x, b.y), ne, x2mul(pack2(a.x, a.y), nw))));
+  const pk2 hi = x2fma(pack2(d.z, d.w), se, x2fma(pack2(c.z, c.w), sw, x2fma(pack2(b.z, b.w), ne, x2mul(pack2(a.z, a.w), nw))));
+  const pk2 dlo = x2sub(lo, pack2(cur.x, cur.y)), dhi = x2sub(hi, pack2(cur.z, cur.w));
+  acc = xadd(acc, fabsf(lo2(dlo)));
+  acc = xadd(acc, fabsf(hi2(dlo)));
+  acc = xadd(acc, fabsf(lo2(dhi)));
+  acc = xadd(acc, fabsf(hi2(dhi)));
   return acc;
 }
 
