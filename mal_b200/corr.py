@@ -56,28 +56,29 @@ class CoordSampler:
         self.fmap1 = fmap1
 
 
-def sample_tgt(tgt_feat, p2, tgt_w):
-    """PoseUpdate.sample_tgt (dualrefine/networks/utils/utils.py:383-404): target features at the projected
-    point and its +-1 pixel neighbours (p2: (B,2,1,5,h,w) from depth2gradcoords :213-231) ->
-    (warped_tgt_feat (B,C,h,w), warped_tgt_gradients (B,C,h,w,2), warped_tgt_w (B,1,h,w)).
+def _normalised_grid(points, height, width):
+    """(..., 2) pixel coordinates (x, y) -> grid_sample coordinates for align_corners=False.  The divisors are
+    device tensors: torch's CUDA kernels turn division by a host scalar into a multiplication by its
+    reciprocal, which is not the IEEE division the reference's CPU path performs."""
+    size = torch.tensor([float(width), float(height)], device=points.device, dtype=points.dtype)
+    return 2 * (points + 0.5) / size - 1
 
-    The reference stores the third result in self.warped_tgt_w.  The sampler is mal_b200's grid_sample
-    kernel with ATen's CPU rounding (zeros padding, align_corners=False); gradients reach p2."""
-    batch, _, n1, d1, h1, w1 = p2.shape
-    p2 = p2.permute(2, 0, 4, 5, 3, 1).reshape(batch, h1 * w1, d1, 2)
-    xgrid, ygrid = p2.split([1, 1], dim=-1)
-    # a device tensor as divisor: torch's CUDA kernels turn division by a host scalar into a multiplication
-    # by its reciprocal, which is not the IEEE division the reference's CPU path performs
-    wdiv = torch.full((), float(w1), device=p2.device, dtype=p2.dtype)
-    hdiv = torch.full((), float(h1), device=p2.device, dtype=p2.dtype)
-    xgrid = 2 * (xgrid + 0.5) / wdiv - 1
-    ygrid = 2 * (ygrid + 0.5) / hdiv - 1
-    grid = torch.cat([xgrid, ygrid], dim=-1)
-    f = ops.grid_sample(tgt_feat, grid, padding_mode="zeros", align_corners=False)
-    f = f.view(batch, -1, h1, w1, d1)
-    warped_tgt_feat = f[..., 0]
-    warped_tgt_gradients = torch.stack([(f[..., 1] - f[..., 2]) / 2, (f[..., 3] - f[..., 4]) / 2], dim=-1)
-    grid_0 = grid[:, :, :1]
-    warped_tgt_w = ops.grid_sample(tgt_w.type(grid_0.dtype), grid_0, padding_mode="zeros",
-                                   align_corners=False).reshape(batch, 1, h1, w1)
-    return warped_tgt_feat, warped_tgt_gradients, warped_tgt_w
+
+def sample_tgt(tgt_feat, p2, tgt_w):
+    """PoseUpdate.sample_tgt (dualrefine/networks/utils/utils.py:383-404): the target features at the projected
+    point and at its four +-1 pixel neighbours (p2: (B,2,1,5,h,w) from depth2gradcoords :213-231) ->
+
+        warped_tgt_feat       (B,C,h,w)    the sample at the point itself
+        warped_tgt_gradients  (B,C,h,w,2)  central differences (x, y) of the neighbour samples
+        warped_tgt_w          (B,1,h,w)    the confidence map `tgt_w` sampled at the point
+
+    (the reference keeps the third in self.warped_tgt_w).  The sampler is mal_b200's grid_sample kernel with
+    ATen's CPU rounding (zeros padding, align_corners=False); gradients reach p2."""
+    B, _, _, K, h, w = p2.shape
+    pts = p2[:, :, 0].permute(0, 3, 4, 2, 1).reshape(B, h * w, K, 2)          # (B, pixels, 5 probes, xy)
+    grid = _normalised_grid(pts, h, w)
+    probes = ops.grid_sample(tgt_feat, grid, padding_mode="zeros", align_corners=False).view(B, -1, h, w, K)
+    centre, x_plus, x_minus, y_plus, y_minus = probes.unbind(-1)
+    gradients = torch.stack([(x_plus - x_minus) / 2, (y_plus - y_minus) / 2], dim=-1)
+    weight = ops.grid_sample(tgt_w.to(grid.dtype), grid[:, :, :1], padding_mode="zeros", align_corners=False)
+    return centre, gradients, weight.reshape(B, 1, h, w)
