@@ -409,6 +409,16 @@ def ours(args):
                                         "data pipe, 16 warps/SM at 128 registers, <2% DRAM throughput "
                                         "(profiles/r1_notes.md)"},
                 "kernels": roof,
+                # the same dominant kernel against the fp32 pipe it is actually bound by (informative; the
+                # contract's roofline object above stays HBM): nominal flops = every (pixel, plane, channel)
+                # evaluation x 9 (1 mul + 3 fma + sub + |.|-add), masked samples included although skipped
+                "fp32_view": (lambda fl: {"kernel": dom["kernel"], "nominal_gflop": fl / 1e9,
+                                         "achieved_tflops": fl / (dom["us_per_launch"] * 1e-6) / 1e12,
+                                         "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                                         "frac": fl / (dom["us_per_launch"] * 1e-6) / (148 * 128 * 2 * 1.965e9),
+                                         "peak_source": "148 SMs x 128 fp32 lanes x 2 flop x 1.965 GHz (measured SM clock)"})(
+                    9.0 * args.batch * opt.num_depth_bins * (HEIGHT // 4) * (WIDTH // 4) * opt.matching_channels)
+                if dom["key"] == "cost_volume" else None,
                 # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
                 "step_hbm": {"survey_bytes_per_frame": 20636160,
                              "frac_of_peak": value / world * 20636160 / (peak_gbs * 1e9)}}
