@@ -413,15 +413,18 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 
 // ---- sweep, variant Q: four lanes per pixel ------------------------------------------------------
 // A warp owns 8 consecutive pixels; the 4 lanes of a pixel own the four 16-channel chunks (C <= 64).
-// Per group of 4 depth planes each lane projects ONE plane; descriptors and chunk sums are exchanged
-// through a per-warp shared-memory scratch (one 128-bit store + broadcast loads: half the L1
-// wavefronts of the equivalent shuffles), and each lane then sweeps the 4 planes for its chunk with
-// the 2x2x16 register cache.  No block barrier inside the sweep, and only 8 (not 32) pixels share a
-// warp's re-fetch decision, so a texel block is re-fetched in ~20% instead of ~57% of the warp
-// iterations (profiles/r1_notes.md).
+// Lanes are chunk-major (lane = chunk * 8 + pixel): a quarter-warp - the unit a 128-bit load is processed
+// in - then reads the taps of 8 consecutive pixels of ONE channel quad, 128 contiguous bytes.
+// Per group of CQ_G = 8 depth planes every lane projects TWO planes (branch-free, so the two chains of
+// IEEE divisions interleave); descriptors and chunk sums are exchanged through a per-warp shared-memory
+// scratch (scalar stores + broadcast loads: about half the L1 wavefronts of the equivalent shuffles),
+// and each lane then sweeps the 8 planes for its chunk with the 2x2x16 register cache.  No block barrier
+// inside the sweep, and only 8 (not 32) pixels share a warp's re-fetch decision, so a texel block is
+// re-fetched in ~20% instead of ~57% of the warp iterations (profiles/r1_notes.md).
 // The bilinear blend and the subtraction run on packed fp32 pairs (FFMA2 / FADD2: two channels per
 // instruction, same IEEE results, mal_common.cuh); only the sequential |.| accumulation is scalar:
-// 3.5 instead of 6 issue slots per (pixel, plane, channel).
+// 3.5 instead of 6 issue slots per (pixel, plane, channel).  The current features are read in place
+// (NCHW, once per lane); only the lookup features go through cv_pack_kernel.
 constexpr int CQ_NT = 128;                 // 4 warps = 32 pixels per CTA
 constexpr int CQ_G = 8;                    // depth planes per group: every lane projects two of them
 inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * ((num_bins + 3) / 4 * 4) * CV_PX + 64) * 4; }
