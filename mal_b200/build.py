@@ -26,19 +26,38 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library next to the package."""
+    """Compile every CUDA source (one nvcc per file, in parallel) and link them into one shared library
+    next to the package."""
     if not force and not needs_build():
         return LIB
+    import concurrent.futures
+    import tempfile
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc] + flags + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    flags = [f for f in NVCC_FLAGS if f not in ("--use_fast_math=false", "-shared")]
+    objdir = tempfile.mkdtemp(prefix="mal_b200_obj_")
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        res = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, res
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    log = "".join(r.stderr for _, r in results)
+    failed = [r for _, r in results if r.returncode != 0]
+    if verbose or failed:
+        sys.stderr.write("".join(r.stdout + r.stderr for _, r in (results if verbose else [(None, f) for f in failed])))
+    if failed:
         raise RuntimeError("nvcc failed building libmal_b200.so")
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] +
+                         [o for o, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libmal_b200.so")
     with open(os.path.join(PKG, "csrc", "ptxas.log"), "w") as f:
-        f.write(res.stderr)
+        f.write(log)
+    import shutil
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIB
 
 
