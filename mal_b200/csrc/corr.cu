@@ -84,6 +84,9 @@ struct CorrSite {
   bool tail;             // ATen's remainder columns: interleaved partial sums
 };
 
+// Thread -> work item: x fastest (coalesced coordinate reads and result writes), then y, candidate, level,
+// sample.  (Putting the candidate index next to the 32-pixel segment, so that the warps of a CTA share
+// texel lines, was measured slower: 365 -> 440 us forward.)
 __device__ __forceinline__ bool corr_site(const mal_corr_args& a, size_t i, CorrSite& s) {
   const int h = a.height, w = a.width, D = a.num_samples, L = a.num_levels;
   const size_t total = (size_t)a.batch * L * D * h * w;
@@ -100,6 +103,10 @@ __device__ __forceinline__ bool corr_site(const mal_corr_args& a, size_t i, Corr
   const size_t N = (size_t)h * w * D, j = ((size_t)s.y * w + s.x) * D + s.d;
   s.tail = j >= N / 32 * 32;
   return true;
+}
+
+__host__ __device__ inline size_t corr_threads(const mal_corr_args& a) {
+  return (size_t)a.batch * a.num_levels * a.num_samples * a.height * a.width;
 }
 
 __device__ __forceinline__ Taps corr_taps(const mal_corr_args& a, const CorrSite& s, float cx, float cy) {
@@ -144,7 +151,36 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_kernel(const mal_corr_args 
     float total = 0.0f;   // acc[1] of ATen's cascade
     if (!s.tail) {
       float acc = 0.0f;
-      for (int q = 0; q < Qg; q++) {
+      int q = 0;
+      // one 16-channel chunk at a time: all 16 tap loads and 16 feature loads are issued before the first
+      // is consumed (the kernel is bound by load latency, not by issue slots)
+      for (; q + 4 <= Qg; q += 4) {
+        float4 ta[4], tb[4], tc[4], td[4];
+        float fv[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int qq = hd * Qg + q + j;
+          const float4* plane = f2 + (size_t)qq * lhw;
+          ta[j] = tap4(plane, t.v00, t.o00); tb[j] = tap4(plane, t.v01, t.o01);
+          tc[j] = tap4(plane, t.v10, t.o10); td[j] = tap4(plane, t.v11, t.o11);
+          const float* f = f1 + (size_t)qq * 4 * hw;
+#pragma unroll
+          for (int e = 0; e < 4; e++) fv[j][e] = __ldg(f + e * hw);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const pk2 lo = x2fma(pack2(td[j].x, td[j].y), se, x2fma(pack2(tc[j].x, tc[j].y), sw, x2fma(pack2(tb[j].x, tb[j].y), ne, x2mul(pack2(ta[j].x, ta[j].y), nw))));
+          const pk2 hi = x2fma(pack2(td[j].z, td[j].w), se, x2fma(pack2(tc[j].z, tc[j].w), sw, x2fma(pack2(tb[j].z, tb[j].w), ne, x2mul(pack2(ta[j].z, ta[j].w), nw))));
+          const pk2 dlo = x2sub(pack2(fv[j][0], fv[j][1]), lo), dhi = x2sub(pack2(fv[j][2], fv[j][3]), hi);
+          acc = xadd(acc, fabsf(lo2(dlo)));
+          acc = xadd(acc, fabsf(hi2(dlo)));
+          acc = xadd(acc, fabsf(lo2(dhi)));
+          acc = xadd(acc, fabsf(hi2(dhi)));
+        }
+        total = xadd(total, acc);   // every 16 channels
+        acc = 0.0f;
+      }
+      for (; q < Qg; q++) {   // channels beyond the last full chunk
         const int qq = hd * Qg + q;
         const Quad v = blend4(f2 + (size_t)qq * lhw, t, nw, ne, sw, se);
         const float* f = f1 + (size_t)qq * 4 * hw;
@@ -154,12 +190,12 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_kernel(const mal_corr_args 
         acc = xadd(acc, fabsf(hi2(dlo)));
         acc = xadd(acc, fabsf(lo2(dhi)));
         acc = xadd(acc, fabsf(hi2(dhi)));
-        if ((q & 3) == 3) { total = xadd(total, acc); acc = 0.0f; }   // every 16 channels
       }
       total = xadd(acc, total);   // a trailing partial chunk (acc[0]) joins last
     } else {
       // four interleaved partial sums (channel % 4 == component), cascaded every 16 rows
       pk2 plo = dup2(0.0f), phi = dup2(0.0f), alo = dup2(0.0f), ahi = dup2(0.0f);
+#pragma unroll 4
       for (int q = 0; q < Qg; q++) {
         const int qq = hd * Qg + q;
         const Quad v = blend4(f2 + (size_t)qq * lhw, t, nw, ne, sw, se);
@@ -211,35 +247,52 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
   for (int hd = 0; hd < a.num_head; hd++) {
     const float g = __ldg(a.grad_out + s.out_index + (size_t)hd * a.num_samples * hw) / (float)Cg;
     if (g == 0.0f) continue;
-    for (int q = 0; q < Qg; q++) {
-      const int qq = hd * Qg + q;
-      const float4* plane = f2 + (size_t)qq * lhw;
-      const float4 va = tap4(plane, t.v00, t.o00), vb = tap4(plane, t.v01, t.o01);
-      const float4 vc = tap4(plane, t.v10, t.o10), vd = tap4(plane, t.v11, t.o11);
-      const float* f = f1 + (size_t)qq * 4 * hw;
-      float sg[4];
-      const float av[4] = {va.x, va.y, va.z, va.w}, bv[4] = {vb.x, vb.y, vb.z, vb.w};
-      const float cv[4] = {vc.x, vc.y, vc.z, vc.w}, dv[4] = {vd.x, vd.y, vd.z, vd.w};
+    // QB channel quads at a time: their tap and feature loads are all issued before the first is consumed
+    constexpr int QB = 2;
+    for (int q0 = 0; q0 < Qg; q0 += QB) {
+      float4 ta[QB], tb[QB], tc[QB], td[QB];
+      float fv[QB][4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float sv = xfma(dv[k], t.se, xfma(cv[k], t.sw, xfma(bv[k], t.ne, xmul(av[k], t.nw))));
-        const float df = __ldg(f + k * hw) - sv;
-        sg[k] = df > 0.0f ? g : (df < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1
-        gix -= sg[k] * ((bv[k] - av[k]) * ey + (dv[k] - cv[k]) * t.ty);
-        giy -= sg[k] * ((cv[k] - av[k]) * ex + (dv[k] - bv[k]) * t.tx);
-      }
-      if (a.grad_fmap1) {
-        float* g1 = a.grad_fmap1 + ((size_t)s.b * C + (size_t)qq * 4) * hw + pix;
+      for (int j = 0; j < QB; j++) {
+        if (q0 + j < Qg) {
+          const int qq = hd * Qg + q0 + j;
+          const float4* plane = f2 + (size_t)qq * lhw;
+          ta[j] = tap4(plane, t.v00, t.o00); tb[j] = tap4(plane, t.v01, t.o01);
+          tc[j] = tap4(plane, t.v10, t.o10); td[j] = tap4(plane, t.v11, t.o11);
+          const float* f = f1 + (size_t)qq * 4 * hw;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (sg[k] != 0.0f) red_add(g1 + k * hw, sg[k]);
+          for (int e = 0; e < 4; e++) fv[j][e] = __ldg(f + e * hw);
+        }
       }
-      if (gp && (sg[0] != 0.0f || sg[1] != 0.0f || sg[2] != 0.0f || sg[3] != 0.0f)) {
-        float4* gq = gp + (size_t)qq * lhw;
-        if (t.v00) red_add4(gq + t.o00, -sg[0] * t.nw, -sg[1] * t.nw, -sg[2] * t.nw, -sg[3] * t.nw);
-        if (t.v01) red_add4(gq + t.o01, -sg[0] * t.ne, -sg[1] * t.ne, -sg[2] * t.ne, -sg[3] * t.ne);
-        if (t.v10) red_add4(gq + t.o10, -sg[0] * t.sw, -sg[1] * t.sw, -sg[2] * t.sw, -sg[3] * t.sw);
-        if (t.v11) red_add4(gq + t.o11, -sg[0] * t.se, -sg[1] * t.se, -sg[2] * t.se, -sg[3] * t.se);
+#pragma unroll
+      for (int j = 0; j < QB; j++) {
+        if (q0 + j < Qg) {
+          const int qq = hd * Qg + q0 + j;
+          float sg[4];
+          const float av[4] = {ta[j].x, ta[j].y, ta[j].z, ta[j].w}, bv[4] = {tb[j].x, tb[j].y, tb[j].z, tb[j].w};
+          const float cv[4] = {tc[j].x, tc[j].y, tc[j].z, tc[j].w}, dv[4] = {td[j].x, td[j].y, td[j].z, td[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float sv = xfma(dv[k], t.se, xfma(cv[k], t.sw, xfma(bv[k], t.ne, xmul(av[k], t.nw))));
+            const float df = fv[j][k] - sv;
+            sg[k] = df > 0.0f ? g : (df < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1
+            gix -= sg[k] * ((bv[k] - av[k]) * ey + (dv[k] - cv[k]) * t.ty);
+            giy -= sg[k] * ((cv[k] - av[k]) * ex + (dv[k] - bv[k]) * t.tx);
+          }
+          if (a.grad_fmap1) {
+            float* g1 = a.grad_fmap1 + ((size_t)s.b * C + (size_t)qq * 4) * hw + pix;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (sg[k] != 0.0f) red_add(g1 + k * hw, sg[k]);
+          }
+          if (gp && (sg[0] != 0.0f || sg[1] != 0.0f || sg[2] != 0.0f || sg[3] != 0.0f)) {
+            float4* gq = gp + (size_t)qq * lhw;
+            if (t.v00) red_add4(gq + t.o00, -sg[0] * t.nw, -sg[1] * t.nw, -sg[2] * t.nw, -sg[3] * t.nw);
+            if (t.v01) red_add4(gq + t.o01, -sg[0] * t.ne, -sg[1] * t.ne, -sg[2] * t.ne, -sg[3] * t.ne);
+            if (t.v10) red_add4(gq + t.o10, -sg[0] * t.sw, -sg[1] * t.sw, -sg[2] * t.sw, -sg[3] * t.sw);
+            if (t.v11) red_add4(gq + t.o11, -sg[0] * t.se, -sg[1] * t.se, -sg[2] * t.se, -sg[3] * t.se);
+          }
+        }
       }
     }
   }
@@ -302,7 +355,7 @@ extern "C" int mal_corr_lookup(const mal_corr_args* args, mal_stream_t stream) {
   int rc = corr_check(a, "mal_corr_lookup");
   if (rc) return rc;
   MAL_REQUIRE(a.out, "mal_corr_lookup: out is required");
-  const size_t total = (size_t)a.batch * a.num_levels * a.num_samples * a.height * a.width;
+  const size_t total = corr_threads(a);
   launch(corr_lookup_kernel, dim3((unsigned)((total + CR_NT - 1) / CR_NT)), dim3(CR_NT), 0, (cudaStream_t)stream, a);
   return check_launch("corr_lookup_kernel");
 }
@@ -314,7 +367,7 @@ extern "C" int mal_corr_lookup_backward(const mal_corr_args* args, mal_stream_t 
   if (rc) return rc;
   MAL_REQUIRE(a.grad_out && (a.grad_coords || a.grad_fmap1 || a.grad_pyramid),
               "mal_corr_lookup_backward: grad_out and at least one gradient output are required");
-  const size_t total = (size_t)a.batch * a.num_levels * a.num_samples * a.height * a.width;
+  const size_t total = corr_threads(a);
   launch(corr_lookup_bwd_kernel, dim3((unsigned)((total + CR_NT - 1) / CR_NT)), dim3(CR_NT), 0, (cudaStream_t)stream, a);
   return check_launch("corr_lookup_bwd_kernel");
 }
