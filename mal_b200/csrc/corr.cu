@@ -346,6 +346,8 @@ static int corr_check(const mal_corr_args& a, const char* who) {
   MAL_REQUIRE(a.channels / a.num_head <= 256, "%s: more than 256 channels per head changes ATen's summation tree", who);
   MAL_REQUIRE((a.height >> (a.num_levels - 1)) > 0 && (a.width >> (a.num_levels - 1)) > 0, "%s: too many levels", who);
   MAL_REQUIRE(a.fmap1 && a.pyramid && a.coords, "%s: fmap1 / pyramid / coords are required", who);
+  MAL_REQUIRE(((uintptr_t)a.pyramid & 15) == 0 && ((uintptr_t)a.grad_pyramid & 15) == 0,
+              "%s: pyramid buffers must be 16-byte aligned (128-bit loads and reductions)", who);
   return MAL_OK;
 }
 
