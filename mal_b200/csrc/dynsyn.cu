@@ -30,6 +30,7 @@ __device__ __forceinline__ void fill_pixel(const uint8_t* __restrict__ mask, con
   const size_t hw = (size_t)H * W;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};   // cascade_sum: 16-element chunks
   bool hit = false;
+#pragma unroll 4   // independent mask loads of several instances in flight
   for (int n = 0; n < N; n++) {
     const int sy = y - dx[n], sx = x - dy[n];
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -46,20 +47,39 @@ __device__ __forceinline__ void fill_pixel(const uint8_t* __restrict__ mask, con
   *any = hit;
 }
 
-__global__ void __launch_bounds__(DS_NT) dyn_extents_kernel(const uint8_t* __restrict__ mask_last,
+constexpr int DX_NT = 1024;   // one CTA per (instance, frame); 16 mask bytes per load
+
+struct __align__(16) MaskWords { unsigned w[4]; };
+
+__global__ void __launch_bounds__(DX_NT) dyn_extents_kernel(const uint8_t* __restrict__ mask_last,
                                                            const uint8_t* __restrict__ mask_next, int H, int W,
                                                            int* __restrict__ ext /*[N][2][4]*/) {
-  __shared__ int red[4][DS_NT / 32];
+  __shared__ int red[4][DX_NT / 32];
   const int n = blockIdx.x, which = blockIdx.y;
-  const uint8_t* m = (which == 0 ? mask_last : mask_next) + (size_t)n * H * W;
+  const int total = H * W;
+  const uint8_t* m = (which == 0 ? mask_last : mask_next) + (size_t)n * total;
   int low = 0, top = 0x7fffffff, right = 0, left = 0x7fffffff;
-  for (int i = threadIdx.x; i < H * W; i += DS_NT) {
-    if (m[i]) {
-      const int h = i / W, w = i - h * W;
-      if (h >= 1) { low = max(low, h); top = min(top, h); }     // (mask * grid_h).sum(2) is 0 on row 0
-      if (w >= 1) { right = max(right, w); left = min(left, w); }
+  auto visit = [&](int i) {
+    const int h = i / W, w = i - h * W;
+    if (h >= 1) { low = max(low, h); top = min(top, h); }     // (mask * grid_h).sum(2) is 0 on row 0
+    if (w >= 1) { right = max(right, w); left = min(left, w); }
+  };
+  // the bulk of a mask is zero: read it 16 bytes at a time and only decode the words that are not
+  const int nvec = (((uintptr_t)m & 15) == 0) ? total / 16 : 0;
+  const MaskWords* mv = reinterpret_cast<const MaskWords*>(m);
+  for (int v = threadIdx.x; v < nvec; v += DX_NT) {
+    const MaskWords q = mv[v];
+    if ((q.w[0] | q.w[1] | q.w[2] | q.w[3]) == 0u) continue;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (q.w[k] == 0u) continue;
+#pragma unroll
+      for (int bt = 0; bt < 4; bt++)
+        if ((q.w[k] >> (8 * bt)) & 0xffu) visit(v * 16 + k * 4 + bt);
     }
   }
+  for (int i = nvec * 16 + threadIdx.x; i < total; i += DX_NT)
+    if (m[i]) visit(i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     low = max(low, __shfl_xor_sync(0xffffffffu, low, o));
@@ -71,7 +91,7 @@ __global__ void __launch_bounds__(DS_NT) dyn_extents_kernel(const uint8_t* __res
   if ((threadIdx.x & 31) == 0) { red[0][warp] = low; red[1][warp] = top; red[2][warp] = right; red[3][warp] = left; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int wv = 1; wv < DS_NT / 32; wv++) {
+    for (int wv = 1; wv < DX_NT / 32; wv++) {
       low = max(low, red[0][wv]); top = min(top, red[1][wv]); right = max(right, red[2][wv]); left = min(left, red[3][wv]);
     }
     int* e = ext + (n * 2 + which) * 4;
@@ -107,6 +127,7 @@ __global__ void __launch_bounds__(DS_NT) dyn_compose_kernel(const mal_dynamic_in
   for (size_t p = (size_t)blockIdx.x * DS_NT + threadIdx.x; p < hw; p += (size_t)gridDim.x * DS_NT) {
     const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
     bool m_or = false, bg = false, bg2 = false;
+#pragma unroll 4
     for (int n = 0; n < N; n++) {
       const bool ml = a.mask_last[(size_t)n * hw + p] != 0, mn = a.mask_next[(size_t)n * hw + p] != 0;
       m_or |= ml | mn;
@@ -236,7 +257,7 @@ extern "C" int mal_dynamic_instance(const mal_dynamic_instance_args* args, mal_s
   cudaStream_t st = (cudaStream_t)stream;
   int* ext = a.workspace;
   int* delta = a.workspace + (size_t)a.num * 8;
-  launch(dyn_extents_kernel, dim3(a.num, 2), dim3(DS_NT), 0, st, a.mask_last, a.mask_next, a.height, a.width, ext);
+  launch(dyn_extents_kernel, dim3(a.num, 2), dim3(DX_NT), 0, st, a.mask_last, a.mask_next, a.height, a.width, ext);
   int rc = check_launch("dyn_extents_kernel");
   if (rc) return rc;
   launch(dyn_delta_kernel, dim3((a.num + 63) / 64), dim3(64), 0, st, (const int*)ext, a.num, a.replace, delta);
