@@ -358,6 +358,7 @@ def ours(args):
         e0.record()
         for i in range(args.steps):
             step_fn(args.warmup + i)
+        st.finish()   # the last step's LossBalancing update (earlier ones overlap the following step)
         e1.record()
         barrier()
         windows.append((t0, time.time()))

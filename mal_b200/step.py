@@ -113,7 +113,16 @@ def _head_op(cur, look, poses, K, inv_K, bins):
 
 
 def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None):
-    """The same step as `step_losses` + backward, as 20 launches of libmal_b200 and nothing else:
+    """fused_step_main + fused_step_tail in one go (see there)."""
+    ctx = fused_step_main(handle, b, opt, has_ins=has_ins, multi_has_ins=multi_has_ins, side_streams=side_streams)
+    return fused_step_tail(handle, b, opt, weights, ctx)
+
+
+def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_streams=None):
+    """Everything of the fused step that does not depend on the loss-balancing weights (every kernel but the
+    last); returns the intermediates fused_step_tail needs.
+
+    The same step as `step_losses` + backward, as 20 launches of libmal_b200 and nothing else:
     no autograd graph, no intermediate depth maps, no one-element torch kernels.  The scalar tail
     and the gradient hand-over are `mal_step_combine` (csrc/step.cu).  Needs opt.distil.
 
@@ -173,6 +182,16 @@ def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, 
                         mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
                         inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
     branch.join(1)
+    return dict(head=head, mask=mask, teacher=teacher, student=student, ens=ens, sm_t=sm_t, sm_s=sm_s, mt=mt,
+                ident=ident)
+
+
+def fused_step_tail(handle, b, opt, weights, ctx):
+    """mal_step_combine: the only kernel that reads the LossBalancing weights.  MalStep replays it as its own
+    graph so that the host-side weight update of step i-1 overlaps the heavy kernels of step i."""
+    B, H, W = opt.batch_size, opt.height, opt.width
+    head, mask, teacher, student, ens = ctx["head"], ctx["mask"], ctx["teacher"], ctx["student"], ctx["ens"]
+    sm_t, sm_s, mt, ident = ctx["sm_t"], ctx["sm_s"], ctx["mt"], ctx["ident"]
     comb = raw.step_combine(handle, batch=B, height=H, width=W, weights=weights if opt.loss_blc else None,
                             sums_teacher=teacher["sums"], sums_student=student["sums"], smooth_teacher=sm_t["loss"],
                             smooth_student=sm_s["loss"], main_sums=mt["sums"], K=b["K"],
@@ -267,6 +286,7 @@ class MalStep:
         self._scalars_host = torch.empty(8, dtype=torch.float32).pin_memory()
         self.launches_per_step = None
         self._layout = None
+        self._pending = None   # (event, iteration) of the step whose LossBalancing update is still due
         self.copy_stream = torch.cuda.Stream(self.device)
         # parallel branches only inside a captured graph: there every buffer is static, so tensors
         # produced on one stream and consumed on another need no allocator bookkeeping
@@ -330,15 +350,23 @@ class MalStep:
     # -- one step ------------------------------------------------------------------------------
     def _run(self, buf):
         if self.fused:
-            from . import _capi
-            with torch.no_grad():
-                return fused_step(_capi.lib(), buf, self.opt, self.weights, side_streams=self.side_streams)
+            return self._run_tail(buf, self._run_main(buf))
         leaves = {k: buf[k] for k in LEAVES}
         total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights)
         grads = torch.autograd.grad(total, [leaves[k] for k in LEAVES])
         scalars = torch.stack([total.detach(), loss_list[0].detach(), loss_list[-1].detach(),
                                losses["reproj_loss/0"].detach()])
         return scalars, grads, outputs
+
+    def _run_main(self, buf):
+        from . import _capi
+        with torch.no_grad():
+            return fused_step_main(_capi.lib(), buf, self.opt, side_streams=self.side_streams)
+
+    def _run_tail(self, buf, ctx):
+        from . import _capi
+        with torch.no_grad():
+            return fused_step_tail(_capi.lib(), buf, self.opt, self.weights, ctx)
 
     def _capture(self, sl):
         side = torch.cuda.Stream(self.device)
@@ -350,9 +378,31 @@ class MalStep:
         torch.cuda.synchronize(self.device)
         raw.LAUNCHES[0] = 0
         sl["graph"] = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(sl["graph"]):
-            sl["static"] = self._run(sl["buf"])
+        if self.fused:
+            # two graphs sharing one memory pool: everything up to the weights, then the kernel that reads them
+            with torch.cuda.graph(sl["graph"]):
+                ctx = self._run_main(sl["buf"])
+            sl["graph_tail"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(sl["graph_tail"], pool=sl["graph"].pool()):
+                sl["static"] = self._run_tail(sl["buf"], ctx)
+            sl["ctx"] = ctx
+        else:
+            with torch.cuda.graph(sl["graph"]):
+                sl["static"] = self._run(sl["buf"])
         self.launches_per_step = raw.LAUNCHES[0]
+
+    def finish(self):
+        """Apply the LossBalancing update of the last step (it is otherwise applied while the next step's
+        heavy kernels run).  Call before reading `blc` / `weights` on the host."""
+        if self._pending is None:
+            return
+        ev, it = self._pending
+        self._pending = None
+        ev.synchronize()
+        self.blc.record_scores(it, [float(self._scalars_host[1]), float(self._scalars_host[2])])
+        w0, w1 = self.blc.update_weight(it, self.lambda_for_adjust)
+        self._w_host[0], self._w_host[1] = float(w0), float(w1)
+        self.weights.copy_(self._w_host, non_blocking=True)
 
     def __call__(self, slot=0, sync_weights=True):
         """Run the step on the batch loaded in `slot`.  Returns (scalars, grads, outputs): scalars is
@@ -362,23 +412,35 @@ class MalStep:
         if sl.get("ready") is not None:
             cur.wait_event(sl["ready"])
             sl["ready"] = None
+        # LossBalancing (host fp64, like the reference) needs two scalars of step i-1 before step i's weights are
+        # final - but only the last kernel of a step reads the weights.  So: replay the heavy part of step i,
+        # finish step i-1's host update while it runs, upload the weights, replay the tail.
         if self.use_graph:
             if sl["graph"] is None:
                 self._capture(sl)
+            if not self.fused:
+                self.finish()          # the op-by-op graph reads the weights throughout
             sl["graph"].replay()
+            if self.fused:
+                self.finish()
+                sl["graph_tail"].replay()
             res = sl["static"]
         else:
             raw.LAUNCHES[0] = 0
-            res = self._run(sl["buf"])
+            if self.fused:
+                ctx = self._run_main(sl["buf"])
+                self.finish()
+                res = self._run_tail(sl["buf"], ctx)
+            else:
+                self.finish()
+                res = self._run(sl["buf"])
             self.launches_per_step = raw.LAUNCHES[0]
         sl["done"] = torch.cuda.Event()
         sl["done"].record(cur)
         if self.blc is not None and sync_weights:
             self._scalars_host[:res[0].numel()].copy_(res[0], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            self.blc.record_scores(self.index_iter, [float(self._scalars_host[1]), float(self._scalars_host[2])])
-            w0, w1 = self.blc.update_weight(self.index_iter, self.lambda_for_adjust)
-            self._w_host[0], self._w_host[1] = float(w0), float(w1)
-            self.weights.copy_(self._w_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._pending = (ev, self.index_iter)
         self.index_iter += 1
         return res

@@ -94,4 +94,40 @@ def test_malstep_loss_balancing_follows_reference():
         assert abs(float(scalars[0]) - float(total)) <= 2e-5 * abs(float(total))
         ref.compute_loss(loss_list, it)
         w = ref.update_weight(it, 3.0)
+        st.finish()   # the host-side update of a step is otherwise applied while the next step's kernels run
         assert np.allclose(st.blc.w_list, ref.w_list, rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_pipelined_loss_balancing_equals_the_synchronous_sequence():
+    """The host-side weight update of step i-1 is applied while step i's heavy kernels run (only the last
+    kernel reads the weights): totals, weights and gradients of every step equal those of a run that
+    finishes each update before starting the next step."""
+    opt = S.default_opt(2, 64, 96, num_depth_bins=32, matching_channels=32)
+    batches = []
+    for i in range(2):
+        b = S.synthetic_batch(opt, seed=11)
+        b["noise_mono"] = torch.randn(b["noise_mono"].shape, generator=torch.Generator().manual_seed(200 + i))
+        b["mono_disp"] = (b["mono_disp"] * (1.0 + 0.05 * i)).clamp(0, 1)
+        batches.append(b)
+    runs = []
+    for pipelined in (False, True):
+        st = S.MalStep(opt, use_graph=True, num_train_data=64, lambda_for_adjust=3.0, slots=2)
+        for i in range(2):
+            st.load(batches[i], slot=i)
+        seq = []
+        for it in range(5):
+            scalars, grads, _ = st(it % 2)
+            if not pipelined:
+                st.finish()
+            torch.cuda.synchronize()
+            seq.append((scalars.clone().cpu(), [g.clone().cpu() for g in grads]))
+        st.finish()
+        runs.append((seq, np.array(st.blc.w_list)))
+    (a, wa), (b, wb) = runs
+    assert np.all(np.isfinite(wa)) and np.array_equal(wa, wb)
+    assert len({float(s[0][0]) for s in a}) > 1          # the weights did change the total from step to step
+    for (sa, ga), (sb, gb) in zip(a, b):
+        assert torch.equal(sa, sb)
+        for x, y in zip(ga, gb):
+            assert torch.equal(x, y)
