@@ -173,6 +173,20 @@ class LossBalancing:
         self.train_metrics = np.zeros((num_train_data, 7))
         self.num_data = num_train_data
         self.bs = bs
+        # Running column sums of train_scores[0:_rows]: numpy's mean over axis 0 adds the rows one after the
+        # other, so a sum kept row by row is the same fp64 number (checked in tests/test_api.py) and
+        # update_weight stays O(1) instead of re-reading every score recorded so far.  Any write that is not
+        # "the next row" (a new epoch restarting at index 0, a skipped step) drops the shortcut until the next
+        # update_weight rebuilds it from the array.
+        self._rows = 0
+        self._sum = np.zeros(num_loss)
+
+    def _recorded(self, index_record, scores):
+        if index_record == self._rows:
+            self._sum = self._sum + np.asarray(scores, dtype=np.float64)
+            self._rows += 1
+        else:
+            self._rows = -1   # out of order: the next update_weight recomputes from train_scores
 
     def compute_loss(self, loss_list, index_iter):
         loss = 0
@@ -185,6 +199,7 @@ class LossBalancing:
                 if scores is None:   # one device->host read per step instead of bs * num_loss
                     scores = [float(v.detach()) if torch.is_tensor(v) else float(v) for v in loss_list[:self.num_loss]]
                 self.train_scores[index_record, :] = scores
+                self._recorded(index_record, scores)
         return loss
 
     def record_scores(self, index_iter, scores):
@@ -194,9 +209,19 @@ class LossBalancing:
             index_record = self.bs * index_iter + index_batch
             if index_record < self.num_data:
                 self.train_scores[index_record, :] = scores
+                self._recorded(index_record, scores)
+
+    def _mean_scores(self, i):
+        lo, hi = self.last_rebalancing_iter * self.bs, min((i + 1) * self.bs, self.num_data)
+        if lo == 0 and hi > 0 and self._rows == hi:
+            return self._sum / hi
+        window = self.train_scores[lo:(i + 1) * self.bs, :]
+        if lo == 0 and hi > 0:   # rebuild the running sum exactly as numpy's mean accumulates it
+            self._sum, self._rows = np.add.reduce(window, axis=0), hi
+        return window.mean(axis=0)
 
     def update_weight(self, i, current_lambda_for_adjust):
-        mean = self.train_scores[self.last_rebalancing_iter * self.bs:(i + 1) * self.bs, :].mean(axis=0)
+        mean = self._mean_scores(i)
         total_loss = np.sum(mean * self.w_list)
         if self.weight_initialization and not self.weight_initialization_done:
             for k in range(self.num_loss):

@@ -392,3 +392,19 @@ def test_grid_sample_matches_torch_cpu(op_device, padding, align):
     assert torch.equal(got.detach().cpu(), want.detach())
     got_g, = torch.autograd.grad((got * w.to(dev)).sum(), g_d)
     assert _gerr(got_g, want_g) < GRAD_RTOL
+
+
+def test_loss_balancing_running_mean_is_the_reference_mean():
+    """LossBalancing.update_weight keeps column sums instead of re-reading every recorded score (the
+    reference's mean runs over all of them, every step): same fp64 weights over a long sequential run, over
+    an epoch restart (rows overwritten from index 0) and past the end of the score table."""
+    rng = np.random.default_rng(3)
+    bs, n_data = 4, 4 * 260
+    ours, ref = loss_utils.LossBalancing(2, n_data, bs), O.LossBalancing(2, n_data, bs)
+    for epoch in range(2):
+        for it in range(300):           # 300 * 4 rows > 1040: the last steps fall off the table
+            scores = [0.4 + 0.1 * rng.random(), 0.01 + 0.01 * rng.random()]
+            ours.record_scores(it, scores)
+            ref.compute_loss(scores, it)
+            assert np.array_equal(np.array(ours.update_weight(it, 3.0)), np.array(ref.update_weight(it, 3.0))), (epoch, it)
+    assert np.array_equal(ours.train_scores, ref.train_scores)
