@@ -4,7 +4,9 @@ This module is a restatement, in plain torch-on-CPU fp32, of the arithmetic the
 reference (YuejiangDong/MAL) performs on the path SURVEY.md section 8 scopes:
 backproject -> project -> bilinear warp -> SSIM+L1 -> min-reprojection/automask
 -> MAL temporal/distillation selection, the plane-sweep matching cost volume,
-the smoothness term and the host-side loss balancers.
+the smoothness term, the host-side loss balancers, DynamicDepth's forward warp,
+the temporal-hint image synthesis and DualRefine's epipolar correlation lookup
+(CoordSampler, sample_tgt).
 
 Rules (see DESIGN.md "Oracle"):
   * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
