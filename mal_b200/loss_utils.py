@@ -36,13 +36,15 @@ __all__ = ["compute_reprojection_loss", "compute_loss_masks", "compute_mono_loss
 class WarpSpec:
     """What the fused kernel needs to re-create outputs[("color", f, scale)] on the fly."""
 
-    __slots__ = ("disp", "K", "inv_K", "T", "convention", "min_depth", "max_depth", "depth_is_disp")
+    __slots__ = ("disp", "K", "inv_K", "T", "convention", "min_depth", "max_depth", "depth_is_disp",
+                 "source_scale")
 
     def __init__(self, disp, K, inv_K, T, convention=raw.CONV_MANYDEPTH, min_depth=0.1, max_depth=100.0,
-                 depth_is_disp=True):
+                 depth_is_disp=True, source_scale=0):
         self.disp, self.K, self.inv_K, self.T = disp, K, inv_K, list(T)
         self.convention, self.min_depth, self.max_depth = convention, min_depth, max_depth
         self.depth_is_disp = depth_is_disp
+        self.source_scale = source_scale   # v1_multiscale: images / intrinsics of the disparity's own scale
 
 
 def _no_ssim(ssim):
@@ -77,11 +79,11 @@ def _candidates(inputs, outputs, scale, with_syn):
     return dict(src=[outputs[("color", f, scale)] for f in (-1, 1)], syn=syn, mode=raw.PHOTO_PRED)
 
 
-def identity_reprojection(ssim, inputs):
+def identity_reprojection(ssim, inputs, source_scale=0):
     """min over f of compute_reprojection_loss(inputs[("color", f, 0)], target), loss_utils.py:92-101."""
-    target = inputs[("color", 0, 0)]
+    target = inputs[("color", 0, source_scale)]
     with torch.no_grad():
-        _, ident, _ = ops.photo(target, [inputs[("color", -1, 0)], inputs[("color", 1, 0)]],
+        _, ident, _ = ops.photo(target, [inputs[("color", -1, source_scale)], inputs[("color", 1, source_scale)]],
                                 mode=raw.PHOTO_PRED, no_ssim=_no_ssim(ssim))
     return ident
 

@@ -1,8 +1,12 @@
 """MultiLossManager (manydepth/multilossmanager.py:6-88): multi-loss re-balancing after
 "Multi-loss Rebalancing Algorithm for Monocular Depth Estimation" (ECCV 2020).
 
-The reference never imports this class but BASELINE.json names it, so the API is
-kept: get_total_loss(losses, current_batch_size, update, weights_list) and
+This file is a PORT: the reference never imports the class but BASELINE.json names it, so
+its scalar arithmetic is restated op for op (fp32 torch scalars).  Deviations, all in code the reference
+cannot execute: `np.sum(tensor * tensor)` (multilossmanager.py:62,71,83) raises TypeError with torch >= 2 /
+numpy 2 - torch.sum is used; `weights_list` may be a tensor.  Pinned against the reference class (with that
+one numpy call shimmed) by oracle/pin_against_reference.py::pin_multilossmanager and tests/test_host_side.py.
+API kept: get_total_loss(losses, current_batch_size, update, weights_list) and
 rebalancing(current_lambda, epoch, logfile).  It is a handful of scalar updates per epoch and
 stays on the host side of the boundary, in torch, on whatever device it is given.
 """
@@ -28,8 +32,11 @@ class MultiLossManager:
 
     def get_total_loss(self, losses, current_batch_size, update=True, weights_list=None):
         """Weighted sum of `losses` (num_losses,) -> (loss, cur_ptr); records the weighted terms."""
-        if weights_list:
-            self.loss_weights = weights_list
+        # the reference writes `if weights_list: self.loss_weights = weights_list`, which only works for a
+        # non-empty python sequence that then fails in the product below; accept a sequence or a tensor
+        if weights_list is not None and len(weights_list):
+            self.loss_weights = torch.as_tensor(weights_list, dtype=self.loss_weights.dtype,
+                                                device=self.loss_weights.device)
         loss_item = self.loss_weights * losses
         loss = loss_item.sum(dim=0)
         if update:

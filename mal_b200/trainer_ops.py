@@ -47,13 +47,16 @@ class _Ssim:
 def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False):
     """Per scale: up-sample disp, disp -> depth, and describe the two source-frame warps."""
     H, W = _o(opt, "height"), _o(opt, "width")
-    if _o(opt, "v1_multiscale"):
-        raise NotImplementedError("v1_multiscale (per-scale source images) is not on the MAL path")
+    v1 = bool(_o(opt, "v1_multiscale"))
     for scale in range(_o(opt, "sclm") + 1):
         disp = outputs[("disp", scale)]
-        # trainer.py:1093-1097.  The fused kernels read the low-resolution disparity directly
-        # (mal_photo_args.depth_height); the full-resolution depth map is only built for the dict.
-        disp_full = disp if disp.shape[-2:] == (H, W) else ops.upsample_bilinear(disp, (H, W))
+        # trainer.py:1089-1095: v1_multiscale warps at the disparity's own scale (images, K of that scale);
+        # otherwise the disparity is up-sampled to the full image.  The fused kernels read the
+        # low-resolution disparity directly (mal_photo_args.depth_height); the full-resolution depth map
+        # is only built for the dict.
+        ss = scale if v1 else 0
+        hs, ws = (disp.shape[-2], disp.shape[-1]) if v1 else (H, W)
+        disp_full = disp if disp.shape[-2:] == (hs, ws) else ops.upsample_bilinear(disp, (hs, ws))
         _, depth = disp_to_depth(disp_full, _o(opt, "min_depth"), _o(opt, "max_depth"))
         outputs[("depth", 0, scale)] = depth
         Ts = []
@@ -61,19 +64,20 @@ def generate_images_pred(inputs, outputs, opt, is_multi=False, materialize=False
             T = outputs[("cam_T_cam", 0, frame_id)]
             Ts.append(T.detach() if is_multi else T)   # "don't update posenet based on multi frame prediction"
             if not _o(opt, "disable_automasking"):
-                outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
-        outputs[("warp_spec", scale)] = WarpSpec(disp, inputs[("K", 0)], inputs[("inv_K", 0)], Ts,
-                                                 _o(opt, "convention"), _o(opt, "min_depth"), _o(opt, "max_depth"))
+                outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, ss)]
+        outputs[("warp_spec", scale)] = WarpSpec(disp, inputs[("K", ss)], inputs[("inv_K", ss)], Ts,
+                                                 _o(opt, "convention"), _o(opt, "min_depth"), _o(opt, "max_depth"),
+                                                 source_scale=ss)
         if materialize:
             from .layers import BackprojectDepth, Project3D
             B = disp.shape[0]
-            back, proj = BackprojectDepth(B, H, W), Project3D(B, H, W, convention=_o(opt, "convention"))
+            back, proj = BackprojectDepth(B, hs, ws), Project3D(B, hs, ws, convention=_o(opt, "convention"))
             for T, frame_id in zip(Ts, _o(opt, "frame_ids")[1:]):
-                cam = back(depth, inputs[("inv_K", 0)])
-                pix = proj(cam, inputs[("K", 0)], T)
+                cam = back(depth, inputs[("inv_K", ss)])
+                pix = proj(cam, inputs[("K", ss)], T)
                 outputs[("sample", frame_id, scale)] = pix
                 outputs[("color", frame_id, scale)] = ops.grid_sample(
-                    inputs[("color", frame_id, 0)], pix, padding_mode="border",
+                    inputs[("color", frame_id, ss)], pix, padding_mode="border",
                     align_corners=_o(opt, "convention") == raw.CONV_MANYDEPTH)
     return outputs
 
@@ -99,23 +103,30 @@ def compute_matching_mask(outputs):
 def compute_losses(inputs, outputs, opt, is_multi=False, has_ins=False, noises=None):
     """Trainer.compute_losses: the non-distil loss over opt.sclm+1 scales.  Returns (losses, [])."""
     losses, total_loss = {}, 0
-    target = inputs[("color", 0, 0)]
     ssim = _Ssim(_o(opt, "no_ssim"))
     num_scales = _o(opt, "sclm") + 1
-    ident = None
+    idents = {}
     for scale in range(num_scales):
         spec = outputs[("warp_spec", scale)]
+        ss = spec.source_scale                      # 0 unless v1_multiscale (trainer.py:1260-1263)
+        target = inputs[("color", 0, ss)]
         with_syn = (not is_multi) and _o(opt, "temporal") and has_ins
-        kw = dict(src=[inputs[("color", f, 0)] for f in (-1, 1)],
+        kw = dict(src=[inputs[("color", f, ss)] for f in (-1, 1)],
                   syn=[outputs[("syn", f, scale)] for f in (-1, 1)] if with_syn else None, depth=spec.disp,
                   K=spec.K, inv_K=spec.inv_K, T=spec.T, convention=spec.convention, depth_is_disp=True,
                   min_depth=spec.min_depth, max_depth=spec.max_depth, no_ssim=ssim.no_ssim)
         consistency_loss = 0
         if not is_multi:
+            # trainer.py:1292-1311: the identity loss is ALWAYS computed and compared; disable_automasking
+            # only drops the tie-break noise (and its randn draw)
+            if ss not in idents:
+                idents[ss] = identity_reprojection(ssim, inputs, ss)
+            ident = idents[ss]
             if not _o(opt, "disable_automasking"):
-                ident = identity_reprojection(ssim, inputs) if ident is None else ident
                 noise = _draw_noise(ident.shape, target.device, None if noises is None else noises[scale])
-                kw.update(identity_min=ident, noise=noise)
+            else:
+                noise = torch.zeros_like(ident)
+            kw.update(identity_min=ident, noise=noise)
             sums, _, sel = ops.photo(target, **kw)
         else:
             if not _o(opt, "disable_automasking") and noises is None:

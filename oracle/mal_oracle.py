@@ -195,22 +195,25 @@ def normalised_smooth_loss(disp, img):
 # --------------------------------------------------------------------------
 def images_pred(inputs, outputs, frame_ids=(0, -1, 1), num_scales=1, height=192, width=640,
                 min_depth=0.1, max_depth=100.0, is_multi=False, convention=MANYDEPTH,
-                automask=True):
-    """Trainer.generate_images_pred, manydepth/trainer.py:1078-1158 (v1_multiscale off)."""
+                automask=True, v1_multiscale=False):
+    """Trainer.generate_images_pred, manydepth/trainer.py:1078-1158.  v1_multiscale (:1089-1095)
+    keeps the disparity at its own scale and warps the images / intrinsics of that scale."""
     for scale in range(num_scales):
-        disp = upsample_disp(outputs[("disp", scale)], height, width)
+        ss = scale if v1_multiscale else 0
+        hs, ws = (height // 2 ** scale, width // 2 ** scale) if v1_multiscale else (height, width)
+        disp = outputs[("disp", scale)] if v1_multiscale else upsample_disp(outputs[("disp", scale)], height, width)
         _, depth = disp_to_depth(disp, min_depth, max_depth)
         outputs[("depth", 0, scale)] = depth
         for fid in frame_ids[1:]:
             T = outputs[("cam_T_cam", 0, fid)]
             if is_multi:
                 T = T.detach()
-            cam = backproject(depth, inputs[("inv_K", 0)])
-            grid = project3d(cam, inputs[("K", 0)], T, height, width, convention)
+            cam = backproject(depth, inputs[("inv_K", ss)])
+            grid = project3d(cam, inputs[("K", ss)], T, hs, ws, convention)
             outputs[("sample", fid, scale)] = grid
-            outputs[("color", fid, scale)] = warp(inputs[("color", fid, 0)], grid, convention)
+            outputs[("color", fid, scale)] = warp(inputs[("color", fid, ss)], grid, convention)
             if automask:
-                outputs[("color_identity", fid, scale)] = inputs[("color", fid, 0)]
+                outputs[("color_identity", fid, scale)] = inputs[("color", fid, ss)]
     return outputs
 
 
@@ -327,29 +330,30 @@ def main_losses(inputs, outputs, mono_reproj, ensemble_reproj, *, batch_size,
 def trainer_compute_losses(inputs, outputs, *, num_scales=1, is_multi=False, temporal=False,
                            has_ins=False, automask=True, motion_masking=True,
                            matching_augmentation=True, batch_size=None, no_ssim=False,
-                           smoothness=1e-3, noises=None):
+                           smoothness=1e-3, noises=None, v1_multiscale=False):
     """Trainer.compute_losses, manydepth/trainer.py:1248-1475 (the non-distil path,
     one pass per scale, total / num_scales).  dynamicdepth/trainer.py:1006-1128 uses
     the same chain over opt.scales."""
     losses, total = {}, 0
     aux = {}
-    target = inputs[("color", 0, 0)]
     for scale in range(num_scales):
+        ss = scale if v1_multiscale else 0          # source_scale, trainer.py:1260-1263
+        target = inputs[("color", 0, ss)]
         cands = [reprojection_loss(outputs[("color", f, scale)], target, no_ssim) for f in (-1, 1)]
         if (not is_multi) and temporal and has_ins:
             cands += [reprojection_loss(outputs[("syn", f, scale)], target, no_ssim)
                       for f in (-1, 1)]
         cands = torch.cat(cands, 1)
-        ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, no_ssim)
+        ident = torch.cat([reprojection_loss(inputs[("color", f, ss)], target, no_ssim)
                            for f in (-1, 1)], 1)
         ident, _ = torch.min(ident, dim=1, keepdim=True)
         reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
         if automask:
             nz = noises[scale] if noises is not None else torch.randn(ident.shape)
             ident = ident + nz * 0.00001
-            mask = loss_masks(reproj, ident)
-        else:
-            mask = loss_masks(reproj, None)
+        # trainer.py:1292-1311: disable_automasking only skips the tie-break noise; the identity loss is
+        # still compared (compute_loss_masks always gets it in this trainer)
+        mask = loss_masks(reproj, ident)
         cons_loss = 0
         if is_multi:
             mask = torch.ones_like(mask)

@@ -284,6 +284,30 @@ def run_pin(batch=2, height=96, width=160, seed=7):
         l_ora, _ = O.trainer_compute_losses(inputs, p_ora, num_scales=2, batch_size=batch)
         ok &= _eq("Trainer.compute_losses(2 scales) loss", l_ora["loss"], l_ref["loss"])
 
+        # the two options that change what compute_losses compares: disable_automasking (identity still
+        # compared, no tie-break noise: trainer.py:1292-1311) and v1_multiscale (:1089-1095, :1260-1263)
+        import torch.nn.functional as F
+        for s in (1,):
+            for f in (-1, 1):
+                inputs[("color", f, s)] = F.interpolate(inputs[("color", f, 0)], scale_factor=1 / 2 ** s, mode="area")
+        for v1, no_auto in ((False, True), (True, False), (True, True)):
+            shell3 = reference_trainer_shell(ref, batch, height, width, sclm=1, v1_multiscale=v1,
+                                             disable_automasking=no_auto)
+            for s in (1,):
+                shell3.backproject_depth[s] = ref.layers.BackprojectDepth(batch, height // 2 ** s, width // 2 ** s)
+                shell3.project_3d[s] = ref.layers.Project3D(batch, height // 2 ** s, width // 2 ** s)
+            p_ref, p_ora = pyr("mono"), pyr("mono")
+            shell3.generate_images_pred(inputs, p_ref)
+            O.images_pred(inputs, p_ora, num_scales=2, height=height, width=width, v1_multiscale=v1)
+            torch.manual_seed(3)
+            l_ref, _ = shell3.compute_losses(inputs, p_ref, is_multi=False)
+            torch.manual_seed(3)
+            l_ora, _ = O.trainer_compute_losses(inputs, p_ora, num_scales=2, batch_size=batch, automask=not no_auto,
+                                                v1_multiscale=v1)
+            for k in ("loss", "reproj_loss/0", "reproj_loss/1"):
+                ok &= _eq(f"Trainer.compute_losses(v1_multiscale={v1}, disable_automasking={no_auto}) {k}",
+                          l_ora[k], l_ref[k])
+
     # --- cost volume -----------------------------------------------------------
     cv = make_cost_volume_inputs(batch, height, width, channels=16, num_bins=24, seed=seed,
                                  zero_pose_sample=batch - 1)
@@ -315,6 +339,8 @@ def run_pin(batch=2, height=96, width=160, seed=7):
     print(f"  {'OK ' if good else 'FAIL'} LossBalancing (6 iterations, weights + loss)")
     ok &= good
 
+    ok &= pin_host_side(ref, t)
+
     # ---- DynamicDepth forward_warp --------------------------------------------------------
     import warnings
     fw = reference_forward_warp()
@@ -328,6 +354,48 @@ def run_pin(batch=2, height=96, width=160, seed=7):
     return bool(ok)
 
 
+
+
+def pin_host_side(ref, t):
+    """The product's own host-side ports (no kernel behind them) against the reference modules:
+    mal_b200/pose.py vs manydepth/layers.py:26-100, mal_b200/multilossmanager.py vs
+    manydepth/multilossmanager.py:6-88."""
+    from mal_b200 import pose
+    from mal_b200.multilossmanager import MultiLossManager
+    ok = True
+    for inv in (False, True):
+        ok &= _eq(f"mal_b200.pose.transformation_from_parameters(invert={inv})",
+                  pose.transformation_from_parameters(t[("axisangle", 1)], t[("translation", 1)], inv),
+                  ref.layers.transformation_from_parameters(t[("axisangle", 1)], t[("translation", 1)], inv))
+    ok &= _eq("mal_b200.pose.rot_from_axisangle", pose.rot_from_axisangle(t[("axisangle", -1)]),
+              ref.layers.rot_from_axisangle(t[("axisangle", -1)]))
+    # MultiLossManager.rebalancing calls np.sum(tensor * tensor) (multilossmanager.py:62,71,83), which raises
+    # TypeError with torch >= 2 / numpy 2 (numpy forwards axis=/out= to Tensor.sum).  The class is dead code in
+    # the reference (SURVEY.md F3); pin everything else by running it with that ONE call shimmed to Tensor.sum.
+    R = ref.multilossmanager
+    try:
+        R.MultiLossManager(2, 2, 4, "cpu").rebalancing(0.1, 0)
+        raised = False
+    except TypeError:
+        raised = True
+    print(f"  note reference MultiLossManager.rebalancing raises TypeError as shipped: {raised}")
+    shim = SimpleNamespace(sum=lambda x: x.sum())
+    m_ref, m_ours = R.MultiLossManager(2, 2, 8, "cpu"), MultiLossManager(2, 2, 8, "cpu")
+    gen = torch.Generator().manual_seed(9)
+    good = True
+    with mock.patch.object(R, "np", shim):
+        for epoch in range(4):
+            for _ in range(3):
+                losses = torch.rand(2, generator=gen) + 0.1
+                a, pa = m_ref.get_total_loss(losses, 2)
+                b, pb = m_ours.get_total_loss(losses, 2)
+                good &= bool(torch.equal(a, b)) and pa == pb
+            m_ref.rebalancing(0.4, epoch)
+            m_ours.rebalancing(0.4, epoch)
+            good &= bool(torch.equal(m_ref.loss_weights, m_ours.loss_weights)) and m_ref.cur_ptr == m_ours.cur_ptr
+            good &= bool(torch.equal(torch.as_tensor(m_ref.previous_total_loss), torch.as_tensor(m_ours.previous_total_loss)))
+    print(f"  {'OK ' if good else 'FAIL'} MultiLossManager (4 epochs: totals, pointers, weights, previous_total_loss)")
+    return ok and good
 
 
 def pin_dynamicdepth_match_features(seed=77):

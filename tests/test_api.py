@@ -408,3 +408,46 @@ def test_loss_balancing_running_mean_is_the_reference_mean():
             ref.compute_loss(scores, it)
             assert np.array_equal(np.array(ours.update_weight(it, 3.0)), np.array(ref.update_weight(it, 3.0))), (epoch, it)
     assert np.array_equal(ours.train_scores, ref.train_scores)
+
+
+@pytest.mark.parametrize("v1_multiscale,disable_automasking", [(True, False), (False, True), (True, True)])
+def test_compute_losses_v1_multiscale_and_no_automask(op_device, v1_multiscale, disable_automasking):
+    """Trainer.compute_losses teacher pass with the two options that change what is compared:
+    v1_multiscale (images / intrinsics of the disparity's own scale, manydepth/trainer.py:1089-1095,
+    :1260-1263) and disable_automasking (the identity loss is still compared, only the tie-break
+    noise is dropped, :1292-1311)."""
+    dev = op_device
+    B, H, W, S = 1, 32, 64, 2
+    inputs, t = make_photometric_inputs(B, H, W, num_scales=S, seed=123)
+    for s in range(1, S):
+        for f in (-1, 1):
+            inputs[("color", f, s)] = F.interpolate(inputs[("color", f, 0)], scale_factor=1 / 2 ** s, mode="area")
+    opt = _opt(B, H, W, sclm=S - 1, distil=False, temporal=False, v1_multiscale=v1_multiscale,
+               disable_automasking=disable_automasking)
+    noises = [torch.randn(B, 1, H // 2 ** s if v1_multiscale else H, W // 2 ** s if v1_multiscale else W,
+                          generator=torch.Generator().manual_seed(5 + s)) for s in range(S)]
+    disps_c = [t[("mono_disp", s)].clone().requires_grad_(True) for s in range(S)]
+    Tc = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
+    o = {("disp", s): disps_c[s] for s in range(S)}
+    o.update({("cam_T_cam", 0, f): Tc[f] for f in (-1, 1)})
+    O.images_pred(inputs, o, num_scales=S, height=H, width=W, v1_multiscale=v1_multiscale)
+    want, aux = O.trainer_compute_losses(inputs, o, num_scales=S, batch_size=B, noises=noises,
+                                         automask=not disable_automasking, v1_multiscale=v1_multiscale)
+    want_g = torch.autograd.grad(want["loss"], disps_c + [Tc[-1], Tc[1]])
+
+    inputs_d = to_device(inputs, dev)
+    disps = [t[("mono_disp", s)].clone().to(dev).requires_grad_(True) for s in range(S)]
+    Td = {f: t[("cam_T_cam", 0, f)].clone().to(dev).requires_grad_(True) for f in (-1, 1)}
+    od = {("disp", s): disps[s] for s in range(S)}
+    od.update({("cam_T_cam", 0, f): Td[f] for f in (-1, 1)})
+    trainer_ops.generate_images_pred(inputs_d, od, opt)
+    got, _ = trainer_ops.compute_losses(inputs_d, od, opt, noises=[n.to(dev) for n in noises])
+    for k in want:
+        assert _close(got[k], want[k]), k
+    for s in range(S):
+        sel = od[("mal_selection", s)].cpu().numpy()
+        assert np.array_equal(sel & 0x7F, aux[("frame_idx", s)].numpy().astype(np.uint8))
+        assert np.array_equal(sel >> 7, aux[("mask", s)].numpy().astype(np.uint8))      # bit-exact automask
+    g = torch.autograd.grad(got["loss"], disps + [Td[-1], Td[1]])
+    for a, b in zip(g, want_g):
+        assert _gerr(a, b) < GRAD_RTOL
