@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 
   const bool cv_min = DYN && a.cv_min;
   for (int i = tid; i < nb * CV_PX; i += CV_NT) { cost[i] = cv_min ? 1.0f : 0.0f; cnt[i] = 0.0f; }
+  // a NaN / Inf among a pixel's current features also poisons its masked planes (NaN * 0 in the reference,
+  // resnet_encoder.py:211-212); flagged per pixel by whichever warp holds the offending chunk
+  __shared__ int s_poison[CV_PX];
+  if (tid < CV_PX) s_poison[tid] = 0;
   // occlusion handling applies to samples whose matching augmentation is off (aug_mask == 0)
   const float* occ = nullptr;
   if (DYN && a.occ && a.occ_mode != 0 && !(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
@@ -276,6 +280,14 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 #pragma unroll
         for (int j = 0; j < 4; j++)
           cq[j] = pix_ok ? ldg4(curq + (size_t)(ch * 4 + j) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!DYN) {
+          bool bad = false;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            bad |= !(fabsf(cq[j].x) < INFINITY) || !(fabsf(cq[j].y) < INFINITY) || !(fabsf(cq[j].z) < INFINITY) ||
+                   !(fabsf(cq[j].w) < INFINITY);
+          if (bad) s_poison[lane] = 1;
+        }
         float4 t00[4], t01[4], t10[4], t11[4];
         int coff = -1;
         const int* po = d_off + lane;
@@ -332,6 +344,8 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
             cost[o] = xadd(cost[o], diff);
             if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
           }
+        } else if (!DYN && pix_ok && s_poison[lane]) {
+          cost[(g0 + k) * CV_PX + lane] = NAN;   // masked plane of a poisoned pixel: NaN * 0
         }
       }
       // the next group's P phase rewrites the descriptors only after the barrier below
@@ -352,12 +366,14 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
     else v = xdiv(cost[o], xadd(cnt[o], 1e-7f));         // cost_volume / (counts + 1e-7)
     cost[o] = v;
     vmax = fmaxf(vmax, v);
+    if (v != v) s_poison[lane] = 2;   // torch.max propagates NaN, fmaxf drops it
   }
   scr[warp * CV_PX + lane] = vmax;
   __syncthreads();
   vmax = scr[lane];
 #pragma unroll
   for (int q = 1; q < CV_WARPS; q++) vmax = fmaxf(vmax, scr[q * CV_PX + lane]);
+  if (s_poison[lane] == 2) vmax = NAN;
   __syncthreads();
 
   float npos = 0.0f, best = INFINITY;
@@ -373,7 +389,8 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
     // compute_confidence_mask(cost_volume * (1 - missing_mask))
     if (xmul(out, xsub(1.0f, miss)) > 0.0f) npos += 1.0f;
     float viz = (out == 0.0f) ? 100.0f : out;       // viz_cost_vol[viz_cost_vol == 0] = 100
-    if (viz < best || (viz != viz && best == best)) { best = viz; besti = k; }   // first min; NaN wins like torch
+    // first min; the first NaN wins like torch.min; an all-+Inf column keeps its first plane
+    if (besti == 0x7fffffff || viz < best || (viz != viz && best == best)) { best = viz; besti = k; }
   }
   scr[(0 * CV_WARPS + warp) * CV_PX + lane] = npos;
   scr[(1 * CV_WARPS + warp) * CV_PX + lane] = best;
@@ -392,6 +409,7 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
   }
   const int thr = a.num_bins_threshold > 0 ? a.num_bins_threshold : nb;
   const float conf = (conf_n == (float)thr) ? 1.0f : 0.0f;
+  besti = min(max(besti, 0), nb - 1);   // never index the bins out of range
   if (pix_ok) {
     const size_t vol = (size_t)b * nb * hw;
     for (int k = k0; k < k1; k++) {
@@ -466,6 +484,9 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
 
   const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
   pk2 ncur[4][2];   // -current features of this lane's chunk (w - cur == w + (-cur))
+  // A NaN / Inf among the pixel's current features poisons its masked planes too: the reference multiplies
+  // |warped - cur|.mean(1) by the edge mask (NaN * 0 = NaN, resnet_encoder.py:211-212) instead of skipping them.
+  int poisoned = 0;
   {
     // read straight from the NCHW input (once per lane: 16 scalar loads; channels beyond C are zero
     // padding): the current features need no packing pass
@@ -477,11 +498,14 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       for (int e = 0; e < 4; e++) {
         const int ch = sub * 16 + j * 4 + e;
         v[e] = (pix_ok && active && ch < a.channels) ? __ldg(cur + (size_t)ch * hw) : 0.0f;
+        poisoned |= !(fabsf(v[e]) < INFINITY);
       }
       ncur[j][0] = pack2(-v[0], -v[1]);
       ncur[j][1] = pack2(-v[2], -v[3]);
     }
   }
+  poisoned |= __shfl_xor_sync(0xffffffffu, poisoned, 8);
+  poisoned |= __shfl_xor_sync(0xffffffffu, poisoned, 16);
   const pk2 one2 = dup2(1.0f), mone2 = dup2(-1.0f);
   const float inv_channels = (a.channels & (a.channels - 1)) == 0 ? 1.0f / (float)a.channels : 0.0f;
 
@@ -528,7 +552,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
         tx[u] = xsub(ux, x0);
         ty[u] = xsub(uy, y0);
       }
-      if (!__any_sync(0xffffffffu, (off[0] & off[1]) >= 0)) continue;   // 8 pixels x 8 planes all masked
+      if (!__any_sync(0xffffffffu, (off[0] & off[1]) >= 0 || poisoned)) continue;   // 8 pixels x 8 planes all masked
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         s_tx[warp][sub + 4 * u][pl] = tx[u];
@@ -592,6 +616,8 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
           const int o = cq_idx(k0 + sub + 4 * u, col);
           cost[o] = xadd(cost[o], diff);
           if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+        } else if (poisoned && pix_ok && k0 + sub + 4 * u < nb) {
+          cost[cq_idx(k0 + sub + 4 * u, col)] = NAN;   // masked plane of a poisoned pixel: NaN * 0
         }
       }
     }
@@ -600,14 +626,19 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
 
   // ---- epilogue: lane `sub` of a pixel owns planes sub, sub+4, ... ---------------------------------
   float vmax = -INFINITY;
+  int has_nan = 0;
   for (int k = sub; k < nb; k += 4) {
     const int o = cq_idx(k, col);
     const float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));
     cost[o] = v;
     vmax = fmaxf(vmax, v);
+    has_nan |= (v != v);
   }
   vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
   vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
+  has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, 8);
+  has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, 16);
+  if (has_nan) vmax = NAN;   // torch.max propagates NaN, fmaxf drops it
   float npos = 0.0f, best = INFINITY;
   int besti = 0x7fffffff;
   for (int k = sub; k < nb; k += 4) {
@@ -620,15 +651,20 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     cnt[o] = miss;
     if (xmul(out, xsub(1.0f, miss)) > 0.0f) npos += 1.0f;
     const float viz = (out == 0.0f) ? 100.0f : out;
-    if (viz < best) { best = viz; besti = k; }
+    // first min; the first NaN wins like torch.min (and like cv_sweep_kernel); an all-+Inf column keeps
+    // its first plane
+    if (besti == 0x7fffffff || viz < best || (viz != viz && best == best)) { best = viz; besti = k; }
   }
 #pragma unroll
   for (int m = 8; m <= 16; m <<= 1) {
     npos += __shfl_xor_sync(0xffffffffu, npos, m);
     const float ov = __shfl_xor_sync(0xffffffffu, best, m);
     const int oi = __shfl_xor_sync(0xffffffffu, besti, m);
-    if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    const bool on = ov != ov, mn = best != best;
+    const bool take = on ? (!mn || oi < besti) : (!mn && (ov < best || (ov == best && oi < besti)));
+    if (take) { best = ov; besti = oi; }
   }
+  besti = min(max(besti, 0), nb - 1);   // never index the bins out of range
   const int thr = a.num_bins_threshold > 0 ? a.num_bins_threshold : nb;
   const float conf = (npos == (float)thr) ? 1.0f : 0.0f;
   if (pix_ok) {

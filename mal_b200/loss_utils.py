@@ -223,6 +223,14 @@ class LossBalancing:
         return window.mean(axis=0)
 
     def update_weight(self, i, current_lambda_for_adjust):
+        # A loss whose recorded mean is 0 (e.g. distil_loss == 0 in the first step) makes the reference divide by
+        # zero: its weight becomes inf, previous_total_loss NaN, and two updates later (inf / inf) both weights
+        # are NaN for the rest of the run.  Same arithmetic here (pinned), without numpy's
+        # RuntimeWarnings; mal_b200.step.MalStep warns once when such weights reach the device.
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return self._update_weight(i, current_lambda_for_adjust)
+
+    def _update_weight(self, i, current_lambda_for_adjust):
         mean = self._mean_scores(i)
         total_loss = np.sum(mean * self.w_list)
         if self.weight_initialization and not self.weight_initialization_done:

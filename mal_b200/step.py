@@ -20,6 +20,7 @@ from __future__ import annotations
 
 from types import SimpleNamespace
 
+import numpy as np
 import torch
 
 from . import loss_utils, ops, raw, trainer_ops
@@ -287,6 +288,7 @@ class MalStep:
         self.launches_per_step = None
         self._layout = None
         self._pending = None   # (event, iteration) of the step whose LossBalancing update is still due
+        self._warned_weights = False
         self.copy_stream = torch.cuda.Stream(self.device)
         # parallel branches only inside a captured graph: there every buffer is static, so tensors
         # produced on one stream and consumed on another need no allocator bookkeeping
@@ -372,8 +374,12 @@ class MalStep:
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(2):
-                self._run(sl["buf"])
+            branches, self.side_streams = self.side_streams, None   # fork only under capture (static buffers)
+            try:
+                for _ in range(2):
+                    self._run(sl["buf"])
+            finally:
+                self.side_streams = branches
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         raw.LAUNCHES[0] = 0
@@ -401,6 +407,13 @@ class MalStep:
         ev.synchronize()
         self.blc.record_scores(it, [float(self._scalars_host[1]), float(self._scalars_host[2])])
         w0, w1 = self.blc.update_weight(it, self.lambda_for_adjust)
+        if not (np.isfinite(w0) and np.isfinite(w1)) and not self._warned_weights:
+            # the reference's LossBalancing does this too when a recorded loss mean is 0 (loss_utils.py:326);
+            # its next backward is then NaN as well - keep its arithmetic, but say so
+            import warnings
+            warnings.warn("LossBalancing produced non-finite weights (%r, %r) at iteration %d: a loss term was "
+                          "exactly 0, as in the reference the following steps' gradients are not finite" % (w0, w1, it))
+            self._warned_weights = True
         self._w_host[0], self._w_host[1] = float(w0), float(w1)
         self.weights.copy_(self._w_host, non_blocking=True)
 

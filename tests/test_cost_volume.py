@@ -107,3 +107,27 @@ def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool):
         plain, _ = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
                                             cv["inv_K"], cv["bins"], look_img, cv_min, aug, False, False, 1, 0.7)
         assert not torch.equal(plain[0], want_vol[0]) and torch.equal(plain[1], want_vol[1])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("C", [32, 80])   # 32: four-lanes-per-pixel sweep; 80 (5 chunks): one-pixel-per-lane sweep
+def test_cost_volume_nan_and_inf_features(backend, C):
+    """A NaN / +Inf in the current features poisons every plane of that pixel (the reference multiplies the
+    channel mean by the edge mask, NaN * 0, and the max-fill spreads it).  torch.min then returns the first
+    NaN; the arg-min must follow and never leave [0, bins) (it indexes the depth bins for lowest_cost)."""
+    h, dev = handle_and_device(backend)
+    cv = make_cost_volume_inputs(1, 64, 96, channels=C, num_lookup=1, num_bins=24, seed=31, max_bin=10.0)
+    cv["current_feats"][0, 3, 7, 9] = float("nan")
+    cv["current_feats"][0, 5, 9, 14] = float("inf")
+    vol, miss = O.match_features(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"], cv["inv_K"],
+                                 cv["bins"])
+    low, idx = O.lowest_cost(vol, cv["bins"])
+    out = _run(h, dev, cv)
+    am = out["argmin"].cpu().long()
+    assert int(am.min()) >= 0 and int(am.max()) < 24
+    assert np.array_equal(out["cost_volume"].cpu().numpy(), vol.numpy(), equal_nan=True)
+    assert torch.equal(out["missing_mask"].cpu(), miss)
+    assert torch.equal(am, idx)
+    assert torch.equal(out["lowest_cost"].cpu(), low)
+    # both pixels end up all-NaN in the reference: a masked plane is NaN * 0 (Inf * 0) and max-filling spreads it
+    assert bool(torch.isnan(vol[0, :, 7, 9]).all()) and bool(torch.isnan(vol[0, :, 9, 14]).all())

@@ -68,3 +68,25 @@ def test_multilossmanager_follows_the_reference_arithmetic():
     # weights_list overrides, update=False leaves the record alone
     total, ptr = m.get_total_loss(torch.tensor([1.0, 2.0]), B, update=False, weights_list=torch.tensor([0.25, 0.75]))
     assert float(total) == 1.75 and ptr == 0
+
+
+def test_loss_balancing_zero_loss_term_follows_the_reference():
+    """distil_loss == 0 in the first step: the reference divides by the zero mean (loss_utils.py:326), the
+    weight becomes inf and previous_total_loss NaN (weights frozen for a step: NaN > 0 is False at :338), then
+    inf / inf makes both weights NaN.
+    The product mirrors that state for state (the oracle's LossBalancing is pinned against the reference)."""
+    from mal_b200.loss_utils import LossBalancing
+    ours, ora = LossBalancing(2, 64, 2), O.LossBalancing(2, 64, 2)
+    seq = [(0.7, 0.0), (0.6, 0.01), (0.5, 0.02)]
+    for it, (a, b) in enumerate(seq):
+        ll = [torch.tensor(a), torch.tensor(b)]
+        assert torch.equal(torch.as_tensor(ours.compute_loss(ll, it)), torch.as_tensor(ora.compute_loss(ll, it)))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = ora.update_weight(it, 0.3)
+        got = ours.update_weight(it, 0.3)
+        assert np.array_equal(np.array(got), np.array(want), equal_nan=True), (it, got, want)
+        assert np.array_equal(ours.previous_total_loss, ora.previous_total_loss, equal_nan=True)
+        if it == 0:
+            assert got[0] == 0.25 and np.isinf(got[1]) and np.isnan(ours.previous_total_loss)
+    # step 1: NaN > 0 is False, the weights stay; step 2: inf / inf -> NaN reaches both weights
+    assert np.isnan(got[0]) and np.isnan(got[1])
