@@ -180,6 +180,16 @@ typedef struct mal_smooth_args {
   float* grad_disp;           /* (B,1,h,w) with_grad: d loss / d disp                         */
   float* workspace;           /* mal_smooth_workspace_floats() floats                         */
   float* loss;                /* (1)                                                          */
+  /* a second disparity scored against the same image in the same launch (teacher + student of one step:
+     the edge weights are computed once); NULL: one term                                              */
+  const float* disp_b;        /* (B,1,h,w) optional                                           */
+  float* grad_disp_b;         /* (B,1,h,w) with_grad and disp_b                               */
+  float* loss_b;              /* (1)       with disp_b                                        */
+  int32_t defer_fix;          /* 1 (normalise + with_grad): grad_disp[_b] are left as d loss / d (normalised
+                                 disp) and `stats` tells the consumer how to chain through the normalisation:
+                                 d loss / d disp_i = (g_i - stats[b][t][0] / (h*w)) * stats[b][t][1]
+                                 (mal_step_combine does this while it adds the gradient planes)   */
+  float* stats;               /* (B,2,2) optional: per sample and term [L_b, 1 / (mean_b + 1e-7)]    */
 } mal_smooth_args;
 
 size_t mal_smooth_workspace_floats(int batch, int height, int width);
@@ -314,6 +324,9 @@ typedef struct mal_step_combine_args {
   float* grad_disp_teacher;     /* (B,1,H,W) d total / d teacher disparity                    */
   float* grad_disp_student;     /* (B,1,H,W) d total / d student disparity                    */
   float* grad_T[2];             /* (B,4,4)   d total / d cam_T_cam for frames -1,+1           */
+  const float* smooth_stats;    /* (B,2,2) optional: mal_smooth_forward(defer_fix=1).stats of ONE dual call
+                                   (term 0 = teacher, 1 = student); gs_teacher / gs_student are then the
+                                   deferred planes and the chain through the mean-normalisation is applied here */
 } mal_step_combine_args;
 
 int mal_step_combine(const mal_step_combine_args* args, mal_stream_t stream);

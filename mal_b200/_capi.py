@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmal_b200.so")
+LIB_PATH = os.environ.get("MAL_B200_LIB") or os.path.join(_PKG, "libmal_b200.so")   # override: A/B tuning runs only
 
 c_float_p = C.c_void_p  # raw device addresses are passed as integers
 
@@ -43,7 +43,7 @@ class StepCombineArgs(C.Structure):
         ("K", C.c_void_p), ("gd_teacher", C.c_void_p), ("gs_teacher", C.c_void_p), ("gP_teacher", C.c_void_p),
         ("gd_student", C.c_void_p), ("gs_student", C.c_void_p), ("g_cons", C.c_void_p), ("g_distil", C.c_void_p),
         ("g_distil_mono", C.c_void_p), ("scalars", C.c_void_p), ("grad_disp_teacher", C.c_void_p),
-        ("grad_disp_student", C.c_void_p), ("grad_T", C.c_void_p * 2),
+        ("grad_disp_student", C.c_void_p), ("grad_T", C.c_void_p * 2), ("smooth_stats", C.c_void_p),
     ]
 
 
@@ -92,6 +92,8 @@ class SmoothArgs(C.Structure):
         ("normalise", C.c_int32), ("with_grad", C.c_int32),
         ("disp", C.c_void_p), ("img", C.c_void_p), ("grad_disp", C.c_void_p),
         ("workspace", C.c_void_p), ("loss", C.c_void_p),
+        ("disp_b", C.c_void_p), ("grad_disp_b", C.c_void_p), ("loss_b", C.c_void_p),
+        ("defer_fix", C.c_int32), ("stats", C.c_void_p),
     ]
 
 

@@ -5,155 +5,207 @@
 //     dn    = disp / (mean_hw(disp) + 1e-7)
 //     loss  = mean_x( |dn[x] - dn[x+1]| * exp(-mean_c |I[x] - I[x+1]|) ) + the same along y
 //
-// Kernels (all deterministic, no atomics):
-//   1  smooth_mean_kernel      per-sample 1 / (mean(disp) + 1e-7)               (normalise only)
-//   2  smooth_main_kernel      one thread per pixel: it owns its right and down edges (loss) and
-//                              re-derives its left and up edges for the gradient, so the backward
-//                              needs no scatter, no shared tile and no barrier; per-CTA loss partials
-//   3  smooth_finalize_kernel  fixed-order reduction -> loss, per-sample loss share
-//   4  smooth_fix_kernel       chain through the normalisation:  the loss is homogeneous of degree 1
-//                              in dn, so sum_j g'_j dn_j = L_b and
-//                              d loss / d disp_i = (g'_i - L_b / HW) / (mean_b + 1e-7)
-// HBM traffic: disp 4 + img 12 B/px read, grad 4 B/px written (+ 8 B/px for the fix pass).
+// ONE launch scores one or two disparities (teacher and student share the image, so the edge weights -
+// the exp() and three of the five planes read per pixel - are computed once for both):
+//   smooth_kernel<VEC, DUAL>  a thread owns VEC (4 when rows are 16-byte multiples) horizontally adjacent
+//       pixels: 128-bit loads of its row and of the rows above / below, its right and down edges for the
+//       loss, its left and up edges re-derived for the gradient - no scatter, no shared tile, no barrier in
+//       the main part.  The loss is homogeneous of degree 1 in dn, so the kernel works on the UN-normalised
+//       disparity and only accumulates sum(disp) beside the raw loss: no mean pass has to run first.
+//       The last CTA of a sample (ticket) reduces the per-CTA partials in a fixed order:
+//           s_b = 1 / (mean_b + 1e-7),  L_b = s_b * raw_b,   loss = sum_b L_b (last sample, sample order)
+//   smooth_fix_kernel         chains the gradient through the normalisation,
+//           d loss / d disp_i = (g'_i - L_b / HW) * s_b          (sum_j g'_j dn_j = L_b by homogeneity)
+//       unless the caller asked to defer it (`defer_fix`): mal_step_combine applies it while it adds the
+//       gradient planes up anyway.
+// HBM traffic: disp 4 (8) + img 12 B/px read, grad 4 (8) B/px written (+ 8 B/px per term for the fix pass).
 #include "mal_math.cuh"
 
 namespace mal {
 
-constexpr int SM_TW = 32, SM_TH = 8, SM_NT = 256;
-constexpr int SM_SPLIT = 8;    // CTAs per sample in the mean pass
+constexpr int SM_TH = 8, SM_NT = 256;   // a CTA covers 8 rows x 32 threads x VEC pixels
 
 struct SmoothWs {   // offsets into the float workspace
-  size_t mean_part, partials, lb, total;
+  size_t partials, stats, tickets, total;
 };
 __host__ __device__ inline SmoothWs smooth_ws(int batch, int tiles) {
   SmoothWs w;
-  w.mean_part = 0;
-  w.partials = w.mean_part + (size_t)batch * SM_SPLIT;
-  w.lb = w.partials + (size_t)batch * tiles;
-  w.total = w.lb + (size_t)batch * 2;   // [L_b, 1 / (mean_b + eps)]
+  w.partials = 0;                                        // [batch][tiles][4]: sum(disp), raw loss  x 2 terms
+  w.stats = w.partials + (size_t)batch * tiles * 4;      // [batch][2 terms][2]: L_b, 1 / (mean_b + eps)
+  w.tickets = w.stats + (size_t)batch * 4;               // [batch] + [1] unsigned
+  w.total = w.tickets + (size_t)batch + 1 + 3;
   return w;
 }
 
-// partial sums of disp: SM_SPLIT CTAs per sample, 4 independent loads in flight per thread
-__global__ void __launch_bounds__(1024) smooth_mean_kernel(const float* __restrict__ disp, int hw,
-                                                          float* __restrict__ part) {
-  __shared__ float red[32];
-  const int b = blockIdx.y, sp = blockIdx.x;
-  const int per = (hw + SM_SPLIT - 1) / SM_SPLIT;
-  const int i1 = min(hw, (sp + 1) * per);
-  const float* d = disp + (size_t)b * hw;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int i = sp * per + threadIdx.x;
-  for (; i + 3 * 1024 < i1; i += 4 * 1024) {
-    a0 += __ldg(d + i); a1 += __ldg(d + i + 1024); a2 += __ldg(d + i + 2048); a3 += __ldg(d + i + 3072);
+template <int VEC>
+struct SmVec { float v[VEC]; };
+template <int VEC>
+__device__ __forceinline__ SmVec<VEC> sm_ld(const float* __restrict__ p) {
+  SmVec<VEC> r;
+  if (VEC == 4) {
+#ifdef MAL_EMU
+    const float4 t = *reinterpret_cast<const float4*>(p);
+#else
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+#endif
+    r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
   }
-  for (; i < i1; i += 1024) a0 += __ldg(d + i);
-  float acc = warp_sum((a0 + a1) + (a2 + a3));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int wv = 0; wv < 32; wv++) t += red[wv];
-    part[b * SM_SPLIT + sp] = t;
-  }
+  return r;
 }
-
-// 1 / (mean(disp) + 1e-7) from the partial sums, in a fixed order
-__device__ __forceinline__ float smooth_scale(const float* __restrict__ part, int b, int hw) {
-  float t = 0.0f;
-#pragma unroll
-  for (int k = 0; k < SM_SPLIT; k++) t += __ldg(part + b * SM_SPLIT + k);
-  return 1.0f / (t / (float)hw + 1e-7f);
+__device__ __forceinline__ float sm_weight(float r0, float g0, float b0, float r1, float g1, float b1, float inv_n) {
+  return expf(-(fabsf(r0 - r1) + fabsf(g0 - g1) + fabsf(b0 - b1)) * (1.0f / 3.0f)) * inv_n;
 }
+__device__ __forceinline__ float sm_sign(float g, float w) { return g > 0.f ? w : (g < 0.f ? -w : 0.f); }
 
-struct SmPix { float d, r, g, b; };   // scaled disparity and colour of one pixel
-
-__device__ __forceinline__ SmPix sm_load(const float* __restrict__ d, const float* __restrict__ im, int hw, int o,
-                                         float sc) {
-  SmPix p;
-  p.d = __ldg(d + o) * sc; p.r = __ldg(im + o); p.g = __ldg(im + hw + o); p.b = __ldg(im + 2 * hw + o);
-  return p;
-}
-
-// signed, weighted edge term between pixels p and q (q = right or lower neighbour of p):
-// w = exp(-mean_c |dI|) * inv_n carries the sign of (dn[p] - dn[q]); *absval gets |ddn| * w.
-__device__ __forceinline__ float edge_term(const SmPix& p, const SmPix& q, float inv_n, float* absval) {
-  const float g = p.d - q.d;
-  const float wgt = expf(-(fabsf(p.r - q.r) + fabsf(p.g - q.g) + fabsf(p.b - q.b)) * (1.0f / 3.0f)) * inv_n;
-  *absval = fabsf(g) * wgt;
-  return g > 0.f ? wgt : (g < 0.f ? -wgt : 0.f);
-}
-
-// One thread per pixel, no shared tile: the pixel owns its right and down edges (loss) and
-// re-derives its left and up edges for the gradient; every neighbour is loaded once (L1).
-__global__ void __launch_bounds__(SM_NT) smooth_main_kernel(const mal_smooth_args a, const float inv_nx,
-                                                           const float inv_ny, const int tiles_x,
-                                                           const int tiles) {
-  __shared__ float red[SM_NT / 32];
+template <int VEC, bool DUAL>
+__global__ void __launch_bounds__(SM_NT) smooth_kernel(const mal_smooth_args a, const float inv_nx, const float inv_ny,
+                                                      const int tiles_x, const int tiles) {
+  constexpr int ND = DUAL ? 2 : 1;
+  __shared__ float red[SM_NT / 32][4];
+  __shared__ double tot[4];
+  __shared__ int s_last;
   const int H = a.height, W = a.width, hw = H * W;
   const int b = blockIdx.z;
-  const int x = blockIdx.x * SM_TW + (threadIdx.x % SM_TW), y = blockIdx.y * SM_TH + threadIdx.x / SM_TW;
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * VEC, y = blockIdx.y * SM_TH + (threadIdx.x >> 5);
   const SmoothWs ws = smooth_ws(a.batch, tiles);
-  const float sc = a.normalise ? smooth_scale(a.workspace + ws.mean_part, b, hw) : 1.0f;
-  const float* d = a.disp + (size_t)b * hw;
   const float* im = a.img + (size_t)b * 3 * hw;
-  float acc = 0.0f;
+  const float* dp[2] = {a.disp + (size_t)b * hw, DUAL ? a.disp_b + (size_t)b * hw : nullptr};
+  float* gp[2] = {a.grad_disp ? a.grad_disp + (size_t)b * hw : nullptr,
+                  (DUAL && a.grad_disp_b) ? a.grad_disp_b + (size_t)b * hw : nullptr};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // sum(disp), raw loss per term
   if (x < W && y < H) {
     const int o = y * W + x;
-    const SmPix c = sm_load(d, im, hw, o, sc);
-    float g = 0.0f, av;
-    if (x + 1 < W) { g += edge_term(c, sm_load(d, im, hw, o + 1, sc), inv_nx, &av); acc += av; }
-    if (y + 1 < H) { g += edge_term(c, sm_load(d, im, hw, o + W, sc), inv_ny, &av); acc += av; }
-    if (a.with_grad) {
-      if (x > 0) g -= edge_term(sm_load(d, im, hw, o - 1, sc), c, inv_nx, &av);
-      if (y > 0) g -= edge_term(sm_load(d, im, hw, o - W, sc), c, inv_ny, &av);
-      a.grad_disp[(size_t)b * hw + o] = g;   // d loss / d dn; the fix pass chains through the normalisation
+    const bool has_r = x + VEC < W, has_l = x > 0, has_d = y + 1 < H, has_u = y > 0;
+    const bool grad = a.with_grad != 0;
+    // edge weights: right edge of every own pixel, the left edge of the first, down and up edges
+    float wr[VEC], wd[VEC], wu[VEC], wl = 0.0f;
+    {
+      SmVec<VEC> c[3], dn[3], up[3];
+      float rn[3] = {0.f, 0.f, 0.f}, ln[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        c[ch] = sm_ld<VEC>(im + (size_t)ch * hw + o);
+        if (has_d) dn[ch] = sm_ld<VEC>(im + (size_t)ch * hw + o + W);
+        if (grad && has_u) up[ch] = sm_ld<VEC>(im + (size_t)ch * hw + o - W);
+        if (has_r) rn[ch] = __ldg(im + (size_t)ch * hw + o + VEC);
+        if (grad && has_l) ln[ch] = __ldg(im + (size_t)ch * hw + o - 1);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; v++) {
+        const bool last = v == VEC - 1;
+        const float r1 = last ? rn[0] : c[0].v[(v + 1) % VEC], g1 = last ? rn[1] : c[1].v[(v + 1) % VEC],
+                    b1 = last ? rn[2] : c[2].v[(v + 1) % VEC];
+        wr[v] = (!last || has_r) ? sm_weight(c[0].v[v], c[1].v[v], c[2].v[v], r1, g1, b1, inv_nx) : 0.0f;
+        wd[v] = has_d ? sm_weight(c[0].v[v], c[1].v[v], c[2].v[v], dn[0].v[v], dn[1].v[v], dn[2].v[v], inv_ny) : 0.0f;
+        wu[v] = (grad && has_u) ? sm_weight(up[0].v[v], up[1].v[v], up[2].v[v], c[0].v[v], c[1].v[v], c[2].v[v], inv_ny) : 0.0f;
+      }
+      if (grad && has_l) wl = sm_weight(ln[0], ln[1], ln[2], c[0].v[0], c[1].v[0], c[2].v[0], inv_nx);
+    }
+#pragma unroll
+    for (int t = 0; t < ND; t++) {
+      const float* d = dp[t];
+      const SmVec<VEC> c = sm_ld<VEC>(d + o);
+      SmVec<VEC> dn, up;
+      if (has_d) dn = sm_ld<VEC>(d + o + W);
+      if (grad && has_u) up = sm_ld<VEC>(d + o - W);
+      const float rn = has_r ? __ldg(d + o + VEC) : 0.0f, ln = (grad && has_l) ? __ldg(d + o - 1) : 0.0f;
+      float g[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) g[v] = 0.0f;
+      float sum_d = 0.0f, loss = 0.0f;
+#pragma unroll
+      for (int v = 0; v < VEC; v++) {
+        sum_d += c.v[v];
+        const bool last = v == VEC - 1;
+        if (!last || has_r) {
+          const float e = c.v[v] - (last ? rn : c.v[(v + 1) % VEC]);
+          loss += fabsf(e) * wr[v];
+          const float sg = sm_sign(e, wr[v]);
+          g[v] += sg;
+          if (!last) g[(v + 1) % VEC] -= sg;   // the same edge is the next pixel's left edge
+        }
+        if (has_d) {
+          const float e = c.v[v] - dn.v[v];
+          loss += fabsf(e) * wd[v];
+          g[v] += sm_sign(e, wd[v]);
+        }
+        if (grad && has_u) g[v] -= sm_sign(up.v[v] - c.v[v], wu[v]);
+      }
+      if (grad && has_l) g[0] -= sm_sign(ln - c.v[0], wl);
+      acc[t * 2] = sum_d;
+      acc[t * 2 + 1] = loss;
+      if (grad && gp[t]) {   // d loss / d dn up to the per-sample scale; chained through the normalisation later
+        if (VEC == 4) *reinterpret_cast<float4*>(gp[t] + o) = make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]);
+        else gp[t][o] = g[0];
+      }
     }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  // ---- per-CTA partials ----------------------------------------------------------------------------------
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = v;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  if (threadIdx.x < 4) {
     float t = 0.0f;
-    for (int wv = 0; wv < SM_NT / 32; wv++) t += red[wv];
-    a.workspace[ws.partials + (size_t)b * tiles + blockIdx.y * tiles_x + blockIdx.x] = t;
+    for (int wv = 0; wv < SM_NT / 32; wv++) t += red[wv][threadIdx.x];
+    a.workspace[ws.partials + ((size_t)b * tiles + tile) * 4 + threadIdx.x] = t;
   }
-}
-
-__global__ void __launch_bounds__(1024) smooth_finalize_kernel(const mal_smooth_args a, const int tiles) {
-  double* per_sample = reinterpret_cast<double*>(dyn_smem());   // [batch]
-  const SmoothWs ws = smooth_ws(a.batch, tiles);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int b = warp; b < a.batch; b += nwarp) {
+  // ---- ticketed reduction: last CTA of the sample, then last sample ----------------------------------------
+  unsigned* tickets = reinterpret_cast<unsigned*>(a.workspace + ws.tickets);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + b, 1u) == (unsigned)(tiles - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile float* part = a.workspace + ws.partials + (size_t)b * tiles * 4;
+  if (warp < 2 * ND) {
     double s = 0.0;
-    for (int t = lane; t < tiles; t += 32) s += (double)a.workspace[ws.partials + (size_t)b * tiles + t];
+    for (int t = lane; t < tiles; t += 32) s += (double)part[(size_t)t * 4 + warp];
     s = warp_sum(s);
-    if (lane == 0) {
-      per_sample[b] = s;
-      a.workspace[ws.lb + b * 2] = (float)s;
-      if (a.normalise) a.workspace[ws.lb + b * 2 + 1] = smooth_scale(a.workspace + ws.mean_part, b, a.height * a.width);
-    }
+    if (lane == 0) tot[warp] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int b = 0; b < a.batch; b++) s += per_sample[b];
-    a.loss[0] = (float)s;
+    float* stats = a.workspace + ws.stats + (size_t)b * 4;
+    for (int t = 0; t < ND; t++) {
+      const float sc = a.normalise ? 1.0f / ((float)tot[t * 2] / (float)hw + 1e-7f) : 1.0f;
+      stats[t * 2] = (float)((double)sc * tot[t * 2 + 1]);   // L_b
+      stats[t * 2 + 1] = sc;
+      if (a.stats) { a.stats[(size_t)b * 4 + t * 2] = stats[t * 2]; a.stats[(size_t)b * 4 + t * 2 + 1] = sc; }
+    }
+    __threadfence();
+    if (atomicAdd(tickets + a.batch, 1u) == (unsigned)(a.batch - 1)) {
+      __threadfence();
+      const volatile float* st = a.workspace + ws.stats;
+      for (int t = 0; t < ND; t++) {
+        double s = 0.0;
+        for (int i = 0; i < a.batch; i++) s += (double)st[(size_t)i * 4 + t * 2];
+        (t == 0 ? a.loss : a.loss_b)[0] = (float)s;
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(SM_NT) smooth_fix_kernel(const mal_smooth_args a, const int tiles) {
+__global__ void __launch_bounds__(SM_NT) smooth_fix_kernel(const mal_smooth_args a, const int tiles, const int term) {
   const SmoothWs ws = smooth_ws(a.batch, tiles);
   const size_t hw = (size_t)a.height * a.width, total = (size_t)a.batch * hw;
+  float* g = term == 0 ? a.grad_disp : a.grad_disp_b;
   for (size_t i = (size_t)blockIdx.x * SM_NT + threadIdx.x; i < total; i += (size_t)gridDim.x * SM_NT) {
     const int b = (int)(i / hw);
-    const float lb = a.workspace[ws.lb + b * 2], sc = a.workspace[ws.lb + b * 2 + 1];   // sc = 1 / (mean + 1e-7)
-    a.grad_disp[i] = (a.grad_disp[i] - lb / (float)hw) * sc;
+    const float lb = a.workspace[ws.stats + (size_t)b * 4 + term * 2], sc = a.workspace[ws.stats + (size_t)b * 4 + term * 2 + 1];
+    g[i] = (g[i] - lb / (float)hw) * sc;
   }
 }
 
-inline int smooth_tiles(int height, int width, int* tx) {
-  int x = (width + SM_TW - 1) / SM_TW, y = (height + SM_TH - 1) / SM_TH;
+inline int smooth_tiles(int height, int width, int vec, int* tx) {
+  int x = (width + 32 * vec - 1) / (32 * vec), y = (height + SM_TH - 1) / SM_TH;
   if (tx) *tx = x;
   return x * y;
 }
@@ -163,7 +215,7 @@ inline int smooth_tiles(int height, int width, int* tx) {
 using namespace mal;
 
 extern "C" size_t mal_smooth_workspace_floats(int batch, int height, int width) {
-  return smooth_ws(batch, smooth_tiles(height, width, nullptr)).total;
+  return smooth_ws(batch, smooth_tiles(height, width, 1, nullptr)).total;   // the scalar tiling is the larger one
 }
 
 extern "C" int mal_smooth_forward(const mal_smooth_args* args, mal_stream_t stream) {
@@ -174,31 +226,35 @@ extern "C" int mal_smooth_forward(const mal_smooth_args* args, mal_stream_t stre
   MAL_REQUIRE(a.batch <= 65535, "mal_smooth_forward: batch %d exceeds gridDim.z", a.batch);
   MAL_REQUIRE(a.disp && a.img && a.workspace && a.loss, "mal_smooth_forward: disp/img/workspace/loss are required");
   if (a.with_grad) MAL_REQUIRE(a.grad_disp, "mal_smooth_forward: with_grad needs grad_disp");
+  const bool dual = a.disp_b != nullptr;
+  if (dual) MAL_REQUIRE(a.loss_b && (!a.with_grad || a.grad_disp_b), "mal_smooth_forward: disp_b needs loss_b (and grad_disp_b)");
+  if (a.defer_fix) MAL_REQUIRE(a.stats, "mal_smooth_forward: defer_fix needs stats");
   cudaStream_t st = (cudaStream_t)stream;
+  auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool vec = a.width % 4 == 0 && al(a.disp) && al(a.img) && al(a.grad_disp) && al(a.disp_b) && al(a.grad_disp_b);
   int tiles_x;
-  const int tiles = smooth_tiles(a.height, a.width, &tiles_x);
-  const int hw = a.height * a.width;
-  if (a.normalise) {
-    launch(smooth_mean_kernel, dim3(SM_SPLIT, a.batch), dim3(1024), 0, st, a.disp, hw,
-           a.workspace + smooth_ws(a.batch, tiles).mean_part);
-    int rc = check_launch("smooth_mean_kernel");
-    if (rc) return rc;
-  }
+  const int tiles = smooth_tiles(a.height, a.width, vec ? 4 : 1, &tiles_x);
+  const SmoothWs ws = smooth_ws(a.batch, tiles);
+  cudaMemsetAsync(a.workspace + ws.tickets, 0, (size_t)(a.batch + 1) * sizeof(unsigned), st);
   // gdx.mean() over (B,1,H,W-1) and gdy.mean() over (B,1,H-1,W)
   const float inv_nx = (float)(1.0 / ((double)a.batch * a.height * (a.width - 1)));
   const float inv_ny = (float)(1.0 / ((double)a.batch * (a.height - 1) * a.width));
   dim3 grid(tiles_x, tiles / tiles_x, a.batch);
-  launch(smooth_main_kernel, grid, dim3(SM_NT), 0, st, a, inv_nx, inv_ny, tiles_x, tiles);
-  int rc = check_launch("smooth_main_kernel");
+  if (vec) {
+    if (dual) launch(smooth_kernel<4, true>, grid, dim3(SM_NT), 0, st, a, inv_nx, inv_ny, tiles_x, tiles);
+    else launch(smooth_kernel<4, false>, grid, dim3(SM_NT), 0, st, a, inv_nx, inv_ny, tiles_x, tiles);
+  } else {
+    if (dual) launch(smooth_kernel<1, true>, grid, dim3(SM_NT), 0, st, a, inv_nx, inv_ny, tiles_x, tiles);
+    else launch(smooth_kernel<1, false>, grid, dim3(SM_NT), 0, st, a, inv_nx, inv_ny, tiles_x, tiles);
+  }
+  int rc = check_launch("smooth_kernel");
   if (rc) return rc;
-  launch(smooth_finalize_kernel, dim3(1), dim3(1024), (size_t)a.batch * 8 + 16, st, a, tiles);
-  rc = check_launch("smooth_finalize_kernel");
-  if (rc) return rc;
-  if (a.with_grad && a.normalise) {
-    size_t total = (size_t)a.batch * hw;
+  if (a.with_grad && a.normalise && !a.defer_fix) {
+    size_t total = (size_t)a.batch * a.height * a.width;
     size_t blk = (total + SM_NT - 1) / SM_NT;
     if (blk > 148 * 8) blk = 148 * 8;
-    launch(smooth_fix_kernel, dim3((unsigned)blk), dim3(SM_NT), 0, st, a, tiles);
+    for (int term = 0; term < (dual ? 2 : 1); term++)
+      launch(smooth_fix_kernel, dim3((unsigned)blk), dim3(SM_NT), 0, st, a, tiles, term);
     rc = check_launch("smooth_fix_kernel");
   }
   return rc;

@@ -58,6 +58,13 @@ __global__ void __launch_bounds__(ST_NT) step_combine_kernel(const mal_step_comb
       gc[0] = a.g_cons[e]; gd[0] = a.g_distil[e];
       if (a.g_distil_mono) gm[0] = a.g_distil_mono[e];
     }
+    if (a.smooth_stats) {   // chain the smoothness planes through disp / (mean + 1e-7): (g - L_b / HW) * s_b
+      const size_t hw = (size_t)a.height * a.width;
+      const float* sv = a.smooth_stats + (e / hw) * 4;   // a vector never straddles two samples (HW % VEC == 0)
+      const float lt = __ldg(sv) / (float)hw, sct = __ldg(sv + 1), ls = __ldg(sv + 2) / (float)hw, scs = __ldg(sv + 3);
+#pragma unroll
+      for (int v = 0; v < VEC; v++) { st[v] = (st[v] - lt) * sct; ss[v] = (ss[v] - ls) * scs; }
+    }
     float ot[VEC], os[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
@@ -116,7 +123,7 @@ extern "C" int mal_step_combine(const mal_step_combine_args* args, mal_stream_t 
               "mal_step_combine: a required pointer is NULL");
   const size_t n = (size_t)a.batch * a.height * a.width;
   auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  const bool vec = n % 4 == 0 && al(a.gd_teacher) && al(a.gs_teacher) && al(a.gd_student) && al(a.gs_student) &&
+  const bool vec = ((size_t)a.height * a.width) % 4 == 0 && al(a.gd_teacher) && al(a.gs_teacher) && al(a.gd_student) && al(a.gs_student) &&
                    al(a.g_cons) && al(a.g_distil) && al(a.g_distil_mono) && al(a.grad_disp_teacher) &&
                    al(a.grad_disp_student);
   size_t blk = (n / (vec ? 4 : 1) + ST_NT - 1) / ST_NT;

@@ -66,9 +66,9 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
-    finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
-    stream ordered after this call): a scheduler uses it to keep the tiny reduction kernel off the critical
-    path between two heavy kernels."""
+    The per-tile partial sums are reduced by the kernel's own last CTAs (ticketed, deterministic).
+    finalize=False skips that: `sums` / `grad_P` stay unreduced until photo_finalize(handle, out) is called
+    (on any stream ordered after this call) - or for good, when only the per-pixel maps are wanted."""
     B, C3, H, W = target.shape
     if C3 != 3:
         raise ValueError("target must be (B,3,H,W)")
@@ -126,7 +126,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     a.skip_finalize = 0 if finalize else 1
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
-    LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
+    LAUNCHES[0] += 1   # photo_kernel (its last CTAs do the reduction unless finalize=False)
     out["_keepalive"] = (partials,)
     out["_args"] = a
     return out
@@ -185,19 +185,28 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     return out
 
 
-def smooth(handle, *, disp, img, normalise=True, with_grad=False):
-    """mal_smooth_forward -> {"loss": (1,), "grad_disp": (B,1,h,w)}."""
+def smooth(handle, *, disp, img, normalise=True, with_grad=False, disp_b=None, defer_fix=False):
+    """mal_smooth_forward -> {"loss": (1,), "grad_disp": (B,1,h,w)} (+ "loss_b", "grad_disp_b" with `disp_b`: a second
+    disparity scored against the same image in the same launch; + "stats" (B,2,2)).  defer_fix leaves the
+    gradient planes un-chained through the mean-normalisation for mal_step_combine(smooth_stats=...)."""
     B, _, h, w = disp.shape
     disp, img = _f32(disp, "disp", (B, 1, h, w)), _f32(img, "img", (B, 3, h, w))
-    dev = _same_device([disp, img])
+    disp_b = _f32(disp_b, "disp_b", (B, 1, h, w))
+    dev = _same_device([disp, img, disp_b])
     new = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    out = {"loss": new((1,)), "grad_disp": new((B, 1, h, w)) if with_grad else None}
+    dual = disp_b is not None
+    out = {"loss": new((1,)), "grad_disp": new((B, 1, h, w)) if with_grad else None,
+           "loss_b": new((1,)) if dual else None, "grad_disp_b": new((B, 1, h, w)) if (with_grad and dual) else None,
+           "stats": new((B, 2, 2))}
     ws = new((handle.mal_smooth_workspace_floats(B, h, w),))
     a = _capi.SmoothArgs()
     a.batch, a.height, a.width, a.normalise, a.with_grad = B, h, w, int(normalise), int(with_grad)
     a.disp, a.img, a.grad_disp, a.workspace, a.loss = _ptr(disp), _ptr(img), _ptr(out["grad_disp"]), _ptr(ws), _ptr(out["loss"])
+    a.disp_b, a.grad_disp_b, a.loss_b = _ptr(disp_b), _ptr(out["grad_disp_b"]), _ptr(out["loss_b"])
+    a.defer_fix, a.stats = int(bool(defer_fix) and normalise and with_grad), _ptr(out["stats"])
     _capi.check(handle.mal_smooth_forward(C.byref(a), _stream(disp)), handle)
-    LAUNCHES[0] += 2 + int(normalise) + int(normalise and with_grad)   # [mean] main finalize [fix]
+    fix = normalise and with_grad and not defer_fix
+    LAUNCHES[0] += 1 + (int(fix) * (2 if dual else 1))   # smooth_kernel [+ smooth_fix_kernel per term]
     out["_keepalive"] = (ws,)
     return out
 
@@ -332,7 +341,7 @@ def ssim_backward(handle, x, y, grad_out, want_grad_y=True):
 
 def step_combine(handle, *, batch, height, width, weights, sums_teacher, sums_student, smooth_teacher,
                  smooth_student, main_sums, K, gd_teacher, gs_teacher, gP_teacher, gd_student, gs_student,
-                 g_cons, g_distil, g_distil_mono=None, smoothness=1e-3):
+                 g_cons, g_distil, g_distil_mono=None, smoothness=1e-3, smooth_stats=None):
     """mal_step_combine -> {"scalars": (8,), "grad_disp_teacher", "grad_disp_student", "grad_T": [2 x (B,4,4)]}."""
     dev = gd_teacher.device
     plane = (batch, 1, height, width)
@@ -350,6 +359,7 @@ def step_combine(handle, *, batch, height, width, weights, sums_teacher, sums_st
     a.gd_student, a.gs_student = _ptr(_f32(gd_student, "gd_student", plane)), _ptr(_f32(gs_student, "gs_student", plane))
     a.g_cons, a.g_distil = _ptr(_f32(g_cons, "g_cons", plane)), _ptr(_f32(g_distil, "g_distil", plane))
     a.g_distil_mono = _ptr(_f32(g_distil_mono, "g_distil_mono", plane))
+    a.smooth_stats = _ptr(_f32(smooth_stats, "smooth_stats", (batch, 2, 2)))
     a.scalars = _ptr(out["scalars"])
     a.grad_disp_teacher, a.grad_disp_student = _ptr(out["grad_disp_teacher"]), _ptr(out["grad_disp_student"])
     a.grad_T[0], a.grad_T[1] = _ptr(out["grad_T"][0]), _ptr(out["grad_T"][1])

@@ -152,23 +152,21 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
                                apply_confidence=True, want_missing=False)
         mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
                                  mono_is_disp=True, min_depth=lo, max_depth=hi)
-    with branch(1):   # smoothness of both disparities
-        sm_t = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True)
-        sm_s = raw.smooth(handle, disp=multi, img=tgt, normalise=True, with_grad=True)
-    # main chain: identity -> teacher -> ensemble.  The per-pass reductions (photo_finalize_kernel: 12 CTAs,
-    # ~6 us) are not needed before step_combine, so each is forked onto the smoothness branch, where it runs
-    # in the tail of the next heavy kernel instead of between two of them.
+    with branch(1):   # smoothness of both disparities: one launch, the chain through the normalisation is
+        # applied by mal_step_combine
+        sm = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True, disp_b=multi, defer_fix=True)
+        sm_t = {"loss": sm["loss"], "grad_disp": sm["grad_disp"], "_k": sm}
+        sm_s = {"loss": sm["loss_b"], "grad_disp": sm["grad_disp_b"], "stats": sm["stats"]}
+    # main chain: identity -> teacher -> ensemble.  The per-pass reductions run inside the photometric kernel
+    # (its last CTAs, ticketed), so there is nothing to schedule around them.
     def later(out):
-        with branch(1):
-            raw.photo_finalize(handle, out)
         return out
 
     # (the identity and ensemble passes only feed their per-pixel maps forward: their sums are never read)
     ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
                       finalize=False)["min_reproj"]
     teacher = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None,
-                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, finalize=False,
-                              **geom))
+                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, **geom))
     ens = None
     if not opt.no_ens:
         ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
@@ -176,8 +174,7 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     branch.join(0)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
     student = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
-                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, finalize=False,
-                              **geom))
+                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, **geom))
     dual = bool(opt.dual_distil) and ens is None
     mt = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
                         mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
@@ -199,7 +196,7 @@ def fused_step_tail(handle, b, opt, weights, ctx):
                             gd_teacher=teacher["grad_depth"], gs_teacher=sm_t["grad_disp"],
                             gP_teacher=teacher["grad_P"], gd_student=student["grad_depth"],
                             gs_student=sm_s["grad_disp"], g_cons=mt["grad_cons"], g_distil=mt["grad_distil"],
-                            g_distil_mono=mt["grad_distil_mono"])
+                            g_distil_mono=mt["grad_distil_mono"], smooth_stats=sm_s["stats"])
     outputs = {"cost_volume": head["cost_volume"], "lowest_cost": head["lowest_cost"],
                "confidence_mask": head["confidence"], "consistency_mask": mask,
                "mal_distil_index": mt["distil_index"], "consistency_target/0": mt["consistency_target"],

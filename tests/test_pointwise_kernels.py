@@ -39,6 +39,32 @@ def test_smooth_loss_and_gradient(backend, shape, normalise):
     assert torch.equal(out2["loss"], out["loss"])
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("shape", [(2, 32, 48), (1, 19, 77)])   # 48: 128-bit path; 77: scalar path
+def test_smooth_two_disparities_one_launch(backend, shape):
+    """Teacher and student disparity against the same image in one launch (the edge weights are shared), and
+    the deferred chain through the mean-normalisation: (g - L_b / HW) * s_b  ==  the single-term results."""
+    h, dev = handle_and_device(backend)
+    B, H, W = shape
+    inputs, t = make_photometric_inputs(B, H, W, seed=33)
+    img = inputs[("color", 0, 0)].to(dev)
+    da, db = t[("mono_disp", 0)].to(dev), t[("multi_disp", 0)].to(dev)
+    one_a = raw.smooth(h, disp=da, img=img, normalise=True, with_grad=True)
+    one_b = raw.smooth(h, disp=db, img=img, normalise=True, with_grad=True)
+    two = raw.smooth(h, disp=da, img=img, normalise=True, with_grad=True, disp_b=db)
+    assert torch.equal(two["loss"], one_a["loss"]) and torch.equal(two["loss_b"], one_b["loss"])
+    assert torch.equal(two["grad_disp"], one_a["grad_disp"]) and torch.equal(two["grad_disp_b"], one_b["grad_disp"])
+    lazy = raw.smooth(h, disp=da, img=img, normalise=True, with_grad=True, disp_b=db, defer_fix=True)
+    st = lazy["stats"]
+    for g, want, term in ((lazy["grad_disp"], one_a["grad_disp"], 0), (lazy["grad_disp_b"], one_b["grad_disp"], 1)):
+        fixed = (g - st[:, term, 0].view(B, 1, 1, 1) / (H * W)) * st[:, term, 1].view(B, 1, 1, 1)
+        assert _gerr(fixed.cpu(), want.cpu()) < 1e-6
+    # against the oracle as well
+    for d, loss in ((t[("mono_disp", 0)], two["loss"]), (t[("multi_disp", 0)], two["loss_b"])):
+        want = O.normalised_smooth_loss(d, inputs[("color", 0, 0)])
+        assert abs(float(loss) - float(want)) <= LOSS_RTOL * abs(float(want))
+
+
 def _main_case(B, H, W, seed):
     inputs, t = make_photometric_inputs(B, H, W, seed=seed)
     gen = torch.Generator().manual_seed(seed + 1)
