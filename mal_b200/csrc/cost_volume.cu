@@ -186,7 +186,7 @@ __device__ __noinline__ float pooled_chunk_l1(const mal_cost_volume_args& a, con
 }
 
 template <int CONV, int MINB, bool DYN>
-__global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp) {
+__global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = a.height, w = a.width, hw = h * w;
   const int nb = a.num_bins, nchunks = Cp / CV_CHUNK, nquads = Cp / 4;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
         float tx = 0.0f, ty = 0.0f;
         if (inner) {
           float depth = __ldg(a.bins + g0 + k);
-          GridPoint gp = project_grid<CONV>(geom->P, ray, depth, a.eps, h, w);
+          GridPoint gp = project_grid<CONV>(geom->P, ray, depth, a.eps, h, w, &sdiv);
           // edge mask on the sampling location (resnet_encoder.py:196-201)
           float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
           float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
@@ -459,7 +459,7 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
 }
 
 template <int CONV, int MINB>
-__global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp) {
+__global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
   __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
   __shared__ int s_o[4][CQ_G][8];                          // [warp][plane][pixel] tap origin or -1
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       for (int u = 0; u < 2; u++) {
         const int kk = k0 + sub + 4 * u;
         const float depth = __ldg(a.bins + min(kk, nb - 1));
-        const GridPoint gp = project_grid<CONV>(geom.P, ray, depth, a.eps, h, w);
+        const GridPoint gp = project_grid<CONV>(geom.P, ray, depth, a.eps, h, w, &sdiv);
         const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
         const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
         const bool ok = inner && kk < nb && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2);
@@ -728,6 +728,7 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     if (rc) return rc;
   }
   const int tiles = (hw + CV_PX - 1) / CV_PX;
+  const SizeDiv sdiv = size_div(a.height, a.width, a.convention);
   const size_t smem = cv_smem_bytes(Cp / CV_CHUNK, a.num_bins);
   MAL_REQUIRE(smem <= 227 * 1024, "mal_cost_volume_forward: %d bins x %d channels need %zu B of shared memory",
               a.num_bins, a.channels, smem);
@@ -738,18 +739,18 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   if (const char* e = getenv("MAL_CV_MINB")) minb = atoi(e);
 #define MAL_CV_LAUNCH(CONV_)                                                                         \
   do {                                                                                               \
-    if (dyn) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp);             \
-    else if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
-    else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp); \
-    else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp);                \
+    if (dyn) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);             \
+    else if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv); \
+    else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv); \
+    else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);                \
   } while (0)
   if (quad) {
     const size_t qsmem = cq_smem_bytes(a.num_bins);
 #define MAL_CQ_LAUNCH(CONV_)                                                                              \
   do {                                                                                                    \
-    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp);            \
-    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp);       \
-    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp);                      \
+    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);            \
+    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);       \
+    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                      \
   } while (0)
     if (a.convention == MAL_CONV_MANYDEPTH) MAL_CQ_LAUNCH(MAL_CONV_MANYDEPTH);
     else MAL_CQ_LAUNCH(MAL_CONV_DUALREFINE);

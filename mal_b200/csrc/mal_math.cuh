@@ -13,6 +13,8 @@
 // The contract is replayed on the host against torch by the CPU twin (tests/emu): the golden and
 // oracle tests demand torch.equal on every selection, min-reprojection and cost-volume value.
 #pragma once
+#include <cstdlib>
+
 #include "mal_common.cuh"
 
 namespace mal {
@@ -50,9 +52,43 @@ struct Sample {
 
 struct GridPoint { float gx, gy, X, Y, Zp; };
 
+// Project3D divides every coordinate by an image-size constant ((W-1), (H-1) or W, H).  For the constants below
+// the 3-instruction sequence of xdivc (q = RN(x*r), rem = fma(-C,q,x), RN(q + rem*r), r = RN(1/C)) returns the
+// correctly rounded x / C for EVERY finite float x - checked exhaustively over all 2^32 inputs on the host
+// (tests/test_exact_arithmetic.py, MAL_EXHAUSTIVE=1; the only difference is the sign of a zero result for
+// x = -0, which the following "- 0.5" / "- 1" absorbs).  Any other size keeps the IEEE division (48, 160, 192, 640
+// - DualRefine's W, H - fail the check for subnormal quotients and are therefore not listed).
+struct SizeDiv { float cw, rw, ch, rh; int fast; };
+inline bool size_div_verified(int c) {
+  static const int ok[] = {3, 9, 47, 95, 127, 159, 191, 255, 383, 511, 639, 1023};
+  if (c > 0 && (c & (c - 1)) == 0) return true;   // a power of two divides exactly by multiplying
+  for (int v : ok)
+    if (v == c) return true;
+  return false;
+}
+inline SizeDiv size_div(int H, int W, int convention) {
+  const int dw = convention == MAL_CONV_MANYDEPTH ? W - 1 : W, dh = convention == MAL_CONV_MANYDEPTH ? H - 1 : H;
+  SizeDiv d;
+  d.cw = (float)dw; d.ch = (float)dh;
+  d.rw = 1.0f / d.cw; d.rh = 1.0f / d.ch;
+  d.fast = (size_div_verified(dw) && size_div_verified(dh)) ? 1 : 0;
+#ifndef MAL_EMU
+  if (getenv("MAL_NO_FASTDIV")) d.fast = 0;   // tuning runs only
+#endif
+  return d;
+}
+__device__ __forceinline__ float xdiv_size(float x, float c, float r, bool fast) {
+  if (fast) {
+    const float q = xmul(x, r);
+    return xfma(xfma(-c, q, x), r, q);
+  }
+  return xdiv(x, c);
+}
+
 // depth * ray -> P@[cam;1] -> /(z+eps) -> Project3D normalisation to [-1,1]
 template <int CONV>
-__device__ __forceinline__ GridPoint project_grid(const float* P, Ray ray, float depth, float eps, int H, int W) {
+__device__ __forceinline__ GridPoint project_grid(const float* P, Ray ray, float depth, float eps, int H, int W,
+                                                  const SizeDiv* sd = nullptr) {
   float cx = xmul(depth, ray.x), cy = xmul(depth, ray.y), cz = xmul(depth, ray.z);
   GridPoint g;
   g.X = xfma(P[3], 1.0f, xfma(P[2], cz, xfma(P[1], cy, xmul(P[0], cx))));
@@ -60,12 +96,16 @@ __device__ __forceinline__ GridPoint project_grid(const float* P, Ray ray, float
   float Z = xfma(P[11], 1.0f, xfma(P[10], cz, xfma(P[9], cy, xmul(P[8], cx))));
   g.Zp = xadd(Z, eps);
   float px = xdiv(g.X, g.Zp), py = xdiv(g.Y, g.Zp);
+  const bool fast = sd != nullptr && sd->fast;
+  const float cw = sd ? sd->cw : (float)(CONV == MAL_CONV_MANYDEPTH ? W - 1 : W);
+  const float ch = sd ? sd->ch : (float)(CONV == MAL_CONV_MANYDEPTH ? H - 1 : H);
+  const float rw = sd ? sd->rw : 0.0f, rh = sd ? sd->rh : 0.0f;
   if (CONV == MAL_CONV_MANYDEPTH) {
-    g.gx = xmul(xsub(xdiv(px, (float)(W - 1)), 0.5f), 2.0f);
-    g.gy = xmul(xsub(xdiv(py, (float)(H - 1)), 0.5f), 2.0f);
+    g.gx = xmul(xsub(xdiv_size(px, cw, rw, fast), 0.5f), 2.0f);
+    g.gy = xmul(xsub(xdiv_size(py, ch, rh, fast), 0.5f), 2.0f);
   } else {
-    g.gx = xsub(xdiv(xmul(2.0f, xadd(px, 0.5f)), (float)W), 1.0f);
-    g.gy = xsub(xdiv(xmul(2.0f, xadd(py, 0.5f)), (float)H), 1.0f);
+    g.gx = xsub(xdiv_size(xmul(2.0f, xadd(px, 0.5f)), cw, rw, fast), 1.0f);
+    g.gy = xsub(xdiv_size(xmul(2.0f, xadd(py, 0.5f)), ch, rh, fast), 1.0f);
   }
   return g;
 }
@@ -83,8 +123,8 @@ __device__ __forceinline__ float unnormalize(float g, int size) {
 // ... -> grid_sample unnormalise -> border clip
 template <int CONV>
 __device__ __forceinline__ Sample project_pixel(const float* P, Ray ray, float depth, float eps,
-                                                int H, int W) {
-  GridPoint g = project_grid<CONV>(P, ray, depth, eps, H, W);
+                                                int H, int W, const SizeDiv* sd = nullptr) {
+  GridPoint g = project_grid<CONV>(P, ray, depth, eps, H, W, sd);
   Sample s;
   s.X = g.X; s.Y = g.Y; s.Zp = g.Zp;
   float ux = unnormalize<CONV>(g.gx, W), uy = unnormalize<CONV>(g.gy, H);

@@ -10,6 +10,7 @@
 // cudaGetDriverEntryPoint, so the library does not link libcuda) and passed to the kernel inside a
 // __grid_constant__ parameter.  TMA needs a 16-byte aligned base, W * 4 a multiple of 16 and a box no larger
 // than the tensor; tile_map_encode() returns false otherwise and the caller falls back to the plain loader.
+// The box corner's x must be a multiple of 4 elements (16 bytes) as well - the kernel's tiling guarantees it.
 //
 // The CPU twin (MAL_EMU) keeps the geometry in a plain struct and copies synchronously.
 #pragma once
@@ -36,6 +37,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long*, int) {}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
 __device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
 __device__ __forceinline__ void tma_load_3d(float* dst, const TileMap* m, int x, int y, int n, unsigned long long*) {
+  // the hardware raises "illegal instruction" when the box does not start on a 16-byte boundary of the row
+  // (measured on B200: tools/ubench/tma_check.cu) or the destination is not 128-byte aligned
+  if ((x & 3) != 0 || ((uintptr_t)dst & 127) != 0) { fprintf(stderr, "cuda_emu: misaligned TMA box (x=%d, dst=%p)\n", x, (void*)dst); abort(); }
   for (int c = 0; c < m->bn; c++)
     for (int j = 0; j < m->bh; j++)
       for (int i = 0; i < m->bw; i++) {

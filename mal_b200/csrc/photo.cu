@@ -9,19 +9,17 @@
 //   A  (WARP mode) the two warped candidates are produced in place from the staged disparity:
 //      disp->depth->backproject->project->bilinear gather (border)
 //      (manydepth/layers.py:14-23,163-199, trainer.py:1122-1125)
-//   B  one thread scores TWO horizontally adjacent pixels: their 3x3 windows share a 3x4 block that arrives
-//      as six 64-bit shared loads per plane, and the x*x / x*y products of the block are formed once for
-//      both pixels.  3x3 SSIM + L1 per candidate (layers.py:243-257, loss_utils.py:46-55), min/argmin over
-//      candidates (:103), tie-break noise + automask (:105-109, :27-44), multi-frame mask (:192-194); masked
-//      partial sums (:112-113).  The candidate loop is rolled (one copy of the SSIM code whatever the number
-//      of candidates); the target-side moments are computed once per pixel up front.  With gradients, the
-//      SSIM derivative coefficients of the running minimum are left in shared memory for the ring of pixels
-//      around the tile.
+//   B  per pixel of the loss region: 3x3 SSIM + L1 per candidate (layers.py:243-257,
+//      loss_utils.py:46-55), min/argmin over candidates (:103), tie-break noise + automask
+//      (:105-109, :27-44), multi-frame mask (:192-194); masked partial sums (:112-113).
+//      With gradients, the SSIM derivative coefficients of the selected candidate are left in
+//      shared memory for the ring of pixels around the tile.  (A two-pixels-per-thread variant with 64-bit
+//      shared loads and shared products was measured: same instruction count, bank conflicts and spills -
+//      profiles/r2_notes.md.)
 //   C  (grad) per tile pixel: gather the 3x3 neighbourhood's coefficients (atomics-free SSIM
 //      backward), add the L1 term, then chain through the bilinear sampler, the projection and
 //      backprojection to d/d depth and d/d(K@T); per-CTA partials go to a workspace.
-//   D  the last CTA of a sample (ticket) reduces that sample's partials in a fixed order, the last sample
-//      forms the masked mean: deterministic, and no separate reduction launch.
+// A second tiny kernel reduces the per-CTA partials in a fixed order (deterministic).
 //
 // HBM traffic per pixel (WARP mode, 2+2 candidates, grad): reads 9 (target+2 src... gathers hit
 // L2/L1) x 4 B x 3 ch + depth/noise/identity/mask 16 B, writes min_reproj 4 + sel 1 + grad 4 B.
@@ -36,7 +34,9 @@ constexpr int PH_TW = 32;
 constexpr int PH_TH = 16;
 constexpr int PH_NT = 256;
 constexpr int PH_NPART = 26;  // 2 x 12 dL/dP + sum(w*reproj) + sum(w)
-constexpr int PH_VW = 36;     // value-tile row pitch: 144-byte rows (a legal TMA box), even (64-bit row loads)
+constexpr int PH_VW = 40;     // value-tile row pitch: the tile starts 4 columns left of the CTA's first pixel - a TMA box
+                              // must start on a 16-byte boundary of the row (measured: tools/ubench/tma_check.cu)
+constexpr int PH_OX = 4;
 
 struct PhotoTile {
   int HL, HV;          // loss halo (gradient ring), value halo = HL + 1
@@ -55,7 +55,8 @@ constexpr int PH_SMALL = 40 + 8 * PH_NPART + 8 + 4;   // Geom (padded), reductio
 inline size_t photo_smem_bytes(bool grad, bool warp, int ncand) {
   PhotoTile t = photo_tile(grad);
   size_t fl = (size_t)(1 + ncand) * t.TS + PH_SMALL;
-  if (grad) fl += (size_t)11 * t.LN;                 // the staged disparity aliases the coefficient planes
+  if (grad) fl += (size_t)10 * t.LN + (t.LN + 7) / 8 * 2;   // 9 coefficient planes, weights, selection bytes; the staged
+                                                        // disparity aliases the coefficient planes
   else if (warp) fl += (size_t)2 * ((t.VN + 31) / 32 * 32);
   return fl * 4 + 128;
 }
@@ -64,51 +65,16 @@ struct PhotoMaps {   // TMA descriptors of the tensors a CTA stages, one __grid_
   TileMap tgt, src[2], syn[2], depth, depth_b;
 };
 
-// 3 rows x 4 columns of a value-tile plane: the union of the 3x3 windows of two adjacent pixels
-__device__ __forceinline__ void ld_block(const float* p, float (&v)[3][4]) {
-#pragma unroll
-  for (int r = 0; r < 3; r++) {
-    const float2 lo = *reinterpret_cast<const float2*>(p + r * PH_VW);
-    const float2 hi = *reinterpret_cast<const float2*>(p + r * PH_VW + 2);
-    v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = hi.x; v[r][3] = hi.y;
-  }
-}
-// running row-major sum of pixel e's 3x3 window inside a block, as avg_pool2d accumulates it
-__device__ __forceinline__ float sum9_win(const float (&v)[3][4], int e) {
-  float s = v[0][e];
-  s = xadd(s, v[0][e + 1]); s = xadd(s, v[0][e + 2]);
-#pragma unroll
-  for (int r = 1; r < 3; r++) {
-    s = xadd(s, v[r][e]); s = xadd(s, v[r][e + 1]); s = xadd(s, v[r][e + 2]);
-  }
-  return s;
-}
-// ssim_terms with the target-side products handed in (mu_y*mu_y and sig_y are shared by every candidate)
-__device__ __forceinline__ SsimTerms ssim_terms_y(float mu_x, float mu_y, float mu_yy, float sig_y, float exx, float exy) {
-  SsimTerms t;
-  t.mu_x = mu_x; t.mu_y = mu_y;
-  const float mu_xx = xmul(mu_x, mu_x);
-  const float sig_x = xsub(exx, mu_xx);
-  const float sig_xy = xsub(exy, xmul(mu_x, mu_y));
-  t.A = xadd(xmul(xmul(2.0f, mu_x), mu_y), MAL_C1);
-  t.Bq = xadd(xmul(2.0f, sig_xy), MAL_C2);
-  t.Cq = xadd(xadd(mu_xx, mu_yy), MAL_C1);
-  t.D = xadd(xadd(sig_x, sig_y), MAL_C2);
-  t.n = xmul(t.A, t.Bq);
-  t.d = xmul(t.Cq, t.D);
-  t.v = xmul(xsub(1.0f, xdiv(t.n, t.d)), 0.5f);
-  return t;
-}
-
 template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC>
 __global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4)
 photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, const int ncand, const float min_disp,
-             const float disp_range, const int use_tma) {
+             const float disp_range, const int use_tma, const SizeDiv sdiv) {
   const PhotoTile tl = photo_tile(GRAD);
   const int tid = threadIdx.x;
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * PH_TW, y0 = blockIdx.y * PH_TH;
-  const int ox = x0 - tl.HV, oy = y0 - tl.HV;       // image coordinates of value-tile element (0, 0)
+  const int ox = x0 - PH_OX, oy = y0 - tl.HV;       // image coordinates of value-tile element (0, 0)
+  constexpr int BS = PH_OX - 1 - (GRAD ? 1 : 0);    // loss column lx's 3x3 window starts at value column lx + BS
   const int H = a.height, W = a.width;
   const size_t HW = (size_t)H * W;
   // low-resolution disparity, up-sampled on the fly (mal_photo_args.depth_height / depth_width)
@@ -129,15 +95,19 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   float* after = sx + (size_t)ncand * tl.TS;
   float* coef = after;                                // [9][LN]      (GRAD)
   float* lw = coef + 9 * tl.LN;                       // [LN] weights (GRAD)
-  int* lsel = reinterpret_cast<int*>(lw + tl.LN);     // [LN] selected candidate or -1
+  signed char* lsel = reinterpret_cast<signed char*>(lw + tl.LN);   // [LN] selected candidate or -1
   float* dep = after;                                 // [VN] disparity tile (aliases coef: dead before phase B)
   float* dep_b = dep + (tl.VN + 31) / 32 * 32;        // [VN] second disparity (ensemble pass, never with GRAD)
-  float* small = after + (GRAD ? 11 * tl.LN : (WARP ? 2 * ((tl.VN + 31) / 32 * 32) : 0));
+  float* small = after + (GRAD ? 10 * tl.LN + (tl.LN + 7) / 8 * 2 : (WARP ? 2 * ((tl.VN + 31) / 32 * 32) : 0));
   Geom* geom = reinterpret_cast<Geom*>(small);
   float* red = small + 40;                            // [8][PH_NPART]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red + 8 * PH_NPART + 8);
-  int* s_flag = reinterpret_cast<int*>(mbar + 1);
 
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+    // the finalize kernel's ticket (see photo_finalize_kernel); it launches after this kernel ends
+    float* tail = a.partials + (size_t)gridDim.x * gridDim.y * gridDim.z * PH_NPART;
+    reinterpret_cast<unsigned*>(tail + (size_t)gridDim.z * 2)[gridDim.z] = 0u;
+  }
   // ---- phase 0: camera constants, TMA requests ------------------------------------------------------------
   if (tid == 0 && use_tma) mbar_init(mbar, 1);
   if (WARP) {
@@ -177,8 +147,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   }
   // Elements outside the image: TMA delivered zeros; ReflectionPad2d(1) wants the mirrored pixel (and tiles
   // hanging over the right / bottom edge want any in-range value).  Only border CTAs have such elements.
-  // Without TMA the same loop stages every element.  Thread i patches exactly the elements it consumes in
-  // phase A (same index map), the rest is consumed after the barrier that ends phase A.
+  // Without TMA the same loop stages every element.
   const bool over = ox < 0 || oy < 0 || ox + PH_VW > W || oy + tl.VH > H;
   if (!use_tma || over) {
     for (int i = tid; i < tl.VN; i += PH_NT) {
@@ -210,13 +179,15 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
         if (a.depth_b) dep_b[i] = __ldg(a.depth_b + (size_t)b * HW + o);
       }
     }
+    if (WARP) __syncthreads();   // phase A reads the disparity tile through a different index map (CTA-uniform branch)
   }
 
   // ---- phase A: warped candidates -------------------------------------------------------------------------
   if (WARP) {
-    for (int i = tid; i < tl.VN; i += PH_NT) {
-      const int ty = i / PH_VW, tx = i - ty * PH_VW;
-      if (!GRAD && tx >= PH_TW + 2) continue;   // without the gradient ring only 34 columns are read
+    constexpr int NEED = PH_TW + 2 * (GRAD ? 1 : 0) + 2;   // only the columns some 3x3 window reaches
+    for (int j = tid; j < NEED * tl.VH; j += PH_NT) {
+      const int ty = j / NEED, tx = BS + j - ty * NEED;
+      const int i = ty * PH_VW + tx;
       const int ry = min(max(reflect_index(oy + ty, H), 0), H - 1), rx = min(max(reflect_index(ox + tx, W), 0), W - 1);
       float dv;
       if (lowres) {   // F.interpolate(disp, [H, W], bilinear) read straight from the low-resolution plane
@@ -231,7 +202,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       Ray ray = pixel_ray(geom->iK, (float)rx, (float)ry);
 #pragma unroll
       for (int f = 0; f < 2; f++) {
-        Sample s = project_pixel<CONV>(geom->P[f], ray, dv, a.eps, H, W);
+        Sample s = project_pixel<CONV>(geom->P[f], ray, dv, a.eps, H, W, &sdiv);
         Taps t = make_taps(s.ix, s.iy, H, W);
         const float* src = a.src[f] + (size_t)b * 3 * HW;
 #pragma unroll
@@ -241,147 +212,121 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   }
   __syncthreads();
 
-  // ---- phase B: losses, selection, weights ---------------------------------------------------------------
+  // ---- phase B: losses, selection, weights -----------------------------------------------
   const bool automask = a.identity_min != nullptr;
-  // warped candidates always carry a gradient; the temporal-hint candidates when the caller asked
-  // for d/d syn (autograd then carries it into the warped images image_synthesis copied from)
-  const bool syn_grad = GRAD && (SYNG || !WARP) && a.grad_syn[0] != nullptr;
-  const float keep = a.sample_mask ? xsub(1.0f, __ldg(a.sample_mask + b)) : 1.0f;
   float acc_loss = 0.0f, acc_w = 0.0f;
-  const int lwp = tl.LW / 2;
-  for (int j = tid; j < tl.LH * lwp; j += PH_NT) {
-    const int ly = j / lwp, lx = 2 * (j - ly * lwp);
-    const int i0 = ly * tl.LW + lx;                       // loss-tile index of the left pixel
-    const int gy = y0 - tl.HL + ly, gxl = x0 - tl.HL + lx;
-    const bool row_ok = gy >= 0 && gy < H;
-    bool in_img[2];
-    in_img[0] = row_ok && gxl >= 0 && gxl < W;
-    in_img[1] = row_ok && gxl + 1 >= 0 && gxl + 1 < W;
-    if (!in_img[0] && !in_img[1]) {
-      if (GRAD) { lsel[i0] = -1; lsel[i0 + 1] = -1; lw[i0] = 0.0f; lw[i0 + 1] = 0.0f; }
+  // Work is handed out in warp-sized tasks so that the 32 lanes of a task read 32 consecutive
+  // words of a value-tile row (conflict-free): LH row tasks cover columns 0..31 of the loss
+  // region; the LW-32 leftover columns (the gradient halo) are packed column-major into extra tasks.
+  const int extra_items = (tl.LW - 32) * tl.LH;
+  const int ntasks = tl.LH + (extra_items + 31) / 32;
+  for (int task = tid >> 5; task < ntasks; task += PH_NT / 32) {
+    int ly, lx;
+    if (task < tl.LH) {
+      ly = task; lx = tid & 31;
+    } else {
+      const int j = (task - tl.LH) * 32 + (tid & 31);
+      if (j >= extra_items) continue;
+      ly = j % tl.LH; lx = 32 + j / tl.LH;
+    }
+    const int i = ly * tl.LW + lx;
+    int gy = y0 - tl.HL + ly, gx = x0 - tl.HL + lx;
+    bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    if (!in_img) {
+      if (GRAD) { lsel[i] = -1; lw[i] = 0.0f; }
       continue;
     }
-    const int vb = ly * PH_VW + lx;                       // top-left of the pair's 3x4 block in a value plane
+    const int vc = (ly + 1) * PH_VW + lx + BS + 1;   // window centre in a value plane
     // per-pixel planes are fetched now so their latency hides behind the SSIM arithmetic
-    const size_t po = (size_t)b * HW + (size_t)gy * W + gxl;
-    float p_ident[2] = {0.0f, 0.0f}, p_noise[2] = {0.0f, 0.0f}, p_mask[2] = {1.0f, 1.0f};
+    const size_t po = (size_t)b * HW + (size_t)gy * W + gx;
+    float p_ident = 0.0f, p_noise = 0.0f, p_mask = 1.0f;
+    if (automask) { p_ident = __ldg(a.identity_min + po); p_noise = __ldg(a.noise + po); }
+    if (a.pixel_mask) p_mask = __ldg(a.pixel_mask + po);
+    float ssum[NC], lsum[NC];   // NC: compiled-in candidate capacity (2 or 4); ncand <= NC are live
+    float cf0[9], cf1[9];
 #pragma unroll
-    for (int e = 0; e < 2; e++)
-      if (in_img[e]) {
-        if (automask) { p_ident[e] = __ldg(a.identity_min + po + e); p_noise[e] = __ldg(a.noise + po + e); }
-        if (a.pixel_mask) p_mask[e] = __ldg(a.pixel_mask + po + e);
-      }
-    // the weight a pixel carries if the automask keeps it (w below is this, or 0)
-    float wpre[2];
+    for (int c = 0; c < 3; c++) {
+      float yw[9];
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      wpre[e] = 1.0f;
-      if (a.pixel_mask) wpre[e] = xmul(wpre[e], p_mask[e]);
-      if (a.sample_mask) wpre[e] = xmul(wpre[e], keep);
-    }
-    // target-side moments, once per pixel and channel
-    float muy[2][3], myy[2][3], sgy[2][3];
-    if (!a.no_ssim) {
+      for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        float y[3][4], yy[3][4];
-        ld_block(sy + c * tl.VN + vb, y);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) yy[r][q] = xmul(y[r][q], y[r][q]);
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          muy[e][c] = xdivc<9>(sum9_win(y, e));
-          const float eyy = xdivc<9>(sum9_win(yy, e));
-          myy[e][c] = xmul(muy[e][c], muy[e][c]);
-          sgy[e][c] = xsub(eyy, myy[e][c]);
-        }
-      }
-    }
-    float rmin[2] = {0.0f, 0.0f};
-    int idx[2] = {0, 0};
-#pragma unroll 1
-    for (int k = 0; k < ncand; k++) {
-      const float* X = sx + (size_t)k * tl.TS + vb;
-      float ss[2] = {0.0f, 0.0f}, ls[2] = {0.0f, 0.0f};
-      float cf[2][9];
-      const bool want_cf = GRAD && k < 2 && !a.no_ssim;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        float y[3][4], x[3][4];
-        ld_block(sy + c * tl.VN + vb, y);
-        ld_block(X + c * tl.VN, x);
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const float l1 = fabsf(xsub(y[1][e + 1], x[1][e + 1]));
-          ls[e] = (c == 0) ? l1 : xadd(ls[e], l1);
-        }
-        if (!a.no_ssim) {
-          float xx[3][4], xy[3][4];
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) { xx[r][q] = xmul(x[r][q], x[r][q]); xy[r][q] = xmul(x[r][q], y[r][q]); }
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const float mu_x = xdivc<9>(sum9_win(x, e));
-            const float exx = xdivc<9>(sum9_win(xx, e));
-            const float exy = xdivc<9>(sum9_win(xy, e));
-            const SsimTerms t = ssim_terms_y(mu_x, muy[e][c], myy[e][c], sgy[e][c], exx, exy);
-            const float sv = clamp01(t.v);
-            ss[e] = (c == 0) ? sv : xadd(ss[e], sv);
-            if (want_cf) ssim_coefs(t, cf[e][c * 3], cf[e][c * 3 + 1], cf[e][c * 3 + 2]);
-          }
-        }
+        for (int dx = 0; dx < 3; dx++) yw[dy * 3 + dx] = sy[c * tl.VN + vc + (dy - 1) * PH_VW + dx - 1];
+      float mu_y = 0.f, eyy = 0.f;
+      if (!a.no_ssim) {
+        mu_y = xdivc<9>(sum9(yw));
+        eyy = xdivc<9>(sum9_prod(yw, yw));
       }
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const float l1m = xdivc<3>(ls[e]);
-        const float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ss[e])), xmul(0.15f, l1m));
-        if (k == 0 || lk < rmin[e]) {          // first index wins ties, like torch.min
-          rmin[e] = lk; idx[e] = k;
-          if (want_cf && in_img[e]) {
-            const float sc = wpre[e] * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
+      for (int k = 0; k < NC; k++) {
+        if (k < ncand) {
+          const float* X = sx + (size_t)k * tl.TS + c * tl.VN + vc;
+          float xw[9];
 #pragma unroll
-            for (int q = 0; q < 9; q++) coef[q * tl.LN + i0 + e] = cf[e][q] * sc;
+          for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) xw[dy * 3 + dx] = X[(dy - 1) * PH_VW + dx - 1];
+          float l1 = fabsf(xsub(yw[4], xw[4]));
+          lsum[k] = (c == 0) ? l1 : xadd(lsum[k], l1);
+          if (!a.no_ssim) {
+            float mu_x = xdivc<9>(sum9(xw));
+            float exx = xdivc<9>(sum9_prod(xw, xw));
+            float exy = xdivc<9>(sum9_prod(xw, yw));
+            SsimTerms t = ssim_terms(mu_x, mu_y, exx, eyy, exy);
+            float sv = clamp01(t.v);
+            ssum[k] = (c == 0) ? sv : xadd(ssum[k], sv);
+            if (GRAD && k < 2) {
+              float al, be, ga;
+              ssim_coefs(t, al, be, ga);
+              if (k == 0) { cf0[c * 3] = al; cf0[c * 3 + 1] = be; cf0[c * 3 + 2] = ga; }
+              else        { cf1[c * 3] = al; cf1[c * 3 + 1] = be; cf1[c * 3 + 2] = ga; }
+            }
           }
         }
       }
     }
+    float rmin = 0.f;
+    int idx = 0;
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int i = i0 + e;
-      if (!in_img[e]) {
-        if (GRAD) { lsel[i] = -1; lw[i] = 0.0f; }
-        continue;
+    for (int k = 0; k < NC; k++) {
+      if (k < ncand) {
+        float l1m = xdivc<3>(lsum[k]);
+        float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
+        if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
       }
-      int mbit = 1;
-      if (automask) {
-        const float ident = xadd(p_ident[e], xmul(p_noise[e], 0.00001f));
-        mbit = (ident < rmin[e]) ? 0 : 1;  // argmin([reproj, identity]) == 0, first index wins ties
-      }
-      const float w = mbit ? wpre[e] : 0.0f;
-      const int lxe = lx + e;
-      const bool interior = ly >= tl.HL && ly < tl.HL + PH_TH && lxe >= tl.HL && lxe < tl.HL + PH_TW;
-      if (interior) {
-        if (a.min_reproj) a.min_reproj[po + e] = rmin[e];
-        if (a.selection) a.selection[po + e] = (uint8_t)(idx[e] | (mbit << 7));
-        if (a.weight) a.weight[po + e] = w;
-        acc_loss += xmul(rmin[e], w);
-        acc_w += w;
-      }
-      if (GRAD) {
-        const bool live = (idx[e] < 2 || syn_grad) && w != 0.0f;
-        lsel[i] = live ? idx[e] : -1;
-        lw[i] = w;
-        if (NC > 2 && live && idx[e] >= 2 && !a.no_ssim) {
+    }
+    int mbit = 1;
+    if (automask) {
+      float ident = xadd(p_ident, xmul(p_noise, 0.00001f));
+      mbit = (ident < rmin) ? 0 : 1;  // argmin([reproj, identity]) == 0, first index wins ties
+    }
+    float w = (float)mbit;
+    if (a.pixel_mask) w = xmul(w, p_mask);
+    if (a.sample_mask) w = xmul(w, xsub(1.0f, __ldg(a.sample_mask + b)));
+    const bool interior = ly >= tl.HL && ly < tl.HL + PH_TH && lx >= tl.HL && lx < tl.HL + PH_TW;
+    if (interior) {
+      if (a.min_reproj) a.min_reproj[po] = rmin;
+      if (a.selection) a.selection[po] = (uint8_t)(idx | (mbit << 7));
+      if (a.weight) a.weight[po] = w;
+      acc_loss += xmul(rmin, w);
+      acc_w += w;
+    }
+    if (GRAD) {
+      // warped candidates always carry a gradient; the temporal-hint candidates when the caller asked
+      // for d/d syn (autograd then carries it into the warped images image_synthesis copied from)
+      const bool syn_grad = (SYNG || !WARP) && a.grad_syn[0] != nullptr;
+      const bool live = (idx < 2 || syn_grad) && w != 0.0f;
+      lsel[i] = live ? idx : -1;
+      lw[i] = w;
+      if (live && !a.no_ssim) {
+        const float sc = w * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
+        if (NC <= 2 || idx < 2) {
+#pragma unroll
+          for (int j = 0; j < 9; j++) coef[j * tl.LN + i] = (idx == 0 ? cf0[j] : cf1[j]) * sc;
+        } else {
           // rare path: re-derive the SSIM terms of the selected temporal-hint candidate
-          const float sc = w * (0.85f / 27.0f);
-          const int vc = (ly + 1) * PH_VW + lxe + 1;      // window centre in a value plane
           for (int c = 0; c < 3; c++) {
             float yw[9], xw[9];
-            const float* X = sx + (size_t)idx[e] * tl.TS + c * tl.VN + vc;
+            const float* X = sx + (size_t)idx * tl.TS + c * tl.VN + vc;
 #pragma unroll
             for (int dy = 0; dy < 3; dy++)
 #pragma unroll
@@ -413,7 +358,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       int gy = y0 + qy, gx = x0 + qx;
       if (gy >= H || gx >= W) continue;
       const int lc = (qy + tl.HL) * tl.LW + qx + tl.HL;
-      const int vc = (qy + tl.HV) * PH_VW + qx + tl.HV;
+      const int vc = (qy + tl.HV) * PH_VW + qx + PH_OX;
       // d S / d (candidate image k) at this pixel, for a candidate that is given as an image: the
       // predictions of PRED mode, and the temporal-hint candidates (k >= 2) of either mode
       auto image_grad = [&](int k, float* out) {
@@ -527,7 +472,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
           const float* g = f == 0 ? g0 : g1;
           if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
           const float* P = geom->P[f];
-          Sample s = project_pixel<CONV>(P, ray, dv, a.eps, H, W);
+          Sample s = project_pixel<CONV>(P, ray, dv, a.eps, H, W, &sdiv);
           Taps t = make_taps(s.ix, s.iy, H, W);
           const float* src = a.src[f] + (size_t)b * 3 * HW;
           float gix = 0.f, giy = 0.f;
@@ -571,59 +516,23 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
     if (lane == 0) red[warp * PH_NPART + 25] = v;
   }
   __syncthreads();
+  if (warp != 0) return;   // the hand-over below is warp 0's business: the other warps leave the SM to the next CTA
   const int tiles = gridDim.x * gridDim.y;
-  if (tid < PH_NPART) {
+  if (lane < PH_NPART) {
     float s = 0.0f;
 #pragma unroll
-    for (int wv = 0; wv < PH_NT / 32; wv++) s += red[wv * PH_NPART + tid];
+    for (int wv = 0; wv < PH_NT / 32; wv++) s += red[wv * PH_NPART + lane];
     size_t blk = (size_t)b * tiles + blockIdx.y * gridDim.x + blockIdx.x;
-    a.partials[blk * PH_NPART + tid] = s;
-  }
-  if (a.skip_finalize) return;
-
-  // ---- phase D: ticketed reduction (the tickets were zeroed by a memset node ahead of this launch) ---------
-  // Whichever CTA of a sample finishes last sums that sample's per-CTA partials - one warp per value, lanes
-  // stride the tiles, fp64 - so the result does not depend on scheduling; the last sample then adds the B
-  // per-sample sums in sample order and forms the masked mean (loss_utils.py:113).
-  const int batch = gridDim.z;
-  float* tail = a.partials + (size_t)batch * tiles * PH_NPART;        // [batch][2] per-sample loss sums
-  unsigned* tickets = reinterpret_cast<unsigned*>(tail + (size_t)batch * 2);   // [batch] + [1]
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) *s_flag = (atomicAdd(tickets + b, 1u) == (unsigned)(tiles - 1)) ? 1 : 0;
-  __syncthreads();
-  if (!*s_flag) return;
-  __threadfence();
-  const volatile float* vp = a.partials;
-  for (int v = warp; v < PH_NPART; v += PH_NT / 32) {
-    if (!(GRAD && WARP) && v < 24) continue;   // without pose gradients only the two loss sums are live
-    double s = 0.0;
-    for (int t = lane; t < tiles; t += 32) s += (double)vp[((size_t)b * tiles + t) * PH_NPART + v];
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (v < 24) a.grad_P[b * 24 + v] = (float)s;
-      else tail[b * 2 + (v - 24)] = (float)s;
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0 && atomicAdd(tickets + batch, 1u) == (unsigned)(batch - 1)) {
-    __threadfence();
-    double ls = 0.0, ws = 0.0;
-    for (int i = 0; i < batch; i++) {
-      ls += (double)reinterpret_cast<volatile float*>(tail)[i * 2];
-      ws += (double)reinterpret_cast<volatile float*>(tail)[i * 2 + 1];
-    }
-    const float lf = (float)ls, wf = (float)ws;
-    a.sums[0] = lf;
-    a.sums[1] = wf;
-    a.sums[2] = lf / (wf + 1e-7f);   // loss_utils.py:113
-    a.sums[3] = 0.0f;
+    a.partials[blk * PH_NPART + lane] = s;
   }
 }
 
-// The same reduction as phase D for callers that ran the tile kernel with skip_finalize (e.g. to place the
-// reduction elsewhere in a graph): one CTA per sample, one warp per value, ticketed cross-sample sum.
+// Deterministic reduction of the per-CTA partials: grad_P (B,2,12) and the masked mean.  One CTA per sample,
+// one warp per value, lanes stride the tiles with independent loads in flight; the cross-sample sum of the two
+// loss scalars is done by whichever CTA finishes last (ticket, zeroed by photo_kernel's first CTA), in
+// sample order, so the result does not depend on scheduling.  (Doing this inside photo_kernel's last CTAs was
+// measured: the per-CTA fence + ticket round trip and the single-CTA tail cost 17 us per pass against 6 us for
+// this kernel, which a scheduler can also move off the critical path - profiles/r2_notes.md.)
 __global__ void __launch_bounds__(PH_NPART * 32) photo_finalize_kernel(float* __restrict__ partials, int batch,
                                                                       int tiles, float* __restrict__ sums,
                                                                       float* __restrict__ grad_P) {
@@ -662,14 +571,15 @@ __global__ void __launch_bounds__(PH_NPART * 32) photo_finalize_kernel(float* __
 template <bool WARP, bool GRAD>
 static void photo_dispatch(const mal_photo_args& a, const PhotoMaps& maps, int use_tma, int ncand, float min_disp,
                            float range, dim3 grid, size_t smem, cudaStream_t st) {
+  const SizeDiv sdiv = size_div(a.height, a.width, a.convention);
   const bool lowres = WARP && a.depth_height > 0;
   const bool syng = WARP && GRAD && a.grad_syn[0] != nullptr;   // PRED mode handles grad_syn in its own branch
 #define MAL_PHOTO_LAUNCH2(CONV_, NC_)                                                                        \
   do {                                                                                                      \
-    if (lowres && syng) launch(photo_kernel<WARP, GRAD, CONV_, WARP, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma); \
-    else if (lowres) launch(photo_kernel<WARP, GRAD, CONV_, WARP, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma);          \
-    else if (syng) launch(photo_kernel<WARP, GRAD, CONV_, false, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma);    \
-    else launch(photo_kernel<WARP, GRAD, CONV_, false, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma);                     \
+    if (lowres && syng) launch(photo_kernel<WARP, GRAD, CONV_, WARP, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv); \
+    else if (lowres) launch(photo_kernel<WARP, GRAD, CONV_, WARP, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);          \
+    else if (syng) launch(photo_kernel<WARP, GRAD, CONV_, false, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);    \
+    else launch(photo_kernel<WARP, GRAD, CONV_, false, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);                     \
   } while (0)
   // NC is the compiled-in candidate capacity: the 2-candidate passes never touch the temporal-hint
   // staging / rare-path code (instruction-cache pressure)
@@ -749,11 +659,6 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   }
   const int use_tma = tma ? 1 : 0;
 
-  if (!a.skip_finalize) {   // tickets of phase D
-    const size_t tiles = (size_t)grid.x * grid.y;
-    float* tail = a.partials + (size_t)B * tiles * PH_NPART + (size_t)B * 2;
-    cudaMemsetAsync(tail, 0, (size_t)(B + 1) * sizeof(unsigned), st);
-  }
   if (warp) {
     if (grad) photo_dispatch<true, true>(a, maps, use_tma, ncand, min_disp, range, grid, smem, st);
     else photo_dispatch<true, false>(a, maps, use_tma, ncand, min_disp, range, grid, smem, st);
@@ -761,7 +666,9 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     if (grad) photo_dispatch<false, true>(a, maps, use_tma, ncand, min_disp, range, grid, smem, st);
     else photo_dispatch<false, false>(a, maps, use_tma, ncand, min_disp, range, grid, smem, st);
   }
-  return check_launch("photo_kernel");
+  int rc = check_launch("photo_kernel");
+  if (rc || a.skip_finalize) return rc;
+  return mal_photo_finalize(args, stream);
 }
 
 extern "C" int mal_photo_finalize(const mal_photo_args* args, mal_stream_t stream) {
@@ -771,8 +678,6 @@ extern "C" int mal_photo_finalize(const mal_photo_args* args, mal_stream_t strea
   const bool grad = a.with_grad != 0 && a.mode == MAL_PHOTO_WARP;
   if (grad) MAL_REQUIRE(a.grad_P, "mal_photo_finalize: WARP+grad needs grad_P");
   const int tiles = ((a.width + PH_TW - 1) / PH_TW) * ((a.height + PH_TH - 1) / PH_TH);
-  float* tail = a.partials + (size_t)a.batch * tiles * PH_NPART + (size_t)a.batch * 2;
-  cudaMemsetAsync(tail, 0, (size_t)(a.batch + 1) * sizeof(unsigned), (cudaStream_t)stream);
   launch(photo_finalize_kernel, dim3(a.batch), dim3(PH_NPART * 32), 0, (cudaStream_t)stream, a.partials, a.batch,
          tiles, a.sums, grad ? a.grad_P : (float*)nullptr);
   return check_launch("photo_finalize_kernel");

@@ -136,22 +136,29 @@ __global__ void __launch_bounds__(PW_NT) main_terms_kernel(const mal_main_terms_
     }
   }
   block_reduce2(acc_c, acc_d, red, a.partials + (size_t)blockIdx.x * 2);
-}
-
-// sums[j] = (sum over CTAs of partials[.][j]) * inv_n   (the two .mean() calls)
-__global__ void __launch_bounds__(256) main_terms_finalize_kernel(const float* __restrict__ partials, int nblk,
-                                                                 float inv_n, float* __restrict__ sums) {
-  __shared__ double red[2 * 8];
+  // the last CTA to finish (ticket, zeroed by a memset node ahead of the launch) adds the per-CTA partials
+  // in a fixed order: sums[j] = (sum over CTAs of partials[.][j]) * inv_n   (the two .mean() calls)
+  __shared__ int s_last;
+  __shared__ double dred[2 * PW_NT / 32];
+  const int nblk = gridDim.x;
+  unsigned* ticket = reinterpret_cast<unsigned*>(a.partials + (size_t)nblk * 2);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned)(nblk - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile float* part = a.partials;
   double s0 = 0.0, s1 = 0.0;
-  for (int i = threadIdx.x; i < nblk; i += blockDim.x) { s0 += partials[i * 2]; s1 += partials[i * 2 + 1]; }
+  for (int i = threadIdx.x; i < nblk; i += PW_NT) { s0 += (double)part[i * 2]; s1 += (double)part[i * 2 + 1]; }
   s0 = warp_sum(s0); s1 = warp_sum(s1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red[warp * 2] = s0; red[warp * 2 + 1] = s1; }
+  if (lane == 0) { dred[warp * 2] = s0; dred[warp * 2 + 1] = s1; }
   __syncthreads();
   if (threadIdx.x < 2) {
     double s = 0.0;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) s += red[wv * 2 + threadIdx.x];
-    sums[threadIdx.x] = (float)(s * (double)inv_n);
+    for (int wv = 0; wv < PW_NT / 32; wv++) s += dred[wv * 2 + threadIdx.x];
+    a.sums[threadIdx.x] = (float)(s * (double)inv_n);
   }
 }
 
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(PW_NT) matching_mask_kernel(const mal_matching
 using namespace mal;
 
 extern "C" size_t mal_main_terms_partials_floats(int batch, int height, int width) {
-  return (size_t)main_terms_blocks((size_t)batch * height * width) * 2;
+  return (size_t)main_terms_blocks((size_t)batch * height * width) * 2 + 4;   // + the ticket
 }
 
 extern "C" int mal_main_terms_forward(const mal_main_terms_args* args, mal_stream_t stream) {
@@ -213,12 +220,10 @@ extern "C" int mal_main_terms_forward(const mal_main_terms_args* args, mal_strea
                    aligned(a.ens_reproj) && aligned(a.consistency_target) && aligned(a.grad_cons) &&
                    aligned(a.grad_distil) && aligned(a.grad_distil_mono) && (((uintptr_t)a.distil_index & 3) == 0);
   const int nblk = main_terms_blocks(n);
+  cudaMemsetAsync(a.partials + (size_t)nblk * 2, 0, sizeof(unsigned), st);
   if (vec) launch(main_terms_kernel<4>, dim3(nblk), dim3(PW_NT), 0, st, a, min_disp, range, inv_n);
   else launch(main_terms_kernel<1>, dim3(nblk), dim3(PW_NT), 0, st, a, min_disp, range, inv_n);
-  int rc = check_launch("main_terms_kernel");
-  if (rc) return rc;
-  launch(main_terms_finalize_kernel, dim3(1), dim3(256), 0, st, (const float*)a.partials, nblk, inv_n, a.sums);
-  return check_launch("main_terms_finalize_kernel");
+  return check_launch("main_terms_kernel");
 }
 
 extern "C" int mal_matching_mask(const mal_matching_mask_args* args, mal_stream_t stream) {

@@ -66,9 +66,9 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
-    The per-tile partial sums are reduced by the kernel's own last CTAs (ticketed, deterministic).
-    finalize=False skips that: `sums` / `grad_P` stay unreduced until photo_finalize(handle, out) is called
-    (on any stream ordered after this call) - or for good, when only the per-pixel maps are wanted."""
+    finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
+    stream ordered after this call) - a scheduler uses it to keep the tiny reduction kernel off the critical
+    path between two heavy kernels - or for good, when only the per-pixel maps are wanted."""
     B, C3, H, W = target.shape
     if C3 != 3:
         raise ValueError("target must be (B,3,H,W)")
@@ -126,7 +126,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     a.skip_finalize = 0 if finalize else 1
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
-    LAUNCHES[0] += 1   # photo_kernel (its last CTAs do the reduction unless finalize=False)
+    LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
     out["_keepalive"] = (partials,)
     out["_args"] = a
     return out
@@ -242,7 +242,7 @@ def main_terms(handle, *, multi, mono, pixel_mask, sample_mask=None, mono_reproj
     a.grad_cons, a.grad_distil, a.grad_distil_mono = _ptr(out["grad_cons"]), _ptr(out["grad_distil"]), _ptr(out["grad_distil_mono"])
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     _capi.check(handle.mal_main_terms_forward(C.byref(a), _stream(multi)), handle)
-    LAUNCHES[0] += 2   # main_terms_kernel + main_terms_finalize_kernel
+    LAUNCHES[0] += 1   # main_terms_kernel (its last CTA forms the two means)
     out["_keepalive"] = (partials,)
     return out
 

@@ -157,16 +157,20 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
         sm = raw.smooth(handle, disp=mono, img=tgt, normalise=True, with_grad=True, disp_b=multi, defer_fix=True)
         sm_t = {"loss": sm["loss"], "grad_disp": sm["grad_disp"], "_k": sm}
         sm_s = {"loss": sm["loss_b"], "grad_disp": sm["grad_disp_b"], "stats": sm["stats"]}
-    # main chain: identity -> teacher -> ensemble.  The per-pass reductions run inside the photometric kernel
-    # (its last CTAs, ticketed), so there is nothing to schedule around them.
+    # main chain: identity -> teacher -> ensemble.  The per-pass reductions (photo_finalize_kernel: 12 CTAs,
+    # ~6 us) are not needed before step_combine, so each is forked onto the smoothness branch, where it runs
+    # in the tail of the next heavy kernel instead of between two of them.
     def later(out):
+        with branch(1):
+            raw.photo_finalize(handle, out)
         return out
 
     # (the identity and ensemble passes only feed their per-pixel maps forward: their sums are never read)
     ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
                       finalize=False)["min_reproj"]
     teacher = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None,
-                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, **geom))
+                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, finalize=False,
+                              **geom))
     ens = None
     if not opt.no_ens:
         ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
@@ -174,7 +178,8 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     branch.join(0)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
     student = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
-                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, **geom))
+                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, finalize=False,
+                              **geom))
     dual = bool(opt.dual_distil) and ens is None
     mt = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
                         mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],

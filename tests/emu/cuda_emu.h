@@ -237,6 +237,7 @@ static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *
 template <class T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline float __fmul_rn(float a, float b) { return a * b; }      // TU is built with -ffp-contract=off
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

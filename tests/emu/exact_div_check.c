@@ -17,9 +17,12 @@ static inline float divc(float x, float C) {
 int main(int argc, char** argv) {
   /* argv[1]: stride over the 2^32 bit patterns (1 = exhaustive; a prime stride samples every exponent) */
   const long long stride = argc > 1 ? atoll(argv[1]) : 1;
-  const float consts[2] = {9.0f, 3.0f};
+  /* 9, 3: avg_pool2d windows and channel means (xdivc); the rest: Project3D's image-size divisors
+     (size_div_verified in mal_math.cuh - keep the two lists in step) */
+  const float consts[] = {9.0f, 3.0f, 47.0f, 95.0f, 127.0f, 159.0f, 191.0f, 255.0f, 383.0f, 511.0f, 639.0f, 1023.0f};
+  const int nconst = (int)(sizeof(consts) / sizeof(consts[0]));
   unsigned long long bad_total = 0;
-  for (int ci = 0; ci < 2; ci++) {
+  for (int ci = 0; ci < nconst; ci++) {
     const float C = consts[ci];
     unsigned long long bad = 0, bad_sign = 0;
 #pragma omp parallel for reduction(+ : bad, bad_sign) schedule(static)

@@ -74,7 +74,7 @@ def test_malstep_graph_and_eager(use_graph, fused):
         scalars, grads, outputs = st(0, sync_weights=False)
         torch.cuda.synchronize()
         _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
-    assert st.launches_per_step and st.launches_per_step >= 15
+    assert st.launches_per_step and 8 <= st.launches_per_step <= 12
 
 
 @pytest.mark.gpu

@@ -58,11 +58,39 @@ def main():
                   inv_K=b["inv_K"], T=[b["T_-1"], b["T_1"]], pixel_mask=masks[i % 3], sample_mask=smz[i % 3],
                   with_grad=True)
 
+    fin = os.environ.get("MAL_TIME_NOFIN") is None
+
+    def k_teacher_nf(i):
+        b = bufs[i % 3]
+        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], syn=[b["syn_-1"], b["syn_1"]],
+                  depth=b["mono_disp"], K=b["K"], inv_K=b["inv_K"], T=[b["T_-1"], b["T_1"]],
+                  identity_min=ident[i % 3], noise=b["noise_mono"], with_grad=True, finalize=False)
+
+    def k_student_nf(i):
+        b = bufs[i % 3]
+        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], depth=b["multi_disp"], K=b["K"],
+                  inv_K=b["inv_K"], T=[b["T_-1"], b["T_1"]], pixel_mask=masks[i % 3], sample_mask=smz[i % 3],
+                  with_grad=True, finalize=False)
+
+    def k_cv(i):
+        b = bufs[i % 3]
+        raw.cost_volume(h, current=b["current_feats"], lookup=b["lookup_feats"], poses=b["relative_poses"], K=b["K2"],
+                        inv_K=b["inv_K2"], bins=b["bins"], apply_confidence=True, want_missing=False)
+
+    def k_smooth(i):
+        b = bufs[i % 3]
+        raw.smooth(h, disp=b["mono_disp"], img=b["color_0"], normalise=True, with_grad=True)
+
     res = {}
     with torch.no_grad():
         for name, fn in (("identity", k_ident), ("teacher", k_teacher), ("ensemble", k_ens), ("student", k_student)):
             res[name] = round(timeit(fn), 1)
-    res["sum"] = round(sum(res.values()), 1)
+        res["sum"] = round(sum(res.values()), 1)
+        if fin:
+            res["teacher_nofin"] = round(timeit(k_teacher_nf), 1)
+            res["student_nofin"] = round(timeit(k_student_nf), 1)
+        res["cv"] = round(timeit(k_cv), 1)
+        res["smooth1"] = round(timeit(k_smooth), 1)
     print(tag, json.dumps(res))
 
 
