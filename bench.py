@@ -45,14 +45,19 @@ def parse():
     p.add_argument("--batch", type=int, default=12, help="frames per GPU per step")
     p.add_argument("--sets", type=int, default=3, help="distinct input sets rotated through (L2 hygiene)")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--cpu-frames", type=int, default=2, help="frames per CPU-baseline step")
+    p.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU step (0: the GPU arm's batch)")
     p.add_argument("--skip-cpu-baseline", action="store_true")
+    p.add_argument("--syn-as-data", action="store_true",
+                   help="hand the step ready-made temporal-hint images instead of instance masks (round-1 workload)")
     return p.parse_args()
 
 
 def workload_config(args, batch):
+    hint = ("temporal-hint images given as data" if args.syn_as_data else
+            "temporal hint synthesised inside the step from packed Mask2Former-shaped instance masks "
+            "(warps materialised, image_synthesis, backward through the copies)")
     return {"workload": "ManyDepth+MAL KITTI training-step hot path (configs[1]): --temporal --distil --loss_blc, "
-                        "frames [0,-1,1], 1 scale, 96 depth bins x 64 ch at 48x160",
+                        "frames [0,-1,1], 1 scale, 96 depth bins x 64 ch at 48x160; " + hint,
             "height": HEIGHT, "width": WIDTH, "batch_per_gpu": batch, "global_batch": batch * args.gpus,
             "parallelism": "dp%d (batch-sharded replicas, no data-path collective)" % args.gpus,
             "l2": "inputs rotate over %d sets of ~150 MB (> 126 MB L2)" % args.sets,
@@ -117,22 +122,22 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (the oracle port; the only legs of this file that touch oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(frames):
+def cpu_step_fn(frames, with_masks=True):
     from mal_b200 import step as S
     from oracle.step_oracle import oracle_step   # the oracle's composition of the reference functions
     opt = S.default_opt(frames, HEIGHT, WIDTH)
-    batch = S.synthetic_batch(opt, seed=4242)
+    batch = S.synthetic_batch(opt, seed=4242, with_masks=with_masks)
     return lambda: oracle_step(batch, opt)
 
 
-def time_cpu(frames, steps, warmup, budget_s=None):
+def time_cpu(frames, steps, warmup, budget_s=None, with_masks=True):
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         pass
     torch.set_num_threads(cores)
-    fn = cpu_step_fn(frames)
+    fn = cpu_step_fn(frames, with_masks)
     for _ in range(warmup):
         fn()
     times = []
@@ -152,13 +157,14 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_cpu(args.cpu_frames, args.steps, min(args.warmup, 1), budget_s=150.0)
+    frames = args.cpu_frames or args.batch     # the GPU arm's batch: same config on both arms
+    r = time_cpu(frames, args.steps, min(args.warmup, 1), budget_s=150.0, with_masks=not args.syn_as_data)
     sample = "%d frames/step x %d steps of the same workload (oracle/mal_oracle.py, torch CPU fp32)" % (
         r["frames"], r["steps"])
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.cpu_frames),
+            "config": workload_config(args, frames),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -183,9 +189,15 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
         ident = [raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], mode=raw.PHOTO_PRED,
                            want_selection=False)["min_reproj"] for b in bufs]
 
+    def syn_of(i):   # ready-made, or the images the captured step synthesised into its static buffers
+        b, sl = bufs[i % len(bufs)], st.slots[i % len(bufs)]
+        if "syn_-1" in b:
+            return [b["syn_-1"], b["syn_1"]]
+        return sl["ctx"]["hint"]["syn"]
+
     def photo4(i):
         b = bufs[i % len(bufs)]
-        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], syn=[b["syn_-1"], b["syn_1"]],
+        raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], syn=syn_of(i),
                   depth=b["mono_disp"].detach(), K=b["K"], inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()],
                   identity_min=ident[i % len(bufs)], noise=b["noise_mono"], with_grad=True)
 
@@ -227,6 +239,15 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
         out.append({"kernel": name, "key": key, "us_per_launch": us, "algorithmic_bytes": nbytes,
                     "achieved_gbs": gbs, "frac": gbs / peak_gbs})
     return out
+
+
+def limiter_of(key):
+    """What bounds a kernel, from the ncu counters tools/make_profiles.py extracted into profiles/limiters.json
+    (nothing is hard-coded here: a stale sentence would outlive the kernel it described)."""
+    path = os.path.join(ROOT, "profiles", "limiters.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(key)
 
 
 def next_row_kernels(dev, batch, peak_gbs, iters=10):
@@ -329,7 +350,7 @@ def ours(args):
     host = []
     for i in range(args.sets):
         # pinned host batches in the slot layout: each goes up as one contiguous copy
-        host.append(st.staging(S.synthetic_batch(opt, seed=1234 + 17 * i + 1000 * rank)))
+        host.append(st.staging(S.synthetic_batch(opt, seed=1234 + 17 * i + 1000 * rank, with_masks=not args.syn_as_data)))
     h2d = 0
     for i in range(args.sets):
         h2d = st.load(host[i], slot=i)
@@ -381,6 +402,18 @@ def ours(args):
         st(i % args.sets)                # reads the loss scalars back (pinned) and syncs for LossBalancing
 
     ms_e2e = timed(e2e_step)
+
+    # (3) the same, moving only what the reference itself moves host -> device every step (images, intrinsics, the
+    # CPU-drawn tie-break noise, the instance masks: mal_b200.step.HOST_BORN); disparities, poses and matching
+    # features are network outputs and stay where the networks left them
+    hb = st.load_async(host[0], slot=0, host_born_only=True)
+
+    def e2e_born_step(i):
+        nxt = (i + 1) % args.sets
+        st.load_async(host[nxt], slot=nxt, host_born_only=True)
+        st(i % args.sets)
+
+    ms_born = timed(e2e_born_step)
     launches = st.launches_per_step * args.steps + 0
 
     line = None
@@ -389,6 +422,7 @@ def ours(args):
         sampler.stop()
         clocks = sampler.summary(windows)
         dom = max(roof, key=lambda r: r["us_per_launch"])
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         frames = args.batch * world
         value = frames / (ms_dev * 1e-3)
         e2e = frames / (ms_e2e * 1e-3)
@@ -400,24 +434,28 @@ def ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.batch),
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 16},
+                        "d2h_bytes_per_step": 16, "h2d_gbs_per_rank": h2d / (ms_e2e * 1e-3) / 1e9},
+                "e2e_device_born": {"value": frames / (ms_born * 1e-3), "unit": UNIT, "ms_per_step": ms_born,
+                                    "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 16,
+                                    "h2d_gbs_per_rank": hb / (ms_born * 1e-3) / 1e9,
+                                    "note": "only the tensors the reference's loader / CPU generator delivers cross "
+                                            "PCIe (images, intrinsics, tie-break noise, instance masks); network "
+                                            "outputs stay on the device as in the reference"},
                 "gpu_launches": launches, "launches_per_step": st.launches_per_step, "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak_gbs,
                              "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                              "us_per_launch": dom["us_per_launch"], "algorithmic_bytes": dom["algorithmic_bytes"],
-                             "limiter": "fp32 pipe / issue latency, not HBM: bit-exact fp32 arithmetic (DESIGN.md section 4); "
-                                        "ncu: fma pipe busy 49% of cycles (packed FFMA2), 56% issue slots, 38% L1 "
-                                        "data pipe, 16 warps/SM at 128 registers, <2% DRAM throughput "
-                                        "(profiles/r1_notes.md)"},
+                             "limiter": limiter_of(dom["key"])},
                 "kernels": roof,
                 # the same dominant kernel against the fp32 pipe it is actually bound by (informative; the
                 # contract's roofline object above stays HBM): nominal flops = every (pixel, plane, channel)
                 # evaluation x 9 (1 mul + 3 fma + sub + |.|-add), masked samples included although skipped
                 "fp32_view": (lambda fl: {"kernel": dom["kernel"], "nominal_gflop": fl / 1e9,
                                          "achieved_tflops": fl / (dom["us_per_launch"] * 1e-6) / 1e12,
-                                         "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
-                                         "frac": fl / (dom["us_per_launch"] * 1e-6) / (148 * 128 * 2 * 1.965e9),
-                                         "peak_source": "148 SMs x 128 fp32 lanes x 2 flop x 1.965 GHz (measured SM clock)"})(
+                                         "peak_tflops": 148 * 128 * 2 * sm_hz / 1e12,
+                                         "frac": fl / (dom["us_per_launch"] * 1e-6) / (148 * 128 * 2 * sm_hz),
+                                         "peak_source": "148 SMs x 128 fp32 lanes x 2 flop x %.3f GHz (SM clock sampled "
+                                                        "during the timed region)" % (sm_hz / 1e9)})(
                     9.0 * args.batch * opt.num_depth_bins * (HEIGHT // 4) * (WIDTH // 4) * opt.matching_channels)
                 if dom["key"] == "cost_volume" else None,
                 # whole-step view: SURVEY.md 8(d) compulsory bytes per frame for this configuration
@@ -427,7 +465,7 @@ def ours(args):
             # measured after the timed region; not part of `value`
             line["next_rows"] = next_row_kernels(dev, args.batch, peak_gbs)
         if not args.skip_cpu_baseline and world == 1:
-            r = time_cpu(args.cpu_frames, steps=8, warmup=1, budget_s=25.0)
+            r = time_cpu(args.cpu_frames or 2, steps=8, warmup=1, budget_s=25.0, with_masks=not args.syn_as_data)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": "%d frames/step x %d steps of the same workload through "
                                               "oracle/mal_oracle.py (torch CPU fp32)" % (r["frames"], r["steps"])}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 4
+#define MAL_ABI_VERSION 5
 
 enum {
   MAL_OK = 0,
@@ -392,6 +392,55 @@ int mal_dynamic_instance_backward(const mal_dynamic_instance_args* args, const i
 int mal_fill_dynamic_obj(const uint8_t* mask, const int32_t* delta_x, const int32_t* delta_y, const float* source,
                          const float* img, int num, int channels, int height, int width, float* out,
                          mal_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MAL temporal hint inside one training step, batched over the samples (SURVEY.md section 8f item 1 as the
+ * reference's Trainer runs it: manydepth/trainer.py:1078-1165 materialises outputs[("color", f, 0)], :1161-1162
+ * calls dyn_utils.image_synthesis (:121-170), compute_mono_losses takes the synthesised images as candidates
+ * 2 and 3 and autograd carries d loss / d syn back into the warped images, the depth and the poses).
+ *
+ *   mal_temporal_warp        outputs[("color", f, 0)], f = -1, +1 (BackprojectDepth, Project3D, grid_sample border)
+ *   mal_temporal_pack_masks  Mask2Former-shaped (B,N,H,W) bool masks -> one 32-bit word per pixel, bit n = instance n
+ *   mal_temporal_synthesis   generate_dynamic_instance (:38-119) for every sample: warped -> syn
+ *   mal_temporal_backward    d loss / d syn -> d loss / d warped (optional output) -> accumulated onto `grad_depth`
+ *                            and added to `grad_P` of the photometric pass that produced grad_syn
+ * All four take the same argument block and read the fields they need.  Instance masks: <= 32 matched instances per
+ * sample, same instance order in both frames; counts[b] = 0 leaves the sample's warped images untouched (:133-134).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mal_temporal_args {
+  int32_t batch, height, width;
+  int32_t convention;        /* MAL_CONV_*                                                       */
+  int32_t depth_is_disp;     /* 1: `depth` holds sigmoid disparity                               */
+  int32_t replace;           /* generate_dynamic_instance(replace=...) dead zone (:88-96)        */
+  double min_depth, max_depth;
+  float eps;                 /* Project3D eps                                                    */
+  const float* src[2];       /* (B,3,H,W) inputs[("color", f, 0)], f = -1, +1                    */
+  const float* depth;        /* (B,1,H,W)                                                        */
+  const float* K;            /* (B,4,4)                                                          */
+  const float* inv_K;        /* (B,4,4)                                                          */
+  const float* T[2];         /* (B,4,4)                                                          */
+  float* warped[2];          /* (B,3,H,W) warp: out; synthesis: in                               */
+  const uint32_t* packed_last; /* (B,H,W) bit n: instance n covers the pixel in warped frame -1  */
+  const uint32_t* packed_next; /* (B,H,W) ... frame +1                                           */
+  const int32_t* counts;     /* (B) matched instances per sample                                 */
+  float* syn[2];             /* (B,3,H,W) synthesis: out                                         */
+  int32_t* ext;              /* workspace, B*256 ints: encoded extents [B][2][4][32]             */
+  int32_t* deltas;           /* (B,2,32) synthesis: out (displacement of the frame -1 copies along H, W;
+                                frame +1 uses the negation); backward: in                        */
+  const float* grad_syn[2];  /* (B,3,H,W) backward: d loss / d syn                               */
+  float* grad_warped[2];     /* (B,3,H,W) backward, optional: d loss / d warped                  */
+  float* grad_depth;         /* (B,1,H,W) backward, optional: += d loss / d depth (or disp)      */
+  float* partials;           /* workspace with grad_depth: mal_temporal_partials_floats() floats */
+  float* grad_P;             /* (B,2,12)  with grad_depth: += d loss / d (K@T)[:3,:]             */
+} mal_temporal_args;
+
+size_t mal_temporal_partials_floats(int batch, int height, int width);
+int mal_temporal_warp(const mal_temporal_args* args, mal_stream_t stream);
+int mal_temporal_pack_masks(const uint8_t* masks_last, const uint8_t* masks_next, const int32_t* counts, int batch,
+                            int nmax, int height, int width, uint32_t* packed_last, uint32_t* packed_next,
+                            mal_stream_t stream);
+int mal_temporal_synthesis(const mal_temporal_args* args, mal_stream_t stream);
+int mal_temporal_backward(const mal_temporal_args* args, mal_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * DualRefine epipolar correlation lookup, forward and backward.

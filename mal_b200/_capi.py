@@ -123,6 +123,19 @@ class MatchingMaskArgs(C.Structure):
     ]
 
 
+class TemporalArgs(C.Structure):
+    """struct mal_temporal_args."""
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("convention", C.c_int32),
+        ("depth_is_disp", C.c_int32), ("replace", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double), ("eps", C.c_float),
+        ("src", C.c_void_p * 2), ("depth", C.c_void_p), ("K", C.c_void_p), ("inv_K", C.c_void_p), ("T", C.c_void_p * 2),
+        ("warped", C.c_void_p * 2), ("packed_last", C.c_void_p), ("packed_next", C.c_void_p), ("counts", C.c_void_p),
+        ("syn", C.c_void_p * 2), ("ext", C.c_void_p), ("deltas", C.c_void_p), ("grad_syn", C.c_void_p * 2),
+        ("grad_warped", C.c_void_p * 2), ("grad_depth", C.c_void_p), ("partials", C.c_void_p), ("grad_P", C.c_void_p),
+    ]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mal_abi_version": (C.c_int, []),
@@ -143,6 +156,11 @@ EXPORTS = {
     "mal_dynamic_instance": (C.c_int, [C.POINTER(DynamicInstanceArgs), C.c_void_p]),
     "mal_dynamic_instance_backward": (C.c_int, [C.POINTER(DynamicInstanceArgs)] + [C.c_void_p] * 7),
     "mal_fill_dynamic_obj": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "mal_temporal_partials_floats": (C.c_size_t, [C.c_int] * 3),
+    "mal_temporal_warp": (C.c_int, [C.POINTER(TemporalArgs), C.c_void_p]),
+    "mal_temporal_pack_masks": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 3),
+    "mal_temporal_synthesis": (C.c_int, [C.POINTER(TemporalArgs), C.c_void_p]),
+    "mal_temporal_backward": (C.c_int, [C.POINTER(TemporalArgs), C.c_void_p]),
     "mal_backproject": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_backproject_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mal_project3d_partials_floats": (C.c_size_t, [C.c_int] * 3),
@@ -160,7 +178,7 @@ EXPORTS = {
     "mal_ssim_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 4),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 def bind(handle):

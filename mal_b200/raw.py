@@ -449,6 +449,117 @@ def dynamic_instance_backward(handle, *, mask_last, mask_next, deltas, grad_ori_
     return gl, gn
 
 
+# ---- temporal hint inside the step (csrc/temporal.cu) ---------------------------------------------------------
+def _temporal_args(B, H, W, convention, depth_is_disp, min_depth, max_depth, eps, replace=False):
+    a = _capi.TemporalArgs()
+    a.batch, a.height, a.width, a.convention = B, H, W, convention
+    a.depth_is_disp, a.replace = int(depth_is_disp), int(bool(replace))
+    a.min_depth, a.max_depth, a.eps = float(min_depth), float(max_depth), float(eps)
+    return a
+
+
+def _temporal_geom(a, src, depth, K, inv_K, T, B, H, W):
+    img, keep = (B, 3, H, W), []
+    for i in range(2):
+        s_, t_ = _f32(src[i], f"src[{i}]", img), _f32(T[i], f"T[{i}]", (B, 4, 4))
+        a.src[i], a.T[i] = _ptr(s_), _ptr(t_)
+        keep += [s_, t_]
+    depth, K, inv_K = _f32(depth, "depth", (B, 1, H, W)), _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
+    a.depth, a.K, a.inv_K = _ptr(depth), _ptr(K), _ptr(inv_K)
+    return keep + [depth, K, inv_K]
+
+
+def temporal_warp(handle, *, src, depth, K, inv_K, T, convention=CONV_MANYDEPTH, depth_is_disp=True, min_depth=0.1,
+                  max_depth=100.0, eps=1e-7):
+    """mal_temporal_warp -> [warped(-1), warped(+1)] (B,3,H,W): outputs[("color", f, 0)] of generate_images_pred."""
+    B, _, H, W = src[0].shape
+    a = _temporal_args(B, H, W, convention, depth_is_disp, min_depth, max_depth, eps)
+    keep = _temporal_geom(a, src, depth, K, inv_K, T, B, H, W)
+    out = [torch.empty((B, 3, H, W), dtype=torch.float32, device=src[0].device) for _ in range(2)]
+    a.warped[0], a.warped[1] = _ptr(out[0]), _ptr(out[1])
+    _capi.check(handle.mal_temporal_warp(C.byref(a), _stream(src[0])), handle)
+    LAUNCHES[0] += 1
+    del keep
+    return out
+
+
+def temporal_pack_masks(handle, *, masks_last, masks_next, counts):
+    """(B,N,H,W) bool / uint8 instance masks (N <= 32) -> two (B,H,W) int32 planes, bit n = instance n."""
+    B, N, H, W = masks_last.shape
+    ml, mn = _mask_u8(masks_last, "masks_last", (B, N, H, W)), _mask_u8(masks_next, "masks_next", (B, N, H, W))
+    cnt = counts.to(torch.int32).contiguous()
+    _same_device([ml, mn, cnt])
+    pl = torch.empty((B, H, W), dtype=torch.int32, device=ml.device)
+    pn = torch.empty_like(pl)
+    _capi.check(handle.mal_temporal_pack_masks(_vp(ml), _vp(mn), _vp(cnt), B, N, H, W, _vp(pl), _vp(pn), _stream(ml)), handle)
+    LAUNCHES[0] += 1
+    return pl, pn
+
+
+def _packed(t, name, shape):
+    if t.dtype != torch.int32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous int32 tensor of shape {tuple(shape)}")
+    return t
+
+
+def temporal_synthesis(handle, *, warped, packed_last, packed_next, counts, replace=False):
+    """mal_temporal_synthesis -> {"syn": [2 x (B,3,H,W)], "deltas": (B,2,32) int32}."""
+    B, _, H, W = warped[0].shape
+    a = _temporal_args(B, H, W, CONV_MANYDEPTH, True, 0.1, 100.0, 1e-7, replace)
+    w = [_f32(warped[i], f"warped[{i}]", (B, 3, H, W)) for i in range(2)]
+    pl, pn = _packed(packed_last, "packed_last", (B, H, W)), _packed(packed_next, "packed_next", (B, H, W))
+    cnt = counts.to(torch.int32).contiguous()
+    dev = _same_device([*w, pl, pn, cnt])
+    syn = [torch.empty_like(w[0]), torch.empty_like(w[1])]
+    ext = torch.empty((B, 256), dtype=torch.int32, device=dev)
+    deltas = torch.zeros((B, 2, 32), dtype=torch.int32, device=dev)
+    for i in range(2):
+        a.warped[i], a.syn[i] = _ptr(w[i]), _ptr(syn[i])
+    a.packed_last, a.packed_next, a.counts, a.ext, a.deltas = _ptr(pl), _ptr(pn), _ptr(cnt), _ptr(ext), _ptr(deltas)
+    _capi.check(handle.mal_temporal_synthesis(C.byref(a), _stream(w[0])), handle)
+    LAUNCHES[0] += 2
+    return {"syn": syn, "deltas": deltas, "_keepalive": (ext, cnt, w)}
+
+
+def temporal_backward(handle, *, grad_syn, packed_last, packed_next, counts, deltas, want_grad_warped=True,
+                      src=None, depth=None, K=None, inv_K=None, T=None, grad_depth=None, grad_P=None,
+                      convention=CONV_MANYDEPTH, depth_is_disp=True, min_depth=0.1, max_depth=100.0, eps=1e-7):
+    """mal_temporal_backward: d loss / d syn -> {"grad_warped": [2 x (B,3,H,W)]} and / or, when `grad_depth` and
+    `grad_P` are given (the photometric pass's own planes), the chain into depth and pose accumulated onto them."""
+    B, _, H, W = grad_syn[0].shape
+    a = _temporal_args(B, H, W, convention, depth_is_disp, min_depth, max_depth, eps)
+    g = [_f32(grad_syn[i], f"grad_syn[{i}]", (B, 3, H, W)) for i in range(2)]
+    pl, pn = _packed(packed_last, "packed_last", (B, H, W)), _packed(packed_next, "packed_next", (B, H, W))
+    cnt = counts.to(torch.int32).contiguous()
+    dev = _same_device([*g, pl, pn, cnt, deltas])
+    keep = [cnt]
+    out = {}
+    if src is not None:
+        keep += _temporal_geom(a, src, depth, K, inv_K, T, B, H, W)
+    elif K is not None:
+        K, inv_K = _f32(K, "K", (B, 4, 4)), _f32(inv_K, "inv_K", (B, 4, 4))
+        a.K, a.inv_K = _ptr(K), _ptr(inv_K)
+        for i in range(2):
+            t_ = _f32(T[i], f"T[{i}]", (B, 4, 4))
+            a.T[i] = _ptr(t_)
+            keep.append(t_)
+        keep += [K, inv_K]
+    if want_grad_warped:
+        out["grad_warped"] = [torch.empty_like(g[0]), torch.empty_like(g[1])]
+        a.grad_warped[0], a.grad_warped[1] = _ptr(out["grad_warped"][0]), _ptr(out["grad_warped"][1])
+    if grad_depth is not None:
+        parts = torch.empty((handle.mal_temporal_partials_floats(B, H, W),), dtype=torch.float32, device=dev)
+        a.grad_depth, a.grad_P, a.partials = _ptr(_f32(grad_depth, "grad_depth", (B, 1, H, W))), _ptr(_f32(grad_P, "grad_P", (B, 2, 12))), _ptr(parts)
+        keep.append(parts)
+    for i in range(2):
+        a.grad_syn[i] = _ptr(g[i])
+    a.packed_last, a.packed_next, a.counts, a.deltas = _ptr(pl), _ptr(pn), _ptr(cnt), _ptr(deltas)
+    _capi.check(handle.mal_temporal_backward(C.byref(a), _stream(g[0])), handle)
+    LAUNCHES[0] += 2 if grad_depth is not None else 1
+    out["_keepalive"] = keep
+    return out
+
+
 def grid_sample(handle, img, grid, align_corners=True, border=True):
     B, Cn, H, W = img.shape
     Ho, Wo = grid.shape[1:3]

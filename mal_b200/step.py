@@ -30,6 +30,27 @@ INPUT_KEYS = ("color_0", "color_-1", "color_1", "syn_-1", "syn_1", "mono_disp", 
               "K", "inv_K", "K2", "inv_K2", "current_feats", "lookup_feats", "relative_poses",
               "augmentation_mask", "noise_mono", "noise_main", "bins")
 LEAVES = ("mono_disp", "multi_disp", "T_-1", "T_1")
+# --temporal as the reference runs it (trainer.py:1161-1162): instead of ready-made syn images the batch carries
+# the matched instance masks of the two warped frames, packed one bit per instance (mal_temporal_pack_masks), and
+# the step materialises the warps, synthesises the temporal-hint images and back-propagates through them
+MASK_KEYS = ("masks_last", "masks_next", "mask_counts")
+SYN_KEYS = ("syn_-1", "syn_1")
+
+
+# what the reference's data loader / CPU generator hands to the GPU every step (images, intrinsics, the CPU-drawn
+# tie-break noise of loss_utils.py:105-106 / :178, the segmenter-shaped masks); everything else in a batch is born
+# on the device in the reference (network outputs) and only travels in the all-from-host end-to-end measurement
+HOST_BORN = ("color_0", "color_-1", "color_1", "K", "inv_K", "K2", "inv_K2", "noise_mono", "noise_main", "bins") + MASK_KEYS
+
+
+def batch_keys(batch):
+    """The input keys a batch carries, host-born ones first (so they are one contiguous range of a staged batch):
+    INPUT_KEYS, with the packed instance masks in place of the syn images when the temporal hint is synthesised
+    inside the step."""
+    keys = INPUT_KEYS
+    if "masks_last" in batch:
+        keys = tuple(k for k in INPUT_KEYS if k not in SYN_KEYS) + MASK_KEYS
+    return tuple(k for k in keys if k in HOST_BORN) + tuple(k for k in keys if k not in HOST_BORN)
 
 
 def default_opt(batch, height=192, width=640, **kw):
@@ -41,7 +62,35 @@ def default_opt(batch, height=192, width=640, **kw):
     return SimpleNamespace(**o)
 
 
-def synthetic_batch(opt, seed=1234, normalised_K=None, translation_scale=0.2, adaptive_bins=True):
+def synthetic_masks(opt, seed=1234, max_instances=12, max_shift=8):
+    """Synthetic Mask2Former-shaped matched instance masks for a batch (0-N random
+    rectangles / ellipses per frame, shifted between "last" and "next"), packed one bit per instance:
+    (masks_last, masks_next) int32 (B,H,W) and the per-sample instance counts.  One sample gets no instance."""
+    from .utils.synthetic import make_instance_masks
+    B, H, W = opt.batch_size, opt.height, opt.width
+    gen = torch.Generator().manual_seed(seed + 99)
+    counts = torch.randint(1, max_instances + 1, (B,), generator=gen, dtype=torch.int32)
+    if B > 1:
+        counts[B - 1] = 0
+    pl, pn = torch.zeros(B, H, W, dtype=torch.int64), torch.zeros(B, H, W, dtype=torch.int64)
+    for b in range(B):
+        n = int(counts[b])
+        if n == 0:
+            continue
+        last, nxt = make_instance_masks(n, H, W, seed=seed + 31 * b, max_shift=max_shift)
+        w = (1 << torch.arange(n, dtype=torch.int64)).view(-1, 1, 1)
+        pl[b], pn[b] = (last.long() * w).sum(0), (nxt.long() * w).sum(0)
+    to_i32 = lambda t: torch.where(t >= 2 ** 31, t - 2 ** 32, t).to(torch.int32)
+    return to_i32(pl), to_i32(pn), counts
+
+
+def unpack_masks(packed, count):
+    """(H,W) int32 bit planes of one sample -> (count,H,W) bool."""
+    bits = torch.arange(count, dtype=torch.int64).view(-1, 1, 1)
+    return ((packed.long().unsqueeze(0) >> bits) & 1).bool()
+
+
+def synthetic_batch(opt, seed=1234, normalised_K=None, translation_scale=0.2, adaptive_bins=True, with_masks=False):
     """Seeded synthetic KITTI-shaped host tensors for one step, keyed by INPUT_KEYS.
 
     The camera baseline is a fifth of the nearest depth and (adaptive_bins) the depth hypotheses
@@ -75,12 +124,18 @@ def synthetic_batch(opt, seed=1234, normalised_K=None, translation_scale=0.2, ad
          "current_feats": cv["current_feats"], "lookup_feats": cv["lookup_feats"],
          "relative_poses": cv["relative_poses"], "augmentation_mask": t["augmentation_mask"],
          "noise_mono": t["noise"][0], "noise_main": t["noise"][1], "bins": cv["bins"]}
+    if with_masks:
+        for k in SYN_KEYS:
+            del b[k]
+        b["masks_last"], b["masks_next"], b["mask_counts"] = synthetic_masks(opt, seed=seed)
     return {k: v.contiguous() for k, v in b.items()}
 
 
 def step_losses(b, opt, leaves, weights=None, has_ins=True, multi_has_ins=False):
     """The step on a dict of device tensors `b` (INPUT_KEYS) with `leaves` standing in for the
     network outputs.  Returns (total, loss_list, losses, outputs)."""
+    if "masks_last" in b:
+        raise ValueError("step_losses (op by op) takes ready-made syn images; the in-step synthesis is part of fused_step")
     inputs = {("color", 0, 0): b["color_0"], ("color", -1, 0): b["color_-1"], ("color", 1, 0): b["color_1"],
               ("K", 0): b["K"], ("inv_K", 0): b["inv_K"]}
     cv, lowest_cost, confidence, *_ = _head(b, opt)
@@ -135,10 +190,14 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     of the teacher, of the student, consistency, teacher loss, student loss]; grads follow LEAVES."""
     if not opt.distil:
         raise ValueError("fused_step implements the --distil step; use step_losses otherwise")
+    if "masks_last" in b and opt.main_temporal and multi_has_ins:
+        raise ValueError("main_temporal with in-step synthesis: the student's candidates need their own synthesis "
+                         "pass; hand the step ready-made syn images instead")
     B, H, W = opt.batch_size, opt.height, opt.width
     lo, hi = opt.min_depth, opt.max_depth
     tgt, src = b["color_0"], [b["color_-1"], b["color_1"]]
-    syn = [b["syn_-1"], b["syn_1"]]
+    in_step_syn = "masks_last" in b
+    syn = None if in_step_syn else [b["syn_-1"], b["syn_1"]]
     T = [b["T_-1"], b["T_1"]]
     mono, multi = b["mono_disp"].detach(), b["multi_disp"].detach()
     geom = dict(K=b["K"], inv_K=b["inv_K"], T=[t.detach() for t in T], min_depth=lo, max_depth=hi)
@@ -168,9 +227,25 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     # (the identity and ensemble passes only feed their per-pixel maps forward: their sums are never read)
     ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
                       finalize=False)["min_reproj"]
-    teacher = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.temporal and has_ins) else None,
-                              depth=mono, identity_min=ident, noise=b["noise_mono"], with_grad=True, finalize=False,
-                              **geom))
+    use_syn = opt.temporal and has_ins
+    hint = None
+    if use_syn and in_step_syn:
+        # trainer.py:1122-1125 + :1161-1162: materialise the two warps, synthesise the temporal-hint images
+        warped = raw.temporal_warp(handle, src=src, depth=mono, **geom)
+        hint = raw.temporal_synthesis(handle, warped=warped, packed_last=b["masks_last"], packed_next=b["masks_next"],
+                                      counts=b["mask_counts"])
+        syn = hint["syn"]
+    teacher = raw.photo(handle, target=tgt, src=src, syn=syn if use_syn else None, depth=mono, identity_min=ident,
+                        noise=b["noise_mono"], with_grad=True, finalize=False, want_grad_syn=hint is not None, **geom)
+    with branch(1):
+        raw.photo_finalize(handle, teacher)
+        if hint is not None:
+            # d loss / d syn -> warped images -> onto the teacher pass's d/d disparity plane and d/d(K@T) sums
+            # (on the side branch: it overlaps the ensemble and student passes)
+            hint["back"] = raw.temporal_backward(handle, grad_syn=teacher["grad_syn"], packed_last=b["masks_last"],
+                                                 packed_next=b["masks_next"], counts=b["mask_counts"],
+                                                 deltas=hint["deltas"], want_grad_warped=False, src=src, depth=mono,
+                                                 grad_depth=teacher["grad_depth"], grad_P=teacher["grad_P"], **geom)
     ens = None
     if not opt.no_ens:
         ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
@@ -186,7 +261,7 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
                         inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
     branch.join(1)
     return dict(head=head, mask=mask, teacher=teacher, student=student, ens=ens, sm_t=sm_t, sm_s=sm_s, mt=mt,
-                ident=ident)
+                ident=ident, hint=hint)
 
 
 def fused_step_tail(handle, b, opt, weights, ctx):
@@ -207,7 +282,9 @@ def fused_step_tail(handle, b, opt, weights, ctx):
                "mal_distil_index": mt["distil_index"], "consistency_target/0": mt["consistency_target"],
                ("mal_selection", 0): student["selection"], "mono_reproj": teacher["min_reproj"],
                "multi_reproj": student["min_reproj"], "ensemble_reproj": ens,
-               "_keepalive": (head, teacher, student, sm_t, sm_s, mt, comb, ident)}
+               "_keepalive": (head, teacher, student, sm_t, sm_s, mt, comb, ident, ctx.get("hint"))}
+    if ctx.get("hint") is not None:
+        outputs[("syn", -1, 0)], outputs[("syn", 1, 0)] = ctx["hint"]["syn"]
     grads = (comb["grad_disp_teacher"], comb["grad_disp_student"], comb["grad_T"][0], comb["grad_T"][1])
     return comb["scalars"], grads, outputs
 
@@ -250,12 +327,14 @@ class StagedBatch(dict):
 
 
 def _flat_layout(batch, align=256):
-    off, items = 0, {}
-    for k in INPUT_KEYS:
+    off, items, host_born = 0, {}, 0
+    for k in batch_keys(batch):
         t = batch[k]
         items[k] = (off, tuple(t.shape), t.dtype)
         off += (t.numel() * t.element_size() + align - 1) // align * align
-    return {"items": items, "bytes": off}
+        if k in HOST_BORN:
+            host_born = off
+    return {"items": items, "bytes": off, "host_born_bytes": host_born}
 
 
 def _flat_views(flat, layout):
@@ -298,13 +377,15 @@ class MalStep:
                              if (branches and use_graph) else None)
 
     # -- buffers -------------------------------------------------------------------------------
-    def load_async(self, batch, slot=0):
+    def load_async(self, batch, slot=0, host_born_only=False):
         """Enqueue the host->device copy of a (pinned) batch into `slot` on the copy stream, so it
         overlaps the step running on another slot.  The copy waits for the last step that read the
-        slot; the next `__call__(slot)` waits for the copy."""
+        slot; the next `__call__(slot)` waits for the copy.  host_born_only copies just the tensors the
+        reference's loader delivers (HOST_BORN); the network outputs of the slot stay as they are."""
         sl = self.slots[slot]
         if sl["buf"] is None:
             return self.load(batch, slot)
+        keys = [k for k in batch_keys(batch) if (k in HOST_BORN or not host_born_only)]
         cur = torch.cuda.current_stream(self.device)
         if sl.get("done") is not None:
             self.copy_stream.wait_event(sl["done"])
@@ -312,13 +393,14 @@ class MalStep:
             self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream), torch.no_grad():
             if isinstance(batch, StagedBatch) and batch.flat.numel() == sl["flat"].numel():
-                sl["flat"].copy_(batch.flat, non_blocking=True)
+                n = self._layout["host_born_bytes"] if host_born_only else sl["flat"].numel()
+                sl["flat"][:n].copy_(batch.flat[:n], non_blocking=True)
             else:
-                for k in INPUT_KEYS:
+                for k in keys:
                     sl["buf"][k].copy_(batch[k], non_blocking=True)
             sl["ready"] = torch.cuda.Event()
             sl["ready"].record(self.copy_stream)
-        return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
+        return sum(batch[k].numel() * batch[k].element_size() for k in keys)
 
     def load(self, batch, slot=0, non_blocking=True):
         """Copy one batch (host or device tensors keyed by INPUT_KEYS) into a slot's static buffers.
@@ -336,9 +418,9 @@ class MalStep:
             if isinstance(batch, StagedBatch) and batch.flat.numel() == sl["flat"].numel():
                 sl["flat"].copy_(batch.flat, non_blocking=non_blocking)
             else:
-                for k in INPUT_KEYS:
+                for k in batch_keys(batch):
                     sl["buf"][k].copy_(batch[k], non_blocking=non_blocking)
-        return sum(batch[k].numel() * batch[k].element_size() for k in INPUT_KEYS)
+        return sum(batch[k].numel() * batch[k].element_size() for k in batch_keys(batch))
 
     def staging(self, like):
         """A pinned host batch with the slot layout: fill its tensors (same keys / shapes as `like`) and hand
@@ -347,7 +429,7 @@ class MalStep:
         flat = torch.empty(self._layout["bytes"], dtype=torch.uint8).pin_memory()
         staged = StagedBatch(_flat_views(flat, self._layout))
         staged.flat = flat
-        for k in INPUT_KEYS:
+        for k in batch_keys(like):
             staged[k].copy_(like[k])
         return staged
 

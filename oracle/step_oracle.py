@@ -30,8 +30,23 @@ def oracle_step(b, opt, weights=(0.5, 0.5)):
              "consistency_mask": F.interpolate(conf.unsqueeze(1), [H, W], mode="nearest")[:, 0]}
     for f in (-1, 1):
         mono[("cam_T_cam", 0, f)] = multi[("cam_T_cam", 0, f)] = leaves["T_%d" % f]
-        mono[("syn", f, 0)] = multi[("syn", f, 0)] = b["syn_%d" % f]
+        if "syn_%d" % f in b:
+            mono[("syn", f, 0)] = multi[("syn", f, 0)] = b["syn_%d" % f]
     O.images_pred(inputs, mono, height=H, width=W)
+    if "masks_last" in b:
+        # trainer.py:1161-1162 image_synthesis on the materialised warps (dyn_utils.py:121-170): per sample with
+        # matched instances, generate_dynamic_instance; the copies keep autograd history to the warped images
+        syn = [mono[("color", -1, 0)], mono[("color", 1, 0)]]
+        for s_ in range(B):
+            n = int(b["mask_counts"][s_])
+            if n == 0:
+                continue
+            ml = ((b["masks_last"][s_].long().unsqueeze(0) >> torch.arange(n).view(-1, 1, 1)) & 1).bool()
+            mn = ((b["masks_next"][s_].long().unsqueeze(0) >> torch.arange(n).view(-1, 1, 1)) & 1).bool()
+            ol, on, _ = O.generate_dynamic_instance(ml, mn, mono[("color", -1, 0)][s_], mono[("color", 1, 0)][s_])
+            syn[0] = torch.cat([syn[0][:s_], ol[None], syn[0][s_ + 1:]])
+            syn[1] = torch.cat([syn[1][:s_], on[None], syn[1][s_ + 1:]])
+        mono[("syn", -1, 0)], mono[("syn", 1, 0)] = syn
     mono_losses, mono_reproj, _ = O.mono_losses(inputs, mono, True, True, noise=b["noise_mono"])
     multi[("mono_depth", 0, 0)] = mono[("depth", 0, 0)]
     multi["consistency_mask"] = multi["consistency_mask"] * O.matching_mask(multi)

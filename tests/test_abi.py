@@ -37,7 +37,7 @@ def test_struct_sizes_match_the_c_compiler(tmp_path):
              ("mal_smooth_args", _capi.SmoothArgs), ("mal_main_terms_args", _capi.MainTermsArgs),
              ("mal_matching_mask_args", _capi.MatchingMaskArgs), ("mal_step_combine_args", _capi.StepCombineArgs),
              ("mal_forward_warp_args", _capi.ForwardWarpArgs), ("mal_corr_args", _capi.CorrArgs),
-             ("mal_dynamic_instance_args", _capi.DynamicInstanceArgs)]
+             ("mal_dynamic_instance_args", _capi.DynamicInstanceArgs), ("mal_temporal_args", _capi.TemporalArgs)]
     body = "".join('printf("%%zu\\n", sizeof(%s));' % name for name, _ in pairs)
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "mal_b200.h"\nint main(void){' + body + "return 0;}\n")
