@@ -105,6 +105,9 @@ typedef struct mal_photo_args {
                                (manydepth/trainer.py:1093-1094): the full-resolution disparity never
                                exists.  grad_depth stays (B,1,H,W) = d/d(up-sampled value); take it to
                                the low resolution with mal_upsample_bilinear_backward              */
+  int32_t avg_reprojection; /* opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056):
+                               mean instead of min over the two candidates (no syn); selection index is 0; with
+                               gradients (WARP mode) both warps carry half of it                             */
   int32_t skip_finalize;    /* 1: only the tile kernel runs; `sums` / `grad_P` are produced later by
                                mal_photo_finalize(args, stream) - lets a scheduler keep the tiny
                                reduction off the critical path between two heavy kernels           */

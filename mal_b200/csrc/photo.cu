@@ -52,10 +52,10 @@ __host__ __device__ inline PhotoTile photo_tile(bool grad) {
   return t;
 }
 constexpr int PH_SMALL = 40 + 8 * PH_NPART + 8 + 4;   // Geom (padded), reduction scratch, mbarrier + flag
-inline size_t photo_smem_bytes(bool grad, bool warp, int ncand) {
+inline size_t photo_smem_bytes(bool grad, bool warp, int ncand, bool avg) {
   PhotoTile t = photo_tile(grad);
   size_t fl = (size_t)(1 + ncand) * t.TS + PH_SMALL;
-  if (grad) fl += (size_t)10 * t.LN + (t.LN + 7) / 8 * 2;   // 9 coefficient planes, weights, selection bytes; the staged
+  if (grad) fl += (size_t)(avg ? 19 : 10) * t.LN + (t.LN + 7) / 8 * 2;   // 9 coefficient planes, weights, selection bytes; the staged
                                                         // disparity aliases the coefficient planes
   else if (warp) fl += (size_t)2 * ((t.VN + 31) / 32 * 32);
   return fl * 4 + 128;
@@ -65,8 +65,10 @@ struct PhotoMaps {   // TMA descriptors of the tensors a CTA stages, one __grid_
   TileMap tgt, src[2], syn[2], depth, depth_b;
 };
 
-template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC>
-__global__ void __launch_bounds__(PH_NT, GRAD ? 3 : 4)
+// AVG: opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056): the mean instead of
+// the min over the two warped candidates; both then carry half the gradient (a second set of coefficient planes).
+template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC, bool AVG>
+__global__ void __launch_bounds__(PH_NT, GRAD ? (AVG ? 2 : 3) : 4)
 photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, const int ncand, const float min_disp,
              const float disp_range, const int use_tma, const SizeDiv sdiv) {
   const PhotoTile tl = photo_tile(GRAD);
@@ -93,12 +95,13 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   float* sy = smem;                                   // [3][VN] target
   float* sx = sy + tl.TS;                             // [ncand][TS]: [3][VN] per candidate
   float* after = sx + (size_t)ncand * tl.TS;
-  float* coef = after;                                // [9][LN]      (GRAD)
-  float* lw = coef + 9 * tl.LN;                       // [LN] weights (GRAD)
+  constexpr int NCOEF = AVG ? 18 : 9;
+  float* coef = after;                                // [9][LN] (GRAD; AVG: a second set for candidate 1)
+  float* lw = coef + NCOEF * tl.LN;                   // [LN] weights (GRAD)
   signed char* lsel = reinterpret_cast<signed char*>(lw + tl.LN);   // [LN] selected candidate or -1
   float* dep = after;                                 // [VN] disparity tile (aliases coef: dead before phase B)
   float* dep_b = dep + (tl.VN + 31) / 32 * 32;        // [VN] second disparity (ensemble pass, never with GRAD)
-  float* small = after + (GRAD ? 10 * tl.LN + (tl.LN + 7) / 8 * 2 : (WARP ? 2 * ((tl.VN + 31) / 32 * 32) : 0));
+  float* small = after + (GRAD ? (NCOEF + 1) * tl.LN + (tl.LN + 7) / 8 * 2 : (WARP ? 2 * ((tl.VN + 31) / 32 * 32) : 0));
   Geom* geom = reinterpret_cast<Geom*>(small);
   float* red = small + 40;                            // [8][PH_NPART]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red + 8 * PH_NPART + 8);
@@ -291,7 +294,8 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       if (k < ncand) {
         float l1m = xdivc<3>(lsum[k]);
         float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
-        if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
+        if (AVG) rmin = (k == 0) ? lk : xmul(xadd(rmin, lk), 0.5f);   // .mean(1) of two: (l0 + l1) / 2
+        else if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
       }
     }
     int mbit = 1;
@@ -316,8 +320,12 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       const bool syn_grad = (SYNG || !WARP) && a.grad_syn[0] != nullptr;
       const bool live = (idx < 2 || syn_grad) && w != 0.0f;
       lsel[i] = live ? idx : -1;
-      lw[i] = w;
-      if (live && !a.no_ssim) {
+      lw[i] = AVG ? w * 0.5f : w;
+      if (AVG && live && !a.no_ssim) {
+        const float sc = w * (0.5f * 0.85f / 27.0f);   // both candidates, half the weight each
+#pragma unroll
+        for (int j = 0; j < 9; j++) { coef[j * tl.LN + i] = cf0[j] * sc; coef[(9 + j) * tl.LN + i] = cf1[j] * sc; }
+      } else if (live && !a.no_ssim) {
         const float sc = w * (0.85f / 27.0f);  // weight * 0.85 * (1/3 channels) * (1/9 window)
         if (NC <= 2 || idx < 2) {
 #pragma unroll
@@ -431,6 +439,16 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
             int li = lc + dy * tl.LW + dx;
             int s = lsel[li];
             if (s < 0 || (SYNG && s > 1)) continue;   // only the warped candidates chain into depth / pose here
+            if (AVG) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                g0[c] += m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq0[c] * coef[(c * 3 + 1) * tl.LN + li] +
+                              yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
+                g1[c] += m * (coef[(9 + c * 3) * tl.LN + li] + 2.0f * xq1[c] * coef[(9 + c * 3 + 1) * tl.LN + li] +
+                              yq[c] * coef[(9 + c * 3 + 2) * tl.LN + li]);
+              }
+              continue;
+            }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
               float al = coef[(c * 3) * tl.LN + li], be = coef[(c * 3 + 1) * tl.LN + li],
@@ -448,6 +466,12 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
           float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
 #pragma unroll
           for (int c = 0; c < 3; c++) {
+            if (AVG) {   // lw already carries the 1/2
+              const float d0 = yq[c] - xq0[c], d1 = yq[c] - xq1[c];
+              g0[c] += d0 > 0.f ? -wl : (d0 < 0.f ? wl : 0.f);
+              g1[c] += d1 > 0.f ? -wl : (d1 < 0.f ? wl : 0.f);
+              continue;
+            }
             float d = yq[c] - (s == 0 ? xq0[c] : xq1[c]);      // target - pred
             float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);   // d|t-p|/dp = -sign(t-p)
             if (s == 0) g0[c] += sg; else g1[c] += sg;
@@ -574,22 +598,28 @@ static void photo_dispatch(const mal_photo_args& a, const PhotoMaps& maps, int u
   const SizeDiv sdiv = size_div(a.height, a.width, a.convention);
   const bool lowres = WARP && a.depth_height > 0;
   const bool syng = WARP && GRAD && a.grad_syn[0] != nullptr;   // PRED mode handles grad_syn in its own branch
-#define MAL_PHOTO_LAUNCH2(CONV_, NC_)                                                                        \
-  do {                                                                                                      \
-    if (lowres && syng) launch(photo_kernel<WARP, GRAD, CONV_, WARP, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv); \
-    else if (lowres) launch(photo_kernel<WARP, GRAD, CONV_, WARP, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);          \
-    else if (syng) launch(photo_kernel<WARP, GRAD, CONV_, false, WARP && GRAD, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);    \
-    else launch(photo_kernel<WARP, GRAD, CONV_, false, false, NC_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv);                     \
+#define MAL_PHOTO_GO(CONV_, LOW_, SYNG_, NC_, AVG_) \
+  launch(photo_kernel<WARP, GRAD, CONV_, LOW_, SYNG_, NC_, AVG_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv)
+#define MAL_PHOTO_LAUNCH2(CONV_, NC_)                                       \
+  do {                                                                      \
+    if (lowres && syng) MAL_PHOTO_GO(CONV_, WARP, WARP && GRAD, NC_, false); \
+    else if (lowres) MAL_PHOTO_GO(CONV_, WARP, false, NC_, false);           \
+    else if (syng) MAL_PHOTO_GO(CONV_, false, WARP && GRAD, NC_, false);     \
+    else MAL_PHOTO_GO(CONV_, false, false, NC_, false);                      \
   } while (0)
   // NC is the compiled-in candidate capacity: the 2-candidate passes never touch the temporal-hint
-  // staging / rare-path code (instruction-cache pressure)
-#define MAL_PHOTO_LAUNCH(CONV_)                  \
-  do {                                           \
-    if (ncand > 2) MAL_PHOTO_LAUNCH2(CONV_, 4);  \
-    else MAL_PHOTO_LAUNCH2(CONV_, 2);            \
+  // staging / rare-path code (instruction-cache pressure); avg_reprojection (2 candidates) is its own instance
+#define MAL_PHOTO_LAUNCH(CONV_)                                   \
+  do {                                                            \
+    if (a.avg_reprojection) {                                     \
+      if (lowres) MAL_PHOTO_GO(CONV_, WARP, false, 2, true);      \
+      else MAL_PHOTO_GO(CONV_, false, false, 2, true);            \
+    } else if (ncand > 2) MAL_PHOTO_LAUNCH2(CONV_, 4);            \
+    else MAL_PHOTO_LAUNCH2(CONV_, 2);                             \
   } while (0)
   if (a.convention == MAL_CONV_MANYDEPTH) MAL_PHOTO_LAUNCH(MAL_CONV_MANYDEPTH);
   else MAL_PHOTO_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_PHOTO_GO
 #undef MAL_PHOTO_LAUNCH2
 #undef MAL_PHOTO_LAUNCH
 }
@@ -631,6 +661,12 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }
   const int ncand = single ? 1 : (a.syn[0] ? 4 : 2);
+  if (a.avg_reprojection) {
+    MAL_REQUIRE(ncand == 2, "mal_photo_forward: avg_reprojection averages exactly two candidates (no syn, no single)");
+    MAL_REQUIRE(!(a.with_grad && a.mode == MAL_PHOTO_PRED),
+                "mal_photo_forward: avg_reprojection with gradients is a WARP-mode feature (PRED mode: average the "
+                "single-candidate maps of compute_reprojection_loss)");
+  }
   const bool grad = a.with_grad != 0;
   const bool warp = a.mode == MAL_PHOTO_WARP;
   // disp_to_depth scalars exactly as python computes them (double), then rounded once to fp32
@@ -638,7 +674,7 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   const float min_disp = (float)lo, range = (float)(hi - lo);
   dim3 grid((a.width + PH_TW - 1) / PH_TW, (a.height + PH_TH - 1) / PH_TH, a.batch);
   MAL_REQUIRE(grid.y <= 65535, "mal_photo_forward: image too tall");
-  size_t smem = photo_smem_bytes(grad, warp, ncand);
+  size_t smem = photo_smem_bytes(grad, warp, ncand, a.avg_reprojection != 0);
   cudaStream_t st = (cudaStream_t)stream;
 
   // TMA descriptors for every tensor the CTAs stage whole; any tensor TMA cannot address (rows that are not

@@ -79,12 +79,13 @@ def _candidates(inputs, outputs, scale, with_syn):
     return dict(src=[outputs[("color", f, scale)] for f in (-1, 1)], syn=syn, mode=raw.PHOTO_PRED)
 
 
-def identity_reprojection(ssim, inputs, source_scale=0):
-    """min over f of compute_reprojection_loss(inputs[("color", f, 0)], target), loss_utils.py:92-101."""
+def identity_reprojection(ssim, inputs, source_scale=0, avg_reprojection=False):
+    """min (mean with avg_reprojection) over f of compute_reprojection_loss(inputs[("color", f, 0)], target),
+    loss_utils.py:92-101."""
     target = inputs[("color", 0, source_scale)]
     with torch.no_grad():
         _, ident, _ = ops.photo(target, [inputs[("color", -1, source_scale)], inputs[("color", 1, source_scale)]],
-                                mode=raw.PHOTO_PRED, no_ssim=_no_ssim(ssim))
+                                mode=raw.PHOTO_PRED, no_ssim=_no_ssim(ssim), avg_reprojection=avg_reprojection)
     return ident
 
 

@@ -63,7 +63,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           identity_min=None, noise=None, pixel_mask=None, sample_mask=None,
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
-          want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True):
+          want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True,
+          avg_reprojection=False):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
     finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
@@ -125,6 +126,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.grad_depth, a.grad_P = _ptr(out.get("grad_depth")), _ptr(out.get("grad_P"))
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     a.skip_finalize = 0 if finalize else 1
+    a.avg_reprojection = int(bool(avg_reprojection))
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
     LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
     out["_keepalive"] = (partials,)

@@ -190,8 +190,7 @@ def compute_losses_dualrefine(inputs, outputs, opt, noises=None):
     """dualrefine/trainer.py compute_losses :530-697 (f_thres > 0 branch): per (scale, deq_iter)
     fused photometric pass with automask x consistency mask, consistency towards the deq_iter-0
     depth, smoothness.  Returns the losses dict."""
-    if getattr(opt, "avg_reprojection", False):
-        raise NotImplementedError("avg_reprojection (mean instead of min over frames) is not implemented")
+    avg = bool(getattr(opt, "avg_reprojection", False))   # mean instead of min over frames (:575-586): a kernel mode
     losses, total_loss = {}, 0
     target = inputs[("color", 0, 0)]
     ssim = _Ssim(_o(opt, "no_ssim"))
@@ -206,9 +205,9 @@ def compute_losses_dualrefine(inputs, outputs, opt, noises=None):
             spec = outputs[("warp_spec", scale, it)]
             kw = dict(src=[inputs[("color", f, 0)] for f in (-1, 1)], depth=spec.disp, K=spec.K, inv_K=spec.inv_K,
                       T=spec.T, convention=spec.convention, depth_is_disp=True, min_depth=spec.min_depth,
-                      max_depth=spec.max_depth, no_ssim=ssim.no_ssim)
+                      max_depth=spec.max_depth, no_ssim=ssim.no_ssim, avg_reprojection=avg)
             if automask:
-                ident = identity_reprojection(ssim, inputs) if ident is None else ident
+                ident = identity_reprojection(ssim, inputs, avg_reprojection=avg) if ident is None else ident
                 kw.update(identity_min=ident,
                           noise=_draw_noise(ident.shape, target.device, None if noises is None else noises[draw]))
                 draw += 1

@@ -411,7 +411,8 @@ def dualrefine_images_pred(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, hei
 
 
 def dualrefine_compute_losses(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, automask=True,
-                              motion_masking=True, smoothness=1e-3, noises=None, no_ssim=False):
+                              motion_masking=True, smoothness=1e-3, noises=None, no_ssim=False,
+                              avg_reprojection=False):
     """dualrefine/trainer.py compute_losses :530-697, the f_thres > 0 branch (:543-626): per
     (scale, deq_iter); for deq_iter > 0 the automask is multiplied by the consistency mask and the
     consistency term pulls towards the deq_iter-0 depth; total / len(scales)."""
@@ -428,8 +429,14 @@ def dualrefine_compute_losses(inputs, outputs, scales=(0, 1, 2, 3), n_losses=1, 
             ident = None
             if automask:
                 ident = torch.cat([reprojection_loss(inputs[("color", f, 0)], target, no_ssim) for f in (-1, 1)], 1)
-                ident, _ = torch.min(ident, dim=1, keepdim=True)
-            reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
+                if avg_reprojection:      # dualrefine/trainer.py:575-576
+                    ident = ident.mean(1, keepdim=True)
+                else:
+                    ident, _ = torch.min(ident, dim=1, keepdim=True)
+            if avg_reprojection:          # :585-586
+                reproj, frame_idx = cands.mean(1, keepdim=True), torch.zeros_like(cands[:, :1]).long()
+            else:
+                reproj, frame_idx = torch.min(cands, dim=1, keepdim=True)
             if automask:
                 nz = noises[draw] if noises is not None else torch.randn(ident.shape)
                 draw += 1

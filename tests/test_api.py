@@ -286,15 +286,17 @@ def test_dynamicdepth_matcher(op_device):
         assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
 
 
-def test_dualrefine_losses_match_oracle(op_device):
+@pytest.mark.parametrize("avg", [False, True])
+def test_dualrefine_losses_match_oracle(op_device, avg):
     """BASELINE config 4: DualRefine's per-(scale, deq_iter) losses with half-pixel sampling
-    (dualrefine/trainer.py:395-455, :530-626) - selections bit-exact, losses and gradients."""
+    (dualrefine/trainer.py:395-455, :530-626) - selections bit-exact, losses and gradients; with
+    opt.avg_reprojection the mean instead of the min over the two frames (:575-586)."""
     dev = op_device
     B, H, W = 1, 32, 64
     scales = [0, 1, 2, 3]
     inputs, t = make_photometric_inputs(B, H, W, num_scales=4, seed=61, translation_scale=0.3)
     opt = SimpleNamespace(height=H, width=W, scales=scales, n_losses=1, min_depth=0.1, max_depth=100.0,
-                          disparity_smoothness=1e-3)
+                          disparity_smoothness=1e-3, avg_reprojection=avg)
     keys = [(s, it) for s in scales if s != 1 for it in range(2 if s in (0, 1, 2) else 1)]
     noises = [torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(70 + i)) for i in range(len(keys))]
     cmask = t["consistency_mask"].unsqueeze(1)
@@ -312,7 +314,7 @@ def test_dualrefine_losses_match_oracle(op_device):
 
     inp_c, o_c, leaves_c = build("cpu")
     O.dualrefine_images_pred(inp_c, o_c, scales, 1, H, W)
-    want, aux = O.dualrefine_compute_losses(inp_c, o_c, scales, 1, noises=noises)
+    want, aux = O.dualrefine_compute_losses(inp_c, o_c, scales, 1, noises=noises, avg_reprojection=avg)
     want_g = torch.autograd.grad(want["loss"], leaves_c)
 
     inp_d, o_d, leaves_d = build(dev)
@@ -323,6 +325,7 @@ def test_dualrefine_losses_match_oracle(op_device):
     for s, it in keys:
         sel = o_d[("mal_selection", s, it)].cpu().numpy()
         assert np.array_equal(sel & 0x7F, aux[("frame_idx", s, it)].numpy().astype(np.uint8)), (s, it)
+        assert np.array_equal(sel >> 7, aux[("mask", s, it)].numpy().astype(np.uint8)) or it > 0   # bit-exact automask
     g = torch.autograd.grad(got["loss"], leaves_d)
     for a, b in zip(g, want_g):
         assert _gerr(a, b) < GRAD_RTOL
