@@ -47,6 +47,9 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU step (0: the GPU arm's batch)")
     p.add_argument("--skip-cpu-baseline", action="store_true")
+    p.add_argument("--ddp", action="store_true",
+                   help="time the data-parallel TRAINING step (stand-in nets padded to the reference's parameter count, "
+                        "NCCL gradient all-reduce) instead of the hot path alone")
     p.add_argument("--syn-as-data", action="store_true",
                    help="hand the step ready-made temporal-hint images instead of instance masks (round-1 workload)")
     return p.parse_args()
@@ -480,6 +483,95 @@ def ours(args):
         emit(line)
 
 
+# ------------------------------------------------------------------------------------------------
+# data-parallel training step (config 2 with the networks and the gradient all-reduce)
+# ------------------------------------------------------------------------------------------------
+def ddp_arm(args):
+    """One rank per GPU: stand-in conv nets (cuDNN) + ~40 M ballast parameters -> cost-volume head -> MAL losses
+    through the autograd ops -> backward with DDP's bucketed NCCL all-reduce overlapped -> Adam.  Reports the step
+    time, the share of it spent in the hot path, and the all-reduce time that is NOT hidden behind the backward
+    (step with the all-reduce minus the same step under no_sync)."""
+    import torch.distributed as dist
+    from mal_b200 import _capi, ddp, loss_utils, step as S
+    rank, world, dev = ddp.init_distributed()
+    _capi.check(_capi.lib().mal_check_device(dev.index))
+    opt = S.default_opt(args.batch, HEIGHT, WIDTH)
+    torch.manual_seed(0)
+    net = ddp.StandInNets(opt.matching_channels, opt.num_depth_bins, ballast_params=40_000_000).to(dev)
+    nparams = sum(p.numel() for p in net.parameters())
+    model = ddp.wrap(net, dev)
+    optim = torch.optim.Adam(model.parameters(), 1e-4)
+    blc = loss_utils.LossBalancing(2, 1 << 20, opt.batch_size)
+    sets = [ddp.synthetic_inputs(opt, 1234 + 17 * i + 1000 * rank, dev) for i in range(args.sets)]
+    it = [0]
+
+    def step(i, sync=True):
+        inputs, bins = sets[i % args.sets]
+        if sync or world == 1:
+            ddp.train_step(model, inputs, bins, opt, optim, blc, it[0])
+        else:
+            with model.no_sync():
+                ddp.train_step(model, inputs, bins, opt, optim, blc, it[0])
+        it[0] += 1
+
+    def hot_only(i):
+        # the hot path alone on detached network outputs: forward + backward to the disparities and poses
+        inputs, bins = sets[i % args.sets]
+        with torch.no_grad():
+            mono, outs = net(inputs, bins, opt)
+        for d in (mono, outs):
+            for k in list(d):
+                if torch.is_tensor(d[k]) and d[k].is_floating_point() and k != "augmentation_mask":
+                    d[k] = d[k].detach()
+        leaves = [mono[("disp", 0)].requires_grad_(True), outs[("disp", 0)].requires_grad_(True)]
+        for f in (-1, 1):
+            T = mono[("cam_T_cam", 0, f)].detach().requires_grad_(True)
+            mono[("cam_T_cam", 0, f)] = outs[("cam_T_cam", 0, f)] = T
+            leaves.append(T)
+            mono[("syn", f, 0)] = outs[("syn", f, 0)] = inputs[("syn", f, 0)]
+        from mal_b200 import trainer_ops
+        _, losses = trainer_ops.process_batch_losses(inputs, mono, outs, opt, has_ins=True)
+        torch.autograd.grad(losses["loss"] + losses["distil_loss"], leaves, allow_unused=True)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    steps, warm = min(args.steps, 50), max(3, min(args.warmup, 10))
+    ms_step = timed(lambda i: step(i, True), steps, warm)
+    ms_nosync = timed(lambda i: step(i, False), steps, warm) if world > 1 else ms_step
+    ms_hot = timed(hot_only, steps, warm)
+    if rank == 0:
+        frames = args.batch * world
+        emit({"metric": "ManyDepth+MAL data-parallel training step frames/s @192x640 (stand-in nets, %d parameters)" % nparams,
+              "value": frames / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+              "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic", "config": dict(workload_config(args, args.batch), ddp=True, optimizer="Adam",
+                                                  parameters=nparams, grad_bytes_per_step=4 * nparams),
+              "hot_path_ms": ms_hot, "hot_path_frac": ms_hot / ms_step,
+              "allreduce_exposed_ms": max(0.0, ms_step - ms_nosync), "ms_per_step_no_allreduce": ms_nosync,
+              "note": "hot path through the autograd ops (op by op, ready-made temporal-hint images); the captured-graph "
+                      "MalStep of the default bench is ~2x faster on the same work"})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _RESULT = None   # the process's real stdout, kept for the one JSON line
 
 
@@ -500,6 +592,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.ddp:
+        ddp_arm(args)
     else:
         ours(args)
 

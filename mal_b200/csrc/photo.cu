@@ -414,15 +414,17 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       }
       // (SYNG is a template parameter: the extra code costs the plain teacher pass 3% through the
       // instruction cache even when it never runs)
-      if (SYNG && a.grad_syn[0] != nullptr)
-        for (int k = 2; k < ncand; k++) image_grad(k, a.grad_syn[k - 2]);
-      float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
-      float xq0[3], xq1[3], yq[3];
+      // with SYNG the same neighbourhood walk also collects d S / d syn (the temporal-hint candidates 2, 3): one
+      // selection load per neighbour decides which of the four accumulators it feeds
+      const bool syn_out = SYNG && a.grad_syn[0] != nullptr;
+      float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
+      float xq0[3], xq1[3], xq2[3] = {0.f, 0.f, 0.f}, xq3[3] = {0.f, 0.f, 0.f}, yq[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         xq0[c] = sx[c * tl.VN + vc];
         xq1[c] = ncand > 1 ? sx[(size_t)tl.TS + c * tl.VN + vc] : 0.0f;
         yq[c] = sy[c * tl.VN + vc];
+        if (SYNG && syn_out) { xq2[c] = sx[(size_t)2 * tl.TS + c * tl.VN + vc]; xq3[c] = sx[(size_t)3 * tl.TS + c * tl.VN + vc]; }
       }
       if (!a.no_ssim) {
 #pragma unroll
@@ -438,7 +440,17 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
             float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
             int li = lc + dy * tl.LW + dx;
             int s = lsel[li];
-            if (s < 0 || (SYNG && s > 1)) continue;   // only the warped candidates chain into depth / pose here
+            if (s < 0) continue;
+            if (SYNG && s > 1) {   // a temporal-hint candidate: its gradient goes to grad_syn, not into depth / pose
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const float xq = s == 2 ? xq2[c] : xq3[c];
+                const float v = m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq * coef[(c * 3 + 1) * tl.LN + li] +
+                                     yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
+                if (s == 2) g2[c] += v; else g3[c] += v;
+              }
+              continue;
+            }
             if (AVG) {
 #pragma unroll
               for (int c = 0; c < 3; c++) {
@@ -458,6 +470,24 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
               if (s == 0) g0[c] += v; else g1[c] += v;
             }
           }
+        }
+      }
+      if (SYNG && syn_out) {
+        const int s = lsel[lc];
+        if (s > 1) {
+          const float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const float d = yq[c] - (s == 2 ? xq2[c] : xq3[c]);
+            const float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
+            if (s == 2) g2[c] += sg; else g3[c] += sg;
+          }
+        }
+        const size_t pq = (size_t)gy * W + gx;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          a.grad_syn[0][((size_t)b * 3 + c) * HW + pq] = g2[c];
+          a.grad_syn[1][((size_t)b * 3 + c) * HW + pq] = g3[c];
         }
       }
       {

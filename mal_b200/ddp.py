@@ -31,7 +31,11 @@ from .pose import transformation_from_parameters
 class StandInNets(nn.Module):
     """Tiny convolutional stand-ins producing the tensors the hot path consumes."""
 
-    def __init__(self, matching_channels=64, num_depth_bins=96):
+    def __init__(self, matching_channels=64, num_depth_bins=96, ballast_params=0):
+        """`ballast_params` > 0 pads the pose head with dense layers of about that many parameters, so that the
+        gradient all-reduce has the reference's volume (3 x ResNet18 + decoders, ~40 M fp32 parameters = 160 MB,
+        SURVEY.md section 8e) without rebuilding its conv nets; the layers sit on the path to the poses and get
+        real gradients."""
         super().__init__()
         conv = lambda i, o, s=1: nn.Sequential(nn.Conv2d(i, o, 3, s, 1), nn.ELU())
         self.mono = nn.Sequential(conv(3, 16, 2), conv(16, 16), nn.Upsample(scale_factor=2, mode="nearest"),
@@ -39,8 +43,12 @@ class StandInNets(nn.Module):
         self.feat = nn.Sequential(conv(3, 32, 2), conv(32, matching_channels, 2))           # 1/4 resolution
         self.multi = nn.Sequential(conv(matching_channels + num_depth_bins, 32),
                                    nn.Upsample(scale_factor=4, mode="nearest"), nn.Conv2d(32, 1, 3, 1, 1))
-        self.pose = nn.Sequential(conv(6, 16, 4), conv(16, 16, 4), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
-                                  nn.Linear(16, 6))
+        head = [nn.Linear(16, 6)]
+        if ballast_params > 0:
+            d1 = 4096
+            d2 = max(64, int(ballast_params // d1))
+            head = [nn.Linear(16, d1), nn.ELU(), nn.Linear(d1, d2), nn.ELU(), nn.Linear(d2, 6)]
+        self.pose = nn.Sequential(conv(6, 16, 4), conv(16, 16, 4), nn.AdaptiveAvgPool2d(1), nn.Flatten(), *head)
 
     def predict_pose(self, a, b, invert):
         out = 0.01 * self.pose(torch.cat([a, b], 1)).view(-1, 1, 2, 3)   # repdepth.py:141-170, pose_decoder scale

@@ -85,3 +85,36 @@ def test_two_rank_gloo_training_step(tmp_path):
         assert torch.allclose(a, (x + y) / 2, rtol=1e-5, atol=1e-8)        # DDP averages the per-rank gradients
     for a, b in zip(r0["params"], r1["params"]):
         assert torch.equal(a, b)
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, device = ddp.init_distributed("nccl")
+    torch.manual_seed(0)
+    opt = default_opt(2, 64, 96, num_depth_bins=16, matching_channels=32, loss_blc=False)
+    model = ddp.wrap(ddp.StandInNets(opt.matching_channels, opt.num_depth_bins, ballast_params=200_000).to(device), device)
+    optim = torch.optim.SGD(model.parameters(), 0.05)
+    inputs, bins = ddp.synthetic_inputs(opt, 100 + rank, device)      # each rank has its own batch
+    losses = []
+    for it in range(3):
+        losses.append(float(ddp.train_step(model, inputs, bins, opt, optim)["loss"]))
+    params = [p.detach().cpu().clone() for p in model.module.parameters()]
+    torch.save({"losses": losses, "params": params}, os.path.join(out, f"n{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_two_rank_nccl_training_steps_end_with_identical_parameters(tmp_path):
+    """The data-parallel step on hardware: two ranks (one GPU each) under NCCL, three optimizer steps with the
+    CUDA kernels on the path; rank-local losses differ (no loss collective), parameters end identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    mp.spawn(_nccl_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"n{i}.pt") for i in range(2))
+    assert all(abs(a - b) > 1e-7 for a, b in zip(r0["losses"], r1["losses"]))
+    assert all(l == l for l in r0["losses"] + r1["losses"])
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b)
