@@ -70,6 +70,7 @@ class StandInNets(nn.Module):
                                                   inputs[("inv_K", 2)], bins, apply_confidence=True)
         outputs[("disp", 0)] = torch.sigmoid(self.multi(torch.cat([feats, cv], 1)))
         outputs["lowest_cost"], outputs["consistency_mask"] = low, conf      # matching resolution
+        outputs["cost_volume"] = cv
         B = cur.shape[0]
         outputs["augmentation_mask"] = torch.zeros(B, 1, 1, 1, device=cur.device)
         return mono_outputs, outputs
@@ -109,6 +110,42 @@ def train_step(model, inputs, bins, opt, optimizer=None, loss_blc=None, index_it
     if optimizer is not None:
         optimizer.step()
     return losses
+
+
+def train_step_fused(model, inputs, bins, opt, optimizer=None, loss_blc=None, index_iter=0, noises=None,
+                     lambda_for_adjust=0.0):
+    """The same step with the hot path as the fused libmal_b200 schedule (mal_b200.step.fused_step: ~17 launches,
+    no autograd graph through the losses): the networks' outputs are the leaves, the kernels return d total / d leaf
+    and autograd continues from there into the networks (and DDP's all-reduce).  CUDA only."""
+    from . import _capi, step as S
+    net = model.module if hasattr(model, "module") else model
+    mono_outputs, outputs = model(inputs, bins, opt)
+    B, H, W = opt.batch_size, opt.height, opt.width
+    leaves = [mono_outputs[("disp", 0)], outputs[("disp", 0)], outputs[("cam_T_cam", 0, -1)], outputs[("cam_T_cam", 0, 1)]]
+    dev = leaves[0].device
+    noises = noises or [torch.randn(B, 1, H, W).to(dev, non_blocking=True) for _ in range(2)]   # CPU draw, like the reference
+    b = {"color_0": inputs[("color", 0, 0)], "color_-1": inputs[("color", -1, 0)], "color_1": inputs[("color", 1, 0)],
+         "syn_-1": inputs[("syn", -1, 0)], "syn_1": inputs[("syn", 1, 0)], "K": inputs[("K", 0)], "inv_K": inputs[("inv_K", 0)],
+         "mono_disp": leaves[0].detach(), "multi_disp": leaves[1].detach(), "T_-1": leaves[2].detach(),
+         "T_1": leaves[3].detach(), "augmentation_mask": outputs["augmentation_mask"], "noise_mono": noises[0],
+         "noise_main": noises[1]}
+    head = {"cost_volume": outputs["cost_volume"], "confidence": outputs["consistency_mask"],
+            "lowest_cost": outputs["lowest_cost"]}
+    w = None
+    if loss_blc is not None:
+        w = torch.tensor(loss_blc.w_list, dtype=torch.float32).to(dev, non_blocking=True)
+    with torch.no_grad():
+        scalars, grads, outs = S.fused_step(_capi.lib(), b, opt, w, head=head)
+    if optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    torch.autograd.backward(leaves, [g.reshape(l.shape) for g, l in zip(grads, leaves)])   # DDP all-reduces here
+    if optimizer is not None:
+        optimizer.step()
+    sc = scalars.cpu()
+    if loss_blc is not None:
+        loss_blc.record_scores(index_iter, [float(sc[1]), float(sc[2])])
+        loss_blc.update_weight(index_iter, lambda_for_adjust)
+    return {"loss": sc[0], "reproj_loss/0": sc[4], "distil_loss": sc[2], "_outputs": outs}
 
 
 def synthetic_inputs(opt, seed, device):

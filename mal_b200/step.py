@@ -168,13 +168,14 @@ def _head_op(cur, look, poses, K, inv_K, bins):
     return cv, low, conf
 
 
-def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None):
+def fused_step(handle, b, opt, weights=None, has_ins=True, multi_has_ins=False, side_streams=None, head=None):
     """fused_step_main + fused_step_tail in one go (see there)."""
-    ctx = fused_step_main(handle, b, opt, has_ins=has_ins, multi_has_ins=multi_has_ins, side_streams=side_streams)
+    ctx = fused_step_main(handle, b, opt, has_ins=has_ins, multi_has_ins=multi_has_ins, side_streams=side_streams,
+                          head=head)
     return fused_step_tail(handle, b, opt, weights, ctx)
 
 
-def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_streams=None):
+def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_streams=None, head=None):
     """Everything of the fused step that does not depend on the loss-balancing weights (every kernel but the
     last); returns the intermediates fused_step_tail needs.
 
@@ -206,9 +207,10 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     branch = _Branches(main, side_streams)
 
     with branch(0):   # cost-volume head and the matching mask that only depends on it and the teacher disparity
-        head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"],
-                               poses=b["relative_poses"], K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"],
-                               apply_confidence=True, want_missing=False)
+        if head is None:   # (a caller whose student network already consumed the cost volume hands it in)
+            head = raw.cost_volume(handle, current=b["current_feats"], lookup=b["lookup_feats"],
+                                   poses=b["relative_poses"], K=b["K2"], inv_K=b["inv_K2"], bins=b["bins"],
+                                   apply_confidence=True, want_missing=False)
         mask = raw.matching_mask(handle, lowest_cost=head["lowest_cost"], confidence=head["confidence"], mono=mono,
                                  mono_is_disp=True, min_depth=lo, max_depth=hi)
     with branch(1):   # smoothness of both disparities: one launch, the chain through the normalisation is

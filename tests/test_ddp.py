@@ -97,8 +97,9 @@ def _nccl_worker(rank, world, port, out):
     optim = torch.optim.SGD(model.parameters(), 0.05)
     inputs, bins = ddp.synthetic_inputs(opt, 100 + rank, device)      # each rank has its own batch
     losses = []
-    for it in range(3):
-        losses.append(float(ddp.train_step(model, inputs, bins, opt, optim)["loss"]))
+    for it in range(3):   # first the op-by-op autograd path, then the fused schedule
+        step = ddp.train_step if it == 0 else ddp.train_step_fused
+        losses.append(float(step(model, inputs, bins, opt, optim)["loss"]))
     params = [p.detach().cpu().clone() for p in model.module.parameters()]
     torch.save({"losses": losses, "params": params}, os.path.join(out, f"n{rank}.pt"))
     dist.barrier()
