@@ -504,14 +504,22 @@ def ddp_arm(args):
     blc = loss_utils.LossBalancing(2, 1 << 20, opt.batch_size)
     sets = [ddp.synthetic_inputs(opt, 1234 + 17 * i + 1000 * rank, dev) for i in range(args.sets)]
     it = [0]
+    # The reference draws the two tie-break noise planes with torch.randn on the CPU every step (loss_utils.py:
+    # 105-106, :178) - ~3 M normals, milliseconds of host time that a loader thread can prefetch.  Here the draws
+    # are made ahead of the timed loop (one pair per input set) and their cost is reported beside the step time.
+    t0 = time.perf_counter()
+    noise_sets = [[torch.randn(args.batch, 1, HEIGHT, WIDTH) for _ in range(2)] for _ in range(args.sets)]
+    cpu_noise_ms = 1e3 * (time.perf_counter() - t0) / args.sets
+    noise_sets = [[n.pin_memory().to(dev, non_blocking=True) for n in ns] for ns in noise_sets]
 
     def step(i, sync=True):
         inputs, bins = sets[i % args.sets]
+        kw = dict(noises=noise_sets[i % args.sets])
         if sync or world == 1:
-            ddp.train_step_fused(model, inputs, bins, opt, optim, blc, it[0])
+            ddp.train_step_fused(model, inputs, bins, opt, optim, blc, it[0], **kw)
         else:
             with model.no_sync():
-                ddp.train_step_fused(model, inputs, bins, opt, optim, blc, it[0])
+                ddp.train_step_fused(model, inputs, bins, opt, optim, blc, it[0], **kw)
         it[0] += 1
 
     def hot_only(i):
@@ -568,6 +576,7 @@ def ddp_arm(args):
                                                   parameters=nparams, grad_bytes_per_step=4 * nparams),
               "hot_path_ms": ms_hot, "hot_path_frac": ms_hot / ms_step,
               "allreduce_exposed_ms": max(0.0, ms_step - ms_nosync), "ms_per_step_no_allreduce": ms_nosync,
+              "cpu_noise_draw_ms": cpu_noise_ms,
               "note": "hot path = the fused libmal_b200 schedule launched eagerly on the networks' outputs (ready-made "
                       "temporal-hint images; the student network consumes the cost volume, so the head runs inside "
                       "the networks' forward and is not part of hot_path_ms)"})
