@@ -309,6 +309,43 @@ def next_row_kernels(dev, batch, peak_gbs, iters=10):
          lambda: raw.dynamic_instance(h, mask_last=ml, mask_next=mn, img_last=il, img_next=inx),
          (2 * 12 + 4 * 12) * HEIGHT * Wc),
     ]
+    # the temporal-hint pipeline of the step, batched over the samples (csrc/temporal.cu): warps, packed-mask
+    # synthesis, backward into the disparity and the poses
+    from mal_b200 import step as S
+    topt = S.default_opt(B, HEIGHT, WIDTH)
+    pl, pn, cnt = S.synthetic_masks(topt, seed=7)
+    pl, pn, cnt = pl.to(dev), pn.to(dev), cnt.to(dev)
+    geom = dict(src=src, depth=t[("mono_disp", 0)], K=inputs[("K", 0)], inv_K=inputs[("inv_K", 0)], T=Ts)
+    warped = raw.temporal_warp(h, **geom)
+    hint = raw.temporal_synthesis(h, warped=warped, packed_last=pl, packed_next=pn, counts=cnt)
+    gsyn = [torch.randn(B, 3, HEIGHT, WIDTH, generator=g).to(dev) for _ in range(2)]
+    gd, gP = torch.zeros(B, 1, HEIGHT, WIDTH, device=dev), torch.zeros(B, 2, 12, device=dev)
+    cases += [
+        ("f.1", "tw_warp_kernel: both warped source images of the batch materialised (trainer.py:1111-1125)",
+         lambda: raw.temporal_warp(h, **geom), (24 + 4 + 24) * px),
+        ("f.1", "ts_extents + ts_compose: image_synthesis for the batch from packed instance masks (<= 12 per sample)",
+         lambda: raw.temporal_synthesis(h, warped=warped, packed_last=pl, packed_next=pn, counts=cnt), (8 + 24 + 24) * px),
+        ("f.1", "tb_backward_kernel: d loss / d syn -> disparity and pose gradients",
+         lambda: raw.temporal_backward(h, grad_syn=gsyn, packed_last=pl, packed_next=pn, counts=cnt, deltas=hint["deltas"],
+                                       want_grad_warped=False, grad_depth=gd, grad_P=gP, **geom), (24 + 8 + 24 + 8) * px),
+    ]
+
+    # DynamicDepth (config 5): the pool occlusion fill of the cost volume and the 4-scale loss half
+    from mal_b200.utils.synthetic import make_cost_volume_inputs, CITYSCAPES_K
+    cvd = make_cost_volume_inputs(B, HEIGHT, Wc, channels=64, num_lookup=2, num_bins=96, seed=9, min_bin=0.5, max_bin=20.0,
+                                  translation_scale=0.5, normalised_K=CITYSCAPES_K)
+    cvd = {k: v.to(dev) for k, v in cvd.items()}
+    occ = torch.zeros(B, HEIGHT // 4, Wc // 4)
+    occ[:, 12:30, 40:80] = 1.0                                  # ~12% of the matching-resolution pixels occluded
+    occ = occ.to(dev)
+    aug = torch.zeros(B, 1, 1, 1, device=dev)
+    lcv = B * (HEIGHT // 4) * (Wc // 4)
+    cases.append(("f.4", "cv_sweep_kernel<DYN>: DynamicDepth cost volume, 2 lookup frames, cv_min + pool occlusion fill (radius 1)",
+                  lambda: raw.cost_volume(h, current=cvd["current_feats"], lookup=cvd["lookup_feats"], poses=cvd["relative_poses"],
+                                          K=cvd["K"], inv_K=cvd["inv_K"], bins=cvd["bins"], cv_min=True, occ=occ,
+                                          occ_mode=raw.OCC_POOL, pool_radius=1, pool_th=0.7, aug_mask=aug),
+                  (3 * 64 * 4 + 2 * 96 * 4 + 4) * lcv))
+
     out = []
     with torch.no_grad():
         for row, name, fn, nbytes in cases:
@@ -325,7 +362,50 @@ def next_row_kernels(dev, batch, peak_gbs, iters=10):
             gbs = nbytes / (us * 1e-6) / 1e9
             out.append({"row": row, "kernel": name, "us_per_call": us, "algorithmic_bytes": int(nbytes),
                         "achieved_gbs": gbs, "frac": gbs / peak_gbs})
+    out.append(dynamicdepth_loss_row(dev, B, Wc, peak_gbs))
     return out
+
+
+def dynamicdepth_loss_row(dev, B, Wc, peak_gbs, iters=5):
+    """Config 5's loss half: dynamicdepth/trainer.py compute_losses :1006-1128 over 4 scales with selec_reproj and
+    zero_img, forward + backward to the four disparities and the two poses (the classic path: one PRED-mode
+    SSIM+L1 map per materialised warp, because zero_img makes each map depend on the calls before it)."""
+    from types import SimpleNamespace
+    from mal_b200 import trainer_ops
+    from mal_b200.utils.synthetic import CITYSCAPES_K, make_photometric_inputs, to_device
+    inputs, t = make_photometric_inputs(B, HEIGHT, Wc, num_scales=4, seed=55, normalised_K=CITYSCAPES_K)
+    inputs, t = to_device(inputs, dev), to_device(t, dev)
+    opt = SimpleNamespace(height=HEIGHT, width=Wc, scales=[0, 1, 2, 3], sclm=3, min_depth=0.1, max_depth=100.0,
+                          frame_ids=[0, -1, 1], batch_size=B, disparity_smoothness=1e-3, selec_reproj=True, zero_img=True,
+                          avg_reprojection=False, no_ssim=False, disable_automasking=False)
+    noises = [torch.randn(B, 1, HEIGHT, Wc, device=dev) for _ in range(4)]
+
+    def run():
+        disps = [t[("mono_disp", s)].clone().requires_grad_(True) for s in range(4)]
+        Ts = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
+        o = {("disp", s): disps[s] for s in range(4)}
+        o.update({("cam_T_cam", 0, f): Ts[f] for f in (-1, 1)})
+        inp = dict(inputs)
+        inp[("color", 0, 0)] = inputs[("color", 0, 0)].clone()   # zero_img mutates the target in place
+        trainer_ops.generate_images_pred(inp, o, opt, materialize=True)
+        losses = trainer_ops.compute_losses_dynamicdepth(inp, o, opt, noises=noises)
+        torch.autograd.grad(losses["loss"], disps + [Ts[-1], Ts[1]])
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    nbytes = 4 * (36 + 4 * 1.328125 + 4 * 1.328125 + 16) * B * HEIGHT * Wc * 2   # SURVEY 8(d) A_photo, fwd + bwd
+    gbs = nbytes / (us * 1e-6) / 1e9
+    return {"row": "a11 (DynamicDepth)", "kernel": "compute_losses_dynamicdepth: 4 scales, selec_reproj + zero_img, fwd + bwd "
+            "(op by op through autograd: warps materialised, one SSIM+L1 map per warp)", "us_per_call": us,
+            "algorithmic_bytes": int(nbytes), "achieved_gbs": gbs, "frac": gbs / peak_gbs}
 
 
 def ours(args):

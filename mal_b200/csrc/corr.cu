@@ -25,8 +25,6 @@
 // vector reductions into the quad-interleaved pyramid gradient: one per tap and channel quad) - the same
 // atomics ATen's grid_sampler_2d_backward issues, a quarter as many, without the (B, C, h, w, D)
 // intermediates.
-#include <cstdlib>
-
 #include "mal_math.cuh"
 
 namespace mal {
@@ -305,157 +303,6 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
   }
 }
 
-// ---- backward, pixel-major (C <= 64): no atomics for d/d fmap1, ~2.5x fewer for d/d pyramid ------------------
-// A CTA owns 32 consecutive pixels (lanes) x 8 or 16 channel quads (warps); every thread walks ALL levels and
-// candidates of its pixel for its channel quad.  Consequences:
-//   * d/d fmap1 of a (pixel, channel) is summed in a register over the L x D candidates and stored once - the
-//     per-candidate kernel above issues L x D atomic adds onto each element;
-//   * consecutive candidates of an epipolar line mostly fall into the same 2x2 texel cell: their contributions
-//     to the pyramid gradient are merged in registers and flushed (four 128-bit reductions per quad) only when
-//     the cell changes;
-//   * d/d coords needs the sum over the channel quads: per level the partials go to a shared-memory slab
-//     [candidate][slice][pixel] and are added in slice order after one barrier (deterministic).
-constexpr int CB_MAX_SLICES = 16;   // 8 slices (256 threads) up to 32 channels, 16 (512 threads) up to 64
-
-template <int CB_SLICES, bool PYR>
-__global__ void __launch_bounds__(CB_SLICES * 32) corr_lookup_bwd_px_kernel(const mal_corr_args a) {
-  constexpr int QPL = 1, CB_NT = CB_SLICES * 32;        // one channel quad per thread
-  float* slab = reinterpret_cast<float*>(dyn_smem());   // [D][2][slices][32]
-  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int h = a.height, w = a.width, C = a.channels, Cg = C / a.num_head, Qg = Cg / 4, Qtot = C / 4;
-  const int D = a.num_samples, L = a.num_levels;
-  const size_t hw = (size_t)h * w;
-  const int segs = (int)((hw + 31) / 32);
-  const int b = blockIdx.x / segs;
-  const size_t pix = (size_t)(blockIdx.x - b * segs) * 32 + lane;
-  const bool ok = pix < hw;
-  CorrSite s;
-  s.b = b; s.y = ok ? (int)(pix / w) : 0; s.x = ok ? (int)(pix - (size_t)s.y * w) : 0;
-  const float* f1 = a.fmap1 + (size_t)b * C * hw + pix;
-  float f1v[QPL][4], gf1[QPL][4];
-#pragma unroll
-  for (int j = 0; j < QPL; j++) {
-    const int qq = sl + CB_SLICES * j;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      f1v[j][k] = (ok && qq < Qtot) ? __ldg(f1 + ((size_t)qq * 4 + k) * hw) : 0.0f;
-      gf1[j][k] = 0.0f;
-    }
-  }
-  for (int l = 0; l < L; l++) {
-    s.l = l; s.lh = h >> l; s.lw = w >> l;
-    const size_t lhw = (size_t)s.lh * s.lw;
-    const size_t loff = corr_level_offset(a.batch, C, h, w, l) + (size_t)b * C * lhw;
-    const float4* f2 = reinterpret_cast<const float4*>(a.pyramid + loff);
-    float4* gp = (PYR && a.grad_pyramid) ? reinterpret_cast<float4*>(a.grad_pyramid + loff) : nullptr;
-    // pyramid-gradient contributions of the current texel cell
-    float acc[PYR ? QPL : 1][4][4];
-    Taps cur;
-    cur.o00 = 0; cur.o01 = cur.o10 = cur.o11 = 0; cur.v00 = cur.v01 = cur.v10 = cur.v11 = false;
-    bool have = false;
-    auto flush = [&]() {
-      if (!PYR || !have) return;
-#pragma unroll
-      for (int j = 0; j < QPL; j++) {
-        const int qq = sl + CB_SLICES * j;
-        if (qq >= Qtot) continue;
-        float4* gq = gp + (size_t)qq * lhw;
-        const float (&A)[4][4] = acc[PYR ? j : 0];
-        if (cur.v00 && (A[0][0] != 0.f || A[0][1] != 0.f || A[0][2] != 0.f || A[0][3] != 0.f)) red_add4(gq + cur.o00, A[0][0], A[0][1], A[0][2], A[0][3]);
-        if (cur.v01 && (A[1][0] != 0.f || A[1][1] != 0.f || A[1][2] != 0.f || A[1][3] != 0.f)) red_add4(gq + cur.o01, A[1][0], A[1][1], A[1][2], A[1][3]);
-        if (cur.v10 && (A[2][0] != 0.f || A[2][1] != 0.f || A[2][2] != 0.f || A[2][3] != 0.f)) red_add4(gq + cur.o10, A[2][0], A[2][1], A[2][2], A[2][3]);
-        if (cur.v11 && (A[3][0] != 0.f || A[3][1] != 0.f || A[3][2] != 0.f || A[3][3] != 0.f)) red_add4(gq + cur.o11, A[3][0], A[3][1], A[3][2], A[3][3]);
-      }
-    };
-    for (int d = 0; d < D; d++) {
-      float gix = 0.0f, giy = 0.0f;
-      if (ok && sl < Qtot) {
-        const size_t cbase = (((size_t)b * 2) * L + l) * D + d;
-        const float cx = __ldg(a.coords + cbase * hw + pix);
-        const float cy = __ldg(a.coords + (cbase + (size_t)L * D) * hw + pix);
-        const Taps t = corr_taps(a, s, cx, cy);
-        if (PYR && gp) {
-          const bool same = have && t.o00 == cur.o00 && t.v00 == cur.v00 && t.v01 == cur.v01 && t.v10 == cur.v10 &&
-                            t.v11 == cur.v11;
-          if (!same) {
-            flush();
-#pragma unroll
-            for (int j = 0; j < QPL; j++)
-#pragma unroll
-              for (int tp = 0; tp < 4; tp++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) acc[PYR ? j : 0][tp][k] = 0.0f;
-            cur = t;
-            have = true;
-          }
-        }
-        const float ex = 1.0f - t.tx, ey = 1.0f - t.ty;
-        const size_t obase = (((size_t)b * L + l) * a.num_head * D + d) * hw + pix;
-        float4 ta[QPL], tb[QPL], tc[QPL], td[QPL];
-        float g[QPL];
-#pragma unroll
-        for (int j = 0; j < QPL; j++) {
-          const int qq = sl + CB_SLICES * j;
-          if (qq < Qtot) {
-            const float4* plane = f2 + (size_t)qq * lhw;
-            ta[j] = tap4(plane, t.v00, t.o00); tb[j] = tap4(plane, t.v01, t.o01);
-            tc[j] = tap4(plane, t.v10, t.o10); td[j] = tap4(plane, t.v11, t.o11);
-            g[j] = __ldg(a.grad_out + obase + (size_t)(qq / Qg) * D * hw) / (float)Cg;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < QPL; j++) {
-          const int qq = sl + CB_SLICES * j;
-          if (qq >= Qtot || g[j] == 0.0f) continue;
-          const float av[4] = {ta[j].x, ta[j].y, ta[j].z, ta[j].w}, bv[4] = {tb[j].x, tb[j].y, tb[j].z, tb[j].w};
-          const float cv[4] = {tc[j].x, tc[j].y, tc[j].z, tc[j].w}, dv[4] = {td[j].x, td[j].y, td[j].z, td[j].w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float sv = xfma(dv[k], t.se, xfma(cv[k], t.sw, xfma(bv[k], t.ne, xmul(av[k], t.nw))));
-            const float df = f1v[j][k] - sv;
-            const float sg = df > 0.0f ? g[j] : (df < 0.0f ? -g[j] : 0.0f);   // d|f1 - s| / d f1
-            gix -= sg * ((bv[k] - av[k]) * ey + (dv[k] - cv[k]) * t.ty);
-            giy -= sg * ((cv[k] - av[k]) * ex + (dv[k] - bv[k]) * t.tx);
-            gf1[j][k] += sg;
-            if (PYR && gp) {
-              acc[PYR ? j : 0][0][k] -= sg * t.nw; acc[PYR ? j : 0][1][k] -= sg * t.ne;
-              acc[PYR ? j : 0][2][k] -= sg * t.sw; acc[PYR ? j : 0][3][k] -= sg * t.se;
-            }
-          }
-        }
-      }
-      slab[((d * 2 + 0) * CB_SLICES + sl) * 32 + lane] = gix;
-      slab[((d * 2 + 1) * CB_SLICES + sl) * 32 + lane] = giy;
-    }
-    flush();
-    __syncthreads();
-    if (a.grad_coords) {
-      // ix = ((2 (x + 0.5) / w1 - 1) + 1) * lw / 2 - 0.5  =>  d ix / d x = lw / w1
-      for (int i = threadIdx.x; i < D * 2 * 32; i += CB_NT) {
-        const int px = i & 31, comp = (i >> 5) & 1, d = i >> 6;
-        const size_t p2 = (size_t)(blockIdx.x - b * segs) * 32 + px;
-        if (p2 >= hw) continue;
-        float sum = 0.0f;
-#pragma unroll
-        for (int q = 0; q < CB_SLICES; q++) sum += slab[((d * 2 + comp) * CB_SLICES + q) * 32 + px];
-        const size_t cbase = (((size_t)b * 2) * L + l) * D + d;
-        a.grad_coords[(cbase + (size_t)comp * L * D) * hw + p2] =
-            sum * (comp ? (float)s.lh / (float)h : (float)s.lw / (float)w);
-      }
-    }
-    __syncthreads();
-  }
-  if (a.grad_fmap1 && ok) {
-#pragma unroll
-    for (int j = 0; j < QPL; j++) {
-      const int qq = sl + CB_SLICES * j;
-      if (qq >= Qtot) continue;
-#pragma unroll
-      for (int k = 0; k < 4; k++) a.grad_fmap1[((size_t)b * C + (size_t)qq * 4 + k) * hw + pix] = gf1[j][k];
-    }
-  }
-}
-
 }  // namespace mal
 
 using namespace mal;
@@ -522,22 +369,6 @@ extern "C" int mal_corr_lookup_backward(const mal_corr_args* args, mal_stream_t 
   if (rc) return rc;
   MAL_REQUIRE(a.grad_out && (a.grad_coords || a.grad_fmap1 || a.grad_pyramid),
               "mal_corr_lookup_backward: grad_out and at least one gradient output are required");
-  // up to 64 channels: the pixel-major kernel (d/d fmap1 without atomics, merged pyramid reductions);
-  // MAL_CORR_BWD=candidate forces the one-thread-per-candidate kernel (tuning only)
-  const int slices = a.channels / 4 <= 8 ? 8 : 16;
-  const size_t slab = (size_t)a.num_samples * 2 * slices * 32 * sizeof(float);
-  const char* force = getenv("MAL_CORR_BWD");
-  if (a.channels / 4 <= CB_MAX_SLICES && slab <= 160 * 1024 && !(force && force[0] == 'c')) {
-    const size_t hw = (size_t)a.height * a.width;
-    const dim3 grid((unsigned)(a.batch * ((hw + 31) / 32)));
-    const bool pyr = a.grad_pyramid != nullptr;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (slices == 16 && pyr) launch(corr_lookup_bwd_px_kernel<16, true>, grid, dim3(512), slab, st, a);
-    else if (slices == 16) launch(corr_lookup_bwd_px_kernel<16, false>, grid, dim3(512), slab, st, a);
-    else if (pyr) launch(corr_lookup_bwd_px_kernel<8, true>, grid, dim3(256), slab, st, a);
-    else launch(corr_lookup_bwd_px_kernel<8, false>, grid, dim3(256), slab, st, a);
-    return check_launch("corr_lookup_bwd_px_kernel");
-  }
   const size_t total = corr_threads(a);
   launch(corr_lookup_bwd_kernel, dim3((unsigned)((total + CR_NT - 1) / CR_NT)), dim3(CR_NT), 0, (cudaStream_t)stream, a);
   return check_launch("corr_lookup_bwd_kernel");

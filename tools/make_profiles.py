@@ -58,7 +58,7 @@ def full(tag, rep):
     hdr, units = rows[0], rows[1]
     traffic = {}
     with open(os.path.join(PROF, f"{tag}_ncu_full_summary.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none summary, {tag} (profiles/r1_notes.md has the command)\n")
+        f.write(f"# ncu --set full --clock-control none summary, {tag} (profiles/{tag}_notes.md has the command)\n")
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             f.write(f"\n\n## {name}\n\n")
@@ -73,14 +73,32 @@ def full(tag, rep):
             rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
             traffic.setdefault(name, []).append(float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]])
-    return traffic
+    return traffic, rows
+
+
+def limiter_sentence(hdr, r):
+    """One sentence from the counters that decide what bounds a kernel (no hand-written numbers)."""
+    g = lambda k: float(r[hdr.index(k)]) if k in hdr and r[hdr.index(k)] else float("nan")
+    st = []
+    for i, h in enumerate(hdr):
+        if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and r[i]:
+            st.append((float(r[i]), h.split("issue_stalled_")[1].split("_per_issue")[0]))
+    top = ", ".join("%s %.2f" % (n, v) for v, n in sorted(st, reverse=True)[:3] if n != "selected")
+    return ("not HBM-bound (bit-exact fp32 arithmetic, DESIGN.md section 4): DRAM throughput %.1f%% of peak; issue slots "
+            "%.0f%%, fma pipe %.0f%%, L1 data pipe %.0f%%, %.0f%% of the warp slots resident at %d registers; top stalls "
+            "per issue: %s" % (g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                               g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                               g("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                               g("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                               g("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                               int(g("launch__registers_per_thread")), top))
 
 
 def main():
     tag, lcsv, rep = sys.argv[1:4]
     n, total = launches(tag, lcsv)
     print(f"{tag}: one step = {n} launches, {total:.1f} us serialised")
-    traffic = full(tag, rep)
+    traffic, rows = full(tag, rep)
     pick = lambda pat, idx=0: next((v[min(idx, len(v) - 1)] for k, v in traffic.items() if pat in k), None)
     photo = lambda pat: [v for k, v in traffic.items() if pat in k]
     dram = {"_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, {tag} "
@@ -98,14 +116,24 @@ def main():
     import re
     def first(rx):
         return next((v[0] for k, v in traffic.items() if re.search(rx, k)), None)
-    for key, rx in (("photo_teacher", r"photo_kernel<1, 1, \d, \d, \d, 4>"), ("photo_student", r"photo_kernel<1, 1, \d, \d, \d, 2>"),
-                    ("photo_ensemble", r"photo_kernel<1, 0,"), ("photo_identity", r"photo_kernel<0, 0,"),
-                    ("smooth_main_kernel", r"smooth_main")):
+    pats = (("photo_teacher", r"photo_kernel<1, 1, \d, \d, \d, 4"), ("photo_student", r"photo_kernel<1, 1, \d, \d, \d, 2"),
+            ("photo_ensemble", r"photo_kernel<1, 0,"), ("photo_identity", r"photo_kernel<0, 0,"),
+            ("smooth_kernel", r"smooth_kernel"), ("cost_volume", r"cv_sweep"))
+    for key, rx in pats:
         v = first(rx)
-        if v:
+        if v and key != "cost_volume":
             dram[key] = int(round(v, -5))
     json.dump(dram, open(os.path.join(PROF, "dram_traffic.json"), "w"), indent=1)
     print(json.dumps(dram, indent=1))
+    # what bounds each heavy kernel, in words, from the same capture (bench.py prints it as roofline.limiter)
+    hdr = rows[0]
+    lim = {"_note": f"generated by tools/make_profiles.py from the ncu --set full capture {tag} (profiles/{tag}_ncu_full_summary.txt)"}
+    for key, rx in pats:
+        r = next((r for r in rows[2:] if re.search(rx, r[hdr.index("Kernel Name")])), None)
+        if r is not None:
+            lim[key] = limiter_sentence(hdr, r) + f" (ncu {tag})"
+    json.dump(lim, open(os.path.join(PROF, "limiters.json"), "w"), indent=1)
+    print(json.dumps(lim, indent=1))
 
 
 if __name__ == "__main__":
