@@ -196,7 +196,15 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
         b, sl = bufs[i % len(bufs)], st.slots[i % len(bufs)]
         if "syn_-1" in b:
             return [b["syn_-1"], b["syn_1"]]
-        return sl["ctx"]["hint"]["syn"]
+        if "ctx" in sl:
+            return sl["ctx"]["hint"]["syn"]
+        if "_syn" not in sl:   # eager runs keep no static buffers: synthesise once
+            with torch.no_grad():
+                w = raw.temporal_warp(h, src=[b["color_-1"], b["color_1"]], depth=b["mono_disp"].detach(), K=b["K"],
+                                      inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()])
+                sl["_syn"] = raw.temporal_synthesis(h, warped=w, packed_last=b["masks_last"], packed_next=b["masks_next"],
+                                                    counts=b["mask_counts"])["syn"]
+        return sl["_syn"]
 
     def photo4(i):
         b = bufs[i % len(bufs)]

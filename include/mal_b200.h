@@ -105,6 +105,11 @@ typedef struct mal_photo_args {
                                (manydepth/trainer.py:1093-1094): the full-resolution disparity never
                                exists.  grad_depth stays (B,1,H,W) = d/d(up-sampled value); take it to
                                the low resolution with mal_upsample_bilinear_backward              */
+  float* min_reproj_b;      /* (B,1,H,W) optional, forward-only with four candidates: `min_reproj` is then the min over
+                               candidates 0, 1 and this plane the min over candidates 2, 3 - two independent
+                               2-candidate passes against one target in one launch (the step scores the ensemble
+                               warps and the un-warped sources of the automask, trainer.py:1172-1207 and
+                               loss_utils.py:92-101, together: pass the sources as `syn`)                       */
   int32_t avg_reprojection; /* opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056):
                                mean instead of min over the two candidates (no syn); selection index is 0; with
                                gradients (WARP mode) both warps carry half of it                             */

@@ -30,7 +30,8 @@ class PhotoArgs(C.Structure):
         ("grad_depth", C.c_void_p), ("grad_pred", C.c_void_p * 2), ("partials", C.c_void_p),
         ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
         ("grad_syn", C.c_void_p * 2),
-        ("depth_height", C.c_int32), ("depth_width", C.c_int32), ("avg_reprojection", C.c_int32),
+        ("depth_height", C.c_int32), ("depth_width", C.c_int32), ("min_reproj_b", C.c_void_p),
+        ("avg_reprojection", C.c_int32),
         ("skip_finalize", C.c_int32),
     ]
 

@@ -287,14 +287,16 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
         }
       }
     }
-    float rmin = 0.f;
+    float rmin = 0.f, rmin_b = 0.f;
     int idx = 0;
+    const bool split = NC > 2 && !GRAD && a.min_reproj_b != nullptr;   // two independent 2-candidate mins in one pass
 #pragma unroll
     for (int k = 0; k < NC; k++) {
       if (k < ncand) {
         float l1m = xdivc<3>(lsum[k]);
         float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
         if (AVG) rmin = (k == 0) ? lk : xmul(xadd(rmin, lk), 0.5f);   // .mean(1) of two: (l0 + l1) / 2
+        else if (NC > 2 && split && k >= 2) { if (k == 2 || lk < rmin_b) rmin_b = lk; }   // second min: candidates 2, 3
         else if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
       }
     }
@@ -309,6 +311,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
     const bool interior = ly >= tl.HL && ly < tl.HL + PH_TH && lx >= tl.HL && lx < tl.HL + PH_TW;
     if (interior) {
       if (a.min_reproj) a.min_reproj[po] = rmin;
+      if (NC > 2 && split) a.min_reproj_b[po] = rmin_b;
       if (a.selection) a.selection[po] = (uint8_t)(idx | (mbit << 7));
       if (a.weight) a.weight[po] = w;
       acc_loss += xmul(rmin, w);
@@ -691,6 +694,9 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }
   const int ncand = single ? 1 : (a.syn[0] ? 4 : 2);
+  if (a.min_reproj_b)
+    MAL_REQUIRE(ncand == 4 && !a.with_grad && !a.identity_min && !a.avg_reprojection,
+                "mal_photo_forward: min_reproj_b (a second min over candidates 2, 3) is a forward-only 4-candidate mode");
   if (a.avg_reprojection) {
     MAL_REQUIRE(ncand == 2, "mal_photo_forward: avg_reprojection averages exactly two candidates (no syn, no single)");
     MAL_REQUIRE(!(a.with_grad && a.mode == MAL_PHOTO_PRED),

@@ -64,7 +64,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
           want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True,
-          avg_reprojection=False):
+          avg_reprojection=False, split_min=False):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
     finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
@@ -100,6 +100,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     out["min_reproj"] = new(plane) if want_min_reproj else None
     out["selection"] = new(plane, torch.uint8) if want_selection else None
     out["weight"] = new(plane) if want_weight else None
+    out["min_reproj_b"] = new(plane) if split_min else None   # second min, over the `syn` candidates
     if with_grad and mode == PHOTO_WARP:
         out["grad_depth"], out["grad_P"] = new(plane), new((B, 2, 12))
     if with_grad and mode == PHOTO_PRED:
@@ -127,6 +128,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.partials, a.sums = _ptr(partials), _ptr(out["sums"])
     a.skip_finalize = 0 if finalize else 1
     a.avg_reprojection = int(bool(avg_reprojection))
+    a.min_reproj_b = _ptr(out["min_reproj_b"])
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
     LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
     out["_keepalive"] = (partials,)

@@ -227,8 +227,17 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
         return out
 
     # (the identity and ensemble passes only feed their per-pixel maps forward: their sums are never read)
-    ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
-                      finalize=False)["min_reproj"]
+    if not opt.no_ens:
+        # the ensemble reprojection (trainer.py:1172-1207: both warps under the averaged disparity) and the identity
+        # reprojection of the automask (loss_utils.py:92-101: the un-warped sources) are two 2-candidate mins against
+        # the same target: ONE forward-only pass stages the target and its window moments once for both
+        aux = raw.photo(handle, target=tgt, src=src, syn=src, depth=mono, depth_b=multi, want_selection=False,
+                        finalize=False, split_min=True, **geom)
+        ens, ident = aux["min_reproj"], aux["min_reproj_b"]
+    else:
+        ens = None
+        ident = raw.photo(handle, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False,
+                          finalize=False)["min_reproj"]
     use_syn = opt.temporal and has_ins
     hint = None
     if use_syn and in_step_syn:
@@ -248,10 +257,6 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
                                                  packed_next=b["masks_next"], counts=b["mask_counts"],
                                                  deltas=hint["deltas"], want_grad_warped=False, src=src, depth=mono,
                                                  grad_depth=teacher["grad_depth"], grad_P=teacher["grad_P"], **geom)
-    ens = None
-    if not opt.no_ens:
-        ens = raw.photo(handle, target=tgt, src=src, depth=mono, depth_b=multi, want_selection=False,
-                        finalize=False, **geom)["min_reproj"]
     branch.join(0)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
     student = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
