@@ -77,7 +77,10 @@ def synthetic_masks(opt, seed=1234, max_instances=12, max_shift=8):
         n = int(counts[b])
         if n == 0:
             continue
-        last, nxt = make_instance_masks(n, H, W, seed=seed + 31 * b, max_shift=max_shift)
+        # object-sized instances (a car at this resolution is a few dozen pixels across): half-extents up to
+        # H/8 x W/10, so the masks of a 12-instance frame cover of the order of 15% of the image
+        last, nxt = make_instance_masks(n, H, W, seed=seed + 31 * b, max_shift=max_shift, max_ry=max(6, H // 8),
+                                        max_rx=max(6, W // 10))
         w = (1 << torch.arange(n, dtype=torch.int64)).view(-1, 1, 1)
         pl[b], pn[b] = (last.long() * w).sum(0), (nxt.long() * w).sum(0)
     to_i32 = lambda t: torch.where(t >= 2 ** 31, t - 2 ** 32, t).to(torch.int32)

@@ -118,10 +118,11 @@ def make_cost_volume_inputs(batch=2, height=192, width=640, channels=64, num_loo
             "inv_K": inv_K, "bins": bins}
 
 
-def make_instance_masks(num=6, height=192, width=640, seed=99, max_shift=12, empty=None):
+def make_instance_masks(num=6, height=192, width=640, seed=99, max_shift=12, empty=None, max_ry=None, max_rx=None):
     """Synthetic Mask2Former-shaped matched instance masks: `num` random
     rectangles / ellipses in the "last" frame and the same shapes shifted by up to `max_shift`
-    pixels in the "next" frame; instance `empty` (if given) is absent from the next frame."""
+    pixels in the "next" frame; instance `empty` (if given) is absent from the next frame.
+    Half-extents are drawn from [3, max_ry) x [3, max_rx) (default height // 4, width // 6)."""
     gen = torch.Generator().manual_seed(seed)
     ys = torch.arange(height).view(-1, 1).float()
     xs = torch.arange(width).view(1, -1).float()
@@ -130,8 +131,8 @@ def make_instance_masks(num=6, height=192, width=640, seed=99, max_shift=12, emp
     for n in range(num):
         cy = float(torch.randint(0, height, (1,), generator=gen))
         cx = float(torch.randint(0, width, (1,), generator=gen))
-        ry = float(torch.randint(3, max(4, height // 4), (1,), generator=gen))
-        rx = float(torch.randint(3, max(4, width // 6), (1,), generator=gen))
+        ry = float(torch.randint(3, max(4, max_ry or height // 4), (1,), generator=gen))
+        rx = float(torch.randint(3, max(4, max_rx or width // 6), (1,), generator=gen))
         dy = float(torch.randint(-max_shift, max_shift + 1, (1,), generator=gen))
         dx = float(torch.randint(-max_shift, max_shift + 1, (1,), generator=gen))
         if n % 2 == 0:
