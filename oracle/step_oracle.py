@@ -16,7 +16,7 @@ from . import mal_oracle as O
 LEAVES = ("mono_disp", "multi_disp", "T_-1", "T_1")   # the tensors the networks would have produced
 
 
-def oracle_step(b, opt, weights=(0.5, 0.5)):
+def oracle_step(b, opt, weights=(0.5, 0.5), multi_has_ins=False):
     """manydepth/trainer.py:555-644 (--temporal --distil --loss_blc) through oracle/mal_oracle.py."""
     H, W, B = opt.height, opt.width, opt.batch_size
     leaves = {k: b[k].clone().requires_grad_(True) for k in LEAVES}
@@ -54,6 +54,7 @@ def oracle_step(b, opt, weights=(0.5, 0.5)):
                                  (leaves["mono_disp"].detach() + leaves["multi_disp"].detach()) / 2.0, height=H, width=W)
     O.images_pred(inputs, multi, height=H, width=W, is_multi=True)
     losses, _, loss_list, aux = O.main_losses(inputs, multi, mono_reproj, ens, batch_size=B, loss_blc=True,
+                                              multi_has_ins=bool(multi_has_ins and getattr(opt, "main_temporal", False)),
                                               noise=b["noise_main"])
     loss_list[0] = loss_list[0] + mono_losses["loss"]
     total = B * (weights[0] * loss_list[0] + weights[1] * loss_list[1])

@@ -174,3 +174,30 @@ def test_correlation_lookup_full_size_against_the_oracle():
     out = ops.corr_lookup(f1.to(dev), ops.corr_pyramid(f2d, L), coords.to(dev))
     (g2,) = torch.autograd.grad(out, f2d, go.to(dev))
     assert rel(g2.cpu(), want_g[1]) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["masks", "main_temporal"])
+def test_whole_step_at_batch_12_against_the_oracle(mode):
+    """configs[1] at its full size (batch 12, 192x640, 96 bins x 64 channels) through MalStep's captured graph
+    against oracle_step (a few seconds of CPU): losses 1e-5, gradients 1e-4, cost volume / matching mask /
+    distillation indices bit-exact.  "masks": the temporal hint synthesised inside the step from packed instance
+    masks; "main_temporal": ready-made syn images that the STUDENT pass uses as well (multi_has_ins, a 4-candidate
+    gradient pass with masks, compute_main_losses :146-176)."""
+    from oracle.step_oracle import oracle_step
+    opt = S.default_opt(12, main_temporal=(mode == "main_temporal"))
+    b = S.synthetic_batch(opt, seed=77, with_masks=(mode == "masks"))
+    kw = dict(multi_has_ins=True) if mode == "main_temporal" else {}
+    total, loss_list, grads, aux = oracle_step(b, opt, (0.5, 0.5), **kw)
+    d = to_device(b, torch.device("cuda:0"))
+    with torch.no_grad():
+        scalars, g, outputs = S.fused_step(_capi.lib(), d, opt, torch.full((2,), 0.5, device="cuda:0"), **kw)
+    torch.cuda.synchronize()
+    assert abs(float(scalars[0]) - float(total)) <= 1e-5 * abs(float(total))
+    for a, w in zip((scalars[1], scalars[2]), loss_list):
+        assert abs(float(a) - float(w)) <= 1e-5 * abs(float(w))
+    assert torch.equal(outputs["cost_volume"].cpu(), aux["cv"])
+    assert torch.equal(outputs["consistency_mask"].cpu(), aux["mask"])
+    assert np.array_equal(outputs["mal_distil_index"].cpu().numpy(), aux["distil_idx"].numpy().astype(np.uint8))
+    for a, w, name in zip(g, grads, S.LEAVES):
+        scale = float(w.abs().max())
+        assert float((a.cpu().reshape(w.shape) - w).abs().max()) <= 1e-4 * scale, name
