@@ -376,8 +376,9 @@ def next_row_kernels(dev, batch, peak_gbs, iters=10):
 
 def dynamicdepth_loss_row(dev, B, Wc, peak_gbs, iters=5):
     """Config 5's loss half: dynamicdepth/trainer.py compute_losses :1006-1128 over 4 scales with selec_reproj and
-    zero_img, forward + backward to the four disparities and the two poses (the classic path: one PRED-mode
-    SSIM+L1 map per materialised warp, because zero_img makes each map depend on the calls before it)."""
+    zero_img, forward + backward to the four disparities and the two poses.  Timed twice: the fused path (one
+    photo_kernel<..., DD> pass per scale: warps made in the kernel, identity candidates riding along, zero_img as
+    cumulative per-tile masks) and the op-by-op path (warps materialised, one PRED-mode SSIM+L1 map per warp)."""
     from types import SimpleNamespace
     from mal_b200 import trainer_ops
     from mal_b200.utils.synthetic import CITYSCAPES_K, make_photometric_inputs, to_device
@@ -388,31 +389,37 @@ def dynamicdepth_loss_row(dev, B, Wc, peak_gbs, iters=5):
                           avg_reprojection=False, no_ssim=False, disable_automasking=False)
     noises = [torch.randn(B, 1, HEIGHT, Wc, device=dev) for _ in range(4)]
 
-    def run():
+    def run(fused):
         disps = [t[("mono_disp", s)].clone().requires_grad_(True) for s in range(4)]
         Ts = {f: t[("cam_T_cam", 0, f)].clone().requires_grad_(True) for f in (-1, 1)}
         o = {("disp", s): disps[s] for s in range(4)}
         o.update({("cam_T_cam", 0, f): Ts[f] for f in (-1, 1)})
         inp = dict(inputs)
         inp[("color", 0, 0)] = inputs[("color", 0, 0)].clone()   # zero_img mutates the target in place
-        trainer_ops.generate_images_pred(inp, o, opt, materialize=True)
+        if fused:
+            trainer_ops.generate_images_pred_dynamicdepth(inp, o, opt)
+        else:
+            trainer_ops.generate_images_pred(inp, o, opt, materialize=True)
         losses = trainer_ops.compute_losses_dynamicdepth(inp, o, opt, noises=noises)
         torch.autograd.grad(losses["loss"], disps + [Ts[-1], Ts[1]])
 
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / iters * 1e3
+    us = {}
+    for fused in (True, False):
+        for _ in range(2):
+            run(fused)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            run(fused)
+        e1.record()
+        torch.cuda.synchronize()
+        us[fused] = e0.elapsed_time(e1) / iters * 1e3
     nbytes = 4 * (36 + 4 * 1.328125 + 4 * 1.328125 + 16) * B * HEIGHT * Wc * 2   # SURVEY 8(d) A_photo, fwd + bwd
-    gbs = nbytes / (us * 1e-6) / 1e9
-    return {"row": "a11 (DynamicDepth)", "kernel": "compute_losses_dynamicdepth: 4 scales, selec_reproj + zero_img, fwd + bwd "
-            "(op by op through autograd: warps materialised, one SSIM+L1 map per warp)", "us_per_call": us,
+    gbs = nbytes / (us[True] * 1e-6) / 1e9
+    return {"row": "a11 (DynamicDepth)", "kernel": "compute_losses_dynamicdepth: 4 scales, selec_reproj + zero_img, fwd + bwd, "
+            "fused (one photo_kernel<DD> pass per scale, through autograd; host launch overhead included)",
+            "us_per_call": us[True], "us_per_call_op_by_op": us[False],
             "algorithmic_bytes": int(nbytes), "achieved_gbs": gbs, "frac": gbs / peak_gbs}
 
 

@@ -110,6 +110,16 @@ typedef struct mal_photo_args {
                                2-candidate passes against one target in one launch (the step scores the ensemble
                                warps and the un-warped sources of the automask, trainer.py:1172-1207 and
                                loss_utils.py:92-101, together: pass the sources as `syn`)                       */
+  /* DynamicDepth's compute_losses as one pass per scale (dynamicdepth/trainer.py:958-975, :1006-1128): WARP mode,
+     MAL_CONV_MANYDEPTH, the identity candidates of the automask (inputs[("color", f, 0)]) given as `syn`, `noise`
+     for its tie-break, no `identity_min`.                                                                         */
+  int32_t zero_img;         /* opt.zero_img: a prediction's dark pixels (RGB sum < 0.1) are zeroed in the prediction and
+                               in the target as the reference's calls c0, c1, i0, i1 do one after the other           */
+  int32_t selec_reproj;     /* opt.selec_reproj: where one warp is dark take the other one's loss, where both are, 0      */
+  int32_t ignore_automask;  /* is_multi: the automask is computed (its calls still zero the target) but not applied     */
+  int32_t identity_in_pass; /* selects this mode when neither zero_img nor selec_reproj is set: `syn` holds the identity
+                               candidates, their min (+ noise) is the automask's other side                             */
+  float* target_out;        /* (B,3,H,W) optional: the target as this pass's calls leave it = the next scale's target  */
   int32_t avg_reprojection; /* opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056):
                                mean instead of min over the two candidates (no syn); selection index is 0; with
                                gradients (WARP mode) both warps carry half of it                             */

@@ -31,6 +31,8 @@ class PhotoArgs(C.Structure):
         ("sums", C.c_void_p), ("grad_P", C.c_void_p), ("depth_b", C.c_void_p),
         ("grad_syn", C.c_void_p * 2),
         ("depth_height", C.c_int32), ("depth_width", C.c_int32), ("min_reproj_b", C.c_void_p),
+        ("zero_img", C.c_int32), ("selec_reproj", C.c_int32), ("ignore_automask", C.c_int32), ("identity_in_pass", C.c_int32),
+        ("target_out", C.c_void_p),
         ("avg_reprojection", C.c_int32),
         ("skip_finalize", C.c_int32),
     ]

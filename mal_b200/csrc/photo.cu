@@ -52,9 +52,9 @@ __host__ __device__ inline PhotoTile photo_tile(bool grad) {
   return t;
 }
 constexpr int PH_SMALL = 40 + 8 * PH_NPART + 8 + 4;   // Geom (padded), reduction scratch, mbarrier + flag
-inline size_t photo_smem_bytes(bool grad, bool warp, int ncand, bool avg) {
+inline size_t photo_smem_bytes(bool grad, bool warp, int ncand, bool avg, bool dd = false) {
   PhotoTile t = photo_tile(grad);
-  size_t fl = (size_t)(1 + ncand) * t.TS + PH_SMALL;
+  size_t fl = (size_t)(1 + ncand) * t.TS + PH_SMALL + (dd ? (t.VN + 3) / 4 : 0);
   if (grad) fl += (size_t)(avg ? 19 : 10) * t.LN + (t.LN + 7) / 8 * 2;   // 9 coefficient planes, weights, selection bytes; the staged
                                                         // disparity aliases the coefficient planes
   else if (warp) fl += (size_t)2 * ((t.VN + 31) / 32 * 32);
@@ -67,7 +67,15 @@ struct PhotoMaps {   // TMA descriptors of the tensors a CTA stages, one __grid_
 
 // AVG: opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056): the mean instead of
 // the min over the two warped candidates; both then carry half the gradient (a second set of coefficient planes).
-template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC, bool AVG>
+// DD: DynamicDepth's compute_losses (dynamicdepth/trainer.py:958-975, :1006-1128) as one pass per scale.  The
+// candidates are [warp(-1), warp(+1), source(-1), source(+1)] (the last two are the identity candidates of the
+// automask, staged like temporal-hint images).  zero_img: a prediction's dark pixels (RGB sum < 0.1: DOMD warping
+// holes) are zeroed in the prediction AND, in place, in the shared target - so call k (in the reference's order
+// c0, c1, i0, i1) compares against the target zeroed wherever any of the predictions 0..k is dark: a byte per tile
+// element carries those cumulative masks, the target-side window moments are formed per candidate, and the
+// target as the calls leave it goes to `target_out` for the next scale.  selec_reproj (:1058-1064): where one warp
+// is dark the other one's loss is taken, where both are the loss is 0.
+template <bool WARP, bool GRAD, int CONV, bool LOWRES, bool SYNG, int NC, bool AVG, bool DD = false>
 __global__ void __launch_bounds__(PH_NT, GRAD ? (AVG ? 2 : 3) : 4)
 photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, const int ncand, const float min_disp,
              const float disp_range, const int use_tma, const SizeDiv sdiv) {
@@ -102,6 +110,8 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   float* dep = after;                                 // [VN] disparity tile (aliases coef: dead before phase B)
   float* dep_b = dep + (tl.VN + 31) / 32 * 32;        // [VN] second disparity (ensemble pass, never with GRAD)
   float* small = after + (GRAD ? (NCOEF + 1) * tl.LN + (tl.LN + 7) / 8 * 2 : (WARP ? 2 * ((tl.VN + 31) / 32 * 32) : 0));
+  unsigned char* dm = reinterpret_cast<unsigned char*>(small + PH_SMALL);   // [VN] (DD) bits 0-3: target zeroed for
+                                                                            // call k; bits 4, 5: warp -1 / +1 dark
   Geom* geom = reinterpret_cast<Geom*>(small);
   float* red = small + 40;                            // [8][PH_NPART]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red + 8 * PH_NPART + 8);
@@ -203,13 +213,39 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       }
       if (a.depth_is_disp) dv = xdiv(1.0f, xadd(min_disp, xmul(disp_range, dv)));
       Ray ray = pixel_ray(geom->iK, (float)rx, (float)ry);
+      unsigned dark = 0;
 #pragma unroll
       for (int f = 0; f < 2; f++) {
         Sample s = project_pixel<CONV>(geom->P[f], ray, dv, a.eps, H, W, &sdiv);
         Taps t = make_taps(s.ix, s.iy, H, W);
         const float* src = a.src[f] + (size_t)b * 3 * HW;
+        float v[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) sx[(size_t)f * tl.TS + c * tl.VN + i] = bilinear(src + c * HW, t);
+        for (int c = 0; c < 3; c++) v[c] = bilinear(src + c * HW, t);
+        if (DD && (a.zero_img || a.selec_reproj) && xadd(xadd(v[0], v[1]), v[2]) < 0.1f) {   // pred.sum(1) < 0.1
+          dark |= 1u << f;
+          if (a.zero_img) v[0] = v[1] = v[2] = 0.0f;                              // pred[mask] = 0
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) sx[(size_t)f * tl.TS + c * tl.VN + i] = v[c];
+      }
+      if (DD) {
+        // the identity candidates (un-warped sources, staged by TMA / the plain loader) take part in the zeroing too
+        unsigned cum = a.zero_img ? dark : 0u;            // bit k: the target is zero for call k (c0, c1, i0, i1)
+        cum |= (cum & 1u) << 1;
+        if (NC > 2 && ncand > 2) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            float* X = sx + (size_t)(2 + k) * tl.TS + i;
+            bool dk = false;
+            if (a.zero_img && xadd(xadd(X[0], X[tl.VN]), X[2 * tl.VN]) < 0.1f) {
+              dk = true;
+              X[0] = X[tl.VN] = X[2 * tl.VN] = 0.0f;
+            }
+            if (dk || (cum >> (1 + k)) & 1u) cum |= 1u << (2 + k);
+          }
+        }
+        dm[i] = (unsigned char)(cum | (dark << 4));
       }
     }
   }
@@ -244,24 +280,39 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
     const size_t po = (size_t)b * HW + (size_t)gy * W + gx;
     float p_ident = 0.0f, p_noise = 0.0f, p_mask = 1.0f;
     if (automask) { p_ident = __ldg(a.identity_min + po); p_noise = __ldg(a.noise + po); }
+    if (DD && NC > 2 && ncand > 2 && a.noise) p_noise = __ldg(a.noise + po);
     if (a.pixel_mask) p_mask = __ldg(a.pixel_mask + po);
     float ssum[NC], lsum[NC];   // NC: compiled-in candidate capacity (2 or 4); ncand <= NC are live
     float cf0[9], cf1[9];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      float yw[9];
+    unsigned dmw[DD ? 9 : 1];   // (DD) the window's zeroing masks
+    if (DD) {
 #pragma unroll
       for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++) yw[dy * 3 + dx] = sy[c * tl.VN + vc + (dy - 1) * PH_VW + dx - 1];
+        for (int dx = 0; dx < 3; dx++) dmw[DD ? dy * 3 + dx : 0] = dm[vc + (dy - 1) * PH_VW + dx - 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float yw0[9];
+#pragma unroll
+      for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++) yw0[dy * 3 + dx] = sy[c * tl.VN + vc + (dy - 1) * PH_VW + dx - 1];
       float mu_y = 0.f, eyy = 0.f;
-      if (!a.no_ssim) {
-        mu_y = xdivc<9>(sum9(yw));
-        eyy = xdivc<9>(sum9_prod(yw, yw));
+      if (!a.no_ssim && !DD) {
+        mu_y = xdivc<9>(sum9(yw0));
+        eyy = xdivc<9>(sum9_prod(yw0, yw0));
       }
 #pragma unroll
       for (int k = 0; k < NC; k++) {
         if (k < ncand) {
+          float yw[9];   // the target as call k sees it (DD: zeroed where a prediction up to k is dark)
+#pragma unroll
+          for (int q = 0; q < 9; q++) yw[q] = (DD && ((dmw[DD ? q : 0] >> k) & 1u)) ? 0.0f : yw0[q];
+          if (DD && !a.no_ssim) {
+            mu_y = xdivc<9>(sum9(yw));
+            eyy = xdivc<9>(sum9_prod(yw, yw));
+          }
           const float* X = sx + (size_t)k * tl.TS + c * tl.VN + vc;
           float xw[9];
 #pragma unroll
@@ -287,7 +338,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
         }
       }
     }
-    float rmin = 0.f, rmin_b = 0.f;
+    float rmin = 0.f, rmin_b = 0.f, lk01[2] = {0.f, 0.f};
     int idx = 0;
     const bool split = NC > 2 && !GRAD && a.min_reproj_b != nullptr;   // two independent 2-candidate mins in one pass
 #pragma unroll
@@ -295,15 +346,28 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       if (k < ncand) {
         float l1m = xdivc<3>(lsum[k]);
         float lk = a.no_ssim ? l1m : xadd(xmul(0.85f, xdivc<3>(ssum[k])), xmul(0.15f, l1m));
+        if (DD && k < 2) lk01[k] = lk;
         if (AVG) rmin = (k == 0) ? lk : xmul(xadd(rmin, lk), 0.5f);   // .mean(1) of two: (l0 + l1) / 2
-        else if (NC > 2 && split && k >= 2) { if (k == 2 || lk < rmin_b) rmin_b = lk; }   // second min: candidates 2, 3
+        else if (NC > 2 && (split || DD) && k >= 2) { if (k == 2 || lk < rmin_b) rmin_b = lk; }   // second min: candidates 2, 3
         else if (k == 0 || lk < rmin) { rmin = lk; idx = k; }
       }
+    }
+    bool both_dark = false;
+    if (DD && a.selec_reproj) {   // :1058-1064, in the reference's order of assignments
+      const bool d0 = (dmw[DD ? 4 : 0] >> 4) & 1u, d1 = (dmw[DD ? 4 : 0] >> 5) & 1u;
+      if (d0) { rmin = lk01[1]; idx = 1; }
+      if (d1) { rmin = lk01[0]; idx = 0; }
+      if (d0 && d1) { rmin = 0.0f; both_dark = true; }
     }
     int mbit = 1;
     if (automask) {
       float ident = xadd(p_ident, xmul(p_noise, 0.00001f));
       mbit = (ident < rmin) ? 0 : 1;  // argmin([reproj, identity]) == 0, first index wins ties
+    }
+    if (DD && NC > 2 && ncand > 2) {   // the identity candidates were scored in this pass
+      const float ident = xadd(rmin_b, xmul(p_noise, 0.00001f));
+      mbit = (ident < rmin) ? 0 : 1;
+      if (a.ignore_automask) mbit = 1;   // is_multi: the automask is replaced by the consistency mask (:1077-1085)
     }
     float w = (float)mbit;
     if (a.pixel_mask) w = xmul(w, p_mask);
@@ -314,6 +378,12 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       if (NC > 2 && split) a.min_reproj_b[po] = rmin_b;
       if (a.selection) a.selection[po] = (uint8_t)(idx | (mbit << 7));
       if (a.weight) a.weight[po] = w;
+      if (DD && a.target_out) {   // the target as this scale's calls leave it (zero_img mutates it in place)
+        const bool z = (dmw[DD ? 4 : 0] >> (ncand > 2 ? 3 : 1)) & 1u;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          a.target_out[((size_t)b * 3 + c) * HW + (size_t)gy * W + gx] = z ? 0.0f : sy[c * tl.VN + vc];
+      }
       acc_loss += xmul(rmin, w);
       acc_w += w;
     }
@@ -321,7 +391,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       // warped candidates always carry a gradient; the temporal-hint candidates when the caller asked
       // for d/d syn (autograd then carries it into the warped images image_synthesis copied from)
       const bool syn_grad = (SYNG || !WARP) && a.grad_syn[0] != nullptr;
-      const bool live = (idx < 2 || syn_grad) && w != 0.0f;
+      const bool live = (idx < 2 || syn_grad) && w != 0.0f && !(DD && both_dark);
       lsel[i] = live ? idx : -1;
       lw[i] = AVG ? w * 0.5f : w;
       if (AVG && live && !a.no_ssim) {
@@ -420,6 +490,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       // with SYNG the same neighbourhood walk also collects d S / d syn (the temporal-hint candidates 2, 3): one
       // selection load per neighbour decides which of the four accumulators it feeds
       const bool syn_out = SYNG && a.grad_syn[0] != nullptr;
+      const unsigned dmc = DD ? dm[vc] : 0u;
       float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
       float xq0[3], xq1[3], xq2[3] = {0.f, 0.f, 0.f}, xq3[3] = {0.f, 0.f, 0.f}, yq[3];
 #pragma unroll
@@ -451,6 +522,17 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
                 const float v = m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq * coef[(c * 3 + 1) * tl.LN + li] +
                                      yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
                 if (s == 2) g2[c] += v; else g3[c] += v;
+              }
+              continue;
+            }
+            if (DD) {   // the target value at this pixel as the selected call saw it
+              const bool z = (dmc >> s) & 1u;
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const float xq = s == 0 ? xq0[c] : xq1[c];
+                const float v = m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq * coef[(c * 3 + 1) * tl.LN + li] +
+                                     (z ? 0.0f : yq[c]) * coef[(c * 3 + 2) * tl.LN + li]);
+                if (s == 0) g0[c] += v; else g1[c] += v;
               }
               continue;
             }
@@ -505,11 +587,15 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
               g1[c] += d1 > 0.f ? -wl : (d1 < 0.f ? wl : 0.f);
               continue;
             }
-            float d = yq[c] - (s == 0 ? xq0[c] : xq1[c]);      // target - pred
+            float d = ((DD && ((dmc >> s) & 1u)) ? 0.0f : yq[c]) - (s == 0 ? xq0[c] : xq1[c]);      // target - pred
             float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);   // d|t-p|/dp = -sign(t-p)
             if (s == 0) g0[c] += sg; else g1[c] += sg;
           }
         }
+      }
+      if (DD && a.zero_img) {   // pred[mask] = 0 overwrites the warped pixel: no gradient reaches a dark one
+        if ((dmc >> 4) & 1u) g0[0] = g0[1] = g0[2] = 0.0f;
+        if ((dmc >> 5) & 1u) g1[0] = g1[1] = g1[2] = 0.0f;
       }
       const size_t po = (size_t)gy * W + gx;
       {
@@ -631,8 +717,11 @@ static void photo_dispatch(const mal_photo_args& a, const PhotoMaps& maps, int u
   const SizeDiv sdiv = size_div(a.height, a.width, a.convention);
   const bool lowres = WARP && a.depth_height > 0;
   const bool syng = WARP && GRAD && a.grad_syn[0] != nullptr;   // PRED mode handles grad_syn in its own branch
+  const bool dd = a.zero_img || a.selec_reproj || a.target_out || a.identity_in_pass;   // DynamicDepth's compute_losses mode
 #define MAL_PHOTO_GO(CONV_, LOW_, SYNG_, NC_, AVG_) \
   launch(photo_kernel<WARP, GRAD, CONV_, LOW_, SYNG_, NC_, AVG_>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv)
+#define MAL_PHOTO_DD(LOW_, NC_) \
+  launch(photo_kernel<WARP, GRAD, MAL_CONV_MANYDEPTH, LOW_, false, NC_, false, WARP>, grid, dim3(PH_NT), smem, st, a, maps, ncand, min_disp, range, use_tma, sdiv)
 #define MAL_PHOTO_LAUNCH2(CONV_, NC_)                                       \
   do {                                                                      \
     if (lowres && syng) MAL_PHOTO_GO(CONV_, WARP, WARP && GRAD, NC_, false); \
@@ -644,7 +733,12 @@ static void photo_dispatch(const mal_photo_args& a, const PhotoMaps& maps, int u
   // staging / rare-path code (instruction-cache pressure); avg_reprojection (2 candidates) is its own instance
 #define MAL_PHOTO_LAUNCH(CONV_)                                   \
   do {                                                            \
-    if (a.avg_reprojection) {                                     \
+    if (WARP && CONV_ == MAL_CONV_MANYDEPTH && dd) {              \
+      if (lowres && ncand > 2) MAL_PHOTO_DD(WARP, 4);             \
+      else if (lowres) MAL_PHOTO_DD(WARP, 2);                     \
+      else if (ncand > 2) MAL_PHOTO_DD(false, 4);                 \
+      else MAL_PHOTO_DD(false, 2);                                \
+    } else if (a.avg_reprojection) {                              \
       if (lowres) MAL_PHOTO_GO(CONV_, WARP, false, 2, true);      \
       else MAL_PHOTO_GO(CONV_, false, false, 2, true);            \
     } else if (ncand > 2) MAL_PHOTO_LAUNCH2(CONV_, 4);            \
@@ -652,6 +746,7 @@ static void photo_dispatch(const mal_photo_args& a, const PhotoMaps& maps, int u
   } while (0)
   if (a.convention == MAL_CONV_MANYDEPTH) MAL_PHOTO_LAUNCH(MAL_CONV_MANYDEPTH);
   else MAL_PHOTO_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_PHOTO_DD
 #undef MAL_PHOTO_GO
 #undef MAL_PHOTO_LAUNCH2
 #undef MAL_PHOTO_LAUNCH
@@ -680,8 +775,6 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   if (single)
     MAL_REQUIRE(a.mode == MAL_PHOTO_PRED && !a.syn[0], "mal_photo_forward: a single candidate needs PRED mode, no syn");
   MAL_REQUIRE((a.syn[0] == nullptr) == (a.syn[1] == nullptr), "mal_photo_forward: give both syn candidates or none");
-  MAL_REQUIRE((a.identity_min == nullptr) == (a.noise == nullptr),
-              "mal_photo_forward: automask needs identity_min and noise together");
   MAL_REQUIRE(a.partials && a.sums, "mal_photo_forward: partials/sums workspaces are required");
   if (a.mode == MAL_PHOTO_WARP) {
     MAL_REQUIRE(a.depth && a.K && a.inv_K && a.T[0] && a.T[1], "mal_photo_forward: WARP mode needs depth,K,inv_K,T");
@@ -694,6 +787,17 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }
   const int ncand = single ? 1 : (a.syn[0] ? 4 : 2);
+  const bool dd = a.zero_img || a.selec_reproj || a.target_out || a.identity_in_pass;
+  if (dd) {
+    MAL_REQUIRE(a.mode == MAL_PHOTO_WARP && a.convention == MAL_CONV_MANYDEPTH && !a.identity_min && !a.avg_reprojection &&
+                    !a.min_reproj_b && !a.grad_syn[0],
+                "mal_photo_forward: zero_img / selec_reproj (DynamicDepth) is a WARP-mode pass with the identity "
+                "candidates given as `syn`; no identity_min, avg_reprojection, min_reproj_b or grad_syn");
+    if (a.syn[0]) MAL_REQUIRE(a.noise || a.ignore_automask, "mal_photo_forward: the in-pass automask needs `noise`");
+  } else {
+    MAL_REQUIRE((a.identity_min == nullptr) == (a.noise == nullptr),
+                "mal_photo_forward: automask needs identity_min and noise together");
+  }
   if (a.min_reproj_b)
     MAL_REQUIRE(ncand == 4 && !a.with_grad && !a.identity_min && !a.avg_reprojection,
                 "mal_photo_forward: min_reproj_b (a second min over candidates 2, 3) is a forward-only 4-candidate mode");
@@ -710,7 +814,7 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   const float min_disp = (float)lo, range = (float)(hi - lo);
   dim3 grid((a.width + PH_TW - 1) / PH_TW, (a.height + PH_TH - 1) / PH_TH, a.batch);
   MAL_REQUIRE(grid.y <= 65535, "mal_photo_forward: image too tall");
-  size_t smem = photo_smem_bytes(grad, warp, ncand, a.avg_reprojection != 0);
+  size_t smem = photo_smem_bytes(grad, warp, ncand, a.avg_reprojection != 0, dd);
   cudaStream_t st = (cudaStream_t)stream;
 
   // TMA descriptors for every tensor the CTAs stage whole; any tensor TMA cannot address (rows that are not

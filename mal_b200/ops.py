@@ -59,7 +59,8 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
               identity_min: Optional[Tensor], noise: Optional[Tensor], pixel_mask: Optional[Tensor],
               sample_mask: Optional[Tensor], mode: int, convention: int, depth_is_disp: bool,
               no_ssim: bool, min_depth: float, max_depth: float, eps: float,
-              need_grad: bool, need_grad_syn: bool, avg_reprojection: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+              need_grad: bool, need_grad_syn: bool, avg_reprojection: bool = False, zero_img: bool = False,
+              selec_reproj: bool = False, ignore_automask: bool = False, identity_in_pass: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     h = _lib(target)
     src = [src0] if src1 is None else [src0, src1]
     out = raw.photo(h, target=target, src=src, syn=None if syn0 is None else [syn0, syn1],
@@ -68,18 +69,20 @@ def _photo_op(target: Tensor, src0: Tensor, src1: Optional[Tensor], syn0: Option
                     sample_mask=sample_mask, mode=mode, convention=convention,
                     depth_is_disp=depth_is_disp, no_ssim=no_ssim, with_grad=need_grad,
                     min_depth=min_depth, max_depth=max_depth, eps=eps,
-                    want_grad_syn=need_grad and need_grad_syn and syn0 is not None, avg_reprojection=avg_reprojection)
+                    want_grad_syn=need_grad and need_grad_syn and syn0 is not None, avg_reprojection=avg_reprojection,
+                    zero_img=zero_img, selec_reproj=selec_reproj, ignore_automask=ignore_automask, want_target_out=zero_img,
+                    identity_in_pass=identity_in_pass)
     gp = out.get("grad_pred", [None, None])
     gs = out.get("grad_syn", [None, None])
     pick = lambda v: v if v is not None else _empty(target)   # a fresh tensor each: outputs may not alias
     return (out["sums"], out["min_reproj"], out["selection"], pick(out.get("grad_depth")),
-            pick(out.get("grad_P")), pick(gp[0]), pick(gp[1]), pick(gs[0]), pick(gs[1]))
+            pick(out.get("grad_P")), pick(gp[0]), pick(gp[1]), pick(gs[0]), pick(gs[1]), pick(out.get("target_out")))
 
 
 @_photo_op.register_fake
 def _(target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noise, pixel_mask,
       sample_mask, mode, convention, depth_is_disp, no_ssim, min_depth, max_depth, eps, need_grad, need_grad_syn,
-      avg_reprojection=False):
+      avg_reprojection=False, zero_img=False, selec_reproj=False, ignore_automask=False, identity_in_pass=False):
     B, _, H, W = target.shape
     f = lambda *s: target.new_empty(s)
     warp = mode == raw.PHOTO_WARP
@@ -88,13 +91,14 @@ def _(target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noi
             f(B, 3, H, W) if need_grad and not warp else f(0),
             f(B, 3, H, W) if need_grad and not warp and src1 is not None else f(0),
             f(B, 3, H, W) if need_grad and need_grad_syn and syn0 is not None else f(0),
-            f(B, 3, H, W) if need_grad and need_grad_syn and syn0 is not None else f(0))
+            f(B, 3, H, W) if need_grad and need_grad_syn and syn0 is not None else f(0),
+            f(B, 3, H, W) if zero_img else f(0))
 
 
 def _photo_setup(ctx, inputs, output):
     (target, src0, src1, syn0, syn1, depth, K, inv_K, T0, T1, identity_min, noise, pixel_mask,
      sample_mask, mode, *_rest) = inputs
-    sums, _, _, g_depth, g_P, g_p0, g_p1, g_s0, g_s1 = output
+    sums, _, _, g_depth, g_P, g_p0, g_p1, g_s0, g_s1, _t = output
     ctx.mode = mode
     ctx.need_grad = inputs[21]
     ctx.depth_size = None if depth is None else tuple(depth.shape[-2:])
@@ -107,7 +111,7 @@ def _photo_backward(ctx, g_sums, *_unused):
         raise RuntimeError("mal_b200::photo was run with need_grad=False but a gradient is requested")
     # sums = [S, W, S / (W + 1e-7), 0]; the planes hold d S / d input
     coef = g_sums[0] + g_sums[2] / (sums[1] + 1e-7)
-    grads = [None] * 24
+    grads = [None] * 28
     if g_s0.numel():   # temporal-hint candidates, either mode
         grads[3], grads[4] = coef * g_s0, coef * g_s1
     if ctx.mode == raw.PHOTO_WARP:
@@ -131,8 +135,14 @@ _photo_op.register_autograd(_photo_backward, setup_context=_photo_setup)
 def photo(target, src, *, syn=None, depth=None, K=None, inv_K=None, T=None, identity_min=None,
           noise=None, pixel_mask=None, sample_mask=None, mode=raw.PHOTO_WARP,
           convention=raw.CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False, min_depth=0.1,
-          max_depth=100.0, eps=1e-7, avg_reprojection=False):
-    """Fused photometric loss.  Returns ``(sums, min_reproj, selection)``.
+          max_depth=100.0, eps=1e-7, avg_reprojection=False, zero_img=False, selec_reproj=False,
+          ignore_automask=False, identity_in_pass=False):
+    """Fused photometric loss.  Returns ``(sums, min_reproj, selection)`` (+ the target image as the pass leaves
+    it with ``zero_img``).
+
+    ``zero_img`` / ``selec_reproj`` / ``ignore_automask``: DynamicDepth's compute_losses as one pass per scale
+    (dynamicdepth/trainer.py:958-975, :1006-1128): WARP mode with the identity candidates of the automask given as
+    ``syn`` and ``noise`` for its tie-break (no ``identity_min``).
 
     ``avg_reprojection`` (opt.avg_reprojection of the DualRefine / DynamicDepth trainers): the mean instead of
     the min over the two candidates.
@@ -152,7 +162,10 @@ def photo(target, src, *, syn=None, depth=None, K=None, inv_K=None, T=None, iden
                     syn[0] if syn else None, syn[1] if syn else None, depth, K, inv_K,
                     T[0] if T else None, T[1] if T else None, identity_min, noise, pixel_mask,
                     sample_mask, mode, convention, depth_is_disp, no_ssim, float(min_depth),
-                    float(max_depth), float(eps), need_grad, syn_grad, bool(avg_reprojection))
+                    float(max_depth), float(eps), need_grad, syn_grad, bool(avg_reprojection), bool(zero_img),
+                    bool(selec_reproj), bool(ignore_automask), bool(identity_in_pass))
+    if zero_img:
+        return out[0], out[1], out[2], out[9]
     return out[0], out[1], out[2]
 
 

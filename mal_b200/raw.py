@@ -64,7 +64,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           mode=PHOTO_WARP, convention=CONV_MANYDEPTH, depth_is_disp=True, no_ssim=False,
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
           want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True,
-          avg_reprojection=False, split_min=False):
+          avg_reprojection=False, split_min=False, zero_img=False, selec_reproj=False, ignore_automask=False,
+          want_target_out=False, identity_in_pass=False):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
     finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
@@ -101,6 +102,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     out["selection"] = new(plane, torch.uint8) if want_selection else None
     out["weight"] = new(plane) if want_weight else None
     out["min_reproj_b"] = new(plane) if split_min else None   # second min, over the `syn` candidates
+    out["target_out"] = new(img) if want_target_out else None
     if with_grad and mode == PHOTO_WARP:
         out["grad_depth"], out["grad_P"] = new(plane), new((B, 2, 12))
     if with_grad and mode == PHOTO_PRED:
@@ -129,6 +131,9 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.skip_finalize = 0 if finalize else 1
     a.avg_reprojection = int(bool(avg_reprojection))
     a.min_reproj_b = _ptr(out["min_reproj_b"])
+    a.zero_img, a.selec_reproj, a.ignore_automask = int(bool(zero_img)), int(bool(selec_reproj)), int(bool(ignore_automask))
+    a.identity_in_pass = int(bool(identity_in_pass))
+    a.target_out = _ptr(out["target_out"])
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
     LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
     out["_keepalive"] = (partials,)

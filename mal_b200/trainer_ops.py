@@ -260,6 +260,8 @@ def compute_losses_dynamicdepth(inputs, outputs, opt, is_multi=False, noises=Non
     pass; the SSIM+L1 maps and their gradients still come from the photometric kernel (PRED mode)."""
     if str(getattr(opt, "feat_loss", "false")) == "true":
         raise NotImplementedError("feat_loss (get_feature_metric_loss) is outside the hot path")
+    if ("warp_spec", list(opt.scales)[0]) in outputs and not getattr(opt, "avg_reprojection", False):
+        return _compute_losses_dynamicdepth_fused(inputs, outputs, opt, is_multi, noises)
     zero_img, no_ssim = getattr(opt, "zero_img", True), str(_o(opt, "no_ssim")) in ("True", "true")
     rl = lambda p, t: compute_reprojection_loss_dynamicdepth(p, t, zero_img, no_ssim)
     avg = getattr(opt, "avg_reprojection", False)
@@ -307,6 +309,84 @@ def compute_losses_dynamicdepth(inputs, outputs, opt, is_multi=False, noises=Non
         total_loss = total_loss + loss
         losses["loss/{}".format(scale)] = loss
         outputs[("mal_mask", scale)] = mask
+    losses["loss"] = total_loss / len(scales)
+    return losses
+
+
+def generate_images_pred_dynamicdepth(inputs, outputs, opt, is_multi=False):
+    """dynamicdepth/trainer.py generate_images_pred :906-955 for the fused path: one WarpSpec per scale of
+    opt.scales (the disparity of scale s is up-sampled to the full image inside the kernel), depth maps for the
+    dict; `compute_losses_dynamicdepth` then runs one fused pass per scale.  Pass materialize-style warped images
+    yourself (outputs[("color", f, s)]) to use the op-by-op path instead."""
+    H, W = _o(opt, "height"), _o(opt, "width")
+    for scale in opt.scales:
+        disp = outputs[("disp", scale)]
+        disp_full = disp if disp.shape[-2:] == (H, W) else ops.upsample_bilinear(disp, (H, W))
+        _, depth = disp_to_depth(disp_full, _o(opt, "min_depth"), _o(opt, "max_depth"))
+        outputs[("depth", 0, scale)] = depth
+        Ts = [outputs[("cam_T_cam", 0, f)].detach() if is_multi else outputs[("cam_T_cam", 0, f)] for f in (-1, 1)]
+        outputs[("warp_spec", scale)] = WarpSpec(disp, inputs[("K", 0)], inputs[("inv_K", 0)], Ts, raw.CONV_MANYDEPTH,
+                                                 _o(opt, "min_depth"), _o(opt, "max_depth"))
+    return outputs
+
+
+def _compute_losses_dynamicdepth_fused(inputs, outputs, opt, is_multi, noises):
+    """compute_losses_dynamicdepth with ONE fused photometric pass per scale (photo_kernel<..., DD>): the warps are
+    made in the kernel, the identity candidates ride along as candidates 2 and 3, zero_img's cumulative zeroing of
+    the target is a byte mask per tile element, selec_reproj a per-pixel override; the target as a scale leaves it
+    is handed to the next scale and finally written back into inputs[("color", 0, 0)] like the reference's in-place
+    edits (dynamicdepth/trainer.py:961-965)."""
+    zero_img, no_ssim = getattr(opt, "zero_img", True), str(_o(opt, "no_ssim")) in ("True", "true")
+    selec = getattr(opt, "selec_reproj", True)
+    automask = not _o(opt, "disable_automasking")
+    losses, total_loss = {}, 0
+    scales = list(opt.scales)
+    target0 = inputs[("color", 0, 0)]
+    target = target0
+    for si, scale in enumerate(scales):
+        spec = outputs[("warp_spec", scale)]
+        src = [inputs[("color", f, 0)] for f in (-1, 1)]
+        ident = None
+        if automask:
+            use_ori = (not is_multi) and getattr(opt, "no_teacher_warp", False) and not getattr(opt, "train_teacher_only", False)
+            ident = [inputs[("ori_color" if use_ori else "color", f, 0)] for f in (-1, 1)]
+        noise = None
+        if automask:
+            noise = _draw_noise((target.shape[0], 1) + tuple(target.shape[-2:]), target.device,
+                                None if noises is None else noises[si])
+        pm = sm = None
+        if is_multi:
+            pm = outputs["consistency_mask"] if not _o(opt, "disable_motion_masking") else torch.ones_like(target[:, 0])
+            if not str(_o(opt, "no_matching_augmentation")) == "true":
+                sm = outputs["augmentation_mask"]
+        res = ops.photo(target, src, syn=ident, depth=spec.disp, K=spec.K, inv_K=spec.inv_K, T=spec.T, noise=noise,
+                        pixel_mask=pm, sample_mask=sm, mode=raw.PHOTO_WARP, convention=raw.CONV_MANYDEPTH,
+                        depth_is_disp=True, no_ssim=no_ssim, min_depth=spec.min_depth, max_depth=spec.max_depth,
+                        zero_img=zero_img, selec_reproj=selec, ignore_automask=is_multi, identity_in_pass=True)
+        sums, _, sel = res[0], res[1], res[2]
+        if zero_img:
+            target = res[3]
+        consistency_loss = 0
+        if is_multi:
+            weight = (pm if pm is not None else 1.0) * (1 - sm.reshape(-1, 1, 1) if sm is not None else 1.0)
+            multi_depth, mono_depth = outputs[("depth", 0, scale)], outputs[("mono_depth", 0, scale)].detach()
+            consistency_mask = (1 - weight).unsqueeze(1).float()
+            consistency_loss = (torch.abs(multi_depth - mono_depth) * consistency_mask).mean()
+            outputs["consistency_target/{}".format(scale)] = 1 / (mono_depth * consistency_mask +
+                                                                  multi_depth.detach() * (1 - consistency_mask))
+            losses["consistency_loss/{}".format(scale)] = consistency_loss
+        losses["reproj_loss/{}".format(scale)] = sums[2]
+        loss = sums[2] + consistency_loss
+        # scale 0's smoothness reads the image the reprojection calls have just zeroed in place (:961-965, :1114)
+        color = target if (zero_img and scale == 0) else inputs[("color", 0, scale)]
+        loss = loss + _o(opt, "disparity_smoothness") * ops.smooth(outputs[("disp", scale)], color,
+                                                                   normalise=True) / (2 ** scale)
+        total_loss = total_loss + loss
+        losses["loss/{}".format(scale)] = loss
+        outputs[("mal_selection", scale)] = sel
+    if zero_img:
+        with torch.no_grad():
+            target0.copy_(target)   # the reference zeroes the caller's image in place
     losses["loss"] = total_loss / len(scales)
     return losses
 

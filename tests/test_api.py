@@ -379,6 +379,62 @@ def test_dynamicdepth_losses_match_oracle(op_device, is_multi, selec, zero):
         assert _gerr(a, b) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("is_multi,selec,zero,automask", [(False, True, True, True), (True, True, True, True),
+                                                          (False, False, False, True), (False, True, False, True),
+                                                          (False, False, True, True), (False, True, True, False)])
+def test_dynamicdepth_fused_losses_match_oracle(op_device, is_multi, selec, zero, automask):
+    """BASELINE config 5 on the fused path: generate_images_pred_dynamicdepth leaves a WarpSpec per scale and
+    compute_losses_dynamicdepth runs ONE photometric pass per scale (warps made in the kernel, identity candidates
+    riding along, zero_img's cumulative zeroing of the target, selec_reproj).  Black regions in the source frames
+    give the warps DOMD-style holes (dynamicdepth/trainer.py:906-975, :1006-1128).  Gradients w.r.t. the
+    disparities and poses."""
+    dev = op_device
+    B, H, W = 2, 32, 64
+    res = []
+    for who, dv in (("oracle", torch.device("cpu")), ("ours", dev)):
+        inputs, t = make_photometric_inputs(B, H, W, num_scales=4, seed=77, translation_scale=0.3)
+        inputs[("color", -1, 0)][:, :, 4:14, 6:30] = 0.0
+        inputs[("color", 1, 0)][:, :, 8:20, 20:44] = 0.0
+        inputs[("color", 1, 0)][1, :, 2:9, 3:20] = 0.0
+        inputs = {k: v.to(dv) for k, v in inputs.items()}
+        name = "multi" if is_multi else "mono"
+        disps = [t[(name + "_disp", s)].clone().to(dv).requires_grad_(True) for s in range(4)]
+        Ts = [t[("cam_T_cam", 0, f)].clone().to(dv).requires_grad_(True) for f in (-1, 1)]
+        o = {("disp", s): disps[s] for s in range(4)}
+        o[("cam_T_cam", 0, -1)], o[("cam_T_cam", 0, 1)] = Ts
+        if is_multi:
+            o["consistency_mask"] = t["consistency_mask"].to(dv)
+            o["augmentation_mask"] = torch.tensor([0.0, 1.0]).view(B, 1, 1, 1).to(dv)   # one live, one augmented sample
+            for s in range(4):
+                o[("mono_depth", 0, s)] = (1.0 + 5.0 * t[("mono_disp", 0)]).to(dv)
+        noises = [n.to(dv) for n in t["noise"]]
+        if who == "oracle":
+            O.images_pred(inputs, o, num_scales=4, height=H, width=W, is_multi=is_multi)
+            losses, aux = O.dynamicdepth_compute_losses(inputs, o, (0, 1, 2, 3), is_multi=is_multi, selec_reproj=selec,
+                                                        zero_img=zero, noises=noises, automask=automask)
+            masks = [aux[("mask", s)].reshape(B, H, W) for s in range(4)]
+        else:
+            opt = SimpleNamespace(scales=[0, 1, 2, 3], selec_reproj=selec, zero_img=zero, no_ssim="false", height=H,
+                                  width=W, min_depth=0.1, max_depth=100.0, disable_automasking=not automask,
+                                  disable_motion_masking=False, no_matching_augmentation="false",
+                                  disparity_smoothness=1e-3)
+            trainer_ops.generate_images_pred_dynamicdepth(inputs, o, opt, is_multi=is_multi)
+            losses = trainer_ops.compute_losses_dynamicdepth(inputs, o, opt, is_multi=is_multi, noises=noises)
+            masks = [(o[("mal_selection", s)] >> 7).float().reshape(B, H, W) for s in range(4)]
+        leaves = disps + ([] if is_multi else Ts)     # is_multi detaches the poses
+        grads = torch.autograd.grad(losses["loss"], leaves)
+        res.append((losses, [m.cpu() for m in masks], [g.cpu() for g in grads], inputs[("color", 0, 0)].cpu()))
+    (lo, mo, go, to_), (lk, mk, gk, tk) = res
+    for k in lo:
+        assert _close(lk[k], lo[k]), k
+    if not is_multi and automask:
+        for a, b in zip(mk, mo):
+            assert torch.equal(a, b.float())         # bit-exact automask
+    assert torch.equal(tk, to_)                      # the target image was mutated identically
+    for a, b in zip(gk, go):
+        assert _gerr(a, b) < GRAD_RTOL
+
+
 @pytest.mark.parametrize("padding,align", [("border", True), ("border", False), ("zeros", True), ("zeros", False)])
 def test_grid_sample_matches_torch_cpu(op_device, padding, align):
     """layers.grid_sample: forward bit-identical to torch's CPU F.grid_sample, backward w.r.t. the grid."""

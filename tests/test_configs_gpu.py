@@ -142,3 +142,53 @@ def test_config5_dynamicdepth_forward_warp_and_cost_volume():
                                  look_img.to(DEV), True, aug.to(DEV), False, True, 1, 0.7)
     assert torch.equal(miss.cpu(), want_miss)
     assert torch.equal(vol.cpu(), want_vol)
+
+
+@pytest.mark.parametrize("is_multi", [False, True])
+def test_config5_dynamicdepth_fused_losses_full_size(is_multi):
+    """Config 5's loss half at 192x512 on the fused path (one photo_kernel<DD> pass per scale) against the oracle's
+    compute_losses over materialised warps (dynamicdepth/trainer.py:906-975, :1006-1128): losses within 1e-5, the
+    automask bit-exact, the zeroed target identical, gradients within 1e-4."""
+    B, H, W = 2, 192, 512
+    res = []
+    for who, dv in (("oracle", torch.device("cpu")), ("ours", DEV)):
+        inputs, t = make_photometric_inputs(B, H, W, num_scales=4, seed=511, normalised_K=CITYSCAPES_K,
+                                            translation_scale=0.3)
+        inputs[("color", -1, 0)][:, :, 40:100, 60:200] = 0.0     # DOMD-style holes reach the warps through the sources
+        inputs[("color", 1, 0)][:, :, 70:150, 150:330] = 0.0
+        inputs = {k: v.to(dv) for k, v in inputs.items()}
+        name = "multi" if is_multi else "mono"
+        disps = [t[(name + "_disp", s)].clone().to(dv).requires_grad_(True) for s in range(4)]
+        Ts = [t[("cam_T_cam", 0, f)].clone().to(dv).requires_grad_(True) for f in (-1, 1)]
+        o = {("disp", s): disps[s] for s in range(4)}
+        o[("cam_T_cam", 0, -1)], o[("cam_T_cam", 0, 1)] = Ts
+        if is_multi:
+            o["consistency_mask"] = t["consistency_mask"].to(dv)
+            o["augmentation_mask"] = torch.tensor([0.0, 1.0]).view(B, 1, 1, 1).to(dv)
+            for s in range(4):
+                o[("mono_depth", 0, s)] = (1.0 + 5.0 * t[("mono_disp", 0)]).to(dv)
+        noises = [n.to(dv) for n in t["noise"]]
+        if who == "oracle":
+            O.images_pred(inputs, o, num_scales=4, height=H, width=W, is_multi=is_multi)
+            losses, aux = O.dynamicdepth_compute_losses(inputs, o, (0, 1, 2, 3), is_multi=is_multi, noises=noises)
+            masks = [aux[("mask", s)].reshape(B, H, W).float() for s in range(4)]
+        else:
+            opt = SimpleNamespace(scales=[0, 1, 2, 3], selec_reproj=True, zero_img=True, no_ssim="false", height=H,
+                                  width=W, min_depth=0.1, max_depth=100.0, disable_automasking=False,
+                                  disable_motion_masking=False, no_matching_augmentation="false",
+                                  disparity_smoothness=1e-3)
+            trainer_ops.generate_images_pred_dynamicdepth(inputs, o, opt, is_multi=is_multi)
+            losses = trainer_ops.compute_losses_dynamicdepth(inputs, o, opt, is_multi=is_multi, noises=noises)
+            masks = [(o[("mal_selection", s)] >> 7).float().reshape(B, H, W) for s in range(4)]
+        grads = torch.autograd.grad(losses["loss"], disps + ([] if is_multi else Ts))
+        res.append((losses, [m.cpu() for m in masks], [g.cpu() for g in grads], inputs[("color", 0, 0)].cpu()))
+    (lo, mo, go, to_), (lk, mk, gk, tk) = res
+    for k in lo:
+        assert abs(float(lk[k]) - float(lo[k])) <= 1e-5 * abs(float(lo[k])), k
+    if not is_multi:
+        for a, b in zip(mk, mo):
+            assert torch.equal(a, b)
+    assert torch.equal(tk, to_)
+    assert float((to_ == 0).float().mean()) > 0.02       # the case does zero part of the target
+    for a, b in zip(gk, go):
+        assert _gerr(a, b) < 1e-4
