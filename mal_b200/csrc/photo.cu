@@ -115,6 +115,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   Geom* geom = reinterpret_cast<Geom*>(small);
   float* red = small + 40;                            // [8][PH_NPART]
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red + 8 * PH_NPART + 8);
+  int* syn_flag = reinterpret_cast<int*>(mbar + 1);   // (SYNG) some pixel of the tile selected a temporal-hint candidate
 
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
     // the finalize kernel's ticket (see photo_finalize_kernel); it launches after this kernel ends
@@ -123,6 +124,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   }
   // ---- phase 0: camera constants, TMA requests ------------------------------------------------------------
   if (tid == 0 && use_tma) mbar_init(mbar, 1);
+  if (SYNG && tid == 0) *syn_flag = 0;
   if (WARP) {
     if (tid >= 32 && tid < 56) {
       int f = (tid - 32) / 12, e = (tid - 32) % 12;
@@ -394,6 +396,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       const bool live = (idx < 2 || syn_grad) && w != 0.0f && !(DD && both_dark);
       lsel[i] = live ? idx : -1;
       lw[i] = AVG ? w * 0.5f : w;
+      if (SYNG && live && idx > 1) *syn_flag = 1;   // (every writer stores 1: a benign race)
       if (AVG && live && !a.no_ssim) {
         const float sc = w * (0.5f * 0.85f / 27.0f);   // both candidates, half the weight each
 #pragma unroll
@@ -489,16 +492,14 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
       // instruction cache even when it never runs)
       // with SYNG the same neighbourhood walk also collects d S / d syn (the temporal-hint candidates 2, 3): one
       // selection load per neighbour decides which of the four accumulators it feeds
-      const bool syn_out = SYNG && a.grad_syn[0] != nullptr;
       const unsigned dmc = DD ? dm[vc] : 0u;
-      float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
-      float xq0[3], xq1[3], xq2[3] = {0.f, 0.f, 0.f}, xq3[3] = {0.f, 0.f, 0.f}, yq[3];
+      float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+      float xq0[3], xq1[3], yq[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         xq0[c] = sx[c * tl.VN + vc];
         xq1[c] = ncand > 1 ? sx[(size_t)tl.TS + c * tl.VN + vc] : 0.0f;
         yq[c] = sy[c * tl.VN + vc];
-        if (SYNG && syn_out) { xq2[c] = sx[(size_t)2 * tl.TS + c * tl.VN + vc]; xq3[c] = sx[(size_t)3 * tl.TS + c * tl.VN + vc]; }
       }
       if (!a.no_ssim) {
 #pragma unroll
@@ -514,17 +515,9 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
             float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
             int li = lc + dy * tl.LW + dx;
             int s = lsel[li];
-            if (s < 0) continue;
-            if (SYNG && s > 1) {   // a temporal-hint candidate: its gradient goes to grad_syn, not into depth / pose
-#pragma unroll
-              for (int c = 0; c < 3; c++) {
-                const float xq = s == 2 ? xq2[c] : xq3[c];
-                const float v = m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq * coef[(c * 3 + 1) * tl.LN + li] +
-                                     yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
-                if (s == 2) g2[c] += v; else g3[c] += v;
-              }
-              continue;
-            }
+            // not live, or (SYNG) a temporal-hint candidate: its gradient goes to grad_syn in the loop after this
+            // one, not into depth / pose
+            if (SYNG ? (unsigned)s > 1u : s < 0) continue;
             if (DD) {   // the target value at this pixel as the selected call saw it
               const bool z = (dmc >> s) & 1u;
 #pragma unroll
@@ -555,24 +548,6 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
               if (s == 0) g0[c] += v; else g1[c] += v;
             }
           }
-        }
-      }
-      if (SYNG && syn_out) {
-        const int s = lsel[lc];
-        if (s > 1) {
-          const float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const float d = yq[c] - (s == 2 ? xq2[c] : xq3[c]);
-            const float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
-            if (s == 2) g2[c] += sg; else g3[c] += sg;
-          }
-        }
-        const size_t pq = (size_t)gy * W + gx;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          a.grad_syn[0][((size_t)b * 3 + c) * HW + pq] = g2[c];
-          a.grad_syn[1][((size_t)b * 3 + c) * HW + pq] = g3[c];
         }
       }
       {
@@ -641,6 +616,68 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
         }
         if (a.depth_is_disp) gdepth *= -disp_range * dv * dv;  // d depth / d disp
         a.grad_depth[(size_t)b * HW + po] = gdepth;
+      }
+    }
+    // d S / d syn (the temporal-hint candidates 2, 3), in its own loop: a temporal-hint candidate wins only inside
+    // and next to an instance, so most tiles have no such pixel (a CTA-uniform flag raised in phase B) and only
+    // write their zeros; the others repeat the neighbourhood walk for the pixels that selected candidate 2 or 3.
+    // Keeping this out of the loop above keeps that loop the plain teacher pass's.
+    if (SYNG && WARP && a.grad_syn[0] != nullptr) {
+      const bool has_syn = *syn_flag != 0;
+      for (int i = tid; i < PH_TW * PH_TH; i += PH_NT) {
+        const int qy = i / PH_TW, qx = i - qy * PH_TW;
+        const int gy = y0 + qy, gx = x0 + qx;
+        if (gy >= H || gx >= W) continue;
+        float g2[3] = {0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
+        if (has_syn) {
+          const int lc = (qy + tl.HL) * tl.LW + qx + tl.HL;
+          const int vc = (qy + tl.HV) * PH_VW + qx + PH_OX;
+          float xq2[3], xq3[3], yq[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            xq2[c] = sx[(size_t)2 * tl.TS + c * tl.VN + vc];
+            xq3[c] = sx[(size_t)3 * tl.TS + c * tl.VN + vc];
+            yq[c] = sy[c * tl.VN + vc];
+          }
+          if (!a.no_ssim) {
+            for (int dy = -1; dy <= 1; dy++) {
+              const int py = gy + dy;
+              if (py < 0 || py >= H) continue;
+              const float my = ((py == 0 && dy == -1) || (py == H - 1 && dy == 1)) ? 2.0f : 1.0f;
+              for (int dx = -1; dx <= 1; dx++) {
+                const int px = gx + dx;
+                if (px < 0 || px >= W) continue;
+                const float m = my * (((px == 0 && dx == -1) || (px == W - 1 && dx == 1)) ? 2.0f : 1.0f);
+                const int li = lc + dy * tl.LW + dx;
+                const int s = lsel[li];
+                if (s < 2) continue;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  const float xq = s == 2 ? xq2[c] : xq3[c];
+                  const float v = m * (coef[(c * 3) * tl.LN + li] + 2.0f * xq * coef[(c * 3 + 1) * tl.LN + li] +
+                                       yq[c] * coef[(c * 3 + 2) * tl.LN + li]);
+                  if (s == 2) g2[c] += v; else g3[c] += v;
+                }
+              }
+            }
+          }
+          const int s = lsel[lc];
+          if (s > 1) {
+            const float wl = lw[lc] * (a.no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              const float d = yq[c] - (s == 2 ? xq2[c] : xq3[c]);
+              const float sg = d > 0.f ? -wl : (d < 0.f ? wl : 0.f);
+              if (s == 2) g2[c] += sg; else g3[c] += sg;
+            }
+          }
+        }
+        const size_t pq = (size_t)gy * W + gx;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          a.grad_syn[0][((size_t)b * 3 + c) * HW + pq] = g2[c];
+          a.grad_syn[1][((size_t)b * 3 + c) * HW + pq] = g3[c];
+        }
       }
     }
   }

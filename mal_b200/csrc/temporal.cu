@@ -215,9 +215,11 @@ __global__ void __launch_bounds__(TW_NT) tb_backward_kernel(const mal_temporal_a
   __shared__ Geom geom;
   __shared__ TsDelta d;
   __shared__ float red[TW_NT / 32][TB_NPART];
+  __shared__ int any_grad;   // some pixel of this CTA carried a gradient into the poses
   const int b = blockIdx.z, H = a.height, W = a.width;
   const size_t hw = (size_t)H * W;
   const int n_inst = a.counts[b];
+  if (threadIdx.x == 0) any_grad = 0;
   if (threadIdx.x < 24) {
     const int f = threadIdx.x / 12, e = threadIdx.x % 12;
     geom.P[f][e] = kt_entry(a.K + b * 16, a.T[f] + b * 16, e / 4, e % 4);
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(TW_NT) tb_backward_kernel(const mal_temporal_a
       for (int f = 0; f < 2; f++) {
         const float* g = f == 0 ? gl : gn;
         if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+        any_grad = 1;   // (every writer stores 1)
         const float* P = geom.P[f];
         const Sample s = project_pixel<CONV>(P, ray, dv, a.eps, H, W, &sdiv);
         const Taps t = make_taps(s.ix, s.iy, H, W);
@@ -337,18 +340,25 @@ __global__ void __launch_bounds__(TW_NT) tb_backward_kernel(const mal_temporal_a
       if (gdepth != 0.0f) a.grad_depth[(size_t)b * hw + p] += gdepth;   // onto the photometric kernel's plane
     }
   }
-  // per-CTA d/d(K@T) partials
+  // per-CTA d/d(K@T) partials.  The gradient lives inside and next to the instances: most CTAs carry none and
+  // skip the 24 shuffle trees.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int j = 0; j < 24; j++) {
-    const float v = warp_sum(gP[j]);
-    if (lane == 0) red[warp][j] = v;
-  }
   __syncthreads();
+  const bool live_cta = any_grad != 0;
+  if (live_cta) {
+#pragma unroll
+    for (int j = 0; j < 24; j++) {
+      const float v = warp_sum(gP[j]);
+      if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x < TB_NPART && a.partials) {
     float s = 0.0f;
+    if (live_cta) {
 #pragma unroll
-    for (int wv = 0; wv < TW_NT / 32; wv++) s += red[wv][threadIdx.x];
+      for (int wv = 0; wv < TW_NT / 32; wv++) s += red[wv][threadIdx.x];
+    }
     const size_t tiles = (size_t)gridDim.x * gridDim.y;
     a.partials[((size_t)b * tiles + blockIdx.y * gridDim.x + blockIdx.x) * TB_NPART + threadIdx.x] = s;
   }

@@ -21,7 +21,7 @@ def main():
     agg = defaultdict(lambda: defaultdict(float))
     text = {}
     for r in rows:
-        if len(r) == 2 and r[0] == "File Name":
+        if len(r) == 2 and r[0] in ("File Name", "File Path"):
             fname = r[1].split("/")[-1]
             continue
         if r and r[0] == "Line No":
