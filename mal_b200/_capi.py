@@ -77,7 +77,7 @@ class CostVolumeArgs(C.Structure):
         ("cost_volume", C.c_void_p), ("missing_mask", C.c_void_p), ("confidence", C.c_void_p),
         ("argmin", C.c_void_p), ("lowest_cost", C.c_void_p), ("packed", C.c_void_p),
         ("cv_min", C.c_int32), ("occ_mode", C.c_int32), ("pool_radius", C.c_int32), ("pool_th", C.c_float),
-        ("occ", C.c_void_p), ("aug_mask", C.c_void_p),
+        ("occ", C.c_void_p), ("aug_mask", C.c_void_p), ("desc", C.c_void_p),
     ]
 
 
@@ -149,6 +149,7 @@ EXPORTS = {
     "mal_photo_finalize": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_cost_volume_workspace_floats": (C.c_size_t, [C.c_int] * 5),
+    "mal_cost_volume_desc_floats": (C.c_size_t, [C.c_int] * 6),
     "mal_cost_volume_forward": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),
     "mal_smooth_workspace_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_smooth_forward": (C.c_int, [C.POINTER(SmoothArgs), C.c_void_p]),

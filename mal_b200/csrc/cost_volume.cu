@@ -84,6 +84,28 @@ __global__ void __launch_bounds__(256) cv_pack_kernel(const float* __restrict__ 
   dst[i] = v;
 }
 
+// NCHW -> [C/16][h*w][4] float4 (chunk-major: the 16 channels of a texel's chunk are 64 contiguous bytes), zero
+// padded.  Read by cv_pool_kernel, whose four quad lanes fetch one texel together.
+__global__ void __launch_bounds__(256) cv_pack_cm_kernel(const float* __restrict__ src, float4* __restrict__ dst,
+                                                         int C, int Cp, int hw, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 3);
+  long long r = i >> 2;
+  const int p = (int)(r % hw);
+  r /= hw;
+  const int chunk = (int)(r % (Cp / CV_CHUNK));
+  const long long img = r / (Cp / CV_CHUNK);
+  const int c0 = chunk * CV_CHUNK + q * 4;
+  const float* sp = src + (img * C + c0) * hw + p;
+  float4 v;
+  v.x = (c0 + 0 < C) ? __ldg(sp) : 0.0f;
+  v.y = (c0 + 1 < C) ? __ldg(sp + hw) : 0.0f;
+  v.z = (c0 + 2 < C) ? __ldg(sp + 2 * (size_t)hw) : 0.0f;
+  v.w = (c0 + 3 < C) ? __ldg(sp + 3 * (size_t)hw) : 0.0f;
+  dst[i] = v;
+}
+
 __device__ __forceinline__ float4 ldg4(const float4* p) {
 #ifdef MAL_EMU
   return *p;
@@ -111,6 +133,7 @@ __device__ __forceinline__ float quad_l1(float acc, const float4& a, const float
 
 // ---- DynamicDepth extras (dynamicdepth/networks/resnet_encoder.py:191-202) ---------------------
 constexpr int CV_OCC_BIT = 1 << 30;   // descriptor flag: the projected occlusion mask exceeds pool_th
+constexpr int CV_ZERO_BIT = 1 << 29;  // ... and so does every neighbour of the pool window: the pooled value is 0
 
 // F.grid_sample(occ_mask, pix_locs, zeros, bilinear, align_corners) > pool_th at one location
 template <int CONV>
@@ -135,6 +158,19 @@ __device__ __forceinline__ float4 bilinear4(const float4* __restrict__ plane, co
   return r;
 }
 
+// the same from the chunk-major copy [chunk][h*w][4 quads]: `cell` points at quad q of texel 0
+__device__ __forceinline__ float4 bilinear4_cm(const float4* __restrict__ cell, const Taps& t) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = t.v00 ? ldg4(cell + 4 * (size_t)t.o00) : z, b = t.v01 ? ldg4(cell + 4 * (size_t)t.o01) : z;
+  const float4 c = t.v10 ? ldg4(cell + 4 * (size_t)t.o10) : z, d = t.v11 ? ldg4(cell + 4 * (size_t)t.o11) : z;
+  float4 r;
+  r.x = xfma(d.x, t.se, xfma(c.x, t.sw, xfma(b.x, t.ne, xmul(a.x, t.nw))));
+  r.y = xfma(d.y, t.se, xfma(c.y, t.sw, xfma(b.y, t.ne, xmul(a.y, t.nw))));
+  r.z = xfma(d.z, t.se, xfma(c.z, t.sw, xfma(b.z, t.ne, xmul(a.z, t.nw))));
+  r.w = xfma(d.w, t.se, xfma(c.w, t.sw, xfma(b.w, t.ne, xmul(a.w, t.nw))));
+  return r;
+}
+
 __device__ __forceinline__ float quad_l1_vals(float acc, const float4& v, const float4& cur) {
   acc = xadd(acc, fabsf(xsub(v.x, cur.x)));
   acc = xadd(acc, fabsf(xsub(v.y, cur.y)));
@@ -145,44 +181,186 @@ __device__ __forceinline__ float quad_l1_vals(float acc, const float4& v, const 
 
 // "pool": an occluded sample takes, per channel, the max over its (2r+1)^3 neighbourhood in
 // (bin, y, x) of the warped features with occluded entries zeroed (F.max_pool3d, implicit -inf
-// padding).  Slow path: every neighbour is re-projected and re-sampled; only occluded samples pay.
+// padding).
+// ---- "pool" with a descriptor volume -----------------------------------------------------------
+// The pool window of an occluded sample reads its 26 neighbours in (bin, y, x).  Doing that inside the sweep (one
+// lane walking its window while the other 31 wait, every neighbour re-projected, once per chunk) cost 4.0 of the
+// 4.6 ms of the call at the Cityscapes bench shape.  Instead:
+//   cv_project_kernel   projects every (lookup frame, bin, pixel) ONCE into a descriptor volume
+//                       [B*F][bins][h*w] x {ux, uy, flags} (HBM is idle in this op);
+//   cv_interior_kernel  marks the occluded samples whose whole window is occluded (the inside of a blob: the pooled
+//                       value is 0) and appends the others - the rim, ~2 % of all samples - to a list;
+//   cv_pool_kernel      one warp per listed sample: lanes = 8 neighbour slots x 4 channel quads, max over the slots
+//                       by shuffles, then the |pooled - current| chunk sums in the reference's order -> `parts`;
+//   the sweep           reads descriptors instead of projecting, and one float per (rim sample, chunk).
+// Workspace (floats / ints of size plane = B*F*bins*h*w): ux | uy | flags | list | parts[chunks] | counter (4) |
+// chunk-major copy of the lookup features (B*F*Cp*h*w).
+constexpr int CV_DESC_EDGE = 1;   // pixel and sampling location pass the border masks (:203-212)
+constexpr int CV_DESC_OCC = 2;    // projected occlusion mask > pool_th (:194-195)
+constexpr int CV_DESC_ZERO = 4;   // ... and every sample of its pool window too: the pooled value is 0
+
+__host__ __device__ inline size_t cv_desc_plane(int batch, int num_lookup, int num_bins, int hw) {
+  return (size_t)batch * num_lookup * num_bins * hw;
+}
+// float offset of the chunk-major lookup copy (16-byte aligned), behind the planes and the counter
+__host__ __device__ inline size_t cv_desc_cm_offset(size_t plane, int nchunks) {
+  return ((4 + (size_t)nchunks) * plane + 4 + 3) / 4 * 4;
+}
+
 template <int CONV>
-__device__ __noinline__ float pooled_chunk_l1(const mal_cost_volume_args& a, const CvGeom* geom,
-                                              const float4* __restrict__ lqc, const float* __restrict__ occ,
-                                              const float4* cq, int k, int px, int py) {
-  const int h = a.height, w = a.width, hw = h * w, r = a.pool_radius;
-  float4 m[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) m[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
+__global__ void __launch_bounds__(256) cv_project_kernel(const mal_cost_volume_args a, const SizeDiv sdiv) {
+  __shared__ CvGeom geom;
+  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins;
+  const int k = blockIdx.x % nb, bf = blockIdx.x / nb, b = bf / a.num_lookup;
+  const int tid = threadIdx.x;
+  if (tid < 12) {
+    geom.P[tid] = kt_entry(a.K + b * 16, a.poses + (size_t)bf * 16, tid / 4, tid % 4);
+  } else if (tid < 21) {
+    const int e = tid - 12;
+    geom.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
+  } else if (tid == 21) {
+    const float* T = a.poses + (size_t)bf * 16;
+    float s = 0.0f;
+    for (int e = 0; e < 16; e++) s += T[e];
+    geom.live = (s != 0.0f) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!geom.live) return;   // the sweep skips the frame as well
+  const int p = blockIdx.y * 256 + tid;
+  if (p >= hw) return;
+  const int py = p / w, px = p - py * w;
+  const float* occ = nullptr;
+  if (!(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
+  const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
+  const GridPoint gp = project_grid<CONV>(geom.P, ray, __ldg(a.bins + k), a.eps, h, w, &sdiv);
+  const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
+  const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
+  const bool inner = py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
+  int flags = 0;
+  if (inner && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2)) flags |= CV_DESC_EDGE;
+  if (occ && occluded_at<CONV>(occ, gp, h, w, a.pool_th)) flags |= CV_DESC_OCC;
+  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
+  const size_t o = ((size_t)bf * nb + k) * hw + p;
+  a.desc[o] = unnormalize<CONV>(gp.gx, w);
+  a.desc[plane + o] = unnormalize<CONV>(gp.gy, h);
+  reinterpret_cast<int*>(a.desc)[2 * plane + o] = flags;
+}
+
+// Inside an occluded blob every sample of the pool window is occluded too: the pooled value is 0 and the sweep need
+// not look.  One pass over the flag plane marks those samples (27 independent loads; out-of-range neighbours are
+// clamped onto in-window ones, which leaves the AND unchanged).
+__global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_args a) {
+  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, r = a.pool_radius;
+  const int k = blockIdx.x % nb, bf = blockIdx.x / nb;
+  const int p = blockIdx.y * 256 + threadIdx.x;
+  if (p >= hw) return;
+  int* fl = reinterpret_cast<int*>(a.desc) + 2 * cv_desc_plane(a.batch, a.num_lookup, nb, hw) + (size_t)bf * nb * hw;
+  const int mine = fl[(size_t)k * hw + p];
+  if (!(mine & CV_DESC_OCC)) return;
+  const int py = p / w, px = p - py * w;
+  int all = CV_DESC_OCC;
   for (int dk = -r; dk <= r; dk++) {
-    const int kk = k + dk;
-    if (kk < 0 || kk >= a.num_bins) continue;
-    const float depth = __ldg(a.bins + kk);
+    const int kk = min(max(k + dk, 0), nb - 1);
     for (int dy = -r; dy <= r; dy++) {
-      const int yy = py + dy;
-      if (yy < 0 || yy >= h) continue;
-      for (int dx = -r; dx <= r; dx++) {
-        const int xx = px + dx;
-        if (xx < 0 || xx >= w) continue;
-        const Ray ray = pixel_ray(geom->iK, (float)xx, (float)yy);
-        const GridPoint gp = project_grid<CONV>(geom->P, ray, depth, a.eps, h, w);
-        if (occluded_at<CONV>(occ, gp, h, w, a.pool_th)) continue;       // x[mask] = 0
-        const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
-        if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
-        const Taps t = make_taps(ux, uy, h, w);
+      const int yy = min(max(py + dy, 0), h - 1);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float4 v = bilinear4(lqc + (size_t)j * hw, t);
-          m[j].x = fmaxf(m[j].x, v.x); m[j].y = fmaxf(m[j].y, v.y);
-          m[j].z = fmaxf(m[j].z, v.z); m[j].w = fmaxf(m[j].w, v.w);
-        }
+      for (int dx = -3; dx <= 3; dx++) {
+        if (dx < -r || dx > r) continue;
+        const int xx = min(max(px + dx, 0), w - 1);
+        all &= __ldg(fl + (size_t)kk * hw + (size_t)yy * w + xx);
       }
     }
   }
-  float acc = 0.0f;
+  // (a neighbouring thread may read this word while it is rewritten: it only looks at bit CV_DESC_OCC, which
+  // does not change)
+  if (all & CV_DESC_OCC) {
+    fl[(size_t)k * hw + p] = mine | CV_DESC_ZERO;
+  } else if (mine & CV_DESC_EDGE) {   // a rim sample the sweep will use: cv_pool_kernel's work list (order is
+                                      // irrelevant: every entry owns its output slots)
+    const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
+    int* base = reinterpret_cast<int*>(a.desc);
+    int* counter = base + (4 + (size_t)cv_padded_channels(a.channels) / CV_CHUNK) * plane;
+    base[3 * plane + atomicAdd(counter, 1)] = (int)(((size_t)bf * nb + k) * hw + p);
+  }
+}
+
+// One warp per rim sample.  lane = slot * 4 + quad: slot s handles window neighbours s, s+8, s+16, ... and quad q
+// the channels 4q..4q+3 of each 16-channel chunk, four chunks per pass.
+template <int R>   // pool radius as a constant (1 is the reference's default); 0: read it from the arguments
+__global__ void __launch_bounds__(256, 4) cv_pool_kernel(const mal_cost_volume_args a, const int Cp) {
+  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, r = R ? R : a.pool_radius, side = 2 * r + 1;
+  const int n = side * side * side, nquads = Cp / 4, nchunks = Cp / CV_CHUNK;
+  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
+  const int* list = reinterpret_cast<const int*>(a.desc) + 3 * plane;
+  float* parts = a.desc + 4 * plane;
+  const int count = reinterpret_cast<const int*>(a.desc)[(4 + (size_t)nchunks) * plane];
+  const float4* curq = reinterpret_cast<const float4*>(a.packed);
+  const float4* lookcm = reinterpret_cast<const float4*>(a.desc + cv_desc_cm_offset(plane, nchunks));
+  const int lane = threadIdx.x & 31, slot = lane >> 2, q = lane & 3;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarps) {
+    const int o = __ldg(list + i);
+    const int bf = o / (nb * hw), rem = o - bf * nb * hw, k = rem / hw, p = rem - k * hw;
+    const int py = p / w, px = p - py * w, b = bf / a.num_lookup;
+    const float* d = a.desc + (size_t)bf * nb * hw;
+    const int* dfl = reinterpret_cast<const int*>(a.desc) + 2 * plane + (size_t)bf * nb * hw;
+    const float4* lq = lookcm + (size_t)bf * nquads * hw + q;
+    for (int c0 = 0; c0 < nchunks; c0 += 4) {
+      float4 m[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) acc = quad_l1_vals(acc, m[j], cq[j]);
-  return acc;
+      for (int c = 0; c < 4; c++) m[c] = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
+      for (int j = slot; j < n; j += 8) {
+        const int kk = k + j / (side * side) - r, yy = py + (j / side) % side - r, xx = px + j % side - r;
+        if (kk < 0 || kk >= nb || yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+        const size_t on = (size_t)kk * hw + (size_t)yy * w + xx;
+        const int fl = __ldg(dfl + on);
+        const float ux = __ldg(d + on), uy = __ldg(d + plane + on);
+        if (fl & CV_DESC_OCC) continue;                                                               // x[mask] = 0
+        if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
+        const Taps t = make_taps(ux, uy, h, w);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (c0 + c < nchunks) {
+            const float4 v = bilinear4_cm(lq + (size_t)(c0 + c) * hw * 4, t);
+            m[c].x = fmaxf(m[c].x, v.x); m[c].y = fmaxf(m[c].y, v.y);
+            m[c].z = fmaxf(m[c].z, v.z); m[c].w = fmaxf(m[c].w, v.w);
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int sft = 4; sft <= 16; sft <<= 1) {   // max over the 8 slots
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          m[c].x = fmaxf(m[c].x, __shfl_xor_sync(0xffffffffu, m[c].x, sft));
+          m[c].y = fmaxf(m[c].y, __shfl_xor_sync(0xffffffffu, m[c].y, sft));
+          m[c].z = fmaxf(m[c].z, __shfl_xor_sync(0xffffffffu, m[c].z, sft));
+          m[c].w = fmaxf(m[c].w, __shfl_xor_sync(0xffffffffu, m[c].w, sft));
+        }
+      }
+      // |pooled - current| summed over the chunk's 16 channels in order: the chain runs through lanes 0..3
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float4 cur[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        cur[c] = (lane < 4 && c0 + c < nchunks) ? ldg4(curq + ((size_t)b * nquads + (c0 + c) * 4 + lane) * hw + p)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int qq = 0; qq < 4; qq++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (lane == qq) acc[c] = quad_l1_vals(acc[c], m[c], cur[c]);
+          acc[c] = __shfl_sync(0xffffffffu, acc[c], qq);
+        }
+      }
+      if (lane < 4 && c0 + lane < nchunks) {
+        float mine = acc[0];
+#pragma unroll
+        for (int c = 1; c < 4; c++) if (lane == c) mine = acc[c];
+        parts[(size_t)(c0 + lane) * plane + o] = mine;
+      }
+    }
+  }
 }
 
 template <int CONV, int MINB, bool DYN>
@@ -239,10 +417,45 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 
     const Ray ray = pixel_ray(geom->iK, (float)px, (float)py);
     const float4* lq = lookq + ((size_t)b * a.num_lookup + f) * nquads * hw;
+    // descriptor volume of this (sample, lookup frame): only with the pool fill and only where it applies
+    const size_t dplane = DYN ? cv_desc_plane(a.batch, a.num_lookup, nb, hw) : 0;
+    const float* desc = (DYN && a.desc && occ && a.occ_mode == MAL_CV_OCC_POOL)
+                            ? a.desc + ((size_t)b * a.num_lookup + f) * nb * hw : nullptr;
 
     for (int g0 = 0; g0 < nb; g0 += CV_BG) {
       const int gn = min(CV_BG, nb - g0);
       // ---- P: projection descriptors ---------------------------------------------------------
+      if (DYN && desc) {   // projected once by cv_project_kernel: all of the warp's loads go out together
+        static_assert(CV_BG == 4 * CV_WARPS, "four planes of a group per warp");
+        int fls[4];
+        float uxs[4], uys[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = warp + CV_WARPS * i;
+          const bool live = pix_ok && k < gn;
+          const size_t o = live ? (size_t)(g0 + k) * hw + p : 0;
+          fls[i] = live ? __ldg(reinterpret_cast<const int*>(desc) + 2 * dplane + o) : 0;
+          uxs[i] = __ldg(desc + o);
+          uys[i] = __ldg(desc + dplane + o);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int k = warp + CV_WARPS * i;
+          if (k >= gn) continue;
+          int off = -1;
+          float tx = 0.0f, ty = 0.0f;
+          if (fls[i] & CV_DESC_EDGE) {
+            const float x0 = floorf(uxs[i]), y0 = floorf(uys[i]);
+            off = min(max((int)y0, 0), h - 2) * w + min(max((int)x0, 0), w - 2);
+            tx = xsub(uxs[i], x0);
+            ty = xsub(uys[i], y0);
+            if (fls[i] & CV_DESC_OCC) off |= CV_OCC_BIT | ((fls[i] & CV_DESC_ZERO) ? CV_ZERO_BIT : 0);
+          }
+          d_off[k * CV_PX + lane] = off;
+          d_tx[k * CV_PX + lane] = tx;
+          d_ty[k * CV_PX + lane] = ty;
+        }
+      } else
       for (int k = warp; k < gn; k += CV_WARPS) {
         int off = -1;
         float tx = 0.0f, ty = 0.0f;
@@ -302,8 +515,13 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
               const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
               for (int j = 0; j < 4; j++) acc = quad_l1_vals(acc, one, cq[j]);
-            } else {                                          // warped[mask] = max_pool3d(x)[mask]
-              acc = pooled_chunk_l1<CONV>(a, geom, lqc, occ, cq, g0 + k, px, py);
+            } else if (off & CV_ZERO_BIT) {                   // warped[mask] = max_pool3d(x)[mask], 0 inside a blob
+              const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 4; j++) acc = quad_l1_vals(acc, zero, cq[j]);
+            } else {                                          // ... computed by cv_pool_kernel on the rim
+              acc = __ldg(a.desc + (4 + (size_t)ch) * dplane + ((size_t)b * a.num_lookup + f) * nb * hw +
+                          (size_t)(g0 + k) * hw + p);
             }
             off = -1;
           }
@@ -693,6 +911,12 @@ extern "C" size_t mal_cost_volume_workspace_floats(int batch, int channels, int 
   return (size_t)batch * (1 + num_lookup) * cv_padded_channels(channels) * height * width;
 }
 
+extern "C" size_t mal_cost_volume_desc_floats(int batch, int channels, int num_lookup, int num_bins, int height,
+                                              int width) {
+  return cv_desc_cm_offset(cv_desc_plane(batch, num_lookup, num_bins, height * width), cv_padded_channels(channels) / CV_CHUNK) +
+         (size_t)batch * num_lookup * cv_padded_channels(channels) * height * width;
+}
+
 extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream) {
   MAL_REQUIRE(args != nullptr, "mal_cost_volume_forward: args is NULL");
   const mal_cost_volume_args& a = *args;
@@ -729,6 +953,29 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   }
   const int tiles = (hw + CV_PX - 1) / CV_PX;
   const SizeDiv sdiv = size_div(a.height, a.width, a.convention);
+  if (a.occ && a.occ_mode == MAL_CV_OCC_POOL) {
+    // the pool fill's descriptor volume: every (lookup frame, bin, pixel) projected once, blob interiors marked
+    MAL_REQUIRE(a.desc != nullptr, "mal_cost_volume_forward: MAL_CV_OCC_POOL needs the desc workspace "
+                "(mal_cost_volume_desc_floats)");
+    const size_t rows = (size_t)a.batch * a.num_lookup * a.num_bins;
+    MAL_REQUIRE(rows < (1u << 31) && (hw + 255) / 256 <= 65535, "mal_cost_volume_forward: descriptor grid too large");
+    dim3 pgrid((unsigned)rows, (unsigned)((hw + 255) / 256));
+    if (a.convention == MAL_CONV_MANYDEPTH) launch(cv_project_kernel<MAL_CONV_MANYDEPTH>, pgrid, dim3(256), 0, st, a, sdiv);
+    else launch(cv_project_kernel<MAL_CONV_DUALREFINE>, pgrid, dim3(256), 0, st, a, sdiv);
+    const size_t plane = cv_desc_plane(a.batch, a.num_lookup, a.num_bins, hw);
+    MAL_REQUIRE(plane < (1u << 31), "mal_cost_volume_forward: descriptor volume too large for 32-bit sample indices");
+    cudaMemsetAsync(reinterpret_cast<int*>(a.desc) + (4 + (size_t)Cp / CV_CHUNK) * plane, 0, sizeof(int), st);
+    launch(cv_interior_kernel, pgrid, dim3(256), 0, st, a);
+    {
+      const long long total_l = (long long)a.batch * a.num_lookup * (Cp / 4) * hw;
+      launch(cv_pack_cm_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
+             reinterpret_cast<float4*>(a.desc + cv_desc_cm_offset(plane, Cp / CV_CHUNK)), a.channels, Cp, hw, total_l);
+    }
+    if (a.pool_radius == 1) launch(cv_pool_kernel<1>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
+    else launch(cv_pool_kernel<0>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
+    int rc = check_launch("cv_project_kernel / cv_interior_kernel / cv_pool_kernel");
+    if (rc) return rc;
+  }
   const size_t smem = cv_smem_bytes(Cp / CV_CHUNK, a.num_bins);
   MAL_REQUIRE(smem <= 227 * 1024, "mal_cost_volume_forward: %d bins x %d channels need %zu B of shared memory",
               a.num_bins, a.channels, smem);
@@ -739,7 +986,8 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   if (const char* e = getenv("MAL_CV_MINB")) minb = atoi(e);
 #define MAL_CV_LAUNCH(CONV_)                                                                         \
   do {                                                                                               \
-    if (dyn) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);             \
+    if (dyn && minb <= 3) launch(cv_sweep_kernel<CONV_, 3, true>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);     \
+    else if (dyn) launch(cv_sweep_kernel<CONV_, 4, true>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);        \
     else if (minb <= 3) launch(cv_sweep_kernel<CONV_, 3, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv); \
     else if (minb == 4) launch(cv_sweep_kernel<CONV_, 4, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv); \
     else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);                \

@@ -9,6 +9,7 @@ tensors; nothing in this package ever does.)
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -183,14 +184,19 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     a.packed = _ptr(packed)
     a.cv_min, a.occ_mode, a.pool_radius, a.pool_th = int(bool(cv_min)), int(occ_mode), int(pool_radius), float(pool_th)
     a.occ, a.aug_mask = _ptr(occ), _ptr(aug_mask)
+    # the pool fill projects every (lookup frame, bin, pixel) once into a descriptor volume (12 B per sample) that
+    # the pool windows read their neighbours from
+    desc = None
+    if occ is not None and occ_mode == OCC_POOL:
+        desc = new((handle.mal_cost_volume_desc_floats(B, Cn, F_, nb, h, w),))
+    a.desc = _ptr(desc)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
     # the four-lanes-per-pixel sweep (C <= 64, no DynamicDepth extras) reads the current features in place:
     # lookup pack + sweep; the general kernel packs both operands first
-    import os
     dyn = bool(cv_min) or (occ is not None and occ_mode != OCC_NONE)
     quad = not dyn and (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
-    LAUNCHES[0] += 2 if quad else 3
-    out["_keepalive"] = (packed,)
+    LAUNCHES[0] += (2 if quad else 3) + (4 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_pool
+    out["_keepalive"] = (packed, desc)
     return out
 
 
