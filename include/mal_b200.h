@@ -120,6 +120,9 @@ typedef struct mal_photo_args {
   int32_t identity_in_pass; /* selects this mode when neither zero_img nor selec_reproj is set: `syn` holds the identity
                                candidates, their min (+ noise) is the automask's other side                             */
   float* target_out;        /* (B,3,H,W) optional: the target as this pass's calls leave it = the next scale's target  */
+  const float* warped[2];   /* (B,3,H,W) optional, WARP mode: the warped sources outputs[("color", f, s)] when the caller has
+                               materialised them anyway (trainer.py:1122-1125 feeds them to image_synthesis): the pass
+                               stages them instead of re-warping; gradients still chain through depth / T / src      */
   int32_t avg_reprojection; /* opt.avg_reprojection (dualrefine/trainer.py:575-586, dynamicdepth/trainer.py:1044-1056):
                                mean instead of min over the two candidates (no syn); selection index is 0; with
                                gradients (WARP mode) both warps carry half of it                             */
@@ -178,13 +181,17 @@ typedef struct mal_cost_volume_args {
   float pool_th;               /* pool_th (:195)                                                   */
   const float* occ;            /* (B,h,w) {0,1}: occ_batch > 0 at the matching resolution (:160, :194) */
   const float* aug_mask;       /* (B) occlusion handling only where aug_mask == 0 (:192); NULL: all */
-  float* desc;                 /* workspace of mal_cost_volume_desc_floats() floats, required with MAL_CV_OCC_POOL:
-                                  every (lookup frame, bin, pixel) is projected once into it, the rim of every
-                                  occluded blob is listed there and its pooled chunk sums are formed there       */
+  float* desc;                 /* projection workspace.  With MAL_CV_OCC_POOL (required):
+                                  mal_cost_volume_desc_floats() floats - every (lookup frame, bin, pixel) is projected
+                                  once into it, the rim of every occluded blob is listed there and its pooled chunk
+                                  sums are formed there.  Without the DynamicDepth extras and C <= 64 (optional):
+                                  mal_cost_volume_proj_floats() floats - the projections run in a pre-pass at full
+                                  occupancy instead of inside the sweep; NULL keeps them in the sweep                */
 } mal_cost_volume_args;
 
 size_t mal_cost_volume_workspace_floats(int batch, int channels, int height, int width, int num_lookup);
 size_t mal_cost_volume_desc_floats(int batch, int channels, int num_lookup, int num_bins, int height, int width);
+size_t mal_cost_volume_proj_floats(int batch, int num_lookup, int num_bins, int height, int width);
 int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

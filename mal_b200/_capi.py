@@ -33,6 +33,7 @@ class PhotoArgs(C.Structure):
         ("depth_height", C.c_int32), ("depth_width", C.c_int32), ("min_reproj_b", C.c_void_p),
         ("zero_img", C.c_int32), ("selec_reproj", C.c_int32), ("ignore_automask", C.c_int32), ("identity_in_pass", C.c_int32),
         ("target_out", C.c_void_p),
+        ("warped", C.c_void_p * 2),
         ("avg_reprojection", C.c_int32),
         ("skip_finalize", C.c_int32),
     ]
@@ -150,6 +151,7 @@ EXPORTS = {
     "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_cost_volume_workspace_floats": (C.c_size_t, [C.c_int] * 5),
     "mal_cost_volume_desc_floats": (C.c_size_t, [C.c_int] * 6),
+    "mal_cost_volume_proj_floats": (C.c_size_t, [C.c_int] * 5),
     "mal_cost_volume_forward": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),
     "mal_smooth_workspace_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_smooth_forward": (C.c_int, [C.POINTER(SmoothArgs), C.c_void_p]),

@@ -193,18 +193,36 @@ __device__ __forceinline__ float quad_l1_vals(float acc, const float4& v, const 
 //   cv_pool_kernel      one warp per listed sample: lanes = 8 neighbour slots x 4 channel quads, max over the slots
 //                       by shuffles, then the |pooled - current| chunk sums in the reference's order -> `parts`;
 //   the sweep           reads descriptors instead of projecting, and one float per (rim sample, chunk).
-// Workspace (floats / ints of size plane = B*F*bins*h*w): ux | uy | flags | list | parts[chunks] | counter (4) |
-// chunk-major copy of the lookup features (B*F*Cp*h*w).
+//   (the rim windows overlap: every un-occluded sample next to a blob is warped ONCE into a cache - cv_interior marks
+//   them, cv_slot hands out cache slots, cv_sample fills them - and cv_pool takes its maxima over cached vectors)
+// Workspace: CvDescLayout below.
 constexpr int CV_DESC_EDGE = 1;   // pixel and sampling location pass the border masks (:203-212)
 constexpr int CV_DESC_OCC = 2;    // projected occlusion mask > pool_th (:194-195)
 constexpr int CV_DESC_ZERO = 4;   // ... and every sample of its pool window too: the pooled value is 0
+constexpr int CV_DESC_NEED = 8;   // un-occluded, inside the pool window of a rim sample: its warped vector is cached
+constexpr int CV_DESC_SLOT = 4;   // bits 4..31: cache slot + 1 (0: not cached)
 
 __host__ __device__ inline size_t cv_desc_plane(int batch, int num_lookup, int num_bins, int hw) {
   return (size_t)batch * num_lookup * num_bins * hw;
 }
-// float offset of the chunk-major lookup copy (16-byte aligned), behind the planes and the counter
-__host__ __device__ inline size_t cv_desc_cm_offset(size_t plane, int nchunks) {
-  return ((4 + (size_t)nchunks) * plane + 4 + 3) / 4 * 4;
+// Workspace layout of the pool fill, in floats / ints (plane = B*F*bins*h*w samples).
+struct CvDescLayout {
+  size_t plane, ux, uy, flags, list, parts, counters, cm, list2, cache, total;
+  int cap;   // cache capacity in samples
+};
+__host__ __device__ inline CvDescLayout cv_desc_layout(int batch, int num_lookup, int num_bins, int hw, int Cp) {
+  CvDescLayout L;
+  const int nchunks = Cp / CV_CHUNK;
+  L.plane = cv_desc_plane(batch, num_lookup, num_bins, hw);
+  L.ux = 0; L.uy = L.plane; L.flags = 2 * L.plane; L.list = 3 * L.plane; L.parts = 4 * L.plane;
+  L.counters = (4 + (size_t)nchunks) * L.plane;                  // [0] rim samples, [1] cached samples
+  L.cm = (L.counters + 4 + 3) / 4 * 4;                           // chunk-major lookup copy, 16-byte aligned
+  L.list2 = L.cm + (size_t)batch * num_lookup * Cp * hw;
+  const size_t cap = L.plane / 8 > 1024 ? L.plane / 8 : 1024;    // samples next to an occluded blob: ~2 % in practice
+  L.cap = (int)(cap < 0x07ffffff ? cap : 0x07ffffff);            // (slot + 1) lives in bits 4..31 of the flag word
+  L.cache = (L.list2 + L.cap + 3) / 4 * 4;
+  L.total = L.cache + (size_t)L.cap * Cp;
+  return L;
 }
 
 template <int CONV>
@@ -225,9 +243,12 @@ __global__ void __launch_bounds__(256) cv_project_kernel(const mal_cost_volume_a
     geom.live = (s != 0.0f) ? 1 : 0;
   }
   __syncthreads();
-  if (!geom.live) return;   // the sweep skips the frame as well
   const int p = blockIdx.y * 256 + tid;
   if (p >= hw) return;
+  if (!geom.live) {   // the sweep skips the frame; the passes over the flag plane must see "nothing here"
+    reinterpret_cast<int*>(a.desc)[2 * cv_desc_plane(a.batch, a.num_lookup, nb, hw) + ((size_t)bf * nb + k) * hw + p] = 0;
+    return;
+  }
   const int py = p / w, px = p - py * w;
   const float* occ = nullptr;
   if (!(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
@@ -248,13 +269,16 @@ __global__ void __launch_bounds__(256) cv_project_kernel(const mal_cost_volume_a
 
 // Inside an occluded blob every sample of the pool window is occluded too: the pooled value is 0 and the sweep need
 // not look.  One pass over the flag plane marks those samples (27 independent loads; out-of-range neighbours are
-// clamped onto in-window ones, which leaves the AND unchanged).
-__global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_args a) {
+// clamped onto in-window ones, which leaves the AND unchanged), lists the others (the rim) and marks the
+// un-occluded samples their windows reach.
+__global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_args a, const int Cp) {
   const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, r = a.pool_radius;
   const int k = blockIdx.x % nb, bf = blockIdx.x / nb;
   const int p = blockIdx.y * 256 + threadIdx.x;
   if (p >= hw) return;
-  int* fl = reinterpret_cast<int*>(a.desc) + 2 * cv_desc_plane(a.batch, a.num_lookup, nb, hw) + (size_t)bf * nb * hw;
+  const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, nb, hw, Cp);
+  int* base = reinterpret_cast<int*>(a.desc);
+  int* fl = base + L.flags + (size_t)bf * nb * hw;
   const int mine = fl[(size_t)k * hw + p];
   if (!(mine & CV_DESC_OCC)) return;
   const int py = p / w, px = p - py * w;
@@ -267,98 +291,128 @@ __global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_
       for (int dx = -3; dx <= 3; dx++) {
         if (dx < -r || dx > r) continue;
         const int xx = min(max(px + dx, 0), w - 1);
-        all &= __ldg(fl + (size_t)kk * hw + (size_t)yy * w + xx);
+        all &= fl[(size_t)kk * hw + (size_t)yy * w + xx];   // (plain loads: the words change under this kernel)
       }
     }
   }
-  // (a neighbouring thread may read this word while it is rewritten: it only looks at bit CV_DESC_OCC, which
-  // does not change)
+  // (other threads read and atomicOr these words meanwhile: ZERO goes onto occluded samples only, NEED onto
+  // un-occluded ones only, and readers look at bit CV_DESC_OCC, which never changes)
   if (all & CV_DESC_OCC) {
     fl[(size_t)k * hw + p] = mine | CV_DESC_ZERO;
   } else if (mine & CV_DESC_EDGE) {   // a rim sample the sweep will use: cv_pool_kernel's work list (order is
                                       // irrelevant: every entry owns its output slots)
-    const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
-    int* base = reinterpret_cast<int*>(a.desc);
-    int* counter = base + (4 + (size_t)cv_padded_channels(a.channels) / CV_CHUNK) * plane;
-    base[3 * plane + atomicAdd(counter, 1)] = (int)(((size_t)bf * nb + k) * hw + p);
+    base[L.list + atomicAdd(base + L.counters, 1)] = (int)(((size_t)bf * nb + k) * hw + p);
+    for (int dk = -r; dk <= r; dk++) {
+      const int kk = k + dk;
+      if (kk < 0 || kk >= nb) continue;
+      for (int dy = -r; dy <= r; dy++) {
+        const int yy = py + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = -r; dx <= r; dx++) {
+          const int xx = px + dx;
+          if (xx < 0 || xx >= w) continue;
+          int* nf = fl + (size_t)kk * hw + (size_t)yy * w + xx;
+          if (!(*reinterpret_cast<volatile int*>(nf) & (CV_DESC_OCC | CV_DESC_NEED))) atomicOr(nf, CV_DESC_NEED);
+        }
+      }
+    }
   }
 }
 
-// One warp per rim sample.  lane = slot * 4 + quad: slot s handles window neighbours s, s+8, s+16, ... and quad q
-// the channels 4q..4q+3 of each 16-channel chunk, four chunks per pass.
+// Cache slots for the marked samples (overflowing ones keep slot 0: cv_pool_kernel then warps them itself).
+__global__ void __launch_bounds__(256) cv_slot_kernel(const mal_cost_volume_args a, const int Cp) {
+  const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, a.num_bins, a.height * a.width, Cp);
+  int* base = reinterpret_cast<int*>(a.desc);
+  for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < L.plane; o += (size_t)gridDim.x * 256) {
+    const int word = base[L.flags + o];
+    if (!(word & CV_DESC_NEED)) continue;
+    const int idx = atomicAdd(base + L.counters + 1, 1);
+    if (idx >= L.cap) continue;
+    base[L.flags + o] = word | ((idx + 1) << CV_DESC_SLOT);
+    base[L.list2 + idx] = (int)o;
+  }
+}
+
+// The warped feature vector (all channels) of every cached sample: half a warp per sample, lane = channel quad.
+__global__ void __launch_bounds__(256) cv_sample_kernel(const mal_cost_volume_args a, const int Cp) {
+  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, nquads = Cp / 4;
+  const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, nb, hw, Cp);
+  const int* base = reinterpret_cast<const int*>(a.desc);
+  const int count = min(base[L.counters + 1], L.cap);
+  const float4* lookcm = reinterpret_cast<const float4*>(a.desc + L.cm);
+  float4* cache = reinterpret_cast<float4*>(a.desc + L.cache);
+  const int half = threadIdx.x >> 4, qi0 = threadIdx.x & 15;
+  const int nhalves = gridDim.x * (blockDim.x >> 4);
+  for (int i = blockIdx.x * (blockDim.x >> 4) + half; i < count; i += nhalves) {
+    const int o = __ldg(base + L.list2 + i);
+    const int bf = o / (nb * hw);
+    const float ux = __ldg(a.desc + L.ux + o), uy = __ldg(a.desc + L.uy + o);
+    const bool any = ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f;
+    // keep float -> int defined for wild coordinates: every tap is out of range anyway
+    const Taps t = make_taps(any ? ux : -4.0f, any ? uy : -4.0f, h, w);
+    for (int qi = qi0; qi < nquads; qi += 16) {
+      const float4* cell = lookcm + (size_t)bf * nquads * hw + (size_t)(qi >> 2) * hw * 4 + (qi & 3);
+      cache[(size_t)i * nquads + qi] = any ? bilinear4_cm(cell, t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// One warp per rim sample: lane = neighbour slot (2) x channel quad (16), sixteen quads (four chunks) per pass.  The
+// window's maxima come from the cached vectors; a sample without a slot (cache overflow) is warped here.
 template <int R>   // pool radius as a constant (1 is the reference's default); 0: read it from the arguments
 __global__ void __launch_bounds__(256, 4) cv_pool_kernel(const mal_cost_volume_args a, const int Cp) {
   const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, r = R ? R : a.pool_radius, side = 2 * r + 1;
-  const int n = side * side * side, nquads = Cp / 4, nchunks = Cp / CV_CHUNK;
-  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
-  const int* list = reinterpret_cast<const int*>(a.desc) + 3 * plane;
-  float* parts = a.desc + 4 * plane;
-  const int count = reinterpret_cast<const int*>(a.desc)[(4 + (size_t)nchunks) * plane];
+  const int n = side * side * side, nquads = Cp / 4;
+  const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, nb, hw, Cp);
+  const int* base = reinterpret_cast<const int*>(a.desc);
+  const int count = base[L.counters];
   const float4* curq = reinterpret_cast<const float4*>(a.packed);
-  const float4* lookcm = reinterpret_cast<const float4*>(a.desc + cv_desc_cm_offset(plane, nchunks));
-  const int lane = threadIdx.x & 31, slot = lane >> 2, q = lane & 3;
+  const float4* lookcm = reinterpret_cast<const float4*>(a.desc + L.cm);
+  const float4* cache = reinterpret_cast<const float4*>(a.desc + L.cache);
+  float* parts = a.desc + L.parts;
+  const int lane = threadIdx.x & 31, slot = lane >> 4, ql = lane & 15;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarps) {
-    const int o = __ldg(list + i);
+    const int o = __ldg(base + L.list + i);
     const int bf = o / (nb * hw), rem = o - bf * nb * hw, k = rem / hw, p = rem - k * hw;
     const int py = p / w, px = p - py * w, b = bf / a.num_lookup;
-    const float* d = a.desc + (size_t)bf * nb * hw;
-    const int* dfl = reinterpret_cast<const int*>(a.desc) + 2 * plane + (size_t)bf * nb * hw;
-    const float4* lq = lookcm + (size_t)bf * nquads * hw + q;
-    for (int c0 = 0; c0 < nchunks; c0 += 4) {
-      float4 m[4];
-#pragma unroll
-      for (int c = 0; c < 4; c++) m[c] = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
-      for (int j = slot; j < n; j += 8) {
+    const size_t fbase = (size_t)bf * nb * hw;
+    for (int q0 = 0; q0 < nquads; q0 += 16) {
+      const int qi = q0 + ql;
+      const bool qlive = qi < nquads;
+      float4 m = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
+      for (int j = slot; j < n; j += 2) {
         const int kk = k + j / (side * side) - r, yy = py + (j / side) % side - r, xx = px + j % side - r;
         if (kk < 0 || kk >= nb || yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-        const size_t on = (size_t)kk * hw + (size_t)yy * w + xx;
-        const int fl = __ldg(dfl + on);
-        const float ux = __ldg(d + on), uy = __ldg(d + plane + on);
-        if (fl & CV_DESC_OCC) continue;                                                               // x[mask] = 0
-        if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
-        const Taps t = make_taps(ux, uy, h, w);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          if (c0 + c < nchunks) {
-            const float4 v = bilinear4_cm(lq + (size_t)(c0 + c) * hw * 4, t);
-            m[c].x = fmaxf(m[c].x, v.x); m[c].y = fmaxf(m[c].y, v.y);
-            m[c].z = fmaxf(m[c].z, v.z); m[c].w = fmaxf(m[c].w, v.w);
-          }
+        const size_t on = fbase + (size_t)kk * hw + (size_t)yy * w + xx;
+        const int word = __ldg(base + L.flags + on);
+        if ((word & CV_DESC_OCC) || !qlive) continue;                     // x[mask] = 0
+        float4 v;
+        const int cs = (int)((unsigned)word >> CV_DESC_SLOT);
+        if (cs) {
+          v = ldg4(cache + (size_t)(cs - 1) * nquads + qi);
+        } else {
+          const float ux = __ldg(a.desc + L.ux + on), uy = __ldg(a.desc + L.uy + on);
+          if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
+          const Taps t = make_taps(ux, uy, h, w);
+          v = bilinear4_cm(lookcm + (size_t)bf * nquads * hw + (size_t)(qi >> 2) * hw * 4 + (qi & 3), t);
         }
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
       __syncwarp();
-#pragma unroll
-      for (int sft = 4; sft <= 16; sft <<= 1) {   // max over the 8 slots
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          m[c].x = fmaxf(m[c].x, __shfl_xor_sync(0xffffffffu, m[c].x, sft));
-          m[c].y = fmaxf(m[c].y, __shfl_xor_sync(0xffffffffu, m[c].y, sft));
-          m[c].z = fmaxf(m[c].z, __shfl_xor_sync(0xffffffffu, m[c].z, sft));
-          m[c].w = fmaxf(m[c].w, __shfl_xor_sync(0xffffffffu, m[c].w, sft));
-        }
-      }
-      // |pooled - current| summed over the chunk's 16 channels in order: the chain runs through lanes 0..3
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      float4 cur[4];
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        cur[c] = (lane < 4 && c0 + c < nchunks) ? ldg4(curq + ((size_t)b * nquads + (c0 + c) * 4 + lane) * hw + p)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 16));
+      m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 16));
+      m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 16));
+      m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 16));
+      // |pooled - current| summed over each chunk's 16 channels in order: the chain runs through the chunk's 4 lanes
+      const float4 cur = (lane < 16 && qlive) ? ldg4(curq + ((size_t)b * nquads + qi) * hw + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float acc = 0.0f;
 #pragma unroll
       for (int qq = 0; qq < 4; qq++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          if (lane == qq) acc[c] = quad_l1_vals(acc[c], m[c], cur[c]);
-          acc[c] = __shfl_sync(0xffffffffu, acc[c], qq);
-        }
+        if ((lane & 3) == qq) acc = quad_l1_vals(acc, m, cur);
+        acc = __shfl_sync(0xffffffffu, acc, (lane & ~3) + qq);
       }
-      if (lane < 4 && c0 + lane < nchunks) {
-        float mine = acc[0];
-#pragma unroll
-        for (int c = 1; c < 4; c++) if (lane == c) mine = acc[c];
-        parts[(size_t)(c0 + lane) * plane + o] = mine;
-      }
+      if (lane < 16 && (lane & 3) == 0 && qlive) parts[(size_t)(qi >> 2) * L.plane + o] = acc;
     }
   }
 }
@@ -676,7 +730,56 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
   dst[1] = pack2(v.z, v.w);
 }
 
-template <int CONV, int MINB>
+// Projection pre-pass of the quad sweep: {tap origin or -1, tx, ty} for every (lookup frame, bin, pixel), three planes
+// [B*F][bins][h*w] in mal_cost_volume_args.desc.  Inside the sweep the two projections a lane does per group are
+// long dependent chains (two IEEE divisions each) run by 16 warps per SM at 128 registers; here the same
+// instructions run at full occupancy, one thread per pixel walking CQ_PG planes with the pixel's ray in registers.
+constexpr int CQ_PG = 8;   // planes per pre-pass thread
+template <int CONV>
+__global__ void __launch_bounds__(256) cv_desc_kernel(const mal_cost_volume_args a, const SizeDiv sdiv) {
+  __shared__ CvGeom geom;
+  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins;
+  const int ngroups = (nb + CQ_PG - 1) / CQ_PG;
+  const int grp = blockIdx.x % ngroups, bf = blockIdx.x / ngroups, b = bf / a.num_lookup;
+  const int tid = threadIdx.x;
+  if (tid < 12) {
+    geom.P[tid] = kt_entry(a.K + b * 16, a.poses + (size_t)bf * 16, tid / 4, tid % 4);
+  } else if (tid < 21) {
+    const int e = tid - 12;
+    geom.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
+  } else if (tid == 21) {
+    const float* T = a.poses + (size_t)bf * 16;
+    float s = 0.0f;
+    for (int e = 0; e < 16; e++) s += T[e];
+    geom.live = (s != 0.0f) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!geom.live) return;   // the sweep skips the frame as well
+  const int p = blockIdx.y * 256 + tid;
+  if (p >= hw) return;
+  const int py = p / w, px = p - py * w;
+  const bool inner = py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
+  const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
+  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
+  int* d_off = reinterpret_cast<int*>(a.desc) + (size_t)bf * nb * hw + p;
+  float* d_tx = a.desc + plane + (size_t)bf * nb * hw + p;
+  float* d_ty = d_tx + plane;
+#pragma unroll 2
+  for (int k = grp * CQ_PG; k < min(nb, (grp + 1) * CQ_PG); k++) {
+    const GridPoint gp = project_grid<CONV>(geom.P, ray, __ldg(a.bins + k), a.eps, h, w, &sdiv);
+    const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
+    const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
+    const bool ok = inner && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2);
+    const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
+    const float x0 = floorf(ux), y0 = floorf(uy);
+    const int xi = min(max((int)x0, 0), w - 2), yi = min(max((int)y0, 0), h - 2);
+    d_off[(size_t)k * hw] = ok ? yi * w + xi : -1;
+    d_tx[(size_t)k * hw] = xsub(ux, x0);
+    d_ty[(size_t)k * hw] = xsub(uy, y0);
+  }
+}
+
+template <int CONV, int MINB, bool DESC>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
   __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
@@ -748,12 +851,34 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     const size_t row_stride = (size_t)w * 16, quad_stride = (size_t)hw * 16;
     CqTaps t00, t01, t10, t11;
     int coff = -1;
+    // (DESC) descriptors projected by cv_desc_kernel; the next group's are requested a group ahead
+    const size_t dplane = DESC ? cv_desc_plane(a.batch, a.num_lookup, nb, hw) : 0;
+    const int* g_off = DESC ? reinterpret_cast<const int*>(a.desc) + ((size_t)b * a.num_lookup + f) * nb * hw + p : nullptr;
+    int noff[2] = {-1, -1};
+    float ntx[2] = {0.f, 0.f}, nty[2] = {0.f, 0.f};
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int kk = k0 + sub + 4 * u;
+        const bool v = pix_ok && kk < nb;
+        const size_t o = v ? (size_t)kk * hw : 0;
+        noff[u] = v ? __ldg(g_off + o) : -1;
+        ntx[u] = v ? __ldg(reinterpret_cast<const float*>(g_off) + dplane + o) : 0.0f;
+        nty[u] = v ? __ldg(reinterpret_cast<const float*>(g_off) + 2 * dplane + o) : 0.0f;
+      }
+    };
+    if (DESC) fetch(0);
 
     for (int k0 = 0; k0 < nb; k0 += CQ_G) {
       // ---- this lane's two planes of the group: projection descriptors --------------------------
       // branch-free, so that the two dependent chains (each ends in four IEEE divisions) interleave
       int off[2];
       float tx[2], ty[2];
+      if (DESC) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) { off[u] = noff[u]; tx[u] = ntx[u]; ty[u] = nty[u]; }
+        if (k0 + CQ_G < nb) fetch(k0 + CQ_G);
+      } else
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int kk = k0 + sub + 4 * u;
@@ -913,8 +1038,11 @@ extern "C" size_t mal_cost_volume_workspace_floats(int batch, int channels, int 
 
 extern "C" size_t mal_cost_volume_desc_floats(int batch, int channels, int num_lookup, int num_bins, int height,
                                               int width) {
-  return cv_desc_cm_offset(cv_desc_plane(batch, num_lookup, num_bins, height * width), cv_padded_channels(channels) / CV_CHUNK) +
-         (size_t)batch * num_lookup * cv_padded_channels(channels) * height * width;
+  return cv_desc_layout(batch, num_lookup, num_bins, height * width, cv_padded_channels(channels)).total;
+}
+
+extern "C" size_t mal_cost_volume_proj_floats(int batch, int num_lookup, int num_bins, int height, int width) {
+  return 3 * cv_desc_plane(batch, num_lookup, num_bins, height * width);
 }
 
 extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream) {
@@ -962,15 +1090,17 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     dim3 pgrid((unsigned)rows, (unsigned)((hw + 255) / 256));
     if (a.convention == MAL_CONV_MANYDEPTH) launch(cv_project_kernel<MAL_CONV_MANYDEPTH>, pgrid, dim3(256), 0, st, a, sdiv);
     else launch(cv_project_kernel<MAL_CONV_DUALREFINE>, pgrid, dim3(256), 0, st, a, sdiv);
-    const size_t plane = cv_desc_plane(a.batch, a.num_lookup, a.num_bins, hw);
-    MAL_REQUIRE(plane < (1u << 31), "mal_cost_volume_forward: descriptor volume too large for 32-bit sample indices");
-    cudaMemsetAsync(reinterpret_cast<int*>(a.desc) + (4 + (size_t)Cp / CV_CHUNK) * plane, 0, sizeof(int), st);
-    launch(cv_interior_kernel, pgrid, dim3(256), 0, st, a);
+    const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, a.num_bins, hw, Cp);
+    MAL_REQUIRE(L.plane < (1u << 31), "mal_cost_volume_forward: descriptor volume too large for 32-bit sample indices");
+    cudaMemsetAsync(reinterpret_cast<int*>(a.desc) + L.counters, 0, 4 * sizeof(int), st);
+    launch(cv_interior_kernel, pgrid, dim3(256), 0, st, a, Cp);
     {
       const long long total_l = (long long)a.batch * a.num_lookup * (Cp / 4) * hw;
       launch(cv_pack_cm_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
-             reinterpret_cast<float4*>(a.desc + cv_desc_cm_offset(plane, Cp / CV_CHUNK)), a.channels, Cp, hw, total_l);
+             reinterpret_cast<float4*>(a.desc + L.cm), a.channels, Cp, hw, total_l);
     }
+    launch(cv_slot_kernel, dim3(148 * 8), dim3(256), 0, st, a, Cp);
+    launch(cv_sample_kernel, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     if (a.pool_radius == 1) launch(cv_pool_kernel<1>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     else launch(cv_pool_kernel<0>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     int rc = check_launch("cv_project_kernel / cv_interior_kernel / cv_pool_kernel");
@@ -994,14 +1124,24 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   } while (0)
   if (quad) {
     const size_t qsmem = cq_smem_bytes(a.num_bins);
-#define MAL_CQ_LAUNCH(CONV_)                                                                              \
-  do {                                                                                                    \
-    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);            \
-    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);       \
-    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                      \
+#define MAL_CQ_GO(CONV_, DESC_)                                                                                 \
+  do {                                                                                                          \
+    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);        \
+    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);   \
+    else launch(cv_sweep_quad_kernel<CONV_, 5, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                  \
+  } while (0)
+#define MAL_CQ_LAUNCH(CONV_)                                                                                    \
+  do {                                                                                                          \
+    if (a.desc) {                                                                                               \
+      const int ngroups = (a.num_bins + CQ_PG - 1) / CQ_PG;                                                     \
+      launch(cv_desc_kernel<CONV_>, dim3((unsigned)(a.batch * a.num_lookup * ngroups), (unsigned)((hw + 255) / 256)), \
+             dim3(256), 0, st, a, sdiv);                                                                        \
+      MAL_CQ_GO(CONV_, true);                                                                                   \
+    } else MAL_CQ_GO(CONV_, false);                                                                             \
   } while (0)
     if (a.convention == MAL_CONV_MANYDEPTH) MAL_CQ_LAUNCH(MAL_CONV_MANYDEPTH);
     else MAL_CQ_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_CQ_GO
 #undef MAL_CQ_LAUNCH
     return check_launch("cv_sweep_quad_kernel");
   }

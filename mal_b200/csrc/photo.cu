@@ -137,20 +137,22 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   __syncthreads();
   const float* tgt = a.target + (size_t)b * 3 * HW;
   const bool with_syn = NC > 2 && ncand > 2;
+  // WARP mode with ready-made warped sources: staged like PRED mode's predictions, phase A is skipped
+  const bool pre = WARP && !DD && a.warped[0] != nullptr;
   if (use_tma) {
     if (tid == 0) {
       const unsigned tile_bytes = (unsigned)(3 * tl.VN * 4), plane_bytes = (unsigned)(tl.VN * 4);
       unsigned bytes = tile_bytes;
-      if (!WARP) bytes += tile_bytes * (unsigned)min(ncand, 2);
+      if (!WARP || pre) bytes += tile_bytes * (unsigned)min(ncand, 2);
       if (with_syn) bytes += 2 * tile_bytes;
-      if (dep_tile) bytes += plane_bytes * (a.depth_b ? 2u : 1u);
+      if (dep_tile && !pre) bytes += plane_bytes * (a.depth_b ? 2u : 1u);
       mbar_expect_tx(mbar, bytes);
       tma_load_3d(sy, &maps.tgt, ox, oy, b * 3, mbar);
-      if (!WARP)
+      if (!WARP || pre)
         for (int f = 0; f < min(ncand, 2); f++) tma_load_3d(sx + (size_t)f * tl.TS, &maps.src[f], ox, oy, b * 3, mbar);
       if (with_syn)
         for (int k = 0; k < 2; k++) tma_load_3d(sx + (size_t)(2 + k) * tl.TS, &maps.syn[k], ox, oy, b * 3, mbar);
-      if (dep_tile) {
+      if (dep_tile && !pre) {
         tma_load_3d(dep, &maps.depth, ox, oy, b, mbar);
         if (a.depth_b) tma_load_3d(dep_b, &maps.depth_b, ox, oy, b, mbar);
       }
@@ -180,16 +182,16 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
           for (int c = 0; c < 3; c++)
             sx[(size_t)(2 + k) * tl.TS + c * tl.VN + i] = __ldg(a.syn[k] + ((size_t)b * 3 + c) * HW + o);
       }
-      if (!WARP) {
+      if (!WARP || pre) {
 #pragma unroll
         for (int f = 0; f < 2; f++)
           if (f < ncand) {
+            const float* cand = pre ? a.warped[f] : a.src[f];
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-              sx[(size_t)f * tl.TS + c * tl.VN + i] = __ldg(a.src[f] + ((size_t)b * 3 + c) * HW + o);
+            for (int c = 0; c < 3; c++) sx[(size_t)f * tl.TS + c * tl.VN + i] = __ldg(cand + ((size_t)b * 3 + c) * HW + o);
           }
       }
-      if (dep_tile) {
+      if (dep_tile && !pre) {
         dep[i] = __ldg(a.depth + (size_t)b * HW + o);
         if (a.depth_b) dep_b[i] = __ldg(a.depth_b + (size_t)b * HW + o);
       }
@@ -198,7 +200,7 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
   }
 
   // ---- phase A: warped candidates -------------------------------------------------------------------------
-  if (WARP) {
+  if (WARP && !pre) {
     constexpr int NEED = PH_TW + 2 * (GRAD ? 1 : 0) + 2;   // only the columns some 3x3 window reaches
     for (int j = tid; j < NEED * tl.VH; j += PH_NT) {
       const int ty = j / NEED, tx = BS + j - ty * NEED;
@@ -820,6 +822,12 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
     if (a.depth_is_disp) MAL_REQUIRE(a.min_depth > 0 && a.max_depth > a.min_depth, "mal_photo_forward: bad depth range");
     MAL_REQUIRE((a.depth_height > 0) == (a.depth_width > 0) && a.depth_height >= 0,
                 "mal_photo_forward: depth_height / depth_width must both be set (or both 0)");
+    MAL_REQUIRE((a.warped[0] == nullptr) == (a.warped[1] == nullptr), "mal_photo_forward: give both warped sources or none");
+    if (a.warped[0])
+      MAL_REQUIRE(!a.depth_b && !a.zero_img && !a.selec_reproj && !a.target_out && !a.identity_in_pass,
+                  "mal_photo_forward: `warped` goes with a plain WARP pass (no ensemble disparity, no DynamicDepth mode)");
+  } else if (a.warped[0] || a.warped[1]) {
+    MAL_REQUIRE(false, "mal_photo_forward: `warped` is a WARP-mode input");
   } else if (a.with_grad) {
     MAL_REQUIRE(a.grad_pred[0] && (single || a.grad_pred[1]), "mal_photo_forward: PRED+grad needs grad_pred");
   }
@@ -862,11 +870,13 @@ extern "C" int mal_photo_forward(const mal_photo_args* args, mal_stream_t stream
   bool tma = getenv("MAL_PHOTO_NO_TMA") == nullptr;
   const int W = a.width, H = a.height, B = a.batch;
   tma = tma && tile_map_encode(&maps.tgt, a.target, W, H, B * 3, PH_VW, tl.VH, 3);
-  if (!warp)
-    for (int f = 0; f < (single ? 1 : 2); f++) tma = tma && tile_map_encode(&maps.src[f], a.src[f], W, H, B * 3, PH_VW, tl.VH, 3);
+  const bool pre = warp && a.warped[0] != nullptr;
+  if (!warp || pre)
+    for (int f = 0; f < (single ? 1 : 2); f++)
+      tma = tma && tile_map_encode(&maps.src[f], pre ? a.warped[f] : a.src[f], W, H, B * 3, PH_VW, tl.VH, 3);
   if (ncand > 2)
     for (int k = 0; k < 2; k++) tma = tma && tile_map_encode(&maps.syn[k], a.syn[k], W, H, B * 3, PH_VW, tl.VH, 3);
-  if (warp && a.depth_height == 0) {
+  if (warp && a.depth_height == 0 && !pre) {
     tma = tma && tile_map_encode(&maps.depth, a.depth, W, H, B, PH_VW, tl.VH, 1);
     if (a.depth_b) tma = tma && tile_map_encode(&maps.depth_b, a.depth_b, W, H, B, PH_VW, tl.VH, 1);
   }

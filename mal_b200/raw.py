@@ -66,7 +66,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
           with_grad=False, min_depth=0.1, max_depth=100.0, eps=1e-7,
           want_min_reproj=True, want_selection=True, want_weight=False, want_grad_syn=False, finalize=True,
           avg_reprojection=False, split_min=False, zero_img=False, selec_reproj=False, ignore_automask=False,
-          want_target_out=False, identity_in_pass=False):
+          want_target_out=False, identity_in_pass=False, warped=None):
     """mal_photo_forward.  Returns a dict of output tensors (see include/mal_b200.h).
 
     finalize=False leaves `sums` / `grad_P` unreduced until photo_finalize(handle, out) is called (on any
@@ -81,6 +81,8 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     if len(src) == 1:
         src = [src[0], None]
     syn = [_f32(s, f"syn[{i}]", img) for i, s in enumerate(syn)] if syn is not None else [None, None]
+    # WARP mode: the caller's materialised warped sources are staged instead of re-warped (gradients unchanged)
+    warped = [_f32(s, f"warped[{i}]", img) for i, s in enumerate(warped)] if warped is not None else [None, None]
     plane = (B, 1, H, W)
     # a low-resolution disparity is up-sampled inside the kernel (trainer.py:1093-1094 fused away)
     dplane, dh, dw = plane, 0, 0
@@ -134,6 +136,7 @@ def photo(handle, *, target, src, syn=None, depth=None, depth_b=None, K=None, in
     a.min_reproj_b = _ptr(out["min_reproj_b"])
     a.zero_img, a.selec_reproj, a.ignore_automask = int(bool(zero_img)), int(bool(selec_reproj)), int(bool(ignore_automask))
     a.identity_in_pass = int(bool(identity_in_pass))
+    a.warped[0], a.warped[1] = _ptr(warped[0]), _ptr(warped[1])
     a.target_out = _ptr(out["target_out"])
     _capi.check(handle.mal_photo_forward(C.byref(a), _stream(target)), handle)
     LAUNCHES[0] += 2 if finalize else 1   # photo_kernel (+ photo_finalize_kernel)
@@ -186,16 +189,22 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     a.occ, a.aug_mask = _ptr(occ), _ptr(aug_mask)
     # the pool fill projects every (lookup frame, bin, pixel) once into a descriptor volume (12 B per sample) that
     # the pool windows read their neighbours from
+    dyn = bool(cv_min) or (occ is not None and occ_mode != OCC_NONE)
+    quad = not dyn and (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
     desc = None
     if occ is not None and occ_mode == OCC_POOL:
         desc = new((handle.mal_cost_volume_desc_floats(B, Cn, F_, nb, h, w),))
+    elif quad and not os.environ.get("MAL_CV_NO_DESC"):
+        # the four-lanes-per-pixel sweep with its projections in a pre-pass (MAL_CV_NO_DESC=1: inside the sweep)
+        desc = new((handle.mal_cost_volume_proj_floats(B, F_, nb, h, w),))
     a.desc = _ptr(desc)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
     # the four-lanes-per-pixel sweep (C <= 64, no DynamicDepth extras) reads the current features in place:
     # lookup pack + sweep; the general kernel packs both operands first
-    dyn = bool(cv_min) or (occ is not None and occ_mode != OCC_NONE)
-    quad = not dyn and (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
-    LAUNCHES[0] += (2 if quad else 3) + (4 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_pool
+    if quad:
+        LAUNCHES[0] += 2 + (1 if desc is not None else 0)   # cv_pack (lookup), [cv_desc,] cv_sweep_quad
+    else:
+        LAUNCHES[0] += 3 + (6 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_slot, cv_sample, cv_pool
     out["_keepalive"] = (packed, desc)
     return out
 

@@ -243,14 +243,17 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
                           finalize=False)["min_reproj"]
     use_syn = opt.temporal and has_ins
     hint = None
+    warped = None
     if use_syn and in_step_syn:
         # trainer.py:1122-1125 + :1161-1162: materialise the two warps, synthesise the temporal-hint images
         warped = raw.temporal_warp(handle, src=src, depth=mono, **geom)
         hint = raw.temporal_synthesis(handle, warped=warped, packed_last=b["masks_last"], packed_next=b["masks_next"],
                                       counts=b["mask_counts"])
         syn = hint["syn"]
+    # the teacher pass scores the warps just materialised for the temporal hint instead of re-warping (same bits)
     teacher = raw.photo(handle, target=tgt, src=src, syn=syn if use_syn else None, depth=mono, identity_min=ident,
-                        noise=b["noise_mono"], with_grad=True, finalize=False, want_grad_syn=hint is not None, **geom)
+                        noise=b["noise_mono"], with_grad=True, finalize=False, want_grad_syn=hint is not None,
+                        warped=warped, **geom)
     with branch(1):
         raw.photo_finalize(handle, teacher)
         if hint is not None:

@@ -235,6 +235,8 @@ MAL_EMU_ATOMICS(unsigned)
 MAL_EMU_ATOMICS(unsigned long long)
 static inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
 template <class T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }

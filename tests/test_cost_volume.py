@@ -78,11 +78,14 @@ def test_cost_volume_dualrefine_convention(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("cv_min,set_1,pool", [(True, False, True), (False, True, False), (True, False, False),
-                                               (False, False, True)])
-def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool):
+@pytest.mark.parametrize("cv_min,set_1,pool,speckle", [(True, False, True, False), (False, True, False, False),
+                                                       (True, False, False, False), (False, False, True, False),
+                                                       (True, False, True, True)])
+def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool, speckle):
     """dynamicdepth/networks/resnet_encoder.py:148-249: min over lookup frames and the occlusion
-    fill (set_1 / 3-D max-pool) of the warped features, one sample with augmentation on (no fill)."""
+    fill (set_1 / 3-D max-pool) of the warped features, one sample with augmentation on (no fill).
+    `speckle`: isolated occluded pixels everywhere, so that most samples sit next to one - more than the pool
+    fill's vector cache holds (the overflow is warped in place)."""
     h, dev = handle_and_device(backend)
     B, H, W, C, nb = 2, 64, 96, 32, 20
     cv = make_cost_volume_inputs(B, H, W, channels=C, num_lookup=2, num_bins=nb, seed=91, min_bin=0.5, max_bin=6.0,
@@ -91,6 +94,8 @@ def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool):
     look_img = torch.rand(B, 3, H, W, generator=gen)
     look_img[:, :, 20:44, 24:64] = 0.0
     look_img[:, :, 4:16, 70:90] = 0.01
+    if speckle:
+        look_img[:, :, 0::8, 0::8] = 0.0       # F.interpolate(nearest) keeps every second of these
     aug = torch.zeros(B, 1, 1, 1)
     aug[1] = 1
     want_vol, want_miss = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"],

@@ -189,3 +189,29 @@ def test_ensemble_disparity_average_in_kernel(backend):
                     inv_K=d(inputs[("inv_K", 0)]), T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])],
                     want_selection=False)
     assert torch.equal(out["min_reproj"].cpu(), want)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("shape", [(2, 48, 96), (1, 37, 50)])
+def test_ready_made_warps_give_the_same_bits(backend, shape):
+    """mal_photo_args.warped: a WARP-mode pass that stages the caller's materialised warps (mal_temporal_warp:
+    trainer.py:1122-1125 makes them for image_synthesis) instead of re-warping - every output identical,
+    gradients included; ragged sizes take the plain loader, border tiles the reflected halo."""
+    h, dev = handle_and_device(backend)
+    B, H, W = shape
+    inputs, t = make_photometric_inputs(B, H, W, seed=321)
+    d = lambda x: x.to(dev)
+    tgt, src = d(inputs[("color", 0, 0)]), [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])]
+    geom = dict(K=d(inputs[("K", 0)]), inv_K=d(inputs[("inv_K", 0)]), T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])])
+    warped = raw.temporal_warp(h, src=src, depth=d(t[("mono_disp", 0)]), **geom)
+    ident = raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+    for syn, grad_syn in ((None, False), ([d(t[("syn", -1, 0)]), d(t[("syn", 1, 0)])], True)):
+        kw = dict(target=tgt, src=src, syn=syn, depth=d(t[("mono_disp", 0)]), identity_min=ident, noise=d(t["noise"][0]),
+                  with_grad=True, want_weight=True, want_grad_syn=grad_syn, **geom)
+        want = raw.photo(h, **kw)
+        got = raw.photo(h, warped=warped, **kw)
+        for k in ("sums", "min_reproj", "selection", "weight", "grad_depth", "grad_P"):
+            assert torch.equal(got[k], want[k]), k
+        if grad_syn:
+            for a, b in zip(got["grad_syn"], want["grad_syn"]):
+                assert torch.equal(a, b)
