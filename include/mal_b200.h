@@ -181,17 +181,14 @@ typedef struct mal_cost_volume_args {
   float pool_th;               /* pool_th (:195)                                                   */
   const float* occ;            /* (B,h,w) {0,1}: occ_batch > 0 at the matching resolution (:160, :194) */
   const float* aug_mask;       /* (B) occlusion handling only where aug_mask == 0 (:192); NULL: all */
-  float* desc;                 /* projection workspace.  With MAL_CV_OCC_POOL (required):
-                                  mal_cost_volume_desc_floats() floats - every (lookup frame, bin, pixel) is projected
-                                  once into it, the rim of every occluded blob is listed there and its pooled chunk
-                                  sums are formed there.  Without the DynamicDepth extras and C <= 64 (optional):
-                                  mal_cost_volume_proj_floats() floats - the projections run in a pre-pass at full
-                                  occupancy instead of inside the sweep; NULL keeps them in the sweep                */
+  float* desc;                 /* workspace of mal_cost_volume_desc_floats() floats, required with MAL_CV_OCC_POOL:
+                                  every (lookup frame, bin, pixel) is projected once into it, the rim of every
+                                  occluded blob is listed there, the warped vectors its pool windows reach are
+                                  cached there and its pooled chunk sums are formed there                        */
 } mal_cost_volume_args;
 
 size_t mal_cost_volume_workspace_floats(int batch, int channels, int height, int width, int num_lookup);
 size_t mal_cost_volume_desc_floats(int batch, int channels, int num_lookup, int num_bins, int height, int width);
-size_t mal_cost_volume_proj_floats(int batch, int num_lookup, int num_bins, int height, int width);
 int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

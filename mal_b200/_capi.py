@@ -151,7 +151,6 @@ EXPORTS = {
     "mal_photo_forward": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "mal_cost_volume_workspace_floats": (C.c_size_t, [C.c_int] * 5),
     "mal_cost_volume_desc_floats": (C.c_size_t, [C.c_int] * 6),
-    "mal_cost_volume_proj_floats": (C.c_size_t, [C.c_int] * 5),
     "mal_cost_volume_forward": (C.c_int, [C.POINTER(CostVolumeArgs), C.c_void_p]),
     "mal_smooth_workspace_floats": (C.c_size_t, [C.c_int] * 3),
     "mal_smooth_forward": (C.c_int, [C.POINTER(SmoothArgs), C.c_void_p]),

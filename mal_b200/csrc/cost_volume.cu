@@ -225,11 +225,25 @@ __host__ __device__ inline CvDescLayout cv_desc_layout(int batch, int num_lookup
   return L;
 }
 
+// Warp-aggregated list append: one atomicAdd per warp instead of one per element (a quarter of a million appends to
+// one counter serialise otherwise).  Every lane of the warp must call it; returns the element's index or -1.
+__device__ __forceinline__ int warp_append(int* counter, bool mine) {
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (m == 0u) return -1;
+  const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+  int first = 0;
+  if (lane == leader) first = atomicAdd(counter, __popc(m));
+  first = __shfl_sync(0xffffffffu, first, leader);
+  return mine ? first + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+constexpr int CV_PJ = 8;   // planes per projection thread (the pixel's ray and occlusion row stay in registers)
 template <int CONV>
 __global__ void __launch_bounds__(256) cv_project_kernel(const mal_cost_volume_args a, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
   const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins;
-  const int k = blockIdx.x % nb, bf = blockIdx.x / nb, b = bf / a.num_lookup;
+  const int ngroups = (nb + CV_PJ - 1) / CV_PJ;
+  const int grp = blockIdx.x % ngroups, bf = blockIdx.x / ngroups, b = bf / a.num_lookup;
   const int tid = threadIdx.x;
   if (tid < 12) {
     geom.P[tid] = kt_entry(a.K + b * 16, a.poses + (size_t)bf * 16, tid / 4, tid % 4);
@@ -245,26 +259,31 @@ __global__ void __launch_bounds__(256) cv_project_kernel(const mal_cost_volume_a
   __syncthreads();
   const int p = blockIdx.y * 256 + tid;
   if (p >= hw) return;
+  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
+  const int k0 = grp * CV_PJ, k1 = min(nb, k0 + CV_PJ);
+  float* d_ux = a.desc + (size_t)bf * nb * hw + p;
+  int* d_fl = reinterpret_cast<int*>(a.desc) + 2 * plane + (size_t)bf * nb * hw + p;
   if (!geom.live) {   // the sweep skips the frame; the passes over the flag plane must see "nothing here"
-    reinterpret_cast<int*>(a.desc)[2 * cv_desc_plane(a.batch, a.num_lookup, nb, hw) + ((size_t)bf * nb + k) * hw + p] = 0;
+    for (int k = k0; k < k1; k++) d_fl[(size_t)k * hw] = 0;
     return;
   }
   const int py = p / w, px = p - py * w;
   const float* occ = nullptr;
   if (!(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
   const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
-  const GridPoint gp = project_grid<CONV>(geom.P, ray, __ldg(a.bins + k), a.eps, h, w, &sdiv);
-  const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
-  const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
   const bool inner = py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
-  int flags = 0;
-  if (inner && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2)) flags |= CV_DESC_EDGE;
-  if (occ && occluded_at<CONV>(occ, gp, h, w, a.pool_th)) flags |= CV_DESC_OCC;
-  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
-  const size_t o = ((size_t)bf * nb + k) * hw + p;
-  a.desc[o] = unnormalize<CONV>(gp.gx, w);
-  a.desc[plane + o] = unnormalize<CONV>(gp.gy, h);
-  reinterpret_cast<int*>(a.desc)[2 * plane + o] = flags;
+#pragma unroll 2
+  for (int k = k0; k < k1; k++) {
+    const GridPoint gp = project_grid<CONV>(geom.P, ray, __ldg(a.bins + k), a.eps, h, w, &sdiv);
+    const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
+    const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
+    int flags = 0;
+    if (inner && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2)) flags |= CV_DESC_EDGE;
+    if (occ && occluded_at<CONV>(occ, gp, h, w, a.pool_th)) flags |= CV_DESC_OCC;
+    d_ux[(size_t)k * hw] = unnormalize<CONV>(gp.gx, w);
+    d_ux[plane + (size_t)k * hw] = unnormalize<CONV>(gp.gy, h);
+    d_fl[(size_t)k * hw] = flags;
+  }
 }
 
 // Inside an occluded blob every sample of the pool window is occluded too: the pooled value is 0 and the sweep need
@@ -275,45 +294,46 @@ __global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_
   const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins, r = a.pool_radius;
   const int k = blockIdx.x % nb, bf = blockIdx.x / nb;
   const int p = blockIdx.y * 256 + threadIdx.x;
-  if (p >= hw) return;
   const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, nb, hw, Cp);
   int* base = reinterpret_cast<int*>(a.desc);
   int* fl = base + L.flags + (size_t)bf * nb * hw;
-  const int mine = fl[(size_t)k * hw + p];
-  if (!(mine & CV_DESC_OCC)) return;
+  const int mine = p < hw ? fl[(size_t)k * hw + p] : 0;
   const int py = p / w, px = p - py * w;
-  int all = CV_DESC_OCC;
-  for (int dk = -r; dk <= r; dk++) {
-    const int kk = min(max(k + dk, 0), nb - 1);
-    for (int dy = -r; dy <= r; dy++) {
-      const int yy = min(max(py + dy, 0), h - 1);
+  bool rim = false;
+  if (mine & CV_DESC_OCC) {
+    int all = CV_DESC_OCC;
+    for (int dk = -r; dk <= r; dk++) {
+      const int kk = min(max(k + dk, 0), nb - 1);
+      for (int dy = -r; dy <= r; dy++) {
+        const int yy = min(max(py + dy, 0), h - 1);
 #pragma unroll
-      for (int dx = -3; dx <= 3; dx++) {
-        if (dx < -r || dx > r) continue;
-        const int xx = min(max(px + dx, 0), w - 1);
-        all &= fl[(size_t)kk * hw + (size_t)yy * w + xx];   // (plain loads: the words change under this kernel)
+        for (int dx = -3; dx <= 3; dx++) {
+          if (dx < -r || dx > r) continue;
+          const int xx = min(max(px + dx, 0), w - 1);
+          all &= fl[(size_t)kk * hw + (size_t)yy * w + xx];   // (plain loads: the words change under this kernel)
+        }
       }
     }
+    // (other threads read and atomicOr these words meanwhile: ZERO goes onto occluded samples only, NEED onto
+    // un-occluded ones only, and readers look at bit CV_DESC_OCC, which never changes)
+    if (all & CV_DESC_OCC) fl[(size_t)k * hw + p] = mine | CV_DESC_ZERO;
+    else rim = (mine & CV_DESC_EDGE) != 0;   // a rim sample the sweep will use
   }
-  // (other threads read and atomicOr these words meanwhile: ZERO goes onto occluded samples only, NEED onto
-  // un-occluded ones only, and readers look at bit CV_DESC_OCC, which never changes)
-  if (all & CV_DESC_OCC) {
-    fl[(size_t)k * hw + p] = mine | CV_DESC_ZERO;
-  } else if (mine & CV_DESC_EDGE) {   // a rim sample the sweep will use: cv_pool_kernel's work list (order is
-                                      // irrelevant: every entry owns its output slots)
-    base[L.list + atomicAdd(base + L.counters, 1)] = (int)(((size_t)bf * nb + k) * hw + p);
-    for (int dk = -r; dk <= r; dk++) {
-      const int kk = k + dk;
-      if (kk < 0 || kk >= nb) continue;
-      for (int dy = -r; dy <= r; dy++) {
-        const int yy = py + dy;
-        if (yy < 0 || yy >= h) continue;
-        for (int dx = -r; dx <= r; dx++) {
-          const int xx = px + dx;
-          if (xx < 0 || xx >= w) continue;
-          int* nf = fl + (size_t)kk * hw + (size_t)yy * w + xx;
-          if (!(*reinterpret_cast<volatile int*>(nf) & (CV_DESC_OCC | CV_DESC_NEED))) atomicOr(nf, CV_DESC_NEED);
-        }
+  // cv_pool_kernel's work list (order is irrelevant: every entry owns its output slots)
+  const int at = warp_append(base + L.counters, rim);
+  if (!rim) return;
+  base[L.list + at] = (int)(((size_t)bf * nb + k) * hw + p);
+  for (int dk = -r; dk <= r; dk++) {
+    const int kk = k + dk;
+    if (kk < 0 || kk >= nb) continue;
+    for (int dy = -r; dy <= r; dy++) {
+      const int yy = py + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -r; dx <= r; dx++) {
+        const int xx = px + dx;
+        if (xx < 0 || xx >= w) continue;
+        int* nf = fl + (size_t)kk * hw + (size_t)yy * w + xx;
+        if (!(*reinterpret_cast<volatile int*>(nf) & (CV_DESC_OCC | CV_DESC_NEED))) atomicOr(nf, CV_DESC_NEED);
       }
     }
   }
@@ -323,14 +343,14 @@ __global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_
 __global__ void __launch_bounds__(256) cv_slot_kernel(const mal_cost_volume_args a, const int Cp) {
   const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, a.num_bins, a.height * a.width, Cp);
   int* base = reinterpret_cast<int*>(a.desc);
-  for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < L.plane; o += (size_t)gridDim.x * 256) {
-    const int word = base[L.flags + o];
-    if (!(word & CV_DESC_NEED)) continue;
-    const int idx = atomicAdd(base + L.counters + 1, 1);
-    if (idx >= L.cap) continue;
-    base[L.flags + o] = word | ((idx + 1) << CV_DESC_SLOT);
-    base[L.list2 + idx] = (int)o;
-  }
+  // one word per thread, whole warps together (warp_append); a grid-stride loop here was latency-bound (83 us)
+  const size_t o = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const int word = o < L.plane ? base[L.flags + o] : 0;
+  const bool need = (word & CV_DESC_NEED) != 0;
+  const int idx = warp_append(base + L.counters + 1, need);
+  if (!need || idx >= L.cap) return;
+  base[L.flags + o] = word | ((idx + 1) << CV_DESC_SLOT);
+  base[L.list2 + idx] = (int)o;
 }
 
 // The warped feature vector (all channels) of every cached sample: half a warp per sample, lane = channel quad.
@@ -381,23 +401,36 @@ __global__ void __launch_bounds__(256, 4) cv_pool_kernel(const mal_cost_volume_a
       const int qi = q0 + ql;
       const bool qlive = qi < nquads;
       float4 m = make_float4(0.f, 0.f, 0.f, 0.f);   // the centre is occluded: contributes 0
-      for (int j = slot; j < n; j += 2) {
-        const int kk = k + j / (side * side) - r, yy = py + (j / side) % side - r, xx = px + j % side - r;
-        if (kk < 0 || kk >= nb || yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-        const size_t on = fbase + (size_t)kk * hw + (size_t)yy * w + xx;
-        const int word = __ldg(base + L.flags + on);
-        if ((word & CV_DESC_OCC) || !qlive) continue;                     // x[mask] = 0
-        float4 v;
-        const int cs = (int)((unsigned)word >> CV_DESC_SLOT);
-        if (cs) {
-          v = ldg4(cache + (size_t)(cs - 1) * nquads + qi);
-        } else {
-          const float ux = __ldg(a.desc + L.ux + on), uy = __ldg(a.desc + L.uy + on);
-          if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
-          const Taps t = make_taps(ux, uy, h, w);
-          v = bilinear4_cm(lookcm + (size_t)bf * nquads * hw + (size_t)(qi >> 2) * hw * 4 + (qi & 3), t);
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        // the window's flag words, one per lane, in one round trip; -1: outside the volume
+        int myword = -1;
+        size_t myon = 0;
+        {
+          const int j = j0 + lane;
+          const int kk = k + j / (side * side) - r, yy = py + (j / side) % side - r, xx = px + j % side - r;
+          if (j < n && kk >= 0 && kk < nb && yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            myon = fbase + (size_t)kk * hw + (size_t)yy * w + xx;
+            myword = __ldg(base + L.flags + myon);
+          }
         }
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+#pragma unroll 4
+        for (int jj = 0; jj < 32; jj += 2) {
+          if (j0 + jj >= n) break;   // (warp-uniform)
+          const int word = __shfl_sync(0xffffffffu, myword, jj + slot);
+          const unsigned long long on = __shfl_sync(0xffffffffu, (unsigned long long)myon, jj + slot);
+          if (word == -1 || (word & CV_DESC_OCC) || !qlive || j0 + jj + slot >= n) continue;   // x[mask] = 0
+          float4 v;
+          const int cs = (int)((unsigned)word >> CV_DESC_SLOT);
+          if (cs) {
+            v = ldg4(cache + (size_t)(cs - 1) * nquads + qi);
+          } else {
+            const float ux = __ldg(a.desc + L.ux + on), uy = __ldg(a.desc + L.uy + on);
+            if (!(ux > -2.0f && ux < (float)w + 1.0f && uy > -2.0f && uy < (float)h + 1.0f)) continue;   // all taps are zero
+            const Taps t = make_taps(ux, uy, h, w);
+            v = bilinear4_cm(lookcm + (size_t)bf * nquads * hw + (size_t)(qi >> 2) * hw * 4 + (qi & 3), t);
+          }
+          m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
       }
       __syncwarp();
       m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 16));
@@ -730,56 +763,7 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
   dst[1] = pack2(v.z, v.w);
 }
 
-// Projection pre-pass of the quad sweep: {tap origin or -1, tx, ty} for every (lookup frame, bin, pixel), three planes
-// [B*F][bins][h*w] in mal_cost_volume_args.desc.  Inside the sweep the two projections a lane does per group are
-// long dependent chains (two IEEE divisions each) run by 16 warps per SM at 128 registers; here the same
-// instructions run at full occupancy, one thread per pixel walking CQ_PG planes with the pixel's ray in registers.
-constexpr int CQ_PG = 8;   // planes per pre-pass thread
-template <int CONV>
-__global__ void __launch_bounds__(256) cv_desc_kernel(const mal_cost_volume_args a, const SizeDiv sdiv) {
-  __shared__ CvGeom geom;
-  const int h = a.height, w = a.width, hw = h * w, nb = a.num_bins;
-  const int ngroups = (nb + CQ_PG - 1) / CQ_PG;
-  const int grp = blockIdx.x % ngroups, bf = blockIdx.x / ngroups, b = bf / a.num_lookup;
-  const int tid = threadIdx.x;
-  if (tid < 12) {
-    geom.P[tid] = kt_entry(a.K + b * 16, a.poses + (size_t)bf * 16, tid / 4, tid % 4);
-  } else if (tid < 21) {
-    const int e = tid - 12;
-    geom.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + e % 3];
-  } else if (tid == 21) {
-    const float* T = a.poses + (size_t)bf * 16;
-    float s = 0.0f;
-    for (int e = 0; e < 16; e++) s += T[e];
-    geom.live = (s != 0.0f) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!geom.live) return;   // the sweep skips the frame as well
-  const int p = blockIdx.y * 256 + tid;
-  if (p >= hw) return;
-  const int py = p / w, px = p - py * w;
-  const bool inner = py >= 2 && py < h - 2 && px >= 2 && px < w - 2;
-  const Ray ray = pixel_ray(geom.iK, (float)px, (float)py);
-  const size_t plane = cv_desc_plane(a.batch, a.num_lookup, nb, hw);
-  int* d_off = reinterpret_cast<int*>(a.desc) + (size_t)bf * nb * hw + p;
-  float* d_tx = a.desc + plane + (size_t)bf * nb * hw + p;
-  float* d_ty = d_tx + plane;
-#pragma unroll 2
-  for (int k = grp * CQ_PG; k < min(nb, (grp + 1) * CQ_PG); k++) {
-    const GridPoint gp = project_grid<CONV>(geom.P, ray, __ldg(a.bins + k), a.eps, h, w, &sdiv);
-    const float xv = xmul(xadd(xmul(gp.gx, 0.5f), 0.5f), (float)(w - 1));
-    const float yv = xmul(xadd(xmul(gp.gy, 0.5f), 0.5f), (float)(h - 1));
-    const bool ok = inner && xv >= 2.0f && xv <= (float)(w - 2) && yv >= 2.0f && yv <= (float)(h - 2);
-    const float ux = unnormalize<CONV>(gp.gx, w), uy = unnormalize<CONV>(gp.gy, h);
-    const float x0 = floorf(ux), y0 = floorf(uy);
-    const int xi = min(max((int)x0, 0), w - 2), yi = min(max((int)y0, 0), h - 2);
-    d_off[(size_t)k * hw] = ok ? yi * w + xi : -1;
-    d_tx[(size_t)k * hw] = xsub(ux, x0);
-    d_ty[(size_t)k * hw] = xsub(uy, y0);
-  }
-}
-
-template <int CONV, int MINB, bool DESC>
+template <int CONV, int MINB>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
   __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
@@ -851,34 +835,12 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     const size_t row_stride = (size_t)w * 16, quad_stride = (size_t)hw * 16;
     CqTaps t00, t01, t10, t11;
     int coff = -1;
-    // (DESC) descriptors projected by cv_desc_kernel; the next group's are requested a group ahead
-    const size_t dplane = DESC ? cv_desc_plane(a.batch, a.num_lookup, nb, hw) : 0;
-    const int* g_off = DESC ? reinterpret_cast<const int*>(a.desc) + ((size_t)b * a.num_lookup + f) * nb * hw + p : nullptr;
-    int noff[2] = {-1, -1};
-    float ntx[2] = {0.f, 0.f}, nty[2] = {0.f, 0.f};
-    auto fetch = [&](int k0) {
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int kk = k0 + sub + 4 * u;
-        const bool v = pix_ok && kk < nb;
-        const size_t o = v ? (size_t)kk * hw : 0;
-        noff[u] = v ? __ldg(g_off + o) : -1;
-        ntx[u] = v ? __ldg(reinterpret_cast<const float*>(g_off) + dplane + o) : 0.0f;
-        nty[u] = v ? __ldg(reinterpret_cast<const float*>(g_off) + 2 * dplane + o) : 0.0f;
-      }
-    };
-    if (DESC) fetch(0);
 
     for (int k0 = 0; k0 < nb; k0 += CQ_G) {
       // ---- this lane's two planes of the group: projection descriptors --------------------------
       // branch-free, so that the two dependent chains (each ends in four IEEE divisions) interleave
       int off[2];
       float tx[2], ty[2];
-      if (DESC) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) { off[u] = noff[u]; tx[u] = ntx[u]; ty[u] = nty[u]; }
-        if (k0 + CQ_G < nb) fetch(k0 + CQ_G);
-      } else
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int kk = k0 + sub + 4 * u;
@@ -1041,10 +1003,6 @@ extern "C" size_t mal_cost_volume_desc_floats(int batch, int channels, int num_l
   return cv_desc_layout(batch, num_lookup, num_bins, height * width, cv_padded_channels(channels)).total;
 }
 
-extern "C" size_t mal_cost_volume_proj_floats(int batch, int num_lookup, int num_bins, int height, int width) {
-  return 3 * cv_desc_plane(batch, num_lookup, num_bins, height * width);
-}
-
 extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_stream_t stream) {
   MAL_REQUIRE(args != nullptr, "mal_cost_volume_forward: args is NULL");
   const mal_cost_volume_args& a = *args;
@@ -1088,8 +1046,9 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     const size_t rows = (size_t)a.batch * a.num_lookup * a.num_bins;
     MAL_REQUIRE(rows < (1u << 31) && (hw + 255) / 256 <= 65535, "mal_cost_volume_forward: descriptor grid too large");
     dim3 pgrid((unsigned)rows, (unsigned)((hw + 255) / 256));
-    if (a.convention == MAL_CONV_MANYDEPTH) launch(cv_project_kernel<MAL_CONV_MANYDEPTH>, pgrid, dim3(256), 0, st, a, sdiv);
-    else launch(cv_project_kernel<MAL_CONV_DUALREFINE>, pgrid, dim3(256), 0, st, a, sdiv);
+    dim3 jgrid((unsigned)((size_t)a.batch * a.num_lookup * ((a.num_bins + CV_PJ - 1) / CV_PJ)), (unsigned)((hw + 255) / 256));
+    if (a.convention == MAL_CONV_MANYDEPTH) launch(cv_project_kernel<MAL_CONV_MANYDEPTH>, jgrid, dim3(256), 0, st, a, sdiv);
+    else launch(cv_project_kernel<MAL_CONV_DUALREFINE>, jgrid, dim3(256), 0, st, a, sdiv);
     const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, a.num_bins, hw, Cp);
     MAL_REQUIRE(L.plane < (1u << 31), "mal_cost_volume_forward: descriptor volume too large for 32-bit sample indices");
     cudaMemsetAsync(reinterpret_cast<int*>(a.desc) + L.counters, 0, 4 * sizeof(int), st);
@@ -1099,7 +1058,7 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
       launch(cv_pack_cm_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
              reinterpret_cast<float4*>(a.desc + L.cm), a.channels, Cp, hw, total_l);
     }
-    launch(cv_slot_kernel, dim3(148 * 8), dim3(256), 0, st, a, Cp);
+    launch(cv_slot_kernel, dim3((unsigned)((L.plane + 255) / 256)), dim3(256), 0, st, a, Cp);
     launch(cv_sample_kernel, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     if (a.pool_radius == 1) launch(cv_pool_kernel<1>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     else launch(cv_pool_kernel<0>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
@@ -1124,24 +1083,14 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   } while (0)
   if (quad) {
     const size_t qsmem = cq_smem_bytes(a.num_bins);
-#define MAL_CQ_GO(CONV_, DESC_)                                                                                 \
-  do {                                                                                                          \
-    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);        \
-    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);   \
-    else launch(cv_sweep_quad_kernel<CONV_, 5, DESC_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                  \
-  } while (0)
-#define MAL_CQ_LAUNCH(CONV_)                                                                                    \
-  do {                                                                                                          \
-    if (a.desc) {                                                                                               \
-      const int ngroups = (a.num_bins + CQ_PG - 1) / CQ_PG;                                                     \
-      launch(cv_desc_kernel<CONV_>, dim3((unsigned)(a.batch * a.num_lookup * ngroups), (unsigned)((hw + 255) / 256)), \
-             dim3(256), 0, st, a, sdiv);                                                                        \
-      MAL_CQ_GO(CONV_, true);                                                                                   \
-    } else MAL_CQ_GO(CONV_, false);                                                                             \
+#define MAL_CQ_LAUNCH(CONV_)                                                                              \
+  do {                                                                                                    \
+    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);            \
+    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);       \
+    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                      \
   } while (0)
     if (a.convention == MAL_CONV_MANYDEPTH) MAL_CQ_LAUNCH(MAL_CONV_MANYDEPTH);
     else MAL_CQ_LAUNCH(MAL_CONV_DUALREFINE);
-#undef MAL_CQ_GO
 #undef MAL_CQ_LAUNCH
     return check_launch("cv_sweep_quad_kernel");
   }

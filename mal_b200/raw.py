@@ -194,15 +194,12 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     desc = None
     if occ is not None and occ_mode == OCC_POOL:
         desc = new((handle.mal_cost_volume_desc_floats(B, Cn, F_, nb, h, w),))
-    elif quad and not os.environ.get("MAL_CV_NO_DESC"):
-        # the four-lanes-per-pixel sweep with its projections in a pre-pass (MAL_CV_NO_DESC=1: inside the sweep)
-        desc = new((handle.mal_cost_volume_proj_floats(B, F_, nb, h, w),))
     a.desc = _ptr(desc)
     _capi.check(handle.mal_cost_volume_forward(C.byref(a), _stream(current)), handle)
     # the four-lanes-per-pixel sweep (C <= 64, no DynamicDepth extras) reads the current features in place:
     # lookup pack + sweep; the general kernel packs both operands first
     if quad:
-        LAUNCHES[0] += 2 + (1 if desc is not None else 0)   # cv_pack (lookup), [cv_desc,] cv_sweep_quad
+        LAUNCHES[0] += 2   # cv_pack (lookup), cv_sweep_quad
     else:
         LAUNCHES[0] += 3 + (6 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_slot, cv_sample, cv_pool
     out["_keepalive"] = (packed, desc)

@@ -1,6 +1,6 @@
 """Device timing of the ManyDepth cost-volume head at the bench shape (B x 1 lookup x 96 bins x 64 ch at 48x160),
-CUDA events, rotating over 3 input sets.  A/B switches: MAL_CV_NO_DESC=1 (projections inside the sweep),
-MAL_CV_MINB, MAL_CV_KERNEL=lane.  python tools/time_cv.py [B]"""
+CUDA events, rotating over 3 input sets.  A/B switches: MAL_CV_MINB, MAL_CV_KERNEL=lane, MAL_B200_LIB=<other build>.
+python tools/time_cv.py [B]"""
 import os
 import sys
 
@@ -23,32 +23,17 @@ def main():
         return raw.cost_volume(h, current=b["current_feats"], lookup=b["lookup_feats"], poses=b["relative_poses"], K=b["K2"],
                                inv_K=b["inv_K2"], bins=b["bins"], apply_confidence=True, want_missing=False)
 
-    ref = None
-    for name, env in (("projection pre-pass (cv_desc_kernel) + sweep", {}), ("projections inside the sweep", {"MAL_CV_NO_DESC": "1"})):
-        os.environ.update(env)
-        with torch.no_grad():
-            for i in range(6):
-                out = cv(i)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(30):
-                out = cv(i)
-            e1.record()
-            torch.cuda.synchronize()
-        for k in env:
-            del os.environ[k]
-        vol = cv(0)["cost_volume"] if not env else None
-        print("%-50s %8.1f us" % (name, e0.elapsed_time(e1) / 30 * 1e3), flush=True)
-        if ref is None:
-            ref = cv(0)
-        else:
-            os.environ.update(env)
-            other = cv(0)
-            for k in env:
-                del os.environ[k]
-            same = all(torch.equal(ref[k], other[k]) for k in ("cost_volume", "confidence", "argmin", "lowest_cost"))
-            print("both paths give the same bits:", same)
+    with torch.no_grad():
+        for i in range(6):
+            cv(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(30):
+            cv(i)
+        e1.record()
+        torch.cuda.synchronize()
+    print("cv_pack (lookup) + cv_sweep_quad_kernel  %8.1f us" % (e0.elapsed_time(e1) / 30 * 1e3), flush=True)
 
 
 if __name__ == "__main__":
