@@ -490,6 +490,9 @@ typedef struct mal_corr_args {
   float* grad_coords;     /* (B,2,L,D,h,w) optional, written                                       */
   float* grad_fmap1;      /* (B,C,h,w) optional, ACCUMULATED into: zero it first                   */
   float* grad_pyramid;    /* pyramid layout, optional, ACCUMULATED into: zero it first             */
+  float* workspace;       /* optional, B*C*h*w floats, 16-byte aligned (the call zeroes it): grad_fmap1 is then
+                             gathered channel-quad interleaved with 128-bit reductions (a quarter of the
+                             atomics) and added into grad_fmap1 by a second small kernel                 */
 } mal_corr_args;
 
 size_t mal_corr_pyramid_floats(int batch, int channels, int height, int width, int num_levels);

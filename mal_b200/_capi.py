@@ -87,7 +87,7 @@ class CorrArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "channels", "height", "width", "num_levels", "num_samples",
                                           "num_head")] + \
                [(n, C.c_void_p) for n in ("fmap1", "pyramid", "coords", "out", "grad_out", "grad_coords",
-                                          "grad_fmap1", "grad_pyramid")]
+                                          "grad_fmap1", "grad_pyramid", "workspace")]
 
 
 class SmoothArgs(C.Structure):

@@ -228,6 +228,8 @@ __device__ __forceinline__ void red_add4(float4* p, float x, float y, float z, f
 #endif
 }
 
+// (channel quads per load batch x resident CTAs were swept on the B200 - 1x6, 1x8, 2x6, 4x3, 4x4 -: all within 10 % of
+// 2 quads per batch at the natural register count, profiles/r2_notes.md)
 __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_args a) {
   CorrSite s;
   if (!corr_site(a, (size_t)blockIdx.x * CR_NT + threadIdx.x, s)) return;
@@ -242,8 +244,13 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
   const float* f1 = a.fmap1 + (size_t)s.b * C * hw + pix;
   const float4* f2 = reinterpret_cast<const float4*>(a.pyramid + loff);
   float4* gp = a.grad_pyramid ? reinterpret_cast<float4*>(a.grad_pyramid + loff) : nullptr;
-  float gix = 0.0f, giy = 0.0f;
-  const float ex = 1.0f - t.tx, ey = 1.0f - t.ty;
+  // d/d coords: with s_k = d|f1 - sample| / d sample per channel,
+  //   d/d ix = sum_k s_k ((b_k - a_k) (1 - ty) + (d_k - c_k) ty),  d/d iy = sum_k s_k ((c_k - a_k) (1 - tx) + (d_k - b_k) tx)
+  // are formed from the four tap sums  sum_k s_k a_k ... sum_k s_k d_k  (one packed FMA per tap and channel pair
+  // instead of eight scalar operations per channel: the coordinate-only backward went from 591 to ... us)
+  const pk2 zero2 = pack2(0.0f, 0.0f);
+  pk2 sa2 = zero2, sb2 = zero2, sc2 = zero2, sd2 = zero2;
+  const pk2 nw2 = dup2(t.nw), ne2 = dup2(t.ne), sw2 = dup2(t.sw), se2 = dup2(t.se);
   for (int hd = 0; hd < a.num_head; hd++) {
     const float g = __ldg(a.grad_out + s.out_index + (size_t)hd * a.num_samples * hw) / (float)Cg;
     if (g == 0.0f) continue;
@@ -269,17 +276,26 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
         if (q0 + j < Qg) {
           const int qq = hd * Qg + q0 + j;
           float sg[4];
-          const float av[4] = {ta[j].x, ta[j].y, ta[j].z, ta[j].w}, bv[4] = {tb[j].x, tb[j].y, tb[j].z, tb[j].w};
-          const float cv[4] = {tc[j].x, tc[j].y, tc[j].z, tc[j].w}, dv[4] = {td[j].x, td[j].y, td[j].z, td[j].w};
+          const pk2 a2[2] = {pack2(ta[j].x, ta[j].y), pack2(ta[j].z, ta[j].w)};
+          const pk2 b2[2] = {pack2(tb[j].x, tb[j].y), pack2(tb[j].z, tb[j].w)};
+          const pk2 c2[2] = {pack2(tc[j].x, tc[j].y), pack2(tc[j].z, tc[j].w)};
+          const pk2 d2[2] = {pack2(td[j].x, td[j].y), pack2(td[j].z, td[j].w)};
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float sv = xfma(dv[k], t.se, xfma(cv[k], t.sw, xfma(bv[k], t.ne, xmul(av[k], t.nw))));
-            const float df = fv[j][k] - sv;
-            sg[k] = df > 0.0f ? g : (df < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1
-            gix -= sg[k] * ((bv[k] - av[k]) * ey + (dv[k] - cv[k]) * t.ty);
-            giy -= sg[k] * ((cv[k] - av[k]) * ex + (dv[k] - bv[k]) * t.tx);
+          for (int hh = 0; hh < 2; hh++) {
+            // the sample exactly as the forward rounds it: the sign below is the reference's
+            const pk2 sv = x2fma(d2[hh], se2, x2fma(c2[hh], sw2, x2fma(b2[hh], ne2, x2mul(a2[hh], nw2))));
+            const pk2 df = x2sub(pack2(fv[j][2 * hh], fv[j][2 * hh + 1]), sv);
+            const float d0 = lo2(df), d1 = hi2(df);
+            sg[2 * hh] = d0 > 0.0f ? g : (d0 < 0.0f ? -g : 0.0f);   // d|f1 - s| / d f1 = -d|f1 - s| / d s
+            sg[2 * hh + 1] = d1 > 0.0f ? g : (d1 < 0.0f ? -g : 0.0f);
+            const pk2 sg2 = pack2(sg[2 * hh], sg[2 * hh + 1]);
+            sa2 = x2fma(sg2, a2[hh], sa2); sb2 = x2fma(sg2, b2[hh], sb2);
+            sc2 = x2fma(sg2, c2[hh], sc2); sd2 = x2fma(sg2, d2[hh], sd2);
           }
-          if (a.grad_fmap1) {
+          if (a.workspace) {   // channel-quad interleaved like the pyramid: one 128-bit reduction instead of four
+            if (sg[0] != 0.0f || sg[1] != 0.0f || sg[2] != 0.0f || sg[3] != 0.0f)
+              red_add4(reinterpret_cast<float4*>(a.workspace) + ((size_t)s.b * (C / 4) + qq) * hw + pix, sg[0], sg[1], sg[2], sg[3]);
+          } else if (a.grad_fmap1) {
             float* g1 = a.grad_fmap1 + ((size_t)s.b * C + (size_t)qq * 4) * hw + pix;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -296,11 +312,28 @@ __global__ void __launch_bounds__(CR_NT) corr_lookup_bwd_kernel(const mal_corr_a
       }
     }
   }
+  const float sa = lo2(sa2) + hi2(sa2), sb = lo2(sb2) + hi2(sb2), sc = lo2(sc2) + hi2(sc2), sd = lo2(sd2) + hi2(sd2);
+  const float gix = -((sb - sa) * (1.0f - t.ty) + (sd - sc) * t.ty);
+  const float giy = -((sc - sa) * (1.0f - t.tx) + (sd - sb) * t.tx);
   if (a.grad_coords) {
     // ix = ((2 (x + 0.5) / w1 - 1) + 1) * lw / 2 - 0.5  =>  d ix / d x = lw / w1
     a.grad_coords[cbase * hw + pix] = gix * ((float)s.lw / (float)w);
     a.grad_coords[(cbase + (size_t)a.num_levels * a.num_samples) * hw + pix] = giy * ((float)s.lh / (float)h);
   }
+}
+
+// grad_fmap1 (NCHW) += the channel-quad interleaved workspace; one thread per (quad, pixel)
+__global__ void __launch_bounds__(256) corr_unpack_kernel(const float4* __restrict__ ws, float* __restrict__ dst, int C,
+                                                          int hw, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int p = (int)(i % hw);
+  const size_t r = i / hw;
+  const int q = (int)(r % (C / 4));
+  const size_t img = r / (C / 4);
+  const float4 v = ws[i];
+  float* d = dst + (img * C + (size_t)q * 4) * hw + p;
+  d[0] += v.x; d[hw] += v.y; d[2 * (size_t)hw] += v.z; d[3 * (size_t)hw] += v.w;
 }
 
 }  // namespace mal
@@ -370,6 +403,17 @@ extern "C" int mal_corr_lookup_backward(const mal_corr_args* args, mal_stream_t 
   MAL_REQUIRE(a.grad_out && (a.grad_coords || a.grad_fmap1 || a.grad_pyramid),
               "mal_corr_lookup_backward: grad_out and at least one gradient output are required");
   const size_t total = corr_threads(a);
-  launch(corr_lookup_bwd_kernel, dim3((unsigned)((total + CR_NT - 1) / CR_NT)), dim3(CR_NT), 0, (cudaStream_t)stream, a);
+  cudaStream_t st = (cudaStream_t)stream;
+  mal_corr_args k = a;
+  const size_t nws = (size_t)a.batch * a.channels * a.height * a.width;
+  if (!a.grad_fmap1) k.workspace = nullptr;
+  if (k.workspace) {
+    MAL_REQUIRE(((uintptr_t)k.workspace & 15) == 0, "mal_corr_lookup_backward: the workspace must be 16-byte aligned");
+    cudaMemsetAsync(k.workspace, 0, nws * sizeof(float), st);
+  }
+  launch(corr_lookup_bwd_kernel, dim3((unsigned)((total + CR_NT - 1) / CR_NT)), dim3(CR_NT), 0, st, k);
+  if (k.workspace)
+    launch(corr_unpack_kernel, dim3((unsigned)((nws / 4 + 255) / 256)), dim3(256), 0, st,
+           reinterpret_cast<const float4*>(k.workspace), a.grad_fmap1, a.channels, a.height * a.width, nws / 4);
   return check_launch("corr_lookup_bwd_kernel");
 }

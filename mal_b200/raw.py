@@ -683,6 +683,9 @@ def corr_lookup_backward(handle, fmap1, pyramid, coords, grad_out, num_head=1, w
     g1 = torch.zeros_like(fmap1) if want_fmap1 else None
     gp = torch.zeros_like(pyramid) if want_pyramid else None
     a.grad_out, a.grad_coords, a.grad_fmap1, a.grad_pyramid = _ptr(grad_out), _ptr(gc), _ptr(g1), _ptr(gp)
+    # d/d fmap1 through a channel-quad interleaved workspace (128-bit reductions) and an un-packing kernel
+    ws = torch.empty_like(fmap1) if want_fmap1 else None
+    a.workspace = _ptr(ws)
     _capi.check(handle.mal_corr_lookup_backward(C.byref(a), _stream(fmap1)), handle)
-    LAUNCHES[0] += 1
+    LAUNCHES[0] += 2 if want_fmap1 else 1
     return gc, g1, gp

@@ -37,6 +37,8 @@ def main():
     print("lookup forward   %8.1f us" % timeit(lambda: raw.corr_lookup(hnd, f1, pyr, coords)))
     print("lookup backward  %8.1f us" % timeit(lambda: raw.corr_lookup_backward(hnd, f1, pyr, coords, go)))
     print("backward, coords only %8.1f us" % timeit(lambda: raw.corr_lookup_backward(hnd, f1, pyr, coords, go, want_fmap1=False, want_pyramid=False)))
+    print("backward, coords + fmap1   %8.1f us" % timeit(lambda: raw.corr_lookup_backward(hnd, f1, pyr, coords, go, want_pyramid=False)))
+    print("backward, coords + pyramid %8.1f us" % timeit(lambda: raw.corr_lookup_backward(hnd, f1, pyr, coords, go, want_fmap1=False)))
 
 
 if __name__ == "__main__":
