@@ -194,7 +194,7 @@ __device__ __forceinline__ float quad_l1_vals(float acc, const float4& v, const 
 //                       by shuffles, then the |pooled - current| chunk sums in the reference's order -> `parts`;
 //   the sweep           reads descriptors instead of projecting, and one float per (rim sample, chunk).
 //   (the rim windows overlap: every un-occluded sample next to a blob is warped ONCE into a cache - cv_interior marks
-//   them, cv_slot hands out cache slots, cv_sample fills them - and cv_pool takes its maxima over cached vectors)
+//   them and hands out the cache slots, cv_sample fills them - and cv_pool takes its maxima over cached vectors)
 // Workspace: CvDescLayout below.
 constexpr int CV_DESC_EDGE = 1;   // pixel and sampling location pass the border masks (:203-212)
 constexpr int CV_DESC_OCC = 2;    // projected occlusion mask > pool_th (:194-195)
@@ -333,24 +333,17 @@ __global__ void __launch_bounds__(256) cv_interior_kernel(const mal_cost_volume_
         const int xx = px + dx;
         if (xx < 0 || xx >= w) continue;
         int* nf = fl + (size_t)kk * hw + (size_t)yy * w + xx;
-        if (!(*reinterpret_cast<volatile int*>(nf) & (CV_DESC_OCC | CV_DESC_NEED))) atomicOr(nf, CV_DESC_NEED);
+        if (*reinterpret_cast<volatile int*>(nf) & (CV_DESC_OCC | CV_DESC_NEED)) continue;
+        // whoever sets NEED first hands the sample its cache slot (an overflowing one keeps slot 0: cv_pool_kernel
+        // then warps it itself)
+        if (atomicOr(nf, CV_DESC_NEED) & CV_DESC_NEED) continue;
+        const int idx = atomicAdd(base + L.counters + 1, 1);
+        if (idx >= L.cap) continue;
+        atomicOr(nf, (idx + 1) << CV_DESC_SLOT);
+        base[L.list2 + idx] = (int)((size_t)bf * nb * hw + (size_t)kk * hw + (size_t)yy * w + xx);
       }
     }
   }
-}
-
-// Cache slots for the marked samples (overflowing ones keep slot 0: cv_pool_kernel then warps them itself).
-__global__ void __launch_bounds__(256) cv_slot_kernel(const mal_cost_volume_args a, const int Cp) {
-  const CvDescLayout L = cv_desc_layout(a.batch, a.num_lookup, a.num_bins, a.height * a.width, Cp);
-  int* base = reinterpret_cast<int*>(a.desc);
-  // one word per thread, whole warps together (warp_append); a grid-stride loop here was latency-bound (83 us)
-  const size_t o = (size_t)blockIdx.x * 256 + threadIdx.x;
-  const int word = o < L.plane ? base[L.flags + o] : 0;
-  const bool need = (word & CV_DESC_NEED) != 0;
-  const int idx = warp_append(base + L.counters + 1, need);
-  if (!need || idx >= L.cap) return;
-  base[L.flags + o] = word | ((idx + 1) << CV_DESC_SLOT);
-  base[L.list2 + idx] = (int)o;
 }
 
 // The warped feature vector (all channels) of every cached sample: half a warp per sample, lane = channel quad.
@@ -763,7 +756,11 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
   dst[1] = pack2(v.z, v.w);
 }
 
-template <int CONV, int MINB>
+// DYN: the DynamicDepth variant (dynamicdepth/networks/resnet_encoder.py:148-249): min over the lookup frames
+// (cv_min), and an occluded sample's warped features replaced by 1.0 (set_1) or by the pooled maximum of its window
+// (pool: 0 inside a blob, else the chunk sums cv_pool_kernel left in the workspace).  Either way the lane's 16-channel
+// |.| sum of an occluded sample needs no texels: the two constant cases are formed once per lane.
+template <int CONV, int MINB, bool DYN>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
   __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
@@ -785,7 +782,11 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
 
   float* cost = reinterpret_cast<float*>(dyn_smem());   // [nb][CV_PX]
   float* cnt = cost + (size_t)((nb + 3) / 4 * 4) * CV_PX;
-  for (int k = sub; k < nb; k += 4) { cost[cq_idx(k, col)] = 0.0f; cnt[cq_idx(k, col)] = 0.0f; }
+  const bool cv_min = DYN && a.cv_min;
+  for (int k = sub; k < nb; k += 4) { cost[cq_idx(k, col)] = cv_min ? 1.0f : 0.0f; cnt[cq_idx(k, col)] = 0.0f; }
+  // occlusion handling applies to samples whose matching augmentation is off (aug_mask == 0)
+  const float* occ = nullptr;
+  if (DYN && a.occ && a.occ_mode != 0 && !(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
 
   const float4* lookq = reinterpret_cast<const float4*>(a.packed) + (size_t)a.batch * nquads * hw;
   pk2 ncur[4][2];   // -current features of this lane's chunk (w - cur == w + (-cur))
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       for (int e = 0; e < 4; e++) {
         const int ch = sub * 16 + j * 4 + e;
         v[e] = (pix_ok && active && ch < a.channels) ? __ldg(cur + (size_t)ch * hw) : 0.0f;
-        poisoned |= !(fabsf(v[e]) < INFINITY);
+        if (!DYN) poisoned |= !(fabsf(v[e]) < INFINITY);
       }
       ncur[j][0] = pack2(-v[0], -v[1]);
       ncur[j][1] = pack2(-v[2], -v[3]);
@@ -813,6 +814,20 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   poisoned |= __shfl_xor_sync(0xffffffffu, poisoned, 16);
   const pk2 one2 = dup2(1.0f), mone2 = dup2(-1.0f);
   const float inv_channels = (a.channels & (a.channels - 1)) == 0 ? 1.0f / (float)a.channels : 0.0f;
+  // (DYN) sum over the lane's 16 channels of |1 - cur| and |0 - cur|, in channel order from 0
+  float l1_one = 0.0f, l1_zero = 0.0f;
+  if (DYN && occ) {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        const pk2 d1 = x2add(one2, ncur[q][hh]);
+        l1_one = xadd(xadd(l1_one, fabsf(lo2(d1))), fabsf(hi2(d1)));
+        l1_zero = xadd(xadd(l1_zero, fabsf(lo2(ncur[q][hh]))), fabsf(hi2(ncur[q][hh])));
+      }
+  }
+  const bool pooled = DYN && occ && a.occ_mode == MAL_CV_OCC_POOL;
+  const size_t dplane = DYN ? cv_desc_plane(a.batch, a.num_lookup, nb, hw) : 0;
 
   for (int f = 0; f < a.num_lookup; f++) {
     __syncthreads();
@@ -841,6 +856,16 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       // branch-free, so that the two dependent chains (each ends in four IEEE divisions) interleave
       int off[2];
       float tx[2], ty[2];
+      int pfl[2] = {0, 0};   // (DYN, pool) the pre-passes' verdicts, requested ahead of the projection arithmetic
+      if (DYN && pooled) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int kk = k0 + sub + 4 * u;
+          if (pix_ok && kk < nb)
+            pfl[u] = __ldg(reinterpret_cast<const int*>(a.desc) + 2 * dplane + ((size_t)b * a.num_lookup + f) * nb * hw +
+                           (size_t)kk * hw + p);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 2; u++) {
         const int kk = k0 + sub + 4 * u;
@@ -856,6 +881,13 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
         off[u] = ok ? yi * w + xi : -1;
         tx[u] = xsub(ux, x0);
         ty[u] = xsub(uy, y0);
+        if (DYN && occ && ok) {
+          if (pooled) {   // the pre-passes' verdicts (cv_project_kernel / cv_interior_kernel)
+            if (pfl[u] & CV_DESC_OCC) off[u] |= CV_OCC_BIT | ((pfl[u] & CV_DESC_ZERO) ? CV_ZERO_BIT : 0);
+          } else if (occluded_at<CONV>(occ, gp, h, w, a.pool_th)) {
+            off[u] |= CV_OCC_BIT;
+          }
+        }
       }
       if (!__any_sync(0xffffffffu, (off[0] & off[1]) >= 0 || poisoned)) continue;   // 8 pixels x 8 planes all masked
 #pragma unroll
@@ -875,7 +907,14 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
           const int j = j0 + jj;
           const int o = s_o[warp][j][pl];
           acc[jj] = 0.0f;
-          if (o >= 0 && active) {
+          if (DYN && o >= 0 && (o & CV_OCC_BIT)) {   // an occluded sample: no texels needed
+            if (active) {
+              if (a.occ_mode == MAL_CV_OCC_SET_1) acc[jj] = l1_one;          // warped[mask] = 1.0
+              else if (o & CV_ZERO_BIT) acc[jj] = l1_zero;                    // pooled value 0 inside a blob
+              else acc[jj] = __ldg(a.desc + (4 + (size_t)sub) * dplane + ((size_t)b * a.num_lookup + f) * nb * hw +
+                                   (size_t)(k0 + j) * hw + p);              // the rim: cv_pool_kernel's chunk sum
+            }
+          } else if (o >= 0 && active) {
             if (o != coff) {
               coff = o;
               // two 64-bit pointer increments per channel quad; the taps are fixed offsets from them
@@ -919,8 +958,12 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
           // .mean(1); edge mask == 1.  A power-of-two channel count divides exactly by multiplying.
           const float diff = inv_channels != 0.0f ? xmul(s_mine, inv_channels) : xdiv(s_mine, (float)a.channels);
           const int o = cq_idx(k0 + sub + 4 * u, col);
-          cost[o] = xadd(cost[o], diff);
-          if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+          if (cv_min) {   // diffs[diffs == 0] = 1.0; cost_volume = minimum(diffs, cost_volume)
+            cost[o] = fminf(diff == 0.0f ? 1.0f : diff, cost[o]);
+          } else {
+            cost[o] = xadd(cost[o], diff);
+            if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+          }
         } else if (poisoned && pix_ok && k0 + sub + 4 * u < nb) {
           cost[cq_idx(k0 + sub + 4 * u, col)] = NAN;   // masked plane of a poisoned pixel: NaN * 0
         }
@@ -934,7 +977,8 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   int has_nan = 0;
   for (int k = sub; k < nb; k += 4) {
     const int o = cq_idx(k, col);
-    const float v = xdiv(cost[o], xadd(cnt[o], 1e-7f));
+    const float v = cv_min ? (cost[o] == 1.0f ? 0.0f : cost[o])       // cost_volume[cost_volume == 1] = 0
+                           : xdiv(cost[o], xadd(cnt[o], 1e-7f));       // cost_volume / (counts + 1e-7)
     cost[o] = v;
     vmax = fmaxf(vmax, v);
     has_nan |= (v != v);
@@ -1022,13 +1066,14 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   const int Cp = cv_padded_channels(a.channels);
   const int hw = a.height * a.width;
   const bool dyn = a.cv_min || (a.occ && a.occ_mode != MAL_CV_OCC_NONE);
-  // kernel choice: the four-lanes-per-pixel sweep handles up to 4 chunks (C <= 64) and no
+  // kernel choice: the four-lanes-per-pixel sweep handles up to 4 chunks (C <= 64), with or without the
   // DynamicDepth extras; MAL_CV_KERNEL=lane forces the one-pixel-per-lane kernel (tuning only)
-  bool quad = !dyn && Cp / CV_CHUNK <= 4;
+  bool quad = Cp / CV_CHUNK <= 4;
+  const bool pool = a.occ && a.occ_mode == MAL_CV_OCC_POOL;
   if (const char* e = getenv("MAL_CV_KERNEL")) quad = quad && e[0] != 'l';
   {
     long long total = (long long)a.batch * (Cp / 4) * hw;
-    if (!quad)   // the quad sweep reads the current features in place (NCHW)
+    if (!quad || pool)   // the quad sweep reads the current features in place (NCHW); cv_pool_kernel the packed ones
       launch(cv_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a.current,
              reinterpret_cast<float4*>(a.packed), a.channels, Cp, hw, total);
     long long total_l = total * a.num_lookup;
@@ -1058,7 +1103,6 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
       launch(cv_pack_cm_kernel, dim3((unsigned)((total_l + 255) / 256)), dim3(256), 0, st, a.lookup,
              reinterpret_cast<float4*>(a.desc + L.cm), a.channels, Cp, hw, total_l);
     }
-    launch(cv_slot_kernel, dim3((unsigned)((L.plane + 255) / 256)), dim3(256), 0, st, a, Cp);
     launch(cv_sample_kernel, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     if (a.pool_radius == 1) launch(cv_pool_kernel<1>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
     else launch(cv_pool_kernel<0>, dim3(148 * 8), dim3(256), 0, st, a, Cp);
@@ -1083,14 +1127,20 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
   } while (0)
   if (quad) {
     const size_t qsmem = cq_smem_bytes(a.num_bins);
-#define MAL_CQ_LAUNCH(CONV_)                                                                              \
-  do {                                                                                                    \
-    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);            \
-    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);       \
-    else launch(cv_sweep_quad_kernel<CONV_, 5>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                      \
+#define MAL_CQ_GO(CONV_, DYN_)                                                                                  \
+  do {                                                                                                          \
+    if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3, DYN_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);         \
+    else if (minb == 4) launch(cv_sweep_quad_kernel<CONV_, 4, DYN_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);    \
+    else launch(cv_sweep_quad_kernel<CONV_, 5, DYN_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);                   \
+  } while (0)
+#define MAL_CQ_LAUNCH(CONV_)            \
+  do {                                  \
+    if (dyn) MAL_CQ_GO(CONV_, true);    \
+    else MAL_CQ_GO(CONV_, false);       \
   } while (0)
     if (a.convention == MAL_CONV_MANYDEPTH) MAL_CQ_LAUNCH(MAL_CONV_MANYDEPTH);
     else MAL_CQ_LAUNCH(MAL_CONV_DUALREFINE);
+#undef MAL_CQ_GO
 #undef MAL_CQ_LAUNCH
     return check_launch("cv_sweep_quad_kernel");
   }

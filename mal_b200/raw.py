@@ -190,7 +190,7 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     # the pool fill projects every (lookup frame, bin, pixel) once into a descriptor volume (12 B per sample) that
     # the pool windows read their neighbours from
     dyn = bool(cv_min) or (occ is not None and occ_mode != OCC_NONE)
-    quad = not dyn and (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
+    quad = (Cn + 15) // 16 <= 4 and os.environ.get("MAL_CV_KERNEL", "")[:1] != "l"
     desc = None
     if occ is not None and occ_mode == OCC_POOL:
         desc = new((handle.mal_cost_volume_desc_floats(B, Cn, F_, nb, h, w),))
@@ -199,9 +199,10 @@ def cost_volume(handle, *, current, lookup, poses, K, inv_K, bins, convention=CO
     # the four-lanes-per-pixel sweep (C <= 64, no DynamicDepth extras) reads the current features in place:
     # lookup pack + sweep; the general kernel packs both operands first
     if quad:
-        LAUNCHES[0] += 2   # cv_pack (lookup), cv_sweep_quad
+        # cv_pack (lookup), cv_sweep_quad (+ cv_pack (current), cv_project, cv_interior, cv_pack_cm, cv_sample, cv_pool)
+        LAUNCHES[0] += 2 + (6 if desc is not None else 0)
     else:
-        LAUNCHES[0] += 3 + (6 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_slot, cv_sample, cv_pool
+        LAUNCHES[0] += 3 + (5 if desc is not None else 0)   # + cv_project, cv_interior, cv_pack_cm, cv_sample, cv_pool
     out["_keepalive"] = (packed, desc)
     return out
 

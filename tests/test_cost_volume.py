@@ -81,7 +81,7 @@ def test_cost_volume_dualrefine_convention(backend):
 @pytest.mark.parametrize("cv_min,set_1,pool,speckle", [(True, False, True, False), (False, True, False, False),
                                                        (True, False, False, False), (False, False, True, False),
                                                        (True, False, True, True)])
-def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool, speckle):
+def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool, speckle, monkeypatch):
     """dynamicdepth/networks/resnet_encoder.py:148-249: min over lookup frames and the occlusion
     fill (set_1 / 3-D max-pool) of the warped features, one sample with augmentation on (no fill).
     `speckle`: isolated occluded pixels everywhere, so that most samples sit next to one - more than the pool
@@ -108,6 +108,12 @@ def test_dynamicdepth_cost_volume_variant(backend, cv_min, set_1, pool, speckle)
                aug_mask=aug.to(dev))
     assert torch.equal(out["missing_mask"].cpu(), want_miss)
     assert torch.equal(out["cost_volume"].cpu(), want_vol)
+    # the same through the one-pixel-per-lane kernel (what C > 64 takes)
+    monkeypatch.setenv("MAL_CV_KERNEL", "lane")
+    out2 = _run(h, dev, cv, cv_min=cv_min, occ=occ.to(dev), occ_mode=mode, pool_radius=1, pool_th=0.7,
+                aug_mask=aug.to(dev))
+    monkeypatch.delenv("MAL_CV_KERNEL")
+    assert torch.equal(out2["cost_volume"].cpu(), want_vol) and torch.equal(out2["missing_mask"].cpu(), want_miss)
     if mode != raw.OCC_NONE:   # the fill really changed something, and only on the un-augmented sample
         plain, _ = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"], cv["K"],
                                             cv["inv_K"], cv["bins"], look_img, cv_min, aug, False, False, 1, 0.7)
