@@ -45,11 +45,29 @@ def euler2mat(angle):
     return xmat @ ymat @ zmat
 
 
+def quat2mat(quat):
+    """The first three coefficients of a rotation quaternion (B,3), the scalar part fixed to 1 before
+    normalisation -> rotation matrices (B,3,3)  (dynamicdepth/rigid_warp.py:243-265)."""
+    q = torch.cat([quat[:, :1].detach() * 0 + 1, quat], dim=1)
+    q = q / q.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    w2, x2, y2, z2 = w.pow(2), x.pow(2), y.pow(2), z.pow(2)
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    rows = [w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+            2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+            2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2]
+    return torch.stack(rows, dim=1).reshape(quat.size(0), 3, 3)
+
+
 def pose_vec2mat(vec, rotation_mode="euler"):
-    """6-DoF (tx,ty,tz,rx,ry,rz) (B,6) -> (B,3,4)."""
-    if rotation_mode != "euler":
-        raise NotImplementedError("only rotation_mode='euler' is used by forward_warp")
-    return torch.cat([euler2mat(vec[:, 3:]), vec[:, :3].unsqueeze(-1)], dim=2)
+    """6-DoF (tx,ty,tz,rx,ry,rz) (B,6) -> (B,3,4)  (dynamicdepth/rigid_warp.py:268-284)."""
+    if rotation_mode == "euler":
+        rot = euler2mat(vec[:, 3:])
+    elif rotation_mode == "quat":
+        rot = quat2mat(vec[:, 3:])
+    else:
+        raise ValueError("rotation_mode must be 'euler' or 'quat', got %r" % (rotation_mode,))
+    return torch.cat([rot, vec[:, :3].unsqueeze(-1)], dim=2)
 
 
 def forward_warp_matrices(pose, intrinsics, upscale):
@@ -66,9 +84,9 @@ def forward_warp_matrices(pose, intrinsics, upscale):
 def forward_warp(img, depth, pose, intrinsics, upscale=None, rotation_mode="euler", padding_mode="zeros",
                  matrices=None):
     """Warp `img` (B,C,H,W) with its own `depth` (B,1,H,W) into the view reached by `pose`
-    (B,3,4), z-buffering collisions.  Returns (img_w * valid, depth_w * valid, valid)."""
-    if padding_mode != "zeros":
-        raise NotImplementedError("forward_warp is only ever called with padding_mode='zeros'")
+    (B,3,4), z-buffering collisions.  Returns (img_w * valid, depth_w * valid, valid).
+    `rotation_mode` and `padding_mode` are accepted and unused, exactly as in the reference (its forward_warp goes
+    through pose_vec2mat's default and never samples with a padding mode: rigid_warp.py:534-597)."""
     if upscale is None or int(upscale) != upscale:
         raise ValueError("upscale must be an integer (the reference passes upscale=3)")
     with torch.no_grad():

@@ -707,6 +707,26 @@ def _euler2mat(angle):
     return xmat @ ymat @ zmat
 
 
+def quat2mat(quat):
+    """dynamicdepth/rigid_warp.py:243-265."""
+    nq = torch.cat([quat[:, :1].detach() * 0 + 1, quat], dim=1)
+    nq = nq / nq.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = nq[:, 0], nq[:, 1], nq[:, 2], nq[:, 3]
+    B = quat.size(0)
+    w2, x2, y2, z2 = w.pow(2), x.pow(2), y.pow(2), z.pow(2)
+    wx, wy, wz = w * x, w * y, w * z
+    xy, xz, yz = x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1).reshape(B, 3, 3)
+
+
+def pose_vec2mat(vec, rotation_mode="euler"):
+    """dynamicdepth/rigid_warp.py:268-284."""
+    rot = _euler2mat(vec[:, 3:]) if rotation_mode == "euler" else quat2mat(vec[:, 3:])
+    return torch.cat([rot, vec[:, :3].unsqueeze(-1)], dim=2)
+
+
 def _mat2euler(R):
     """dynamicdepth/rigid_warp.py:175-200."""
     sy = torch.sqrt(R[:, 0, 0] * R[:, 0, 0] + R[:, 1, 0] * R[:, 1, 0])

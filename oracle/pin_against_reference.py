@@ -351,6 +351,11 @@ def run_pin(batch=2, height=96, width=160, seed=7):
     got = O.forward_warp(img, depth_fw, pose, K3, upscale=3)
     for n, a, b in zip(("img_w", "depth_w", "valid"), got, want):
         ok &= _eq("forward_warp " + n, a, b)
+    # pose_vec2mat, both rotation modes (rigid_warp.py:243-284)
+    rw = importlib.import_module("dynamicdepth.rigid_warp")
+    vec = torch.randn(5, 6, generator=torch.Generator().manual_seed(12)) * 0.3
+    for mode in ("euler", "quat"):
+        ok &= _eq("pose_vec2mat " + mode, O.pose_vec2mat(vec, mode), rw.pose_vec2mat(vec, mode))
     return bool(ok)
 
 

@@ -90,3 +90,21 @@ def test_loss_balancing_zero_loss_term_follows_the_reference():
             assert got[0] == 0.25 and np.isinf(got[1]) and np.isnan(ours.previous_total_loss)
     # step 1: NaN > 0 is False, the weights stay; step 2: inf / inf -> NaN reaches both weights
     assert np.isnan(got[0]) and np.isnan(got[1])
+
+
+def test_pose_vec2mat_both_rotation_modes():
+    """mal_b200.rigid_warp.pose_vec2mat / quat2mat against the pinned oracle (dynamicdepth/rigid_warp.py:243-284);
+    a quaternion's matrix is orthonormal with determinant 1."""
+    import torch
+    from mal_b200 import rigid_warp
+    from oracle import mal_oracle as O
+    vec = torch.randn(7, 6, generator=torch.Generator().manual_seed(3)) * 0.4
+    for mode in ("euler", "quat"):
+        got, want = rigid_warp.pose_vec2mat(vec, mode), O.pose_vec2mat(vec, mode)
+        assert torch.equal(got, want), mode
+        R = got[:, :, :3]
+        assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(7, 3, 3), atol=1e-5)
+        assert torch.allclose(torch.linalg.det(R), torch.ones(7), atol=1e-5)
+    import pytest
+    with pytest.raises(ValueError):
+        rigid_warp.pose_vec2mat(vec, "axis")
