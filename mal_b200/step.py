@@ -34,13 +34,17 @@ LEAVES = ("mono_disp", "multi_disp", "T_-1", "T_1")
 # the matched instance masks of the two warped frames, packed one bit per instance (mal_temporal_pack_masks), and
 # the step materialises the warps, synthesises the temporal-hint images and back-propagates through them
 MASK_KEYS = ("masks_last", "masks_next", "mask_counts")
+# --main_temporal (trainer.py:1164-1165): the matched masks of the MULTI pass's warps, optional (the teacher's masks
+# are reused without them)
+MASK_KEYS_MULTI = tuple(k + "_multi" for k in MASK_KEYS)
 SYN_KEYS = ("syn_-1", "syn_1")
 
 
 # what the reference's data loader / CPU generator hands to the GPU every step (images, intrinsics, the CPU-drawn
 # tie-break noise of loss_utils.py:105-106 / :178, the segmenter-shaped masks); everything else in a batch is born
 # on the device in the reference (network outputs) and only travels in the all-from-host end-to-end measurement
-HOST_BORN = ("color_0", "color_-1", "color_1", "K", "inv_K", "K2", "inv_K2", "noise_mono", "noise_main", "bins") + MASK_KEYS
+HOST_BORN = ("color_0", "color_-1", "color_1", "K", "inv_K", "K2", "inv_K2", "noise_mono", "noise_main", "bins") + \
+    MASK_KEYS + MASK_KEYS_MULTI
 
 
 def batch_keys(batch):
@@ -50,6 +54,8 @@ def batch_keys(batch):
     keys = INPUT_KEYS
     if "masks_last" in batch:
         keys = tuple(k for k in INPUT_KEYS if k not in SYN_KEYS) + MASK_KEYS
+        if "masks_last_multi" in batch:
+            keys = keys + MASK_KEYS_MULTI
     return tuple(k for k in keys if k in HOST_BORN) + tuple(k for k in keys if k not in HOST_BORN)
 
 
@@ -194,9 +200,6 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
     of the teacher, of the student, consistency, teacher loss, student loss]; grads follow LEAVES."""
     if not opt.distil:
         raise ValueError("fused_step implements the --distil step; use step_losses otherwise")
-    if "masks_last" in b and opt.main_temporal and multi_has_ins:
-        raise ValueError("main_temporal with in-step synthesis: the student's candidates need their own synthesis "
-                         "pass; hand the step ready-made syn images instead")
     B, H, W = opt.batch_size, opt.height, opt.width
     lo, hi = opt.min_depth, opt.max_depth
     tgt, src = b["color_0"], [b["color_-1"], b["color_1"]]
@@ -265,16 +268,34 @@ def fused_step_main(handle, b, opt, has_ins=True, multi_has_ins=False, side_stre
                                                  grad_depth=teacher["grad_depth"], grad_P=teacher["grad_P"], **geom)
     branch.join(0)
     sample_mask = b["augmentation_mask"].reshape(-1)[:B]
-    student = later(raw.photo(handle, target=tgt, src=src, syn=syn if (opt.main_temporal and multi_has_ins) else None,
-                              depth=multi, pixel_mask=mask, sample_mask=sample_mask, with_grad=True, finalize=False,
-                              **geom))
+    use_syn_s = bool(opt.main_temporal and multi_has_ins)
+    hint_s, warped_s, syn_s = None, None, syn
+    if use_syn_s and in_step_syn:
+        # trainer.py:1164-1165: the multi pass synthesises its own temporal hint from ITS warps (the multi disparity).
+        # The matched masks of those warps come as masks_*_multi; without them the teacher's masks are reused.
+        sfx = "_multi" if "masks_last_multi" in b else ""
+        warped_s = raw.temporal_warp(handle, src=src, depth=multi, **geom)
+        hint_s = raw.temporal_synthesis(handle, warped=warped_s, packed_last=b["masks_last" + sfx],
+                                        packed_next=b["masks_next" + sfx], counts=b["mask_counts" + sfx])
+        syn_s = hint_s["syn"]
+    student = raw.photo(handle, target=tgt, src=src, syn=syn_s if use_syn_s else None, depth=multi, pixel_mask=mask,
+                        sample_mask=sample_mask, with_grad=True, finalize=False, want_grad_syn=hint_s is not None,
+                        warped=warped_s, **geom)
+    with branch(1):
+        raw.photo_finalize(handle, student)
+        if hint_s is not None:
+            sfx = "_multi" if "masks_last_multi" in b else ""
+            hint_s["back"] = raw.temporal_backward(handle, grad_syn=student["grad_syn"], packed_last=b["masks_last" + sfx],
+                                                   packed_next=b["masks_next" + sfx], counts=b["mask_counts" + sfx],
+                                                   deltas=hint_s["deltas"], want_grad_warped=False, src=src, depth=multi,
+                                                   grad_depth=student["grad_depth"], grad_P=student["grad_P"], **geom)
     dual = bool(opt.dual_distil) and ens is None
     mt = raw.main_terms(handle, multi=multi, mono=mono, pixel_mask=mask, sample_mask=sample_mask,
                         mono_reproj=teacher["min_reproj"], ens_reproj=ens, multi_reproj=student["min_reproj"],
                         inputs_are_disp=True, dual_distil=dual, with_grad=True, min_depth=lo, max_depth=hi)
     branch.join(1)
     return dict(head=head, mask=mask, teacher=teacher, student=student, ens=ens, sm_t=sm_t, sm_s=sm_s, mt=mt,
-                ident=ident, hint=hint)
+                ident=ident, hint=hint, hint_s=hint_s)
 
 
 def fused_step_tail(handle, b, opt, weights, ctx):
@@ -295,7 +316,7 @@ def fused_step_tail(handle, b, opt, weights, ctx):
                "mal_distil_index": mt["distil_index"], "consistency_target/0": mt["consistency_target"],
                ("mal_selection", 0): student["selection"], "mono_reproj": teacher["min_reproj"],
                "multi_reproj": student["min_reproj"], "ensemble_reproj": ens,
-               "_keepalive": (head, teacher, student, sm_t, sm_s, mt, comb, ident, ctx.get("hint"))}
+               "_keepalive": (head, teacher, student, sm_t, sm_s, mt, comb, ident, ctx.get("hint"), ctx.get("hint_s"))}
     if ctx.get("hint") is not None:
         outputs[("syn", -1, 0)], outputs[("syn", 1, 0)] = ctx["hint"]["syn"]
     grads = (comb["grad_disp_teacher"], comb["grad_disp_student"], comb["grad_T"][0], comb["grad_T"][1])
@@ -369,8 +390,10 @@ class MalStep:
     input bytes than the L2 holds."""
 
     def __init__(self, opt, device="cuda:0", use_graph=True, slots=1, num_train_data=1 << 20,
-                 lambda_for_adjust=0.0, fused=True, branches=True):
+                 lambda_for_adjust=0.0, fused=True, branches=True, has_ins=True, multi_has_ins=False):
         self.opt, self.device, self.use_graph = opt, torch.device(device), use_graph
+        # Trainer.has_ins / multi_has_ins (image_synthesis found matched instances): fixed for a captured step
+        self.has_ins, self.multi_has_ins = has_ins, multi_has_ins
         self.fused = fused and opt.distil   # libmal_b200-only schedule; False: op-by-op through autograd
         self.slots = [dict(buf=None, graph=None, static=None) for _ in range(slots)]
         self.weights = torch.full((2,), 0.5, device=self.device)
@@ -451,7 +474,8 @@ class MalStep:
         if self.fused:
             return self._run_tail(buf, self._run_main(buf))
         leaves = {k: buf[k] for k in LEAVES}
-        total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights)
+        total, loss_list, losses, outputs = step_losses(buf, self.opt, leaves, self.weights, has_ins=self.has_ins,
+                                                        multi_has_ins=self.multi_has_ins)
         grads = torch.autograd.grad(total, [leaves[k] for k in LEAVES])
         scalars = torch.stack([total.detach(), loss_list[0].detach(), loss_list[-1].detach(),
                                losses["reproj_loss/0"].detach()])
@@ -460,7 +484,8 @@ class MalStep:
     def _run_main(self, buf):
         from . import _capi
         with torch.no_grad():
-            return fused_step_main(_capi.lib(), buf, self.opt, side_streams=self.side_streams)
+            return fused_step_main(_capi.lib(), buf, self.opt, has_ins=self.has_ins, multi_has_ins=self.multi_has_ins,
+                                   side_streams=self.side_streams)
 
     def _run_tail(self, buf, ctx):
         from . import _capi

@@ -53,6 +53,20 @@ def oracle_step(b, opt, weights=(0.5, 0.5), multi_has_ins=False):
     ens = O.images_pred_ensemble(inputs, leaves["T_-1"].detach(), leaves["T_1"].detach(),
                                  (leaves["mono_disp"].detach() + leaves["multi_disp"].detach()) / 2.0, height=H, width=W)
     O.images_pred(inputs, multi, height=H, width=W, is_multi=True)
+    if "masks_last" in b and multi_has_ins and getattr(opt, "main_temporal", False):
+        # trainer.py:1164-1165: the multi pass synthesises its own hint from its own warps
+        sfx = "_multi" if "masks_last_multi" in b else ""
+        syn = [multi[("color", -1, 0)], multi[("color", 1, 0)]]
+        for s_ in range(B):
+            n = int(b["mask_counts" + sfx][s_])
+            if n == 0:
+                continue
+            ml = ((b["masks_last" + sfx][s_].long().unsqueeze(0) >> torch.arange(n).view(-1, 1, 1)) & 1).bool()
+            mn = ((b["masks_next" + sfx][s_].long().unsqueeze(0) >> torch.arange(n).view(-1, 1, 1)) & 1).bool()
+            ol, on, _ = O.generate_dynamic_instance(ml, mn, multi[("color", -1, 0)][s_], multi[("color", 1, 0)][s_])
+            syn[0] = torch.cat([syn[0][:s_], ol[None], syn[0][s_ + 1:]])
+            syn[1] = torch.cat([syn[1][:s_], on[None], syn[1][s_ + 1:]])
+        multi[("syn", -1, 0)], multi[("syn", 1, 0)] = syn
     losses, _, loss_list, aux = O.main_losses(inputs, multi, mono_reproj, ens, batch_size=B, loss_blc=True,
                                               multi_has_ins=bool(multi_has_ins and getattr(opt, "main_temporal", False)),
                                               noise=b["noise_main"])

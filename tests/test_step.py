@@ -84,6 +84,29 @@ def test_fused_step_synthesises_the_temporal_hint_in_step(backend):
     assert not torch.equal(grads[0].cpu(), grads2[0].cpu())
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("own_masks", [False, True])
+def test_fused_step_main_temporal_synthesises_the_students_hint(backend, own_masks):
+    """--main_temporal with instance masks (manydepth/trainer.py:1164-1165): the multi pass synthesises its own
+    temporal hint from ITS warps (the multi disparity) and back-propagates through the copies; `own_masks` hands it
+    the matched masks of those warps (masks_*_multi), otherwise the teacher's are reused."""
+    h, dev = handle_and_device(backend)
+    opt = S.default_opt(3, 32, 64, num_depth_bins=16, matching_channels=16)
+    opt.main_temporal = True
+    b = S.synthetic_batch(opt, seed=5, with_masks=True)
+    if own_masks:
+        other = S.synthetic_batch(opt, seed=6, with_masks=True)
+        for k in S.MASK_KEYS:
+            b[k + "_multi"] = other[k]
+    want = oracle_step(b, opt, (0.4, 0.9), multi_has_ins=True)
+    scalars, grads, outputs = S.fused_step(h, to_device(b, dev), opt, torch.tensor((0.4, 0.9), device=dev), multi_has_ins=True)
+    _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
+    sel = outputs[("mal_selection", 0)].cpu() & 0x7F
+    assert int((sel >= 2).sum()) > 0          # the student really selects its hint candidates somewhere
+    plain = oracle_step(b, opt, (0.4, 0.9), multi_has_ins=False)
+    assert not torch.equal(plain[2][1], want[2][1])   # ... and that changes the gradient of the multi disparity
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_graph,fused,with_masks", [(False, False, False), (True, False, False), (False, True, False),
                                                          (True, True, False), (False, True, True), (True, True, True)])
@@ -98,6 +121,25 @@ def test_malstep_graph_and_eager(use_graph, fused, with_masks):
         torch.cuda.synchronize()
         _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
     assert st.launches_per_step and 8 <= st.launches_per_step <= 17
+
+
+@pytest.mark.gpu
+def test_malstep_main_temporal_with_the_multi_pass_masks():
+    """The captured step with --main_temporal and instance masks for both passes (masks_*_multi travel with the
+    staged batch): three replays against the oracle."""
+    opt = S.default_opt(2, 64, 96, num_depth_bins=32, matching_channels=32)
+    opt.main_temporal = True
+    b = S.synthetic_batch(opt, seed=11, with_masks=True)
+    other = S.synthetic_batch(opt, seed=12, with_masks=True)
+    for k in S.MASK_KEYS:
+        b[k + "_multi"] = other[k]
+    want = oracle_step(b, opt, multi_has_ins=True)
+    st = S.MalStep(opt, use_graph=True, fused=True, multi_has_ins=True)
+    st.load(b)
+    for it in range(3):
+        scalars, grads, outputs = st(0, sync_weights=False)
+        torch.cuda.synchronize()
+        _check(scalars[0], [scalars[1], scalars[2]], grads, outputs, want)
 
 
 @pytest.mark.gpu
