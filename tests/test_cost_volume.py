@@ -142,3 +142,19 @@ def test_cost_volume_nan_and_inf_features(backend, C):
     assert torch.equal(out["lowest_cost"].cpu(), low)
     # both pixels end up all-NaN in the reference: a masked plane is NaN * 0 (Inf * 0) and max-filling spreads it
     assert bool(torch.isnan(vol[0, :, 7, 9]).all()) and bool(torch.isnan(vol[0, :, 9, 14]).all())
+
+
+def test_pool_fill_needs_its_workspace():
+    """MAL_CV_OCC_POOL without the descriptor workspace is an argument error at the C ABI (no silent slow path)."""
+    import ctypes as C
+    from mal_b200 import _capi
+    from tests.emu.emu_lib import emu
+    h = emu()
+    a = _capi.CostVolumeArgs()
+    a.batch, a.channels, a.height, a.width, a.num_lookup, a.num_bins = 1, 16, 8, 8, 1, 4
+    buf = torch.zeros(4096)
+    for f in ("current", "lookup", "poses", "K", "inv_K", "bins", "cost_volume", "packed", "occ"):
+        setattr(a, f, buf.data_ptr())
+    a.occ_mode, a.pool_radius = raw.OCC_POOL, 1
+    assert h.mal_cost_volume_forward(C.byref(a), None) == 1          # MAL_ERR_ARGUMENT
+    assert b"desc workspace" in h.mal_last_error()

@@ -138,6 +138,19 @@ def test_argument_errors_are_reported():
     with pytest.raises(ValueError):
         raw.photo(h, target=inputs[("color", 0, 0)], src=[inputs[("color", -1, 0)][:, :, :8], inputs[("color", 1, 0)]],
                   mode=raw.PHOTO_PRED)
+    # the options added in round 2 refuse the combinations they do not implement
+    tgt, src = inputs[("color", 0, 0)], [inputs[("color", -1, 0)], inputs[("color", 1, 0)]]
+    geom = dict(depth=t[("mono_disp", 0)], K=inputs[("K", 0)], inv_K=inputs[("inv_K", 0)],
+                T=[t[("cam_T_cam", 0, -1)], t[("cam_T_cam", 0, 1)]])
+    with pytest.raises(RuntimeError, match="WARP-mode input"):
+        raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, warped=src)
+    with pytest.raises(RuntimeError, match="plain WARP pass"):
+        raw.photo(h, target=tgt, src=src, warped=src, zero_img=True, want_target_out=True, **geom)
+    ident = raw.photo(h, target=tgt, src=src, mode=raw.PHOTO_PRED, want_selection=False)["min_reproj"]
+    with pytest.raises(RuntimeError, match="DynamicDepth"):
+        raw.photo(h, target=tgt, src=src, identity_min=ident, noise=t["noise"][0], selec_reproj=True, **geom)
+    with pytest.raises(RuntimeError, match="needs `noise`"):
+        raw.photo(h, target=tgt, src=src, syn=src, identity_in_pass=True, **geom)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
