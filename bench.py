@@ -348,7 +348,7 @@ def next_row_kernels(dev, batch, peak_gbs, iters=10):
     occ = occ.to(dev)
     aug = torch.zeros(B, 1, 1, 1, device=dev)
     lcv = B * (HEIGHT // 4) * (Wc // 4)
-    cases.append(("f.4", "cv_sweep_kernel<DYN>: DynamicDepth cost volume, 2 lookup frames, cv_min + pool occlusion fill (radius 1)",
+    cases.append(("f.4", "cv_sweep_quad_kernel<DYN> + pool pre-passes (cv_project / cv_interior / cv_sample / cv_pool): DynamicDepth cost volume, 2 lookup frames, cv_min + pool occlusion fill (radius 1)",
                   lambda: raw.cost_volume(h, current=cvd["current_feats"], lookup=cvd["lookup_feats"], poses=cvd["relative_poses"],
                                           K=cvd["K"], inv_K=cvd["inv_K"], bins=cvd["bins"], cv_min=True, occ=occ,
                                           occ_mode=raw.OCC_POOL, pool_radius=1, pool_th=0.7, aug_mask=aug),
