@@ -206,11 +206,26 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
                                                     counts=b["mask_counts"])["syn"]
         return sl["_syn"]
 
+    # the teacher pass as the step launches it: with the temporal hint synthesised in the step it stages the warps
+    # materialised for the synthesis and also returns d loss / d syn
+    in_step = "masks_last" in bufs[0]
+    warps = {}
+
+    def warped_of(i):
+        j = i % len(bufs)
+        if j not in warps:
+            b = bufs[j]
+            with torch.no_grad():
+                warps[j] = raw.temporal_warp(h, src=[b["color_-1"], b["color_1"]], depth=b["mono_disp"].detach(), K=b["K"],
+                                             inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()])
+        return warps[j]
+
     def photo4(i):
         b = bufs[i % len(bufs)]
         raw.photo(h, target=b["color_0"], src=[b["color_-1"], b["color_1"]], syn=syn_of(i),
                   depth=b["mono_disp"].detach(), K=b["K"], inv_K=b["inv_K"], T=[b["T_-1"].detach(), b["T_1"].detach()],
-                  identity_min=ident[i % len(bufs)], noise=b["noise_mono"], with_grad=True)
+                  identity_min=ident[i % len(bufs)], noise=b["noise_mono"], with_grad=True,
+                  want_grad_syn=in_step, warped=warped_of(i) if in_step else None)
 
     def photo2(i):
         b = bufs[i % len(bufs)]
@@ -226,7 +241,9 @@ def kernel_rooflines(st, opt, peak_gbs, iters=20):
     # algorithmic bytes per launch (fp32, every tensor once):
     cases = [
         # target 12 + src 24 + syn 24 + disp 4 + identity 4 + noise 4 read; min_reproj 4 + sel 1 + grad 4 written
-        ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass)", photo4, 81 * px, "photo_teacher"),
+        # (+ 24 staged warps read + 24 d/d syn written when the hint is synthesised in the step)
+        ("photo_kernel<WARP,GRAD> 4 candidates + automask (teacher pass" + (", staged warps, d/d syn)" if in_step else ")"),
+         photo4, (81 + (48 if in_step else 0)) * px, "photo_teacher"),
         # target 12 + src 24 + disp 4 + mask 4 read; min_reproj 4 + sel 1 + grad 4 written
         ("photo_kernel<WARP,GRAD> 2 candidates + masks (student pass)", photo2, 53 * px, "photo_student"),
         # SURVEY.md 8(d) A_cv without the missing mask (not requested here): current + lookup features read,

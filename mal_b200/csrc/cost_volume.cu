@@ -763,7 +763,7 @@ __device__ __forceinline__ void cq_ld(pk2* dst, const char* p) {
 template <int CONV, int MINB, bool DYN>
 __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_cost_volume_args a, const int Cp, const SizeDiv sdiv) {
   __shared__ CvGeom geom;
-  __shared__ float s_tx[4][CQ_G][8], s_ty[4][CQ_G][8];   // [warp][plane][pixel] bilinear fractions
+  __shared__ __align__(16) float4 s_w[4][CQ_G][8];        // [warp][plane][pixel] bilinear weights {nw, ne, sw, se}
   __shared__ int s_o[4][CQ_G][8];                          // [warp][plane][pixel] tap origin or -1
   __shared__ __align__(16) float4 s_part[4][CQ_G][8];     // [warp][plane][pixel] chunk sums c0..c3
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -892,8 +892,10 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       if (!__any_sync(0xffffffffu, (off[0] & off[1]) >= 0 || poisoned)) continue;   // 8 pixels x 8 planes all masked
 #pragma unroll
       for (int u = 0; u < 2; u++) {
-        s_tx[warp][sub + 4 * u][pl] = tx[u];
-        s_ty[warp][sub + 4 * u][pl] = ty[u];
+        // the four blend weights, formed once per (pixel, plane) here instead of once per lane in the sweep
+        // (the same operations: 1 - t as fma(t, -1, 1) = RN(1 - t))
+        const float e = xsub(1.0f, tx[u]), sfr = xsub(1.0f, ty[u]);
+        s_w[warp][sub + 4 * u][pl] = make_float4(xmul(sfr, e), xmul(sfr, tx[u]), xmul(ty[u], e), xmul(ty[u], tx[u]));
         s_o[warp][sub + 4 * u][pl] = off[u];
       }
       __syncwarp();
@@ -927,9 +929,8 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
                 r0 += quad_stride;
               }
             }
-            const pk2 tx2 = dup2(s_tx[warp][j][pl]), ty2 = dup2(s_ty[warp][j][pl]);
-            const pk2 e2 = x2fma(tx2, mone2, one2), s2 = x2fma(ty2, mone2, one2);   // 1 - tx, 1 - ty
-            const pk2 nw = x2mul(s2, e2), ne = x2mul(s2, tx2), sw = x2mul(ty2, e2), se = x2mul(ty2, tx2);
+            const float4 wv = s_w[warp][j][pl];
+            const pk2 nw = dup2(wv.x), ne = dup2(wv.y), sw = dup2(wv.z), se = dup2(wv.w);
             float s = 0.0f;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
