@@ -59,7 +59,7 @@ __host__ __device__ inline int cv_padded_channels(int C) { return (C + CV_CHUNK 
 
 inline size_t cv_smem_bytes(int nchunks, int num_bins) {
   size_t fl = sizeof(CvGeom) / 4 + 4;
-  fl += (size_t)3 * CV_BG * CV_PX;                 // descriptors: off, tx, ty
+  fl += (size_t)5 * CV_BG * CV_PX;                 // descriptors: off, the four blend weights
   fl += (size_t)nchunks * CV_BG * CV_PX;           // chunk sums
   fl += (size_t)2 * num_bins * CV_PX;              // cost, counts
   fl += (size_t)4 * CV_WARPS * CV_PX;              // epilogue scratch
@@ -457,9 +457,9 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
   float* smem = reinterpret_cast<float*>(dyn_smem());
   CvGeom* geom = reinterpret_cast<CvGeom*>(smem);
   int* d_off = reinterpret_cast<int*>(smem + sizeof(CvGeom) / 4 + 4);   // [BG][PX]
-  float* d_tx = reinterpret_cast<float*>(d_off + CV_BG * CV_PX);
-  float* d_ty = d_tx + CV_BG * CV_PX;
-  float* part = d_ty + CV_BG * CV_PX;                    // [nchunks][BG][PX]
+  float* d_w = reinterpret_cast<float*>(d_off + CV_BG * CV_PX);   // [4][BG][PX] blend weights nw, ne, sw, se: formed
+                                                                  // once per (pixel, plane) here, not once per chunk
+  float* part = d_w + 4 * CV_BG * CV_PX;                 // [nchunks][BG][PX]
   float* cost = part + (size_t)nchunks * CV_BG * CV_PX;  // [nb][PX]
   float* cnt = cost + (size_t)nb * CV_PX;                // [nb][PX]
   float* scr = cnt + (size_t)nb * CV_PX;                 // [4][WARPS][PX]
@@ -532,8 +532,13 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
             if (fls[i] & CV_DESC_OCC) off |= CV_OCC_BIT | ((fls[i] & CV_DESC_ZERO) ? CV_ZERO_BIT : 0);
           }
           d_off[k * CV_PX + lane] = off;
-          d_tx[k * CV_PX + lane] = tx;
-          d_ty[k * CV_PX + lane] = ty;
+          {
+            const float e = xsub(1.0f, tx), sfr = xsub(1.0f, ty);
+            d_w[(0 * CV_BG + k) * CV_PX + lane] = xmul(sfr, e);
+            d_w[(1 * CV_BG + k) * CV_PX + lane] = xmul(sfr, tx);
+            d_w[(2 * CV_BG + k) * CV_PX + lane] = xmul(ty, e);
+            d_w[(3 * CV_BG + k) * CV_PX + lane] = xmul(ty, tx);
+          }
         }
       } else
       for (int k = warp; k < gn; k += CV_WARPS) {
@@ -561,8 +566,13 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
           }
         }
         d_off[k * CV_PX + lane] = off;
-        d_tx[k * CV_PX + lane] = tx;
-        d_ty[k * CV_PX + lane] = ty;
+        {
+          const float e = xsub(1.0f, tx), sfr = xsub(1.0f, ty);
+          d_w[(0 * CV_BG + k) * CV_PX + lane] = xmul(sfr, e);
+          d_w[(1 * CV_BG + k) * CV_PX + lane] = xmul(sfr, tx);
+          d_w[(2 * CV_BG + k) * CV_PX + lane] = xmul(ty, e);
+          d_w[(3 * CV_BG + k) * CV_PX + lane] = xmul(ty, tx);
+        }
       }
       __syncthreads();
 
@@ -584,8 +594,7 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
         float4 t00[4], t01[4], t10[4], t11[4];
         int coff = -1;
         const int* po = d_off + lane;
-        const float* ptx = d_tx + lane;
-        const float* pty = d_ty + lane;
+        const float* pw = d_w + lane;
         float* pp = part + (size_t)ch * CV_BG * CV_PX + lane;
         for (int k = 0; k < gn; k++) {
           int off = po[k * CV_PX];
@@ -617,9 +626,8 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
                 base += hw;
               }
             }
-            const float tx = ptx[k * CV_PX], ty = pty[k * CV_PX];
-            const float e = xsub(1.0f, tx), s = xsub(1.0f, ty);
-            const float nw = xmul(s, e), ne = xmul(s, tx), sw = xmul(ty, e), se = xmul(ty, tx);
+            const float nw = pw[(0 * CV_BG + k) * CV_PX], ne = pw[(1 * CV_BG + k) * CV_PX];
+            const float sw = pw[(2 * CV_BG + k) * CV_PX], se = pw[(3 * CV_BG + k) * CV_PX];
 #pragma unroll
             for (int j = 0; j < 4; j++) acc = quad_l1(acc, t00[j], t01[j], t10[j], t11[j], cq[j], nw, ne, sw, se);
           }
@@ -743,7 +751,15 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 // (NCHW, once per lane); only the lookup features go through cv_pack_kernel.
 constexpr int CQ_NT = 128;                 // 4 warps = 32 pixels per CTA
 constexpr int CQ_G = 8;                    // depth planes per group: every lane projects two of them
-inline size_t cq_smem_bytes(int num_bins) { return ((size_t)2 * ((num_bins + 3) / 4 * 4) * CV_PX + 64) * 4; }
+// The count plane (how many lookup frames gave a non-zero difference) exists only when it is needed: with one lookup
+// frame count == (cost > 0), with cv_min there is no count, and the missing flags of the epilogue fit a lane's
+// register when it owns <= 32 planes.  Shared memory not taken is L1 for the texel re-fetches.
+__host__ __device__ inline bool cq_needs_counts(int num_lookup, int cv_min, int num_bins) {
+  return (num_lookup > 1 && !cv_min) || num_bins > 128;
+}
+inline size_t cq_smem_bytes(int num_bins, bool counts) {
+  return ((size_t)(counts ? 2 : 1) * ((num_bins + 3) / 4 * 4) * CV_PX + 64) * 4;
+}
 // cost / count accumulators: [plane group][pixel][plane & 3] so that the 32 lanes of a warp
 // (8 pixels x 4 planes of a group) hit 32 different banks
 __device__ __forceinline__ int cq_idx(int k, int col) { return (k >> 2) * (4 * CV_PX) + col * 4 + (k & 3); }
@@ -781,9 +797,13 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   const bool active = sub < nchunks;       // lanes beyond the last chunk still project their plane
 
   float* cost = reinterpret_cast<float*>(dyn_smem());   // [nb][CV_PX]
-  float* cnt = cost + (size_t)((nb + 3) / 4 * 4) * CV_PX;
+  float* cnt = cost + (size_t)((nb + 3) / 4 * 4) * CV_PX;   // only with has_cnt
   const bool cv_min = DYN && a.cv_min;
-  for (int k = sub; k < nb; k += 4) { cost[cq_idx(k, col)] = cv_min ? 1.0f : 0.0f; cnt[cq_idx(k, col)] = 0.0f; }
+  const bool has_cnt = cq_needs_counts(a.num_lookup, cv_min, nb);
+  for (int k = sub; k < nb; k += 4) {
+    cost[cq_idx(k, col)] = cv_min ? 1.0f : 0.0f;
+    if (has_cnt) cnt[cq_idx(k, col)] = 0.0f;
+  }
   // occlusion handling applies to samples whose matching augmentation is off (aug_mask == 0)
   const float* occ = nullptr;
   if (DYN && a.occ && a.occ_mode != 0 && !(a.aug_mask && __ldg(a.aug_mask + b) != 0.0f)) occ = a.occ + (size_t)b * hw;
@@ -963,7 +983,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
             cost[o] = fminf(diff == 0.0f ? 1.0f : diff, cost[o]);
           } else {
             cost[o] = xadd(cost[o], diff);
-            if (diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
+            if (has_cnt && diff > 0.0f) cnt[o] = xadd(cnt[o], 1.0f);
           }
         } else if (poisoned && pix_ok && k0 + sub + 4 * u < nb) {
           cost[cq_idx(k0 + sub + 4 * u, col)] = NAN;   // masked plane of a poisoned pixel: NaN * 0
@@ -978,8 +998,10 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   int has_nan = 0;
   for (int k = sub; k < nb; k += 4) {
     const int o = cq_idx(k, col);
-    const float v = cv_min ? (cost[o] == 1.0f ? 0.0f : cost[o])       // cost_volume[cost_volume == 1] = 0
-                           : xdiv(cost[o], xadd(cnt[o], 1e-7f));       // cost_volume / (counts + 1e-7)
+    // (one lookup frame: counts = (diff > 0) = (cost > 0); a NaN cost counts 0 either way)
+    const float c0 = cost[o];
+    const float v = cv_min ? (c0 == 1.0f ? 0.0f : c0)                                             // cost_volume[cost_volume == 1] = 0
+                           : xdiv(c0, xadd(has_cnt ? cnt[o] : (c0 > 0.0f ? 1.0f : 0.0f), 1e-7f));   // cost_volume / (counts + 1e-7)
     cost[o] = v;
     vmax = fmaxf(vmax, v);
     has_nan |= (v != v);
@@ -991,6 +1013,7 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
   if (has_nan) vmax = NAN;   // torch.max propagates NaN, fmaxf drops it
   float npos = 0.0f, best = INFINITY;
   int besti = 0x7fffffff;
+  unsigned missbits = 0u;   // (no count plane) the missing flags of this lane's planes sub, sub + 4, ...
   for (int k = sub; k < nb; k += 4) {
     const int o = cq_idx(k, col);
     const float v = cost[o];
@@ -998,7 +1021,8 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
     float out = v;
     if (a.set_missing_to_max) out = xadd(xmul(v, xsub(1.0f, miss)), xmul(vmax, miss));
     cost[o] = out;
-    cnt[o] = miss;
+    if (has_cnt) cnt[o] = miss;
+    else if (v == 0.0f) missbits |= 1u << (k >> 2);
     if (xmul(out, xsub(1.0f, miss)) > 0.0f) npos += 1.0f;
     const float viz = (out == 0.0f) ? 100.0f : out;
     // first min; the first NaN wins like torch.min (and like cv_sweep_kernel); an all-+Inf column keeps
@@ -1024,7 +1048,8 @@ __global__ void __launch_bounds__(CQ_NT, MINB) cv_sweep_quad_kernel(const mal_co
       float out = cost[o];
       if (a.apply_confidence) out = xmul(out, conf);
       a.cost_volume[vol + (size_t)k * hw + p] = out;
-      if (a.missing_mask) a.missing_mask[vol + (size_t)k * hw + p] = cnt[o];
+      if (a.missing_mask)
+        a.missing_mask[vol + (size_t)k * hw + p] = has_cnt ? cnt[o] : (float)((missbits >> (k >> 2)) & 1u);
     }
     if (sub == 0) {
       const size_t po = (size_t)b * hw + p;
@@ -1127,7 +1152,7 @@ extern "C" int mal_cost_volume_forward(const mal_cost_volume_args* args, mal_str
     else launch(cv_sweep_kernel<CONV_, 5, false>, grid, dim3(CV_NT), smem, st, a, Cp, sdiv);                \
   } while (0)
   if (quad) {
-    const size_t qsmem = cq_smem_bytes(a.num_bins);
+    const size_t qsmem = cq_smem_bytes(a.num_bins, cq_needs_counts(a.num_lookup, a.cv_min, a.num_bins));
 #define MAL_CQ_GO(CONV_, DYN_)                                                                                  \
   do {                                                                                                          \
     if (minb <= 3) launch(cv_sweep_quad_kernel<CONV_, 3, DYN_>, grid, dim3(CQ_NT), qsmem, st, a, Cp, sdiv);         \
