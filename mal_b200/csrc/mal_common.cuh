@@ -174,6 +174,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sums of N <= 32 per-lane values over the warp, all at once: lane j < N returns sum over the lanes of v[j] (the other
+// lanes return padding).  Each butterfly step halves the values a lane still carries (a lane keeps the half its
+// partner sends the other half of), so the whole reduction is 31 shuffles instead of 5 N (N = 24: 31 against 120).
+// Fixed order: deterministic.
+template <int N>
+__device__ __forceinline__ float warp_sum_transposed(const float (&v)[N], int lane) {
+  static_assert(N <= 32, "one value per lane at most");
+  float a[16], b[8], c[4], d[2];
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const float lo = i < N ? v[i < N ? i : 0] : 0.0f, hi = i + 16 < N ? v[i + 16 < N ? i + 16 : 0] : 0.0f;
+    a[i] = (b16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b16 ? lo : hi, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) b[i] = (b8 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, b8 ? a[i] : a[i + 8], 8);
+#pragma unroll
+  for (int i = 0; i < 4; i++) c[i] = (b4 ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, b4 ? b[i] : b[i + 4], 4);
+#pragma unroll
+  for (int i = 0; i < 2; i++) d[i] = (b2 ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, b2 ? c[i] : c[i + 2], 2);
+  return (b1 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, b1 ? d[0] : d[1], 1);
+}
+
 __device__ __forceinline__ int reflect_index(int i, int n) {
   // ReflectionPad2d(1) index map, also safe for |overshoot| <= n-1
   if (i < 0) i = -i;

@@ -686,10 +686,10 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
 
   // ---- per-CTA partials ---------------------------------------------------------------------
   const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int j = 0; j < 24; j++) {
-    float v = (GRAD && WARP) ? warp_sum(gP[j]) : 0.0f;
-    if (lane == 0) red[warp * PH_NPART + j] = v;
+  {
+    // the 24 d/d(K@T) sums of the warp in one transposed reduction (31 shuffles instead of 120)
+    const float v = (GRAD && WARP) ? warp_sum_transposed<24>(gP, lane) : 0.0f;
+    if (lane < 24) red[warp * PH_NPART + lane] = v;
   }
   {
     float v = warp_sum(acc_loss);

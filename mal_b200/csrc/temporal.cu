@@ -346,11 +346,8 @@ __global__ void __launch_bounds__(TW_NT) tb_backward_kernel(const mal_temporal_a
   __syncthreads();
   const bool live_cta = any_grad != 0;
   if (live_cta) {
-#pragma unroll
-    for (int j = 0; j < 24; j++) {
-      const float v = warp_sum(gP[j]);
-      if (lane == 0) red[warp][j] = v;
-    }
+    const float v = warp_sum_transposed<24>(gP, lane);
+    if (lane < 24) red[warp][lane] = v;
     __syncthreads();
   }
   if (threadIdx.x < TB_NPART && a.partials) {
