@@ -686,12 +686,17 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
 
   // ---- per-CTA partials ---------------------------------------------------------------------
   const int warp = tid >> 5, lane = tid & 31;
-  {
-    // the 24 d/d(K@T) sums of the warp in one transposed reduction (31 shuffles instead of 120)
-    const float v = (GRAD && WARP) ? warp_sum_transposed<24>(gP, lane) : 0.0f;
-    if (lane < 24) red[warp * PH_NPART + lane] = v;
-  }
-  {
+  if (GRAD && WARP) {
+    // the 24 d/d(K@T) sums and the two loss sums of the warp in one transposed reduction (31 shuffles instead of 130)
+    float all[PH_NPART];
+#pragma unroll
+    for (int j = 0; j < 24; j++) all[j] = gP[j];
+    all[24] = acc_loss;
+    all[25] = acc_w;
+    const float v = warp_sum_transposed<PH_NPART>(all, lane);
+    if (lane < PH_NPART) red[warp * PH_NPART + lane] = v;
+  } else {
+    if (lane < 24) red[warp * PH_NPART + lane] = 0.0f;
     float v = warp_sum(acc_loss);
     if (lane == 0) red[warp * PH_NPART + 24] = v;
     v = warp_sum(acc_w);
