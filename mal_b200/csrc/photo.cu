@@ -307,8 +307,46 @@ photo_kernel(const mal_photo_args a, const __grid_constant__ PhotoMaps maps, con
         mu_y = xdivc<9>(sum9(yw0));
         eyy = xdivc<9>(sum9_prod(yw0, yw0));
       }
+      // Forward-only passes score the candidates two at a time on packed fp32 pairs (FFMA2 / FADD2 / FMUL2: the same
+      // IEEE operations per half, mal_common.cuh): these passes are the most issue-bound ones (78 % of the issue
+      // slots in the split-min pass, 71 % of its instructions in this loop).
+      constexpr bool PAIRS = !GRAD && !DD;
+      if (PAIRS) {
+        const float mu_yy = xmul(mu_y, mu_y), sig_y = xsub(eyy, mu_yy);
+#pragma unroll
+        for (int k = 0; k + 1 < NC; k += 2) {
+          if (k + 1 < ncand) {
+            const float* X0 = sx + (size_t)k * tl.TS + c * tl.VN + vc;
+            const float* X1 = X0 + tl.TS;
+            pk2 xw2[9];
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+              for (int dx = 0; dx < 3; dx++)
+                xw2[dy * 3 + dx] = pack2(X0[(dy - 1) * PH_VW + dx - 1], X1[(dy - 1) * PH_VW + dx - 1]);
+            const pk2 dl = x2sub(dup2(yw0[4]), xw2[4]);
+            const float l1a = fabsf(lo2(dl)), l1b = fabsf(hi2(dl));
+            lsum[k] = (c == 0) ? l1a : xadd(lsum[k], l1a);
+            lsum[k + 1] = (c == 0) ? l1b : xadd(lsum[k + 1], l1b);
+            if (!a.no_ssim) {
+              pk2 yw2[9];
+#pragma unroll
+              for (int q = 0; q < 9; q++) yw2[q] = dup2(yw0[q]);
+              const pk2 mu_x = x2divc<9>(sum9(xw2));
+              const pk2 exx = x2divc<9>(sum9_prod(xw2, xw2));
+              const pk2 exy = x2divc<9>(sum9_prod(xw2, yw2));
+              SsimTerms t0, t1;
+              ssim_terms2(mu_x, mu_y, mu_yy, sig_y, exx, exy, t0, t1);
+              const float sa = clamp01(t0.v), sb = clamp01(t1.v);
+              ssum[k] = (c == 0) ? sa : xadd(ssum[k], sa);
+              ssum[k + 1] = (c == 0) ? sb : xadd(ssum[k + 1], sb);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int k = 0; k < NC; k++) {
+        if (PAIRS && (k | 1) < ncand) continue;   // scored above as half of a pair
         if (k < ncand) {
           float yw[9];   // the target as call k sees it (DD: zeroed where a prediction up to k is dark)
 #pragma unroll
