@@ -18,7 +18,9 @@
 //             warp  <-> a 16-channel chunk (the cascade-sum granule of the reference, see below)
 //             lane  <-> pixel
 //             Bins are processed in groups of CV_BG.  Per group:
-//               P  all threads: one projection per (pixel, bin) -> {tap offset | masked, tx, ty} in smem
+//               P  all threads: one projection per (pixel, bin) -> {tap offset | masked, the four bilinear
+//                  weights} in smem (formed once here, not once per channel chunk: the blend below is
+//                  fma-pipe-bound)
 //               C  each warp sweeps the group's bins for its chunk.  The 2x2x16 texel block lives in
 //                  registers and is only re-fetched when the integer tap origin moves.  Operand
 //                  delivery is the real limit of this op: a sweep that loaded its 4 taps + 1 feature
@@ -31,6 +33,10 @@
 //                  accumulate over lookup frames.
 //             Epilogue: / (counts + 1e-7), per-pixel max over bins, missing fill, confidence,
 //             first-index arg-min, coalesced plane-by-plane stores.
+//   kernel 2' cv_sweep_quad_kernel (C <= 64, the default): four lanes per pixel, no block barrier in the sweep;
+//             see its own comment further down.  Both sweeps have a DynamicDepth variant (cv_min, set_1 / pool
+//             occlusion fill); the pool fill runs its own pre-passes (cv_project / cv_interior / cv_pack_cm /
+//             cv_sample / cv_pool), described where they are defined.
 //
 // Arithmetic contract (bit-exact against torch CPU, pinned by tests/golden/cost_volume.npz):
 //   projection / grid_sample arithmetic as in mal_math.cuh;  mean over channels = ATen cascade_sum
@@ -742,7 +748,8 @@ __global__ void __launch_bounds__(CV_NT, MINB) cv_sweep_kernel(const mal_cost_vo
 // Per group of CQ_G = 8 depth planes every lane projects TWO planes (branch-free, so the two chains of
 // IEEE divisions interleave); descriptors and chunk sums are exchanged through a per-warp shared-memory
 // scratch (scalar stores + broadcast loads: about half the L1 wavefronts of the equivalent shuffles),
-// and each lane then sweeps the 8 planes for its chunk with the 2x2x16 register cache.  No block barrier
+// and each lane then sweeps the 8 planes for its chunk with the 2x2x16 register cache (the projecting lane also
+// forms the plane's four blend weights, so the sweep reads one float4 per plane).  No block barrier
 // inside the sweep, and only 8 (not 32) pixels share a warp's re-fetch decision, so a texel block is
 // re-fetched in ~20% instead of ~57% of the warp iterations (profiles/r1_notes.md).
 // The bilinear blend and the subtraction run on packed fp32 pairs (FFMA2 / FADD2: two channels per
