@@ -8,7 +8,8 @@
 //      out-of-bounds elements).  Images whose rows are not 16-byte multiples take a plain loader instead.
 //   A  (WARP mode) the two warped candidates are produced in place from the staged disparity:
 //      disp->depth->backproject->project->bilinear gather (border)
-//      (manydepth/layers.py:14-23,163-199, trainer.py:1122-1125)
+//      (manydepth/layers.py:14-23,163-199, trainer.py:1122-1125).  Skipped when the caller hands in the warps it has
+//      materialised anyway (mal_photo_args.warped: staged by TMA like PRED mode's predictions).
 //   B  per pixel of the loss region: 3x3 SSIM + L1 per candidate (layers.py:243-257,
 //      loss_utils.py:46-55), min/argmin over candidates (:103), tie-break noise + automask
 //      (:105-109, :27-44), multi-frame mask (:192-194); masked partial sums (:112-113).
@@ -18,7 +19,10 @@
 //      profiles/r2_notes.md.)
 //   C  (grad) per tile pixel: gather the 3x3 neighbourhood's coefficients (atomics-free SSIM
 //      backward), add the L1 term, then chain through the bilinear sampler, the projection and
-//      backprojection to d/d depth and d/d(K@T); per-CTA partials go to a workspace.
+//      backprojection to d/d depth and d/d(K@T); per-CTA partials (one transposed warp reduction
+//      of all 26 sums) go to a workspace.  d/d syn (the temporal-hint candidates) is formed in a
+//      second, compact loop and only in tiles where phase B saw such a candidate win.
+//   Forward-only passes score their candidates two at a time on packed fp32 pairs in phase B.
 // A second tiny kernel reduces the per-CTA partials in a fixed order (deterministic).
 //
 // HBM traffic per pixel (WARP mode, 2+2 candidates, grad): reads 9 (target+2 src... gathers hit
