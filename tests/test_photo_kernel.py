@@ -228,3 +228,33 @@ def test_ready_made_warps_give_the_same_bits(backend, shape):
         if grad_syn:
             for a, b in zip(got["grad_syn"], want["grad_syn"]):
                 assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("automask", [True, False])
+def test_dynamicdepth_mode_at_the_c_level(backend, automask):
+    """photo_kernel<..., DD> through the raw binding (zero_img + selec_reproj, the identity candidates given as `syn`):
+    masked mean, the zeroed target and d/d disparity against the oracle's compute_losses of one scale
+    (dynamicdepth/trainer.py:958-975, :1006-1128)."""
+    h, dev = handle_and_device(backend)
+    inputs, t = make_photometric_inputs(2, 40, 72, num_scales=1, seed=19, translation_scale=0.3)
+    inputs[("color", -1, 0)][:, :, 4:14, 6:30] = 0.0
+    inputs[("color", 1, 0)][:, :, 18:30, 30:60] = 0.0
+    disp = t[("mono_disp", 0)].clone().requires_grad_(True)
+    o = {("disp", 0): disp, ("cam_T_cam", 0, -1): t[("cam_T_cam", 0, -1)], ("cam_T_cam", 0, 1): t[("cam_T_cam", 0, 1)]}
+    O.images_pred(inputs, o, num_scales=1, height=40, width=72)
+    ref_inputs = {k: v.clone() for k, v in inputs.items()}
+    want, aux = O.dynamicdepth_compute_losses(ref_inputs, o, (0,), noises=t["noise"][:1], automask=automask)
+    want_g, = torch.autograd.grad(want["reproj_loss/0"], disp)
+    d = lambda x: x.to(dev)
+    ident = [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])]
+    out = raw.photo(h, target=d(inputs[("color", 0, 0)]), src=ident, syn=ident if automask else None,
+                    depth=d(t[("mono_disp", 0)]), K=d(inputs[("K", 0)]), inv_K=d(inputs[("inv_K", 0)]),
+                    T=[d(t[("cam_T_cam", 0, -1)]), d(t[("cam_T_cam", 0, 1)])], noise=d(t["noise"][0]) if automask else None,
+                    zero_img=True, selec_reproj=True, identity_in_pass=True, want_target_out=True, with_grad=True)
+    w = float(want["reproj_loss/0"])
+    assert abs(float(out["sums"][2]) - w) <= LOSS_RTOL * abs(w)
+    assert torch.equal(out["target_out"].cpu(), ref_inputs[("color", 0, 0)])
+    if automask:
+        assert torch.equal((out["selection"].cpu() >> 7).float(), aux[("mask", 0)].float())
+    assert _grad_err(out["grad_depth"].cpu() / (out["sums"][1].cpu() + 1e-7), want_g) < GRAD_RTOL

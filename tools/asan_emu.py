@@ -37,7 +37,7 @@ def main():
     E._handle = _capi.bind(ctypes.CDLL(OUT))
     import pytest
     tests = ["test_cost_volume.py", "test_photo_kernel.py", "test_pointwise_kernels.py", "test_forward_warp.py",
-             "test_dyn_utils.py", "test_step.py", "test_corr.py", "test_upsample.py"]
+             "test_dyn_utils.py", "test_step.py", "test_corr.py", "test_upsample.py", "test_temporal.py"]
     # (test_api.py is left out: any C++ exception thrown inside libtorch aborts under a preloaded ASan
     #  - an interception problem that has nothing to do with the kernels)
     sys.exit(pytest.main(["-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider"] +
