@@ -158,3 +158,24 @@ def test_pool_fill_needs_its_workspace():
     a.occ_mode, a.pool_radius = raw.OCC_POOL, 1
     assert h.mal_cost_volume_forward(C.byref(a), None) == 1          # MAL_ERR_ARGUMENT
     assert b"desc workspace" in h.mal_last_error()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_dynamicdepth_pool_fill_radius_2(backend):
+    """--cv_pool_radius 2 (5x5x5 windows): the generic-radius pre-passes and pool kernel against the oracle's
+    max_pool3d (dynamicdepth/networks/resnet_encoder.py:196-202)."""
+    h, dev = handle_and_device(backend)
+    B, H, W, C, nb = 1, 64, 96, 32, 12
+    cv = make_cost_volume_inputs(B, H, W, channels=C, num_lookup=2, num_bins=nb, seed=93, min_bin=0.5, max_bin=6.0,
+                                 translation_scale=0.5)
+    look_img = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(94))
+    look_img[:, :, 16:44, 20:60] = 0.0
+    aug = torch.zeros(B, 1, 1, 1)
+    want_vol, want_miss = O.match_features_dynamic(cv["current_feats"], cv["lookup_feats"], cv["relative_poses"],
+                                                   cv["K"], cv["inv_K"], cv["bins"], look_img, True, aug, False, True,
+                                                   2, 0.7)
+    occ = (O.occlusion_batch(look_img, H // 4, W // 4)[:, 0] > 0).float()
+    out = _run(h, dev, cv, cv_min=True, occ=occ.to(dev), occ_mode=raw.OCC_POOL, pool_radius=2, pool_th=0.7,
+               aug_mask=aug.to(dev))
+    assert torch.equal(out["missing_mask"].cpu(), want_miss)
+    assert torch.equal(out["cost_volume"].cpu(), want_vol)
